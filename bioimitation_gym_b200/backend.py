@@ -1,0 +1,248 @@
+"""ctypes binding of libbio_b200.so and the batched ``VecEnv``.
+
+``VecEnv`` is the vectorised form of the reference's ``OsimEnv``
+(reference ``opensim_environment.py:35-113``): ``reset() -> obs[N, D]`` and
+``step(actions[N, A]) -> (obs, reward[N], done[N], info)`` with
+``info['all_rewards']`` = the reward terms (reference
+``muscle_walking_imitation_env2D.py:358``).  Tensors are torch CUDA tensors
+owned by the env and handed to the C ABI as raw device pointers (zero copy);
+PyTorch is only the allocator / stream provider.
+
+There is no CPU fallback: constructing a ``VecEnv`` without the compiled
+library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Any, Dict, Mapping, Optional
+
+import numpy as np
+
+from . import ctables as ct
+from . import registry, tasks
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libbio_b200.so")
+
+_lib = None
+
+C_API = {
+    "bio_abi_version": (ctypes.c_int, []),
+    "bio_sizeof_model_tables": (ctypes.c_uint64, []),
+    "bio_sizeof_task_config": (ctypes.c_uint64, []),
+    "bio_last_error": (ctypes.c_char_p, []),
+    "bio_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                  ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, ctypes.c_int64,
+                                  ctypes.POINTER(ctypes.c_void_p)]),
+    "bio_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "bio_reset": (ctypes.c_int, [ctypes.c_void_p] * 4),
+    "bio_step": (ctypes.c_int, [ctypes.c_void_p] * 7),
+    "bio_step_host": (ctypes.c_int, [ctypes.c_void_p] * 6),
+    "bio_reset_host": (ctypes.c_int, [ctypes.c_void_p] * 3),
+    "bio_get_state": (ctypes.c_int, [ctypes.c_void_p] * 3),
+    "bio_set_state": (ctypes.c_int, [ctypes.c_void_p] * 3),
+    "bio_eval_debug": (ctypes.c_int, [ctypes.c_void_p] * 4),
+    "bio_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
+    "bio_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "bio_obs_dim": (ctypes.c_int32, [ctypes.c_void_p]),
+    "bio_n_act": (ctypes.c_int32, [ctypes.c_void_p]),
+}
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the CUDA library and declare every symbol of include/bio_b200.h."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). This backend has no CPU fallback." % p)
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in C_API.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    ct.check_abi(lib)
+    if path is None:
+        _lib = lib
+    return lib
+
+
+class BioError(RuntimeError):
+    pass
+
+
+def _check(lib, rc: int, what: str):
+    if rc != 0:
+        msg = lib.bio_last_error()
+        raise BioError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class VecEnv:
+    """N independent envs of one env ID on one CUDA device."""
+
+    def __init__(self, env_id: str, config: Optional[Mapping[str, Any]] = None, model=None, ref=None):
+        import torch
+        self.torch = torch
+        self.lib = load_library()
+        cfg = tasks.merged_config(config)
+        self.env_id = env_id
+        self.config = cfg
+        self.spec, self.cm, self.ref, self.task = registry.build_env_tables(env_id, cfg, model, ref)
+        if not torch.cuda.is_available():
+            raise BioError("no CUDA device available: the batched physics step has no CPU fallback")
+        self.num_envs = int(cfg["num_envs"])
+        self.device_index = int(cfg["device"]) if not isinstance(cfg["device"], str) else \
+            torch.device(cfg["device"]).index or 0
+        self.device = torch.device("cuda", self.device_index)
+        dt = str(cfg["dtype"]).replace("torch.", "")
+        if dt in ("float32", "fp32", "f32"):
+            self.dtype, prec = torch.float32, ct.MACROS["BIO_PREC_F32"]
+        elif dt in ("float64", "fp64", "f64", "double"):
+            self.dtype, prec = torch.float64, ct.MACROS["BIO_PREC_F64"]
+        else:
+            raise ValueError("dtype must be float32 or float64")
+        t = self.cm.tables
+        self.n_act, self.n_dof, self.n_muscles = t.n_act, t.n_dof, t.n_muscles
+        self.obs_dim = self.task.obs_dim
+        self.n_terms = self.task.n_reward_terms
+        self.action_low = np.ctypeslib.as_array(t.act_min)[:self.n_act].copy()
+        self.action_high = np.ctypeslib.as_array(t.act_max)[:self.n_act].copy()
+        if self.spec.torque:
+            # the action space of a torque env is the actuator range (opensim_wrapper.py:39-53)
+            pass
+        self._ref_keep = dict(q=np.ascontiguousarray(self.ref["q"], dtype=np.float64),
+                              u=np.ascontiguousarray(self.ref["u"], dtype=np.float64),
+                              body_pos=np.ascontiguousarray(self.ref["body_pos"], dtype=np.float64),
+                              com_pos=np.ascontiguousarray(self.ref["com_pos"], dtype=np.float64))
+        r = ct.BioRefTables()
+        r.n_rows, r.n_coords = self._ref_keep["q"].shape
+        r.n_refbodies = self._ref_keep["body_pos"].shape[1]
+        r.q = self._ref_keep["q"].ctypes.data
+        r.u = self._ref_keep["u"].ctypes.data
+        r.body_pos = self._ref_keep["body_pos"].ctypes.data
+        r.com_pos = self._ref_keep["com_pos"].ctypes.data
+        h = ctypes.c_void_p()
+        rc = self.lib.bio_create(ctypes.addressof(self.cm.tables), ctypes.addressof(self.task),
+                                 ctypes.addressof(r), self.num_envs, self.device_index, prec,
+                                 int(cfg["seed"]), int(cfg["env_offset"]), ctypes.byref(h))
+        _check(self.lib, rc, "bio_create")
+        self.handle = h
+        N = self.num_envs
+        with torch.cuda.device(self.device):
+            self.obs = torch.zeros((N, self.obs_dim), dtype=self.dtype, device=self.device)
+            self.reward = torch.zeros((N,), dtype=self.dtype, device=self.device)
+            self.done = torch.zeros((N,), dtype=torch.uint8, device=self.device)
+            self.terms = torch.zeros((N, self.n_terms), dtype=self.dtype, device=self.device)
+            self._stats = torch.zeros((16,), dtype=torch.float64, device=self.device)
+
+    # ------------------------------------------------------------------ API
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self, mask=None):
+        """Reference-state reset of all envs (or those with mask != 0)."""
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device, dtype=self.torch.uint8).contiguous()
+        _check(self.lib, self.lib.bio_reset(self.handle, _ptr(m), _ptr(self.obs), self._stream()), "bio_reset")
+        return self.obs
+
+    def step(self, actions):
+        a = actions
+        if a.device != self.device or a.dtype != self.dtype or not a.is_contiguous():
+            a = a.to(device=self.device, dtype=self.dtype).contiguous()
+        if tuple(a.shape) != (self.num_envs, self.n_act):
+            raise ValueError("actions must have shape (%d, %d)" % (self.num_envs, self.n_act))
+        _check(self.lib, self.lib.bio_step(self.handle, _ptr(a), _ptr(self.obs), _ptr(self.reward),
+                                           _ptr(self.done), _ptr(self.terms), self._stream()), "bio_step")
+        return self.obs, self.reward, self.done, {"all_rewards": self.terms}
+
+    def step_host(self, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, done: np.ndarray,
+                  terms: Optional[np.ndarray] = None):
+        """Host-buffer call (numpy / pinned arrays in the env's dtype): H2D, step, D2H, sync."""
+        _check(self.lib, self.lib.bio_step_host(
+            self.handle, actions.ctypes.data, obs.ctypes.data, reward.ctypes.data, done.ctypes.data,
+            terms.ctypes.data if terms is not None else None), "bio_step_host")
+
+    def reset_host(self, obs: np.ndarray, mask: Optional[np.ndarray] = None):
+        _check(self.lib, self.lib.bio_reset_host(
+            self.handle, mask.ctypes.data if mask is not None else None, obs.ctypes.data), "bio_reset_host")
+
+    # ---------------------------------------------------------------- state
+    def _state_struct(self, tensors: Dict[str, Any]):
+        p = ct.BioStatePtrs()
+        for k, v in tensors.items():
+            setattr(p, k, v.data_ptr())
+        return p
+
+    def get_state(self):
+        torch = self.torch
+        N, H = self.num_envs, self.task.horizon
+        mk = lambda *s: torch.zeros(s, dtype=self.dtype, device=self.device)
+        out = dict(q=mk(N, self.n_dof), u=mk(N, self.n_dof), act=mk(N, self.n_muscles), lm=mk(N, self.n_muscles),
+                   last_action=mk(N, self.n_act), history=mk(N, H, self.n_act), old_px=mk(N),
+                   istep=torch.zeros(N, dtype=torch.int32, device=self.device),
+                   first=torch.zeros(N, dtype=torch.int32, device=self.device),
+                   hist_pos=torch.zeros(N, dtype=torch.int32, device=self.device),
+                   episode=torch.zeros(N, dtype=torch.int64, device=self.device))
+        p = self._state_struct(out)
+        _check(self.lib, self.lib.bio_get_state(self.handle, ctypes.addressof(p), self._stream()), "bio_get_state")
+        return out
+
+    def set_state(self, state: Dict[str, Any]):
+        torch = self.torch
+        keep = {}
+        for k, v in state.items():
+            want = torch.int32 if k in ("istep", "first", "hist_pos") else \
+                (torch.int64 if k == "episode" else self.dtype)
+            keep[k] = torch.as_tensor(v).to(device=self.device, dtype=want).contiguous()
+        p = self._state_struct(keep)
+        _check(self.lib, self.lib.bio_set_state(self.handle, ctypes.addressof(p), self._stream()), "bio_set_state")
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def eval_debug(self, controls=None):
+        """One dynamics evaluation at the current state (no integration)."""
+        torch = self.torch
+        N, nd, nm = self.num_envs, self.n_dof, self.n_muscles
+        mk = lambda *s: torch.zeros(s, dtype=self.dtype, device=self.device)
+        out = dict(udot=mk(N, nd), tendon_force=mk(N, nm), fiber_force=mk(N, nm), fiber_vel=mk(N, nm),
+                   act_dot=mk(N, nm), path_len=mk(N, nm), path_vel=mk(N, nm), contact=mk(N, 2, 6),
+                   limit_force=mk(N, self.cm.tables.n_limits), mass_matrix=mk(N, nd, nd), bias=mk(N, nd))
+        p = ct.BioDebugPtrs()
+        for k, v in out.items():
+            if v.numel():
+                setattr(p, k, v.data_ptr())
+        c = None
+        if controls is not None:
+            c = controls.to(device=self.device, dtype=self.dtype).contiguous()
+        _check(self.lib, self.lib.bio_eval_debug(self.handle, _ptr(c), ctypes.addressof(p), self._stream()),
+               "bio_eval_debug")
+        return out
+
+    def stats(self, reset: bool = False):
+        """Device tensor of 16 float64 rollout statistics (see bio_stats in the header)."""
+        _check(self.lib, self.lib.bio_stats(self.handle, _ptr(self._stats), int(reset), self._stream()), "bio_stats")
+        return self._stats
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.bio_launch_count(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.bio_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,462 @@
+// bio_capi.cu -- extern "C" entry points declared in include/bio_b200.h.
+//
+// A handle owns: the model block in the kernel's scalar type (device), the
+// reference tables (device), the SoA env state (device) and the statistics
+// buffer.  I/O buffers of bio_step/bio_reset are caller-owned device pointers;
+// nothing is allocated per step.  There is no CPU fallback: every compute entry
+// point launches a kernel or fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "bio_coop.cuh"
+
+#define COOP_BLOCK 256
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(-2, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                                std::to_string(__LINE__) + ")");                                   \
+    } while (0)
+
+struct HandleBase {
+    int precision = 0, device = 0, n = 0;
+    int64_t launches = 0;
+    BioModelTables model;
+    BioTaskConfig task;
+    unsigned long long seed = 0;
+    long long env_offset = 0;
+    int block = 32;
+    std::vector<void*> allocs;
+    double* stats = nullptr;          // 16 doubles
+    virtual ~HandleBase() {}
+};
+
+template <typename T>
+struct Handle : HandleBase {
+    bio::DevModel<T>* d_model = nullptr;
+    bio::DevTask<T> task_d;
+    bio::EnvState<T> st;
+    size_t smem = 0;
+    int coop_cls = -1;        // -1: thread-per-env kernel, 0/1: cooperative kernel size class
+    size_t coop_smem = 0;
+    // device scratch for the *_host entry points
+    T* h_actions = nullptr; T* h_obs = nullptr; T* h_reward = nullptr; T* h_terms = nullptr;
+    uint8_t* h_done = nullptr; uint8_t* h_mask = nullptr;
+};
+
+template <typename T>
+int dev_alloc(HandleBase* h, T** p, size_t count) {
+    void* q = nullptr;
+    CU(cudaMalloc(&q, (count ? count : 1) * sizeof(T)));
+    CU(cudaMemset(q, 0, (count ? count : 1) * sizeof(T)));
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+template <typename T>
+int upload_ref(HandleBase* h, const double* src, size_t count, const T** dst) {
+    std::vector<T> tmp(count ? count : 1);
+    for (size_t i = 0; i < count; i++) tmp[i] = (T)src[i];
+    T* d = nullptr;
+    int rc = dev_alloc(h, &d, count);
+    if (rc) return rc;
+    CU(cudaMemcpy(d, tmp.data(), count * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = d;
+    return 0;
+}
+
+int pick_block(int n) {
+    // one thread per env: keep every SM sub-partition busy before stacking
+    // warps in a CTA (148 SMs x 4 schedulers)
+    if (n <= 148 * 4 * 32) return 32;
+    if (n <= 148 * 8 * 64) return 64;
+    return 128;
+}
+
+template <typename T>
+int set_kernel_attrs(Handle<T>* h) {
+    h->smem = sizeof(bio::DevModel<T>);
+    CU(cudaFuncSetAttribute(bio::bio_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CU(cudaFuncSetAttribute(bio::bio_reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CU(cudaFuncSetAttribute(bio::bio_eval_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CU(cudaFuncSetAttribute(bio::bio_lm0_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    return 0;
+}
+
+template <typename T>
+int create_impl(const BioModelTables* model, const BioTaskConfig* task, const BioRefTables* ref, int n, int device,
+                unsigned long long seed, long long env_offset, Handle<T>* h) {
+    CU(cudaSetDevice(device));
+    h->device = device;
+    h->n = n;
+    h->model = *model;
+    h->task = *task;
+    h->seed = seed;
+    h->env_offset = env_offset;
+    h->block = pick_block(n);
+    if (const char* e = getenv("BIO_BLOCK")) { int b = atoi(e); if (b >= 32 && b <= 256 && b % 32 == 0) h->block = b; }
+    int rc;
+    if ((rc = set_kernel_attrs(h))) return rc;
+    // cooperative kernel: size class by model, BIO_KERNEL=thread forces the thread-per-env kernel
+    {
+        const char* kv = getenv("BIO_KERNEL");
+        const bool want_coop = !(kv && strcmp(kv, "thread") == 0);
+        typedef bio::CoopCls<0> C0;
+        typedef bio::CoopCls<1> C1;
+        auto fits = [&](int G, int ND, int NM, int NP, int NAX) {
+            return model->n_dof <= ND && model->n_muscles <= NM && model->n_act <= NM && model->n_pathpts <= NP &&
+                   model->n_axes <= NAX && model->n_bodies + model->n_dof <= G &&
+                   model->n_bodies + model->n_obspts <= G && model->n_spheres + model->n_limits <= G &&
+                   model->n_obspts <= COOP_MAXOBS && model->n_coords <= 2 * G && task->n_pd <= G;
+        };
+        const size_t base = ((sizeof(bio::DevModel<T>) + 15) / 16) * 16;
+        if (want_coop && fits(C0::G, C0::ND, C0::NM, C0::NP, C0::NAX)) {
+            h->coop_cls = 0;
+            h->coop_smem = base + (COOP_BLOCK / C0::G) * sizeof(bio::EnvWork<T, 0>);
+            CU(cudaFuncSetAttribute(bio::bio_coop_step_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)h->coop_smem));
+        } else if (want_coop && fits(C1::G, C1::ND, C1::NM, C1::NP, C1::NAX)) {
+            h->coop_cls = 1;
+            h->coop_smem = base + (COOP_BLOCK / C1::G) * sizeof(bio::EnvWork<T, 1>);
+            CU(cudaFuncSetAttribute(bio::bio_coop_step_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)h->coop_smem));
+        }
+    }
+    // model block
+    {
+        bio::DevModel<T>* hm = new bio::DevModel<T>();
+        bio::convert_model(*model, *hm);
+        if (bio::build_obs_desc(*model, *task, *hm) != task->obs_dim) {
+            delete hm;
+            return fail(-1, "obs_dim of the task config does not match the observation layout");
+        }
+        rc = dev_alloc(h, (unsigned char**)&h->d_model, sizeof(bio::DevModel<T>));
+        if (rc) { delete hm; return rc; }
+        cudaError_t e = cudaMemcpy(h->d_model, hm, sizeof(bio::DevModel<T>), cudaMemcpyHostToDevice);
+        delete hm;
+        CU(e);
+    }
+    bio::convert_task(*task, h->task_d);
+    const int nd = model->n_dof, nm = model->n_muscles, na = model->n_act;
+    // reference tables
+    h->task_d.ref_rows = ref->n_rows; h->task_d.ref_coords = ref->n_coords; h->task_d.ref_bodies = ref->n_refbodies;
+    if ((rc = upload_ref<T>(h, ref->q, (size_t)ref->n_rows * ref->n_coords, &h->task_d.ref_q))) return rc;
+    if ((rc = upload_ref<T>(h, ref->u, (size_t)ref->n_rows * ref->n_coords, &h->task_d.ref_u))) return rc;
+    if ((rc = upload_ref<T>(h, ref->body_pos, (size_t)ref->n_rows * ref->n_refbodies * 3, &h->task_d.ref_body_pos))) return rc;
+    if ((rc = upload_ref<T>(h, ref->com_pos, (size_t)ref->n_rows * 3, &h->task_d.ref_com_pos))) return rc;
+    T* lm0 = nullptr;
+    if ((rc = dev_alloc(h, &lm0, (size_t)ref->n_rows * (nm ? nm : 1)))) return rc;
+    h->task_d.ref_lm0 = lm0;
+    if (nm > 0) {
+        const int blk = 32, grid = (ref->n_rows + blk - 1) / blk;
+        bio::bio_lm0_kernel<T><<<grid, blk, h->smem>>>(h->d_model, h->task_d.ref_q, ref->n_rows, ref->n_coords, lm0);
+        h->launches++;
+        CU(cudaGetLastError());
+    }
+    // env state
+    const size_t N = (size_t)n;
+    if ((rc = dev_alloc(h, &h->st.q, N * nd))) return rc;
+    if ((rc = dev_alloc(h, &h->st.u, N * nd))) return rc;
+    if ((rc = dev_alloc(h, &h->st.act, N * nm))) return rc;
+    if ((rc = dev_alloc(h, &h->st.lm, N * nm))) return rc;
+    if ((rc = dev_alloc(h, &h->st.last_action, N * na))) return rc;
+    if ((rc = dev_alloc(h, &h->st.history, N * na * task->horizon))) return rc;
+    if ((rc = dev_alloc(h, &h->st.old_px, N))) return rc;
+    if ((rc = dev_alloc(h, &h->st.ep_return, N))) return rc;
+    if ((rc = dev_alloc(h, &h->st.istep, N))) return rc;
+    if ((rc = dev_alloc(h, &h->st.first, N))) return rc;
+    if ((rc = dev_alloc(h, &h->st.hist_pos, N))) return rc;
+    if ((rc = dev_alloc(h, &h->st.ep_len, N))) return rc;
+    if ((rc = dev_alloc(h, &h->st.episode, N))) return rc;
+    if ((rc = dev_alloc(h, &h->stats, 16))) return rc;
+    // scratch for host entry points
+    if ((rc = dev_alloc(h, &h->h_actions, N * na))) return rc;
+    if ((rc = dev_alloc(h, &h->h_obs, N * task->obs_dim))) return rc;
+    if ((rc = dev_alloc(h, &h->h_reward, N))) return rc;
+    if ((rc = dev_alloc(h, &h->h_terms, N * task->n_reward_terms))) return rc;
+    if ((rc = dev_alloc(h, &h->h_done, N))) return rc;
+    if ((rc = dev_alloc(h, &h->h_mask, N))) return rc;
+    CU(cudaDeviceSynchronize());
+    // initial reference-state reset of all envs
+    const int grid = (n + h->block - 1) / h->block;
+    bio::bio_reset_kernel<T><<<grid, h->block, h->smem>>>(h->d_model, h->task_d, h->st, n, h->seed, h->env_offset,
+                                                         nullptr, nullptr, 0);
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
+int validate(const BioModelTables* m, const BioTaskConfig* t, const BioRefTables* r, int n) {
+    if (!m || !t || !r) return fail(-1, "null table pointer");
+    if (m->abi_version != BIO_ABI_VERSION || t->abi_version != BIO_ABI_VERSION)
+        return fail(-1, "table ABI version mismatch");
+    if (n <= 0) return fail(-1, "n_envs must be positive");
+    if (m->n_bodies < 1 || m->n_bodies > BIO_MAX_BODIES || m->n_dof < 1 || m->n_dof > BIO_MAX_DOF ||
+        m->n_muscles < 0 || m->n_muscles > BIO_MAX_MUSCLES || m->n_act < 1 || m->n_act > BIO_MAX_ACT)
+        return fail(-1, "model sizes out of range");
+    for (int i = 0; i < m->n_muscles; i++)
+        if (m->mus_pt_count[i] > BIO_MAX_MUSCLE_PTS) return fail(-1, "muscle with too many path points");
+    if (t->horizon < 1 || t->horizon > BIO_MAX_HORIZON) return fail(-1, "horizon out of range");
+    if (t->n_substeps < 1) return fail(-1, "n_substeps must be >= 1");
+    if (t->integrator < 0 || t->integrator > BIO_INT_IMPLICIT_DAMPING) return fail(-1, "unknown integrator");
+    if (r->n_coords != m->n_coords) return fail(-1, "reference tables have a different coordinate count");
+    if (r->n_rows < 2 || !r->q || !r->u || !r->body_pos || !r->com_pos) return fail(-1, "bad reference tables");
+    return 0;
+}
+
+template <typename T>
+int step_impl(Handle<T>* h, const void* actions, void* obs, void* reward, uint8_t* done, void* terms,
+              cudaStream_t s) {
+    if (h->coop_cls == 0) {
+        const int epc = COOP_BLOCK / bio::CoopCls<0>::G, grid = (h->n + epc - 1) / epc;
+        bio::bio_coop_step_kernel<T, 0><<<grid, COOP_BLOCK, h->coop_smem, s>>>(
+            h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset, (const T*)actions, (T*)obs, (T*)reward, done,
+            (T*)terms, h->stats);
+    } else if (h->coop_cls == 1) {
+        const int epc = COOP_BLOCK / bio::CoopCls<1>::G, grid = (h->n + epc - 1) / epc;
+        bio::bio_coop_step_kernel<T, 1><<<grid, COOP_BLOCK, h->coop_smem, s>>>(
+            h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset, (const T*)actions, (T*)obs, (T*)reward, done,
+            (T*)terms, h->stats);
+    } else {
+        const int grid = (h->n + h->block - 1) / h->block;
+        bio::bio_step_kernel<T><<<grid, h->block, h->smem, s>>>(h->d_model, h->task_d, h->st, h->n, h->seed,
+                                                               h->env_offset, (const T*)actions, (T*)obs, (T*)reward,
+                                                               done, (T*)terms, h->stats);
+    }
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int reset_impl(Handle<T>* h, const uint8_t* mask, void* obs, cudaStream_t s, int bump) {
+    const int grid = (h->n + h->block - 1) / h->block;
+    bio::bio_reset_kernel<T><<<grid, h->block, h->smem, s>>>(h->d_model, h->task_d, h->st, h->n, h->seed,
+                                                            h->env_offset, mask, (T*)obs, bump);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int transpose(Handle<T>* h, const T* src, T* dst, int k, int to_soa, cudaStream_t s) {
+    const size_t total = (size_t)h->n * k;
+    if (!total) return 0;
+    const int blk = 256;
+    bio::bio_transpose_kernel<T><<<(unsigned)((total + blk - 1) / blk), blk, 0, s>>>(src, dst, h->n, k, to_soa);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int state_impl(Handle<T>* h, const BioStatePtrs* p, cudaStream_t s, bool set) {
+    const int nd = h->model.n_dof, nm = h->model.n_muscles, na = h->model.n_act, H = h->task.horizon;
+    int rc;
+    struct Item { void* user; T* soa; int k; };
+    Item items[] = {{p->q, h->st.q, nd}, {p->u, h->st.u, nd}, {p->act, h->st.act, nm}, {p->lm, h->st.lm, nm},
+                    {p->last_action, h->st.last_action, na}, {p->history, h->st.history, H * na},
+                    {p->old_px, h->st.old_px, 1}};
+    for (auto& it : items) {
+        if (!it.user || it.k == 0) continue;
+        if (set) rc = transpose<T>(h, (const T*)it.user, it.soa, it.k, 1, s);
+        else rc = transpose<T>(h, it.soa, (T*)it.user, it.k, 0, s);
+        if (rc) return rc;
+    }
+    if (p->istep) {
+        if (set) CU(cudaMemcpyAsync(h->st.istep, p->istep, sizeof(int32_t) * h->n, cudaMemcpyDeviceToDevice, s));
+        else CU(cudaMemcpyAsync(p->istep, h->st.istep, sizeof(int32_t) * h->n, cudaMemcpyDeviceToDevice, s));
+    }
+    if (p->first) {
+        if (set) CU(cudaMemcpyAsync(h->st.first, p->first, sizeof(int32_t) * h->n, cudaMemcpyDeviceToDevice, s));
+        else CU(cudaMemcpyAsync(p->first, h->st.first, sizeof(int32_t) * h->n, cudaMemcpyDeviceToDevice, s));
+    }
+    if (p->hist_pos) {
+        if (set) CU(cudaMemcpyAsync(h->st.hist_pos, p->hist_pos, sizeof(int32_t) * h->n, cudaMemcpyDeviceToDevice, s));
+        else CU(cudaMemcpyAsync(p->hist_pos, h->st.hist_pos, sizeof(int32_t) * h->n, cudaMemcpyDeviceToDevice, s));
+    }
+    if (p->episode) {
+        if (set) CU(cudaMemcpyAsync(h->st.episode, p->episode, sizeof(int64_t) * h->n, cudaMemcpyDeviceToDevice, s));
+        else CU(cudaMemcpyAsync(p->episode, h->st.episode, sizeof(int64_t) * h->n, cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+template <typename T>
+int eval_impl(Handle<T>* h, const void* controls, const BioDebugPtrs* o, cudaStream_t s) {
+    bio::DebugOut<T> d;
+    d.udot = (T*)o->udot; d.tendon_force = (T*)o->tendon_force; d.fiber_force = (T*)o->fiber_force;
+    d.fiber_vel = (T*)o->fiber_vel; d.act_dot = (T*)o->act_dot; d.path_len = (T*)o->path_len;
+    d.path_vel = (T*)o->path_vel; d.contact = (T*)o->contact; d.limit_force = (T*)o->limit_force;
+    d.mass_matrix = (T*)o->mass_matrix; d.bias = (T*)o->bias;
+    const int grid = (h->n + h->block - 1) / h->block;
+    bio::bio_eval_kernel<T><<<grid, h->block, h->smem, s>>>(h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset,
+                                                           (const T*)controls, d);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int step_host_impl(Handle<T>* h, const void* actions, void* obs, void* reward, uint8_t* done, void* terms) {
+    const size_t N = h->n;
+    const int na = h->model.n_act, od = h->task.obs_dim, nt = h->task.n_reward_terms;
+    CU(cudaMemcpyAsync(h->h_actions, actions, N * na * sizeof(T), cudaMemcpyHostToDevice, 0));
+    int rc = step_impl<T>(h, h->h_actions, h->h_obs, h->h_reward, h->h_done, h->h_terms, 0);
+    if (rc) return rc;
+    if (obs) CU(cudaMemcpyAsync(obs, h->h_obs, N * od * sizeof(T), cudaMemcpyDeviceToHost, 0));
+    if (reward) CU(cudaMemcpyAsync(reward, h->h_reward, N * sizeof(T), cudaMemcpyDeviceToHost, 0));
+    if (done) CU(cudaMemcpyAsync(done, h->h_done, N, cudaMemcpyDeviceToHost, 0));
+    if (terms) CU(cudaMemcpyAsync(terms, h->h_terms, N * nt * sizeof(T), cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    return 0;
+}
+
+template <typename T>
+int reset_host_impl(Handle<T>* h, const uint8_t* mask, void* obs) {
+    const size_t N = h->n;
+    if (mask) CU(cudaMemcpyAsync(h->h_mask, mask, N, cudaMemcpyHostToDevice, 0));
+    int rc = reset_impl<T>(h, mask ? h->h_mask : nullptr, obs ? h->h_obs : nullptr, 0, 1);
+    if (rc) return rc;
+    if (obs) CU(cudaMemcpyAsync(obs, h->h_obs, N * h->task.obs_dim * sizeof(T), cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    return 0;
+}
+
+}  // namespace
+
+#define DISPATCH(h, expr32, expr64)                                  \
+    (((HandleBase*)(h))->precision == BIO_PREC_F32 ? (expr32) : (expr64))
+#define H32(h) ((Handle<float>*)(HandleBase*)(h))
+#define H64(h) ((Handle<double>*)(HandleBase*)(h))
+
+extern "C" {
+
+int bio_abi_version(void) { return BIO_ABI_VERSION; }
+uint64_t bio_sizeof_model_tables(void) { return sizeof(BioModelTables); }
+uint64_t bio_sizeof_task_config(void) { return sizeof(BioTaskConfig); }
+const char* bio_last_error(void) { return g_err.c_str(); }
+
+int bio_create(const BioModelTables* model, const BioTaskConfig* task, const BioRefTables* ref, int32_t n_envs,
+               int32_t device, int32_t precision, uint64_t seed, int64_t env_offset, bio_handle* out) {
+    if (!out) return fail(-1, "out handle is null");
+    *out = nullptr;
+    int rc = validate(model, task, ref, n_envs);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(-3, "no CUDA device: this backend has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(-1, "device index out of range");
+    if (precision == BIO_PREC_F32) {
+        Handle<float>* h = new (std::nothrow) Handle<float>();
+        if (!h) return fail(-4, "out of host memory");
+        h->precision = precision;
+        rc = create_impl<float>(model, task, ref, n_envs, device, seed, env_offset, h);
+        if (rc) { for (void* p : h->allocs) cudaFree(p); delete h; return rc; }
+        *out = (bio_handle)(HandleBase*)h;
+    } else if (precision == BIO_PREC_F64) {
+        Handle<double>* h = new (std::nothrow) Handle<double>();
+        if (!h) return fail(-4, "out of host memory");
+        h->precision = precision;
+        rc = create_impl<double>(model, task, ref, n_envs, device, seed, env_offset, h);
+        if (rc) { for (void* p : h->allocs) cudaFree(p); delete h; return rc; }
+        *out = (bio_handle)(HandleBase*)h;
+    } else {
+        return fail(-1, "unknown precision");
+    }
+    return 0;
+}
+
+int bio_destroy(bio_handle hh) {
+    if (!hh) return 0;
+    HandleBase* h = (HandleBase*)hh;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+    return 0;
+}
+
+#define ENTER(hh)                                         \
+    if (!(hh)) return fail(-1, "null handle");            \
+    CU(cudaSetDevice(((HandleBase*)(hh))->device))
+
+int bio_reset(bio_handle hh, const uint8_t* mask, void* obs, void* stream) {
+    ENTER(hh);
+    return DISPATCH(hh, reset_impl<float>(H32(hh), mask, obs, (cudaStream_t)stream, 1),
+                    reset_impl<double>(H64(hh), mask, obs, (cudaStream_t)stream, 1));
+}
+
+int bio_step(bio_handle hh, const void* actions, void* obs, void* reward, uint8_t* done, void* reward_terms,
+             void* stream) {
+    ENTER(hh);
+    if (!actions || !obs || !reward || !done) return fail(-1, "bio_step: null buffer");
+    return DISPATCH(hh, step_impl<float>(H32(hh), actions, obs, reward, done, reward_terms, (cudaStream_t)stream),
+                    step_impl<double>(H64(hh), actions, obs, reward, done, reward_terms, (cudaStream_t)stream));
+}
+
+int bio_step_host(bio_handle hh, const void* actions, void* obs, void* reward, uint8_t* done, void* reward_terms) {
+    ENTER(hh);
+    if (!actions) return fail(-1, "bio_step_host: null actions");
+    return DISPATCH(hh, step_host_impl<float>(H32(hh), actions, obs, reward, done, reward_terms),
+                    step_host_impl<double>(H64(hh), actions, obs, reward, done, reward_terms));
+}
+
+int bio_reset_host(bio_handle hh, const uint8_t* mask, void* obs) {
+    ENTER(hh);
+    return DISPATCH(hh, reset_host_impl<float>(H32(hh), mask, obs), reset_host_impl<double>(H64(hh), mask, obs));
+}
+
+int bio_get_state(bio_handle hh, const BioStatePtrs* dst, void* stream) {
+    ENTER(hh);
+    if (!dst) return fail(-1, "null state pointers");
+    return DISPATCH(hh, state_impl<float>(H32(hh), dst, (cudaStream_t)stream, false),
+                    state_impl<double>(H64(hh), dst, (cudaStream_t)stream, false));
+}
+
+int bio_set_state(bio_handle hh, const BioStatePtrs* src, void* stream) {
+    ENTER(hh);
+    if (!src) return fail(-1, "null state pointers");
+    return DISPATCH(hh, state_impl<float>(H32(hh), src, (cudaStream_t)stream, true),
+                    state_impl<double>(H64(hh), src, (cudaStream_t)stream, true));
+}
+
+int bio_eval_debug(bio_handle hh, const void* controls, const BioDebugPtrs* out, void* stream) {
+    ENTER(hh);
+    if (!out) return fail(-1, "null debug pointers");
+    return DISPATCH(hh, eval_impl<float>(H32(hh), controls, out, (cudaStream_t)stream),
+                    eval_impl<double>(H64(hh), controls, out, (cudaStream_t)stream));
+}
+
+int bio_stats(bio_handle hh, double* out16, int32_t reset_after, void* stream) {
+    ENTER(hh);
+    HandleBase* h = (HandleBase*)hh;
+    if (!out16) return fail(-1, "null stats buffer");
+    CU(cudaMemcpyAsync(out16, h->stats, 16 * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (reset_after) CU(cudaMemsetAsync(h->stats, 0, 16 * sizeof(double), (cudaStream_t)stream));
+    return 0;
+}
+
+int64_t bio_launch_count(bio_handle hh) { return hh ? ((HandleBase*)hh)->launches : 0; }
+int32_t bio_obs_dim(bio_handle hh) { return hh ? ((HandleBase*)hh)->task.obs_dim : 0; }
+int32_t bio_n_act(bio_handle hh) { return hh ? ((HandleBase*)hh)->model.n_act : 0; }
+
+}  // extern "C"

@@ -1,0 +1,820 @@
+// bio_coop.cuh -- cooperative step kernel: G lanes of a warp own one env.
+//
+// The thread-per-env kernel (bio_kernels.cuh) leaves a B200 almost idle at the
+// batch sizes the envs are used with (4096 envs = 128 warps on 592 warp
+// schedulers) and keeps its per-env working set in local memory.  Here a
+// half-warp (2D models, <=16 muscles) or a full warp (3D models) steps one env:
+//   lane = muscle   path geometry, Millard equilibrium, activation ODE
+//   lane = body     kinematics per tree level, wrench gather, spatial inertia
+//   lane = sphere / limit / dof / H-entry for contact, limits, joint-space inertia
+// The per-env working set lives in shared memory (EnvWork), phases are separated
+// by __syncwarp(), the model block is shared by the CTA.  Same physics and same
+// operation results as eval_dynamics() in bio_dynamics.cuh; parity against the
+// CPU oracle is tested in fp64 through this kernel.
+#pragma once
+#include "bio_kernels.cuh"
+
+namespace bio {
+
+template <int CLS> struct CoopCls;
+template <> struct CoopCls<0> { enum { G = 16, ND = 10, NM = 16, NP = 48, NAX = 16 }; };
+template <> struct CoopCls<1> { enum { G = 32, ND = 16, NM = 24, NP = 80, NAX = 24 }; };
+
+#define COOP_MAXOBS 12
+
+template <typename T, int CLS>
+struct EnvWork {
+    typedef CoopCls<CLS> C;
+    T q[C::ND], u[C::ND], act[C::NM], lm[C::NM];          // state of the current evaluation
+    T ax_s[C::NAX], ax_ds[C::NAX], ax_dds[C::NAX];
+    T O[4];
+    T R[BIO_MAX_BODIES][9], r[BIO_MAX_BODIES][3], V[BIO_MAX_BODIES][6], A[BIO_MAX_BODIES][6];
+    T S[C::ND][6];
+    union {
+        struct { T ptx[C::NP][3], ptf[C::NP][3], ptq[C::NP]; } pt;   // phases C..E
+        struct { T col[BIO_MAX_SPHERES][C::ND][3]; } jac;             // phase G (implicit damping)
+        struct { T obs_pos[COOP_MAXOBS][3], obs_vel[COOP_MAXOBS][3], comp[BIO_MAX_BODIES][6]; } out;  // full eval
+    } x;
+    T sphx[BIO_MAX_SPHERES][3], sphF[BIO_MAX_SPHERES][3], sphD[BIO_MAX_SPHERES][2];
+    T limf[BIO_MAX_LIMITS], limD[BIO_MAX_LIMITS];
+    T Q[C::ND];
+    T Im[BIO_MAX_BODIES], Ih[BIO_MAX_BODIES][3], II[BIO_MAX_BODIES][6], F[BIO_MAX_BODIES][6];
+    T H[C::ND * (C::ND + 1) / 2], rhs[C::ND];
+    T udot[C::ND], adot[C::NM], lmdot[C::NM];
+    T ffib[C::NM], fact[C::NM];
+    T ctrl[C::NM], curr[C::NM], lastact[C::NM];
+    T com_pos[3], com_vel[3];
+    T contact[2][6];
+    T max_limit, pad_;
+};
+
+template <int G> __device__ __forceinline__ void gsync() { __syncwarp(); }
+
+// ---------------------------------------------------------------------------
+// One evaluation of the dynamics of the env in E (state in E.q/u/act/lm,
+// controls in E.ctrl).  Results: E.udot, E.adot, E.lmdot and, when full, the
+// read-outs for obs / reward / done.  All G lanes of the env must call this.
+// ---------------------------------------------------------------------------
+template <typename T, int CLS>
+__device__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane, const int newton_iters,
+                          const T ext_fx, const int ext_pt, const T h_imp, const bool full) {
+    typedef CoopCls<CLS> C;
+    constexpr int G = C::G;
+    const int nb = m.n_bodies, nd = m.n_dof, nm = m.n_muscles;
+
+    // ---- phase A: joint functions of the coordinates ----
+    for (int a = lane; a < m.n_axes; a += G) {
+        const int d = m.axis_dof[a];
+        T s, ds, dds;
+        func_eval(m, m.axis_func[a], d >= 0 ? E.q[d] : T(0), s, ds, dds);
+        E.ax_s[a] = s; E.ax_ds[a] = ds; E.ax_dds[a] = dds;
+    }
+    gsync<G>();
+
+    // ---- phase B: kinematics, one tree level at a time, lane = body ----
+    for (int lev = 0; lev < m.n_levels; lev++) {
+        if (lane < nb && m.body_level[lane] == lev) {
+            const int b = lane, p = m.body_parent[b];
+            T Rp[9], R[9], r[3], V[6], A[6];
+            if (p >= 0) {
+                for (int c = 0; c < 9; c++) Rp[c] = E.R[p][c];
+                matvec3(Rp, m.body_joint_loc[b], r);
+                for (int c = 0; c < 3; c++) r[c] += E.r[p][c];
+                for (int c = 0; c < 6; c++) { V[c] = E.V[p][c]; A[c] = E.A[p][c]; }
+            } else {
+                Rp[0] = T(1); Rp[1] = T(0); Rp[2] = T(0); Rp[3] = T(0); Rp[4] = T(1); Rp[5] = T(0);
+                Rp[6] = T(0); Rp[7] = T(0); Rp[8] = T(1);
+                for (int c = 0; c < 3; c++) { r[c] = m.body_joint_loc[b][c]; V[c] = V[3 + c] = T(0); A[c] = T(0); A[3 + c] = -m.gravity[c]; }
+            }
+            for (int c = 0; c < 9; c++) R[c] = Rp[c];
+            bool root_open = p < 0;
+            const int ab = m.body_axis_begin[b], ae = ab + m.body_axis_count[b];
+            for (int a = ab; a < ae; a++) {
+                const int d = m.axis_dof[a];
+                if (d >= 0 && (a == ab || m.axis_dof[a - 1] != d))
+                    for (int c = 0; c < 6; c++) E.S[d][c] = T(0);
+            }
+            for (int a = ab; a < ae; a++) {
+                const int d = m.axis_dof[a];
+                const T s = E.ax_s[a], ds = E.ax_ds[a], dds = E.ax_dds[a];
+                T S[6], aw[3];
+                if (m.axis_kind[a] == BIO_AXIS_TRANS) {
+                    matvec3(Rp, m.axis_vec[a], aw);
+                    S[0] = S[1] = S[2] = T(0); S[3] = aw[0]; S[4] = aw[1]; S[5] = aw[2];
+                    for (int c = 0; c < 3; c++) r[c] += aw[c] * s;
+                } else {
+                    if (root_open) { for (int c = 0; c < 3; c++) { E.O[c] = r[c]; r[c] = T(0); } root_open = false; }
+                    matvec3(R, m.axis_vec[a], aw);
+                    S[0] = aw[0]; S[1] = aw[1]; S[2] = aw[2];
+                    cross3(r, aw, S + 3);
+                    T sn, cs;
+                    Num<T>::sincos(s, &sn, &cs);
+                    const T ax = m.axis_vec[a][0], ay = m.axis_vec[a][1], az = m.axis_vec[a][2], vv = T(1) - cs;
+                    const T K[9] = {cs + ax * ax * vv, ax * ay * vv - az * sn, ax * az * vv + ay * sn,
+                                    ay * ax * vv + az * sn, cs + ay * ay * vv, ay * az * vv - ax * sn,
+                                    az * ax * vv - ay * sn, az * ay * vv + ax * sn, cs + az * az * vv};
+                    T Rn[9];
+                    for (int i = 0; i < 3; i++)
+                        for (int j = 0; j < 3; j++)
+                            Rn[3 * i + j] = R[3 * i] * K[j] + R[3 * i + 1] * K[3 + j] + R[3 * i + 2] * K[6 + j];
+                    for (int c = 0; c < 9; c++) R[c] = Rn[c];
+                }
+                if (d >= 0) {
+                    const T qd = E.u[d], sd = ds * qd, acc = dds * qd * qd;
+                    T c1[3], c2[3], c3[3];
+                    cross3(V, S, c1); cross3(V, S + 3, c2); cross3(V + 3, S, c3);
+                    for (int c = 0; c < 3; c++) {
+                        E.S[d][c] += ds * S[c];
+                        E.S[d][3 + c] += ds * S[3 + c];
+                        A[c] += S[c] * acc + c1[c] * sd;
+                        A[3 + c] += S[3 + c] * acc + (c2[c] + c3[c]) * sd;
+                    }
+                    for (int c = 0; c < 6; c++) V[c] += S[c] * sd;
+                }
+            }
+            if (root_open) { for (int c = 0; c < 3; c++) { E.O[c] = r[c]; r[c] = T(0); } }
+            for (int c = 0; c < 9; c++) E.R[b][c] = R[c];
+            for (int c = 0; c < 3; c++) E.r[b][c] = r[c];
+            for (int c = 0; c < 6; c++) { E.V[b][c] = V[c]; E.A[b][c] = A[c]; }
+        }
+        gsync<G>();
+    }
+
+    // ---- phase C: lane = muscle ----
+    if (lane < nm) {
+        const int i = lane;
+        int pidx[BIO_MAX_MUSCLE_PTS];
+        int np = 0;
+        const int pb = m.mus_pt_begin[i], pe = pb + m.mus_pt_count[i];
+        for (int p = pb; p < pe; p++) {
+            const int kind = m.pt_kind[p], d = m.pt_dof[p], b = m.pt_body[p];
+            T loc[3];
+            E.x.pt.ptq[p] = T(0);
+            if (kind == BIO_PT_CONDITIONAL) {
+                const T v = E.q[d];
+                if (!(v >= m.pt_range[p][0] - T(1e-5) && v <= m.pt_range[p][1] + T(1e-5))) {
+                    for (int c = 0; c < 3; c++) E.x.pt.ptf[p][c] = T(0);
+                    continue;
+                }
+            }
+            if (kind == BIO_PT_MOVING) {
+                T d1, d2;
+                for (int c = 0; c < 3; c++) func_eval(m, m.pt_func[p][c], E.q[d], loc[c], d1, d2);
+            } else {
+                for (int c = 0; c < 3; c++) loc[c] = m.pt_loc[p][c];
+            }
+            T x[3];
+            matvec3(E.R[b], loc, x);
+            for (int c = 0; c < 3; c++) { x[c] += E.r[b][c]; E.x.pt.ptx[p][c] = x[c]; E.x.pt.ptf[p][c] = T(0); }
+            pidx[np++] = p;
+        }
+        T L = T(0);
+        for (int s = 0; s + 1 < np; s++) {
+            const T* x0 = E.x.pt.ptx[pidx[s]];
+            const T* x1 = E.x.pt.ptx[pidx[s + 1]];
+            const T dx = x1[0] - x0[0], dy = x1[1] - x0[1], dz = x1[2] - x0[2];
+            L += Num<T>::sqrt(dx * dx + dy * dy + dz * dz);
+        }
+        const T fiso = m.mus_fiso[i], lopt = m.mus_lopt[i], h = m.mus_height[i], beta = m.mus_beta[i];
+        const T amin = m.mus_amin[i], lmin = m.mus_lm_min[i];
+        const T lmi = E.lm[i];
+        const T lmc = lmi < lmin ? lmin : lmi;
+        const T lat = Num<T>::sqrt(lmc * lmc - h * h);
+        const T cosa = lat / lmc;
+        T fal, fpe, ft, fv, dfv, dtmp;
+        curve_eval(m, 0, lmc / lopt, fal, dtmp);
+        curve_eval(m, 2, lmc / lopt, fpe, dtmp);
+        curve_eval(m, 3, (L - lat) / m.mus_lts[i], ft, dtmp);
+        const T ac = clampv(E.act[i], amin, T(1));
+        const T afal = ac * fal;
+        T vn = T(0);
+        for (int it = 0; it < newton_iters; it++) {
+            curve_eval(m, 1, vn, fv, dfv);
+            const T err = (afal * fv + fpe + beta * vn) * cosa - ft;
+            const T derr = (afal * dfv + beta) * cosa;
+            const T delta = -err / derr;
+            vn += delta;
+            if (Num<T>::abs(delta) < Num<T>::newton_tol()) break;
+        }
+        if (lmi <= lmin && vn < T(0)) vn = T(0);
+        E.lmdot[i] = vn * m.mus_vmax[i] * lopt;
+        const T ec = clampv(E.ctrl[i], amin, T(1));
+        const T tau = ec > ac ? m.mus_tact[i] * (T(0.5) + T(1.5) * ac) : m.mus_tdeact[i] / (T(0.5) + T(1.5) * ac);
+        E.adot[i] = (ec - ac) / tau;
+        const T tension = fiso * ft;
+        if (full) {
+            curve_eval(m, 1, vn, fv, dfv);
+            E.fact[i] = fiso * afal * fv;
+            E.ffib[i] = fiso * (afal * fv + fpe + beta * vn);
+        }
+        for (int s = 0; s + 1 < np; s++) {
+            const int p0 = pidx[s], p1 = pidx[s + 1];
+            const T dx = E.x.pt.ptx[p1][0] - E.x.pt.ptx[p0][0], dy = E.x.pt.ptx[p1][1] - E.x.pt.ptx[p0][1],
+                    dz = E.x.pt.ptx[p1][2] - E.x.pt.ptx[p0][2];
+            const T il = tension / Num<T>::sqrt(dx * dx + dy * dy + dz * dz);
+            const T f[3] = {dx * il, dy * il, dz * il};
+            for (int c = 0; c < 3; c++) { E.x.pt.ptf[p0][c] += f[c]; E.x.pt.ptf[p1][c] -= f[c]; }
+        }
+        // generalized force of moving points: f . R_b dloc/dq
+        for (int s = 0; s < np; s++) {
+            const int p = pidx[s];
+            if (m.pt_kind[p] != BIO_PT_MOVING) continue;
+            T dloc[3], yv, d2, dw[3];
+            for (int c = 0; c < 3; c++) func_eval(m, m.pt_func[p][c], E.q[m.pt_dof[p]], yv, dloc[c], d2);
+            matvec3(E.R[m.pt_body[p]], dloc, dw);
+            E.x.pt.ptq[p] = dot3(E.x.pt.ptf[p], dw);
+        }
+    }
+    // ---- phase D: lane = contact sphere | coordinate limit ----
+    if (lane < m.n_spheres) {
+        const int s = lane, b = m.sph_body[s];
+        T xc[3];
+        matvec3(E.R[b], m.sph_loc[s], xc);
+        for (int c = 0; c < 3; c++) xc[c] += E.r[b][c];
+        const T rad = m.sph_radius[s];
+        const T depth = rad - (xc[1] + E.O[1]);
+        T F[3] = {T(0), T(0), T(0)}, D0 = T(0), D1 = T(0);
+        T p[3] = {xc[0], T(-0.5) * depth - E.O[1], xc[2]};
+        if (depth > T(0)) {
+            T v[3];
+            cross3(E.V[b], p, v);
+            for (int c = 0; c < 3; c++) v[c] += E.V[b][3 + c];
+            const T vn = -v[1];
+            const T kk = m.sph_k[s];
+            const T fH = T(4.0 / 3.0) * kk * depth * Num<T>::sqrt(rad * kk * depth);
+            const T f = fH * (T(1) + T(1.5) * m.sph_c[s] * vn);
+            if (f > T(0)) {
+                F[1] = f;
+                const T vs = Num<T>::sqrt(v[0] * v[0] + v[2] * v[2]);
+                const T vrel = vs / m.sph_vt[s];
+                const T strib = m.sph_ud[s] + T(2) * (m.sph_us[s] - m.sph_ud[s]) / (T(1) + vrel * vrel);
+                if (vs != T(0)) {
+                    const T ff = f * ((vrel < T(1) ? vrel : T(1)) * strib + m.sph_uv[s] * vs);
+                    F[0] = -ff * v[0] / vs;
+                    F[2] = -ff * v[2] / vs;
+                }
+                D0 = f * ((vrel < T(1) ? T(1) / m.sph_vt[s] : T(1) / vs) * strib + m.sph_uv[s]);
+                D1 = T(1.5) * m.sph_c[s] * fH;
+            }
+        }
+        for (int c = 0; c < 3; c++) { E.sphx[s][c] = p[c]; E.sphF[s][c] = F[c]; }
+        E.sphD[s][0] = D0; E.sphD[s][1] = D1;
+    } else if (lane - m.n_spheres < m.n_limits) {
+        const int l = lane - m.n_spheres, d = m.lim_dof[l];
+        const T w = m.lim_w[l], qq = E.q[d];
+        const T sup = step5((qq - m.lim_qup[l]) / w);
+        const T slo = T(1) - step5((qq - (m.lim_qlo[l] - w)) / w);
+        E.limf[l] = -m.lim_kup[l] * sup * (qq - m.lim_qup[l]) + m.lim_klo[l] * slo * (m.lim_qlo[l] - qq) -
+                    m.lim_damp[l] * (sup + slo) * E.u[d];
+        E.limD[l] = m.lim_damp[l] * (sup + slo);
+    }
+    gsync<G>();
+
+    // ---- phase E: lane = body (wrench gather, inertia, body force) | dof (generalized forces) ----
+    if (lane < nb) {
+        const int b = lane;
+        T Wn[3] = {T(0), T(0), T(0)}, Wf[3] = {T(0), T(0), T(0)};
+        for (int k = m.body_pt_begin[b]; k < m.body_pt_begin[b] + m.body_pt_count[b]; k++) {
+            const int p = m.body_pt_list[k];
+            const T f[3] = {E.x.pt.ptf[p][0], E.x.pt.ptf[p][1], E.x.pt.ptf[p][2]};
+            T n[3];
+            cross3(E.x.pt.ptx[p], f, n);   // ptx of an inactive point is stale but its force is 0
+            for (int c = 0; c < 3; c++) { Wn[c] += (f[0] != T(0) || f[1] != T(0) || f[2] != T(0)) ? n[c] : T(0); Wf[c] += f[c]; }
+        }
+        for (int s = 0; s < m.n_spheres; s++) {
+            if (m.sph_body[s] != b) continue;
+            T n[3];
+            cross3(E.sphx[s], E.sphF[s], n);
+            for (int c = 0; c < 3; c++) { Wn[c] += n[c]; Wf[c] += E.sphF[s][c]; }
+        }
+        if (ext_pt >= 0 && m.obs_body[ext_pt] == b) {
+            T x[3], n[3];
+            const T fx[3] = {ext_fx, T(0), T(0)};
+            matvec3(E.R[b], m.obs_loc[ext_pt], x);
+            for (int c = 0; c < 3; c++) x[c] += E.r[b][c];
+            cross3(x, fx, n);
+            for (int c = 0; c < 3; c++) { Wn[c] += n[c]; Wf[c] += fx[c]; }
+        }
+        T cpos[3];
+        matvec3(E.R[b], m.body_com[b], cpos);
+        for (int c = 0; c < 3; c++) cpos[c] += E.r[b][c];
+        const T* R = E.R[b];
+        const T* i6 = m.body_inertia[b];
+        T t[9];
+        for (int r_ = 0; r_ < 3; r_++) {
+            t[3 * r_ + 0] = R[3 * r_] * i6[0] + R[3 * r_ + 1] * i6[3] + R[3 * r_ + 2] * i6[4];
+            t[3 * r_ + 1] = R[3 * r_] * i6[3] + R[3 * r_ + 1] * i6[1] + R[3 * r_ + 2] * i6[5];
+            t[3 * r_ + 2] = R[3 * r_] * i6[4] + R[3 * r_ + 1] * i6[5] + R[3 * r_ + 2] * i6[2];
+        }
+        const T mb = m.body_mass[b], cc = dot3(cpos, cpos);
+        T I6[6];
+        I6[0] = t[0] * R[0] + t[1] * R[1] + t[2] * R[2] + mb * (cc - cpos[0] * cpos[0]);
+        I6[1] = t[3] * R[3] + t[4] * R[4] + t[5] * R[5] + mb * (cc - cpos[1] * cpos[1]);
+        I6[2] = t[6] * R[6] + t[7] * R[7] + t[8] * R[8] + mb * (cc - cpos[2] * cpos[2]);
+        I6[3] = t[0] * R[3] + t[1] * R[4] + t[2] * R[5] - mb * cpos[0] * cpos[1];
+        I6[4] = t[0] * R[6] + t[1] * R[7] + t[2] * R[8] - mb * cpos[0] * cpos[2];
+        I6[5] = t[3] * R[6] + t[4] * R[7] + t[5] * R[8] - mb * cpos[1] * cpos[2];
+        const T hh[3] = {mb * cpos[0], mb * cpos[1], mb * cpos[2]};
+        T V[6], A[6];
+        for (int c = 0; c < 6; c++) { V[c] = E.V[b][c]; A[c] = E.A[b][c]; }
+        T IV[6], IA[6], t1[3], t2[3];
+        IV[0] = I6[0] * V[0] + I6[3] * V[1] + I6[4] * V[2];
+        IV[1] = I6[3] * V[0] + I6[1] * V[1] + I6[5] * V[2];
+        IV[2] = I6[4] * V[0] + I6[5] * V[1] + I6[2] * V[2];
+        cross3(hh, V + 3, t1); cross3(hh, V, t2);
+        for (int j = 0; j < 3; j++) { IV[j] += t1[j]; IV[3 + j] = mb * V[3 + j] - t2[j]; }
+        IA[0] = I6[0] * A[0] + I6[3] * A[1] + I6[4] * A[2];
+        IA[1] = I6[3] * A[0] + I6[1] * A[1] + I6[5] * A[2];
+        IA[2] = I6[4] * A[0] + I6[5] * A[1] + I6[2] * A[2];
+        cross3(hh, A + 3, t1); cross3(hh, A, t2);
+        for (int j = 0; j < 3; j++) { IA[j] += t1[j]; IA[3 + j] = mb * A[3 + j] - t2[j]; }
+        T c1[3], c2[3], c3[3];
+        cross3(V, IV, c1); cross3(V + 3, IV + 3, c2); cross3(V, IV + 3, c3);
+        E.Im[b] = mb;
+        for (int j = 0; j < 3; j++) {
+            E.Ih[b][j] = hh[j];
+            E.F[b][j] = IA[j] + c1[j] + c2[j] - Wn[j];
+            E.F[b][3 + j] = IA[3 + j] + c3[j] - Wf[j];
+        }
+        for (int j = 0; j < 6; j++) E.II[b][j] = I6[j];
+    } else if (lane - nb < nd) {
+        const int d = lane - nb;
+        T qf = T(0);
+        for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == d) qf += E.limf[l];
+        for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += E.x.pt.ptq[p]; }
+        if (m.is_torque) for (int a = 0; a < m.n_act; a++) if (m.act_dof[a] == d) qf += E.ctrl[a];
+        E.Q[d] = qf;
+    }
+    gsync<G>();
+
+    // ---- full evaluation read-outs (pt region is dead now) ----
+    if (full) {
+        if (lane < nb) {
+            const int b = lane;
+            T cpos[3], vc[3];
+            matvec3(E.R[b], m.body_com[b], cpos);
+            for (int c = 0; c < 3; c++) cpos[c] += E.r[b][c];
+            cross3(E.V[b], cpos, vc);
+            for (int c = 0; c < 3; c++) { E.x.out.comp[b][c] = m.body_mass[b] * cpos[c]; E.x.out.comp[b][3 + c] = m.body_mass[b] * (vc[c] + E.V[b][3 + c]); }
+        } else if (lane - nb < m.n_obspts) {
+            const int p = lane - nb, b = m.obs_body[p];
+            T x[3], v[3];
+            matvec3(E.R[b], m.obs_loc[p], x);
+            for (int c = 0; c < 3; c++) x[c] += E.r[b][c];
+            cross3(E.V[b], x, v);
+            for (int c = 0; c < 3; c++) { E.x.out.obs_pos[p][c] = x[c] + E.O[c]; E.x.out.obs_vel[p][c] = v[c] + E.V[b][3 + c]; }
+        }
+        gsync<G>();
+        if (lane < 3) {
+            T ms = T(0), ps = T(0);
+            for (int b = 0; b < nb; b++) { ms += E.x.out.comp[b][lane]; ps += E.x.out.comp[b][3 + lane]; }
+            const T im = T(1) / m.total_mass;
+            E.com_pos[lane] = ms * im + E.O[lane];
+            E.com_vel[lane] = ps * im;
+        } else if (lane < 5) {
+            const int g = lane - 3;
+            T w[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+            for (int s = 0; s < m.n_spheres; s++) {
+                if (m.sph_group[s] != g) continue;
+                const T pa[3] = {E.sphx[s][0] + E.O[0], E.sphx[s][1] + E.O[1], E.sphx[s][2] + E.O[2]};
+                T n[3];
+                cross3(pa, E.sphF[s], n);
+                for (int c = 0; c < 3; c++) { w[c] += E.sphF[s][c]; w[3 + c] += n[c]; }
+            }
+            for (int c = 0; c < 6; c++) E.contact[g][c] = w[c];
+        } else if (lane == 5) {
+            T mx = T(0);
+            for (int l = 0; l < m.n_limits; l++) { const T a = Num<T>::abs(E.limf[l]); mx = a > mx ? a : mx; }
+            E.max_limit = mx;
+        }
+    }
+
+    // ---- phase F: composite inertias / subtree forces, parents gather from children ----
+    for (int lev = m.n_levels - 2; lev >= 0; lev--) {
+        if (lane < nb && m.body_level[lane] == lev) {
+            const int b = lane;
+            for (int c_ = b + 1; c_ < nb; c_++) {
+                if (m.body_parent[c_] != b) continue;
+                E.Im[b] += E.Im[c_];
+                for (int j = 0; j < 3; j++) E.Ih[b][j] += E.Ih[c_][j];
+                for (int j = 0; j < 6; j++) { E.II[b][j] += E.II[c_][j]; E.F[b][j] += E.F[c_][j]; }
+            }
+        }
+        gsync<G>();
+    }
+
+    // ---- phase G: joint-space inertia entries (lane = entry), bias ----
+    if (h_imp > T(0)) {
+        // contact Jacobian columns col[s][d] = w_d x p_s + v_d for the dofs on the sphere's chain
+        for (int tsk = lane; tsk < m.n_spheres * nd; tsk += G) {
+            const int s = tsk / nd, d = tsk % nd;
+            const int last = m.body_last_dof[m.sph_body[s]];
+            T cv[3] = {T(0), T(0), T(0)};
+            if (E.sphD[s][1] > T(0) && ((m.dof_anc_mask[last] >> d) & 1u)) {
+                cross3(E.S[d], E.sphx[s], cv);
+                for (int c = 0; c < 3; c++) cv[c] += E.S[d][3 + c];
+            }
+            for (int c = 0; c < 3; c++) E.x.jac.col[s][d][c] = cv[c];
+        }
+        gsync<G>();
+    }
+    for (int e = lane; e < m.n_entries; e += G) {
+        const int i = m.ent_i[e], j = m.ent_j[e], b = m.dof_body[i];
+        const T* S = E.S[i];
+        T IS[6], t1[3], t2[3];
+        IS[0] = E.II[b][0] * S[0] + E.II[b][3] * S[1] + E.II[b][4] * S[2];
+        IS[1] = E.II[b][3] * S[0] + E.II[b][1] * S[1] + E.II[b][5] * S[2];
+        IS[2] = E.II[b][4] * S[0] + E.II[b][5] * S[1] + E.II[b][2] * S[2];
+        cross3(E.Ih[b], S + 3, t1); cross3(E.Ih[b], S, t2);
+        for (int c = 0; c < 3; c++) { IS[c] += t1[c]; IS[3 + c] = E.Im[b] * S[3 + c] - t2[c]; }
+        T v = T(0);
+        for (int c = 0; c < 6; c++) v += E.S[j][c] * IS[c];
+        if (h_imp > T(0)) {
+            for (int s = 0; s < m.n_spheres; s++) {
+                const T* ci = E.x.jac.col[s][i];
+                const T* cj = E.x.jac.col[s][j];
+                v += h_imp * (E.sphD[s][0] * (ci[0] * cj[0] + ci[2] * cj[2]) + E.sphD[s][1] * ci[1] * cj[1]);
+            }
+            if (i == j)
+                for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == i) v += h_imp * E.limD[l];
+        }
+        E.H[i * (i + 1) / 2 + j] = v;
+        if (i == j) {
+            T bi = T(0);
+            for (int c = 0; c < 6; c++) bi += S[c] * E.F[b][c];
+            E.rhs[i] = E.Q[i] - bi;
+        }
+    }
+    gsync<G>();
+
+    // ---- phase H: sparse L^T D L along the tree and solve (serial, lane 0) ----
+    if (lane == 0) {
+        for (int kq = nd - 1; kq >= 0; kq--) {
+            const T dk = E.H[kq * (kq + 1) / 2 + kq];
+            for (int i = m.dof_parent[kq]; i >= 0; i = m.dof_parent[i]) {
+                const T a = E.H[kq * (kq + 1) / 2 + i] / dk;
+                for (int j = i; j >= 0; j = m.dof_parent[j]) E.H[i * (i + 1) / 2 + j] -= a * E.H[kq * (kq + 1) / 2 + j];
+                E.H[kq * (kq + 1) / 2 + i] = a;
+            }
+        }
+        for (int i = nd - 1; i >= 0; i--)
+            for (int j = m.dof_parent[i]; j >= 0; j = m.dof_parent[j]) E.rhs[j] -= E.H[i * (i + 1) / 2 + j] * E.rhs[i];
+        for (int i = 0; i < nd; i++) E.rhs[i] /= E.H[i * (i + 1) / 2 + i];
+        for (int i = 0; i < nd; i++) {
+            T v = E.rhs[i];
+            for (int j = m.dof_parent[i]; j >= 0; j = m.dof_parent[j]) v -= E.H[i * (i + 1) / 2 + j] * E.rhs[j];
+            E.rhs[i] = v;
+            E.udot[i] = v;
+        }
+    }
+    gsync<G>();
+}
+
+// state <-> work buffer helpers (lane d < nd owns a dof, lane k < nm owns a muscle)
+template <typename T, int CLS>
+__device__ __forceinline__ void coop_clamp(const DevModel<T>& m, EnvWork<T, CLS>& E, int lane) {
+    if (lane < m.n_muscles) {
+        E.act[lane] = clampv(E.act[lane], m.mus_amin[lane], T(1));
+        if (E.lm[lane] < m.mus_lm_min[lane]) E.lm[lane] = m.mus_lm_min[lane];
+    }
+}
+
+template <typename T, int CLS>
+__device__ void coop_integrate(const DevModel<T>& m, const DevTask<T>& c, EnvWork<T, CLS>& E, int lane, int istep,
+                               unsigned long long seed, unsigned long long env) {
+    constexpr int G = CoopCls<CLS>::G;
+    const int nd = m.n_dof, nm = m.n_muscles;
+    const T h = c.dt / T(c.n_substeps);
+    const T t0 = T(istep) * c.dt;
+    const int ext_pt = c.perturb ? c.perturb_obspt : -1;
+    const bool isd = lane < nd, ism = lane < nm;
+    for (int sub = 0; sub < c.n_substeps; sub++) {
+        const T t = t0 + T(sub) * h;
+        if (c.integrator == BIO_INT_SEMI_IMPLICIT_EULER || c.integrator == BIO_INT_IMPLICIT_DAMPING) {
+            coop_eval<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, t), ext_pt,
+                              c.integrator == BIO_INT_IMPLICIT_DAMPING ? h : T(0), false);
+            if (isd) { const T un = E.u[lane] + h * E.udot[lane]; E.u[lane] = un; E.q[lane] += h * un; }
+            if (ism) { E.act[lane] += h * E.adot[lane]; E.lm[lane] += h * E.lmdot[lane]; }
+        } else if (c.integrator == BIO_INT_RK2_MIDPOINT) {
+            const T q0 = isd ? E.q[lane] : T(0), u0 = isd ? E.u[lane] : T(0);
+            const T a0 = ism ? E.act[lane] : T(0), l0 = ism ? E.lm[lane] : T(0);
+            coop_eval<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, t), ext_pt, T(0), false);
+            const T hh = T(0.5) * h;
+            if (isd) { E.q[lane] = q0 + hh * u0; E.u[lane] = u0 + hh * E.udot[lane]; }
+            if (ism) { E.act[lane] = a0 + hh * E.adot[lane]; E.lm[lane] = l0 + hh * E.lmdot[lane]; }
+            coop_clamp(m, E, lane);
+            gsync<G>();
+            coop_eval<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, t + hh), ext_pt, T(0), false);
+            if (isd) { const T um = E.u[lane]; E.q[lane] = q0 + h * um; E.u[lane] = u0 + h * E.udot[lane]; }
+            if (ism) { E.act[lane] = a0 + h * E.adot[lane]; E.lm[lane] = l0 + h * E.lmdot[lane]; }
+        } else {  // classic RK4
+            const T q0 = isd ? E.q[lane] : T(0), u0 = isd ? E.u[lane] : T(0);
+            const T a0 = ism ? E.act[lane] : T(0), l0 = ism ? E.lm[lane] : T(0);
+            T aq = T(0), au = T(0), aa = T(0), al = T(0);
+            for (int r = 0; r < 4; r++) {
+                const T wgt = (r == 0 || r == 3) ? T(1) : T(2);
+                const T cn = r == 2 ? T(1) : T(0.5);
+                coop_eval<T, CLS>(m, E, lane, c.newton_iters,
+                                  perturb_force(c, seed, env, t + (r == 0 ? T(0) : (r == 3 ? h : T(0.5) * h))), ext_pt,
+                                  T(0), false);
+                if (isd) { aq += wgt * E.u[lane]; au += wgt * E.udot[lane]; }
+                if (ism) { aa += wgt * E.adot[lane]; al += wgt * E.lmdot[lane]; }
+                if (r < 3) {
+                    if (isd) { const T us = E.u[lane]; E.q[lane] = q0 + cn * h * us; E.u[lane] = u0 + cn * h * E.udot[lane]; }
+                    if (ism) { E.act[lane] = a0 + cn * h * E.adot[lane]; E.lm[lane] = l0 + cn * h * E.lmdot[lane]; }
+                    coop_clamp(m, E, lane);
+                    gsync<G>();
+                }
+            }
+            const T h6 = h / T(6);
+            if (isd) { E.q[lane] = q0 + h6 * aq; E.u[lane] = u0 + h6 * au; }
+            if (ism) { E.act[lane] = a0 + h6 * aa; E.lm[lane] = l0 + h6 * al; }
+        }
+        coop_clamp(m, E, lane);
+        gsync<G>();
+    }
+}
+
+// sum over the G lanes of the env (butterfly, same order on every lane)
+template <typename T, int G>
+__device__ __forceinline__ T group_sum(T v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
+    return v;
+}
+template <typename T, int G>
+__device__ __forceinline__ T group_max(T v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) { const T w = __shfl_xor_sync(0xffffffffu, v, o, G); v = w > v ? w : v; }
+    return v;
+}
+
+// observation slot o of the env (descriptor table built on the host)
+template <typename T, int CLS>
+__device__ __forceinline__ T obs_value(const DevModel<T>& m, const DevTask<T>& c, const EnvWork<T, CLS>& E, int istep,
+                                       int row_next, const T* pel, int o) {
+    const int desc = m.obs_desc[o], kind = desc >> 16, idx = desc & 0xffff;
+    switch (kind) {
+        case 0: { const T ph = T(istep) / T(c.cycle); return ph - Num<T>::floor(ph); }
+        case 1: return m.coord_dof[idx] >= 0 ? E.q[m.coord_dof[idx]] : m.coord_const[idx];
+        case 2: return m.coord_dof[idx] >= 0 ? E.u[m.coord_dof[idx]] : T(0);
+        case 3: return m.coord_dof[idx] >= 0 ? E.udot[m.coord_dof[idx]] : T(0);
+        case 4: return c.ref_q[(size_t)row_next * c.ref_coords + idx];
+        case 5: return c.ref_u[(size_t)row_next * c.ref_coords + idx];
+        case 6: return E.x.out.obs_pos[idx / 3][idx % 3] - pel[idx % 3];
+        case 7: return E.com_pos[idx] - pel[idx];
+        case 8: return E.x.out.obs_vel[idx / 3][idx % 3];
+        case 9: return E.com_vel[idx];
+        case 10: return E.act[idx];
+        case 11: return E.lm[idx];
+        case 12: return E.lmdot[idx];
+        default: {
+            const T weight = Num<T>::abs(m.total_mass * m.gravity[1]);
+            const int g = idx / 6, j = idx % 6;
+            return E.contact[g][j] / (j < 3 ? weight : weight * c.height);
+        }
+    }
+}
+
+template <typename T, int CLS>
+__device__ void coop_write_obs(const DevModel<T>& m, const DevTask<T>& c, const EnvWork<T, CLS>& E, int lane, int istep,
+                               T* orow) {
+    constexpr int G = CoopCls<CLS>::G;
+    T pel[3] = {T(0), T(0), T(0)};
+    for (int i = 0; i < m.n_coords; i++) {
+        const int pt = m.coord_pelvis_trans[i];
+        if (pt) pel[pt - 1] = E.q[m.coord_dof[i]];
+    }
+    const int row_next = ref_row(c, istep + 1);
+    for (int o = lane; o < c.obs_dim; o += G) orow[o] = obs_value<T, CLS>(m, c, E, istep, row_next, pel, o);
+}
+
+template <typename T, int CLS>
+__global__ void __launch_bounds__(256)
+bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, const EnvState<T> st, int n,
+                     unsigned long long seed, long long env_offset, const T* __restrict__ actions,
+                     T* __restrict__ obs, T* __restrict__ reward, uint8_t* __restrict__ done, T* __restrict__ terms,
+                     double* __restrict__ stats) {
+    typedef CoopCls<CLS> C;
+    constexpr int G = C::G;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const DevModel<T>& m = stage_model(gm, smem);
+    EnvWork<T, CLS>* works = reinterpret_cast<EnvWork<T, CLS>*>(smem + ((sizeof(DevModel<T>) + 15) / 16) * 16);
+    const int slot = threadIdx.x / G, lane = threadIdx.x % G;
+    const int envs_per_cta = blockDim.x / G;
+    const int i = blockIdx.x * envs_per_cta + slot;
+    // all lanes of an env take the same branch; envs of a warp may differ only in i >= n
+    const bool valid = i < n;
+    const int ii = valid ? i : n - 1;          // out-of-range groups shadow the last env, stores are masked
+    EnvWork<T, CLS>& E = works[slot];
+    const unsigned long long env = (unsigned long long)(env_offset + ii);
+    const int na = m.n_act, nd = m.n_dof, nm = m.n_muscles, Hh = c.horizon;
+    const bool isd = lane < nd, ism = lane < nm, isa = lane < na;
+
+    if (isd) { E.q[lane] = st.q[(size_t)lane * n + ii]; E.u[lane] = st.u[(size_t)lane * n + ii]; }
+    if (ism) { E.act[lane] = st.act[(size_t)lane * n + ii]; E.lm[lane] = st.lm[(size_t)lane * n + ii]; }
+    int istep = st.istep[ii];
+    int hist_pos = st.hist_pos[ii];
+    const bool first = st.first[ii] != 0;
+
+    // ---- action pre-processing: lane = actuator ----
+    T action = isa ? actions[(size_t)ii * na + lane] : T(0);
+    const bool lane_nan = action != action;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (0xffffu << ((threadIdx.x & 31) / G * G));
+    const bool nan = (__ballot_sync(0xffffffffu, lane_nan) & gmask) != 0u;
+    gsync<G>();   // E.q / E.u visible for the PD law
+    if (nan) {
+        action = T(0);
+    } else if (c.use_pd) {
+        T tau = T(0);
+        if (lane < c.n_pd) {
+            const int cx = c.pd_x_coord[lane], cv = c.pd_v_coord[lane];
+            const T x = m.coord_dof[cx] >= 0 ? E.q[m.coord_dof[cx]] : m.coord_const[cx];
+            const T v = m.coord_dof[cv] >= 0 ? E.u[m.coord_dof[cv]] : T(0);
+            tau = c.pd_kp[lane] * (action - x) + c.pd_kv[lane] * (-v);
+        }
+        action = tau;
+    }
+    T last_action = T(0), curr = T(0);
+    if (isa) {
+        if (first) {
+            last_action = action;
+            if (valid) for (int hh = 0; hh < Hh; hh++) st.history[((size_t)hh * na + lane) * n + ii] = action;
+        } else {
+            last_action = st.last_action[(size_t)lane * n + ii];
+        }
+    }
+    if (first) hist_pos = 0;
+    if (isa) {
+        if (valid) st.history[((size_t)hist_pos * na + lane) * n + ii] = action;
+        T sum = T(0);
+        for (int hh = 0; hh < Hh; hh++) sum += (hh == hist_pos) ? action : st.history[((size_t)hh * na + lane) * n + ii];
+        curr = sum / T(Hh);
+        E.ctrl[lane] = clampv(c.feed_mean_action ? curr : action, m.act_min[lane], m.act_max[lane]);
+    }
+    hist_pos = (hist_pos + 1) % Hh;
+    gsync<G>();
+
+    // ---- integrate one control step, evaluate at the new state ----
+    coop_integrate<T, CLS>(m, c, E, lane, istep, seed, env);
+    istep += 1;
+    const int ext_pt = c.perturb ? c.perturb_obspt : -1;
+    coop_eval<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, T(istep) * c.dt), ext_pt, T(0), true);
+    gsync<G>();
+    T* orow = obs + (size_t)ii * c.obs_dim;
+    if (valid) coop_write_obs<T, CLS>(m, c, E, lane, istep, orow);
+
+    // ---- reward (env2D.py:267-358): lane-parallel partial sums ----
+    const int row = ref_row(c, istep);
+    T qpart = T(0);
+    for (int k = lane; k < m.n_coords; k += G) {
+        const int d = m.coord_dof[k];
+        const T v = d >= 0 ? E.q[d] : m.coord_const[k];
+        const T dd = v - c.ref_q[(size_t)row * c.ref_coords + k];
+        qpart += dd * dd;
+    }
+    const T qerr = group_sum<T, G>(qpart) / T(m.n_coords);
+    T px = T(0), py = T(0);
+    for (int k = 0; k < m.n_coords; k++) {
+        if (m.coord_pelvis_trans[k] == 1) px = E.q[m.coord_dof[k]];
+        if (m.coord_pelvis_trans[k] == 2) py = E.q[m.coord_dof[k]];
+    }
+    const T com_err = body_mse(E.com_pos, c.ref_com_pos + (size_t)row * 3);
+    const T position_r = Num<T>::exp(T(-30) * qerr);
+    const T com_r = Num<T>::exp(T(-20) * com_err);
+    // feet terms: lanes 0..7 each take one (side, body)
+    T fpart = T(0);
+    if (lane < 8) {
+        const int sd = lane / 4, j = lane % 4;
+        fpart = body_mse(E.x.out.obs_pos[c.rew_obspt[sd][j]],
+                         c.ref_body_pos + ((size_t)row * c.ref_bodies + c.rew_refbody[sd][j]) * 3);
+    }
+    // sum of the 4 bodies of each side: butterfly over 4 lanes
+    fpart += __shfl_xor_sync(0xffffffffu, fpart, 1, G);
+    fpart += __shfl_xor_sync(0xffffffffu, fpart, 2, G);
+    const T foot_r = T(0.5) * Num<T>::exp(T(-20) * __shfl_sync(0xffffffffu, fpart, 0, G));
+    const T foot_l = T(0.5) * Num<T>::exp(T(-20) * __shfl_sync(0xffffffffu, fpart, 4, G));
+    T effort, a_error = T(0);
+    if (c.effort_torque) {
+        const T s2 = group_sum<T, G>(isa ? curr * curr : T(0));
+        effort = Num<T>::sqrt(s2) / (c.max_actuation * T(na * na));
+    } else {
+        T a2 = T(0), cot = T(0);
+        if (ism) {
+            const int k = lane;
+            const T hp = T(1.5707963267948966);
+            a2 = E.act[k] * E.act[k];
+            const T l = m.mus_slow_twitch[k];
+            T se, ce, sa, ca;
+            Num<T>::sincos(hp * E.ctrl[k], &se, &ce);
+            Num<T>::sincos(hp * E.act[k], &sa, &ca);
+            const T fa = T(40) * l * se + T(133) * (T(1) - l) * (T(1) - ce);
+            const T fm = T(74) * l * sa + T(111) * (T(1) - l) * (T(1) - ca);
+            const T ln = E.lm[k] / m.mus_lopt[k], v = E.lmdot[k];
+            T g = T(0);
+            if (ln < T(0.5)) g = T(0.5); else if (ln < T(1)) g = ln; else if (ln < T(1.5)) g = T(-2) * ln + T(3);
+            const T es = T(0.25) * E.ffib[k] * -v, ew = E.fact[k] * -v;
+            cot = m.mus_cot_mass[k] * fa + m.mus_cot_mass[k] * g * fm + (es > T(0) ? es : T(0)) + (ew > T(0) ? ew : T(0));
+        }
+        const T total = T(1.51) * m.total_mass + group_sum<T, G>(cot);
+        a_error = Num<T>::exp(T(-2) * Num<T>::sqrt(group_sum<T, G>(a2)));
+        effort = total / (T(20) * T(nm * nm));
+    }
+    const T old_px = st.old_px[ii];
+    const T progress_coord = c.effort_use_dy ? py : px;
+    const T prog = progress_coord - old_px + T(1);
+    const T effort_r = Num<T>::exp(-effort / (prog > T(1) ? prog : T(1)));
+    const T dact = isa ? curr - last_action : T(0);
+    const T action_r = Num<T>::exp(-c.action_r_scale * Num<T>::sqrt(group_sum<T, G>(dact * dact)));
+    T imit = position_r * com_r;
+    if (c.reward_use_feet) imit *= (foot_l + foot_r);
+    T rew = (T(0.5) + c.w_imitate) * imit + c.w_effort * effort_r + c.w_action * action_r;
+
+    // ---- termination (env2D.py:237-265) ----
+    T acc = T(0);
+    bool fin = true;
+    if (isd) {
+        acc = Num<T>::abs(E.udot[lane]);
+        fin = isfinite(E.q[lane]) && isfinite(E.u[lane]) && isfinite(E.udot[lane]);
+    }
+    const T maxacc = group_max<T, G>(acc);
+    const bool finite = isfinite(rew) && ((__ballot_sync(0xffffffffu, !fin) & gmask) == 0u);
+    int reason = 0;
+    if (!finite) { reason = BIO_DONE_NONFINITE; rew = T(0); }
+    else if (E.x.out.obs_pos[c.term_obspt][1] < c.term_height) reason = BIO_DONE_HEIGHT;
+    else if (E.max_limit > c.term_limit_force) reason = BIO_DONE_LIMIT_FORCE;
+    else if (maxacc > c.term_acc) reason = BIO_DONE_ACCEL;
+    else if (istep >= c.n_steps) reason = BIO_DONE_HORIZON;
+    else if (c.term_feet_cross && E.x.out.obs_pos[c.feet_obspt[0]][2] - E.x.out.obs_pos[c.feet_obspt[1]][2] < T(0)) reason = BIO_DONE_FEET_CROSS;
+
+    T ep_return = st.ep_return[ii] + rew;
+    int ep_len = st.ep_len[ii] + 1;
+    long long episode = st.episode[ii];
+    int first_next = 0;
+    if (valid && lane == 0) {
+        reward[ii] = rew;
+        done[ii] = reason != 0;
+        if (terms) {
+            T* tr = terms + (size_t)ii * c.n_reward_terms;
+            const bool z = reason == BIO_DONE_NONFINITE;
+            tr[0] = z ? T(0) : position_r; tr[1] = z ? T(0) : com_r; tr[2] = z ? T(0) : foot_l; tr[3] = z ? T(0) : foot_r;
+            if (c.n_reward_terms > 4) tr[4] = z ? T(0) : a_error;
+        }
+        if (stats) {
+            if (nan) atomicAdd(&stats[10], 1.0);
+            if (reason) {
+                atomicAdd(&stats[1], 1.0);
+                atomicAdd(&stats[2], (double)ep_return);
+                atomicAdd(&stats[3], (double)ep_len);
+                int bit = 0;
+                while (!((reason >> bit) & 1)) bit++;
+                atomicAdd(&stats[4 + bit], 1.0);
+            }
+        }
+    }
+    gsync<G>();   // everyone is done with E.x.out before a reset overwrites it
+    if (reason && c.auto_reset) {
+        episode += 1;
+        int idx = 0;
+        if (!c.test_mode && c.reset_max_index > 0)
+            idx = (int)(bio_rand(seed, env, (unsigned long long)episode, 1) % (unsigned long long)(c.reset_max_index + 1));
+        idx = idx > c.ref_rows - 1 ? c.ref_rows - 1 : idx;
+        for (int k = lane; k < m.n_coords; k += G) {
+            const int d = m.coord_dof[k];
+            if (d < 0) continue;
+            E.q[d] = c.ref_q[(size_t)idx * c.ref_coords + k];
+            E.u[d] = c.ref_u[(size_t)idx * c.ref_coords + k];
+        }
+        if (ism) { E.act[lane] = m.mus_default_act[lane]; E.lm[lane] = c.ref_lm0[(size_t)idx * nm + lane]; }
+        if (isa) E.ctrl[lane] = T(0);
+        istep = idx;
+        first_next = 1;
+        ep_return = T(0);
+        ep_len = 0;
+        gsync<G>();
+        coop_eval<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, T(istep) * c.dt), ext_pt, T(0), true);
+        gsync<G>();
+        if (valid) coop_write_obs<T, CLS>(m, c, E, lane, istep, orow);
+    }
+    // ---- write back ----
+    if (valid) {
+        if (isd) { st.q[(size_t)lane * n + ii] = E.q[lane]; st.u[(size_t)lane * n + ii] = E.u[lane]; }
+        if (ism) { st.act[(size_t)lane * n + ii] = E.act[lane]; st.lm[(size_t)lane * n + ii] = E.lm[lane]; }
+        if (isa) st.last_action[(size_t)lane * n + ii] = first_next ? T(0) : curr;
+        if (lane == 0) {
+            st.old_px[ii] = progress_coord;
+            st.istep[ii] = istep;
+            st.first[ii] = first_next;
+            st.hist_pos[ii] = hist_pos;
+            st.ep_return[ii] = ep_return;
+            st.ep_len[ii] = ep_len;
+            st.episode[ii] = episode;
+        }
+    }
+    if (stats && threadIdx.x == 0) {
+        const int rem = n - blockIdx.x * envs_per_cta;
+        atomicAdd(&stats[0], (double)(rem < envs_per_cta ? rem : envs_per_cta));
+    }
+}
+
+}  // namespace bio

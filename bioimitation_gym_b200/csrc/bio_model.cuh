@@ -1,0 +1,274 @@
+// bio_model.cuh -- device-side mirror of BioModelTables / BioTaskConfig in the
+// kernel's scalar type, and the host conversion.  The model block is copied to
+// shared memory once per CTA; all warps read it with uniform (broadcast)
+// addresses.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/bio_b200.h"
+
+namespace bio {
+
+template <typename T>
+struct DevModel {
+    int32_t n_bodies, n_dof, n_axes, n_muscles, n_act, n_pathpts, n_spheres, n_limits;
+    int32_t n_funcs, n_knots, n_obspts, n_coords, is_torque, has_tz, max_pts_per_muscle, pad;
+    T gravity[3];
+    T total_mass;
+    int32_t body_parent[BIO_MAX_BODIES];
+    int32_t body_axis_begin[BIO_MAX_BODIES];
+    int32_t body_axis_count[BIO_MAX_BODIES];
+    T body_mass[BIO_MAX_BODIES];
+    T body_com[BIO_MAX_BODIES][3];
+    T body_inertia[BIO_MAX_BODIES][6];
+    T body_joint_loc[BIO_MAX_BODIES][3];
+    int32_t axis_kind[BIO_MAX_AXES];
+    int32_t axis_dof[BIO_MAX_AXES];
+    int32_t axis_func[BIO_MAX_AXES];
+    T axis_vec[BIO_MAX_AXES][3];
+    int32_t dof_body[BIO_MAX_DOF];
+    int32_t dof_parent[BIO_MAX_DOF];   // nearest ancestor dof on the root path (-1: none)
+    int32_t body_last_dof[BIO_MAX_BODIES];  // deepest dof of the body's own joint
+    uint32_t dof_anc_mask[BIO_MAX_DOF];
+    int32_t func_kind[BIO_MAX_FUNCS];
+    int32_t func_knot_begin[BIO_MAX_FUNCS];
+    int32_t func_knot_count[BIO_MAX_FUNCS];
+    T func_c[BIO_MAX_FUNCS][2];
+    T knot_x[BIO_MAX_KNOTS];
+    T knot_c[BIO_MAX_KNOTS][4];
+    T mus_fiso[BIO_MAX_MUSCLES];
+    T mus_lopt[BIO_MAX_MUSCLES];
+    T mus_lts[BIO_MAX_MUSCLES];
+    T mus_vmax[BIO_MAX_MUSCLES];
+    T mus_tact[BIO_MAX_MUSCLES];
+    T mus_tdeact[BIO_MAX_MUSCLES];
+    T mus_amin[BIO_MAX_MUSCLES];
+    T mus_beta[BIO_MAX_MUSCLES];
+    T mus_default_act[BIO_MAX_MUSCLES];
+    T mus_height[BIO_MAX_MUSCLES];
+    T mus_lm_min[BIO_MAX_MUSCLES];
+    T mus_cot_mass[BIO_MAX_MUSCLES];
+    T mus_slow_twitch[BIO_MAX_MUSCLES];
+    int32_t mus_pt_begin[BIO_MAX_MUSCLES];
+    int32_t mus_pt_count[BIO_MAX_MUSCLES];
+    int32_t pt_body[BIO_MAX_PATHPTS];
+    int32_t pt_kind[BIO_MAX_PATHPTS];
+    int32_t pt_dof[BIO_MAX_PATHPTS];
+    int32_t pt_func[BIO_MAX_PATHPTS][3];
+    T pt_loc[BIO_MAX_PATHPTS][3];
+    T pt_range[BIO_MAX_PATHPTS][2];
+    int32_t sph_body[BIO_MAX_SPHERES];
+    int32_t sph_group[BIO_MAX_SPHERES];
+    T sph_loc[BIO_MAX_SPHERES][3];
+    T sph_radius[BIO_MAX_SPHERES];
+    T sph_k[BIO_MAX_SPHERES];
+    T sph_c[BIO_MAX_SPHERES];
+    T sph_us[BIO_MAX_SPHERES];
+    T sph_ud[BIO_MAX_SPHERES];
+    T sph_uv[BIO_MAX_SPHERES];
+    T sph_vt[BIO_MAX_SPHERES];
+    int32_t lim_dof[BIO_MAX_LIMITS];
+    T lim_kup[BIO_MAX_LIMITS];
+    T lim_qup[BIO_MAX_LIMITS];
+    T lim_klo[BIO_MAX_LIMITS];
+    T lim_qlo[BIO_MAX_LIMITS];
+    T lim_damp[BIO_MAX_LIMITS];
+    T lim_w[BIO_MAX_LIMITS];
+    int32_t act_dof[BIO_MAX_ACT];
+    T act_min[BIO_MAX_ACT];
+    T act_max[BIO_MAX_ACT];
+    int32_t obs_body[BIO_MAX_OBSPTS];
+    T obs_loc[BIO_MAX_OBSPTS][3];
+    int32_t coord_dof[BIO_MAX_COORDS];
+    int32_t coord_pelvis_trans[BIO_MAX_COORDS];
+    T coord_const[BIO_MAX_COORDS];
+    // schedules of the cooperative kernel (bio_coop.cuh), built by convert_model
+    int32_t n_levels, n_moving, n_entries, pad2;
+    int32_t body_level[BIO_MAX_BODIES];
+    int32_t body_pt_begin[BIO_MAX_BODIES];
+    int32_t body_pt_count[BIO_MAX_BODIES];
+    int32_t body_pt_list[BIO_MAX_PATHPTS];
+    int32_t moving_pt[8];
+    int32_t ent_i[BIO_MAX_DOF * (BIO_MAX_DOF + 1) / 2];
+    int32_t ent_j[BIO_MAX_DOF * (BIO_MAX_DOF + 1) / 2];
+    int32_t obs_desc[256];                   // (kind << 16) | index per observation slot
+    // curves: uniform cubic Hermite, rows (y, h*dy/dx)
+    T curve_x0[BIO_N_CURVES];
+    T curve_inv_h[BIO_N_CURVES];
+    T curve_x1[BIO_N_CURVES];
+    T curve_tab[BIO_N_CURVES][BIO_CURVE_N + 1][2];
+};
+
+template <typename T>
+struct DevTask {
+    int32_t n_substeps, integrator, newton_iters, horizon, feed_mean_action, use_pd, n_pd;
+    int32_t test_mode, cycle, n_steps, reset_max_index, ref_mirror, auto_reset;
+    int32_t term_obspt, term_feet_cross, feet_obspt[2];
+    int32_t reward_use_feet, effort_torque, effort_use_dy, n_reward_terms;
+    int32_t rew_obspt[2][4], rew_refbody[2][4];
+    int32_t use_target_obs, use_grf, n_obs_bodies, n_obs_body_vel, obs_dim;
+    int32_t perturb, perturb_obspt, perturb_negative_only;
+    int32_t pd_x_coord[BIO_MAX_ACT], pd_v_coord[BIO_MAX_ACT];
+    T pd_kp[BIO_MAX_ACT], pd_kv[BIO_MAX_ACT];
+    T dt, term_height, term_limit_force, term_acc;
+    T w_imitate, w_effort, w_action, action_r_scale, max_actuation, height;
+    T perturb_thresh, perturb_force;
+    // reference tables (device)
+    int32_t ref_rows, ref_coords, ref_bodies, pad;
+    const T* ref_q;
+    const T* ref_u;
+    const T* ref_body_pos;
+    const T* ref_com_pos;
+    const T* ref_lm0;     // [rows][n_muscles] static fibre equilibrium per reference row
+};
+
+// SoA per-env state, [k][n_envs]
+template <typename T>
+struct EnvState {
+    T* q;
+    T* u;
+    T* act;
+    T* lm;
+    T* last_action;
+    T* history;      // [horizon][n_act][N]
+    T* old_px;
+    T* ep_return;
+    int32_t* istep;
+    int32_t* first;
+    int32_t* hist_pos;
+    int32_t* ep_len;
+    long long* episode;
+};
+
+#define BIO_CP(field)                                                                  \
+    do {                                                                               \
+        const size_t n_ = sizeof(d.field) / sizeof(T);                                 \
+        static_assert(sizeof(s.field) / sizeof(double) == sizeof(d.field) / sizeof(T), \
+                      "field size mismatch: " #field);                                 \
+        const double* sp_ = (const double*)&s.field;                                   \
+        T* dp_ = (T*)&d.field;                                                         \
+        for (size_t i_ = 0; i_ < n_; i_++) dp_[i_] = (T)sp_[i_];                       \
+    } while (0)
+#define BIO_CPI(field)                                                         \
+    do {                                                                       \
+        static_assert(sizeof(s.field) == sizeof(d.field), "int field " #field); \
+        memcpy(&d.field, &s.field, sizeof(d.field));                           \
+    } while (0)
+
+template <typename T>
+void convert_model(const BioModelTables& s, DevModel<T>& d) {
+    memset(&d, 0, sizeof(d));
+    d.n_bodies = s.n_bodies; d.n_dof = s.n_dof; d.n_axes = s.n_axes; d.n_muscles = s.n_muscles;
+    d.n_act = s.n_act; d.n_pathpts = s.n_pathpts; d.n_spheres = s.n_spheres; d.n_limits = s.n_limits;
+    d.n_funcs = s.n_funcs; d.n_knots = s.n_knots; d.n_obspts = s.n_obspts; d.n_coords = s.n_coords;
+    d.is_torque = s.is_torque;
+    d.has_tz = 0;
+    for (int i = 0; i < s.n_coords; i++) if (s.coord_pelvis_trans[i] == 3) d.has_tz = 1;
+    d.max_pts_per_muscle = 0;
+    for (int i = 0; i < s.n_muscles; i++)
+        if (s.mus_pt_count[i] > d.max_pts_per_muscle) d.max_pts_per_muscle = s.mus_pt_count[i];
+    BIO_CP(gravity);
+    d.total_mass = (T)s.total_mass;
+    BIO_CPI(body_parent); BIO_CPI(body_axis_begin); BIO_CPI(body_axis_count);
+    BIO_CP(body_mass); BIO_CP(body_com); BIO_CP(body_inertia); BIO_CP(body_joint_loc);
+    BIO_CPI(axis_kind); BIO_CPI(axis_dof); BIO_CPI(axis_func); BIO_CP(axis_vec);
+    BIO_CPI(dof_body); BIO_CPI(dof_anc_mask);
+    for (int i = 0; i < BIO_MAX_DOF; i++) {
+        d.dof_parent[i] = -1;
+        for (int j = i - 1; j >= 0; j--)
+            if ((s.dof_anc_mask[i] >> j) & 1u) { d.dof_parent[i] = j; break; }
+    }
+    for (int b = 0; b < BIO_MAX_BODIES; b++) {
+        d.body_last_dof[b] = -1;
+        for (int j = 0; j < s.n_dof; j++) if (s.dof_body[j] == b) d.body_last_dof[b] = j;
+    }
+    // tree levels, per-body path-point lists, moving points, coupled (i,j) entries
+    d.n_levels = 0;
+    for (int b = 0; b < s.n_bodies; b++) {
+        d.body_level[b] = s.body_parent[b] < 0 ? 0 : d.body_level[s.body_parent[b]] + 1;
+        if (d.body_level[b] + 1 > d.n_levels) d.n_levels = d.body_level[b] + 1;
+    }
+    {
+        int k = 0;
+        for (int b = 0; b < s.n_bodies; b++) {
+            d.body_pt_begin[b] = k;
+            for (int p = 0; p < s.n_pathpts; p++) if (s.pt_body[p] == b) d.body_pt_list[k++] = p;
+            d.body_pt_count[b] = k - d.body_pt_begin[b];
+        }
+        d.n_moving = 0;
+        for (int p = 0; p < s.n_pathpts; p++)
+            if (s.pt_kind[p] == BIO_PT_MOVING && d.n_moving < 8) d.moving_pt[d.n_moving++] = p;
+        d.n_entries = 0;
+        for (int i = 0; i < s.n_dof; i++)
+            for (int j = 0; j <= i; j++)
+                if ((s.dof_anc_mask[i] >> j) & 1u) { d.ent_i[d.n_entries] = i; d.ent_j[d.n_entries] = j; d.n_entries++; }
+    }
+    BIO_CPI(func_kind); BIO_CPI(func_knot_begin); BIO_CPI(func_knot_count);
+    BIO_CP(func_c); BIO_CP(knot_x); BIO_CP(knot_c);
+    BIO_CP(mus_fiso); BIO_CP(mus_lopt); BIO_CP(mus_lts); BIO_CP(mus_vmax); BIO_CP(mus_tact);
+    BIO_CP(mus_tdeact); BIO_CP(mus_amin); BIO_CP(mus_beta); BIO_CP(mus_default_act);
+    BIO_CP(mus_height); BIO_CP(mus_lm_min); BIO_CP(mus_cot_mass); BIO_CP(mus_slow_twitch);
+    BIO_CPI(mus_pt_begin); BIO_CPI(mus_pt_count);
+    BIO_CPI(pt_body); BIO_CPI(pt_kind); BIO_CPI(pt_dof); BIO_CPI(pt_func);
+    BIO_CP(pt_loc); BIO_CP(pt_range);
+    BIO_CPI(sph_body); BIO_CPI(sph_group);
+    BIO_CP(sph_loc); BIO_CP(sph_radius); BIO_CP(sph_k); BIO_CP(sph_c); BIO_CP(sph_us);
+    BIO_CP(sph_ud); BIO_CP(sph_uv); BIO_CP(sph_vt);
+    BIO_CPI(lim_dof);
+    BIO_CP(lim_kup); BIO_CP(lim_qup); BIO_CP(lim_klo); BIO_CP(lim_qlo); BIO_CP(lim_damp); BIO_CP(lim_w);
+    BIO_CPI(act_dof); BIO_CP(act_min); BIO_CP(act_max);
+    BIO_CPI(obs_body); BIO_CP(obs_loc);
+    BIO_CPI(coord_dof); BIO_CPI(coord_pelvis_trans); BIO_CP(coord_const);
+    BIO_CP(curve_x0); BIO_CP(curve_x1); BIO_CP(curve_tab);
+    for (int c = 0; c < BIO_N_CURVES; c++)
+        d.curve_inv_h[c] = (T)((double)BIO_CURVE_N / (s.curve_x1[c] - s.curve_x0[c]));
+}
+
+// Observation layout as a descriptor per slot (same order as write_obs in
+// bio_kernels.cuh; reference env2D.py:158-230).
+template <typename T>
+int build_obs_desc(const BioModelTables& s, const BioTaskConfig& t, DevModel<T>& d) {
+    int o = 0;
+    auto put = [&](int kind, int idx) { if (o < 256) d.obs_desc[o] = (kind << 16) | idx; o++; };
+    put(0, 0);
+    for (int i = 0; i < s.n_coords; i++) if (!s.coord_pelvis_trans[i]) put(1, i);
+    for (int i = 0; i < s.n_coords; i++) put(2, i);
+    for (int i = 0; i < s.n_coords; i++) put(3, i);
+    if (t.use_target_obs) {
+        for (int i = 0; i < s.n_coords; i++) if (s.coord_pelvis_trans[i] != 1) put(4, i);
+        for (int i = 0; i < s.n_coords; i++) if (s.coord_pelvis_trans[i] != 1) put(5, i);
+    }
+    for (int p = 0; p < t.n_obs_bodies; p++) for (int j = 0; j < 3; j++) put(6, p * 3 + j);
+    for (int j = 0; j < 3; j++) put(7, j);
+    for (int p = 0; p < t.n_obs_body_vel; p++) for (int j = 0; j < 3; j++) put(8, p * 3 + j);
+    for (int j = 0; j < 3; j++) put(9, j);
+    for (int i = 0; i < s.n_muscles; i++) { put(10, i); put(11, i); put(12, i); }
+    if (t.use_grf) for (int g = 0; g < 2; g++) for (int j = 0; j < 6; j++) put(13, g * 6 + j);
+    return o;
+}
+
+template <typename T>
+void convert_task(const BioTaskConfig& s, DevTask<T>& d) {
+    memset(&d, 0, sizeof(d));
+    d.n_substeps = s.n_substeps; d.integrator = s.integrator; d.newton_iters = s.newton_iters;
+    d.horizon = s.horizon; d.feed_mean_action = s.feed_mean_action; d.use_pd = s.use_pd; d.n_pd = s.n_pd;
+    d.test_mode = s.test_mode; d.cycle = s.cycle; d.n_steps = s.n_steps;
+    d.reset_max_index = s.reset_max_index; d.ref_mirror = s.ref_mirror; d.auto_reset = s.auto_reset;
+    d.term_obspt = s.term_obspt; d.term_feet_cross = s.term_feet_cross;
+    d.feet_obspt[0] = s.feet_obspt[0]; d.feet_obspt[1] = s.feet_obspt[1];
+    d.reward_use_feet = s.reward_use_feet; d.effort_torque = s.effort_torque;
+    d.effort_use_dy = s.effort_use_dy; d.n_reward_terms = s.n_reward_terms;
+    BIO_CPI(rew_obspt); BIO_CPI(rew_refbody);
+    d.use_target_obs = s.use_target_obs; d.use_grf = s.use_grf; d.n_obs_bodies = s.n_obs_bodies;
+    d.n_obs_body_vel = s.n_obs_body_vel; d.obs_dim = s.obs_dim;
+    d.perturb = s.perturb; d.perturb_obspt = s.perturb_obspt;
+    d.perturb_negative_only = s.perturb_negative_only;
+    BIO_CPI(pd_x_coord); BIO_CPI(pd_v_coord); BIO_CP(pd_kp); BIO_CP(pd_kv);
+    d.dt = (T)s.dt; d.term_height = (T)s.term_height; d.term_limit_force = (T)s.term_limit_force;
+    d.term_acc = (T)s.term_acc; d.w_imitate = (T)s.w_imitate; d.w_effort = (T)s.w_effort;
+    d.w_action = (T)s.w_action; d.action_r_scale = (T)s.action_r_scale;
+    d.max_actuation = (T)s.max_actuation; d.height = (T)s.height;
+    d.perturb_thresh = (T)s.perturb_thresh; d.perturb_force = (T)s.perturb_force;
+}
+
+}  // namespace bio

