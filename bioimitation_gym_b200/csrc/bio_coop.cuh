@@ -38,7 +38,10 @@ struct EnvWork {
     T sphx[BIO_MAX_SPHERES][3], sphF[BIO_MAX_SPHERES][3], sphD[BIO_MAX_SPHERES][2];
     T limf[BIO_MAX_LIMITS], limD[BIO_MAX_LIMITS];
     T Q[C::ND];
-    T Im[BIO_MAX_BODIES], Ih[BIO_MAX_BODIES][3], II[BIO_MAX_BODIES][6], F[BIO_MAX_BODIES][6];
+    // spatial inertia about O and body force per body: [0] mass, [1..3] m*c, [4..9] I (xx yy zz xy xz yz),
+    // [10..15] force (n; f); turned into composite / subtree sums in place
+    T BI[BIO_MAX_BODIES][16];
+    T IS[C::ND][6];                                        // I^c_body(i) * S_i
     T H[C::ND * (C::ND + 1) / 2], rhs[C::ND];
     T udot[C::ND], adot[C::NM], lmdot[C::NM];
     T ffib[C::NM], fact[C::NM];
@@ -49,6 +52,21 @@ struct EnvWork {
 };
 
 template <int G> __device__ __forceinline__ void gsync() { __syncwarp(); }
+
+// column K of a row-major 3x3 (times a sign), and R <- R * Rot(e_K, angle) as a mix of the two other columns
+template <typename T, int K>
+__device__ __forceinline__ void axis_col(const T* R, T sg, T* aw) {
+    aw[0] = sg * R[K]; aw[1] = sg * R[3 + K]; aw[2] = sg * R[6 + K];
+}
+template <typename T, int I1, int I2>
+__device__ __forceinline__ void rot_cols(T* R, T cs, T sn) {
+#pragma unroll
+    for (int row = 0; row < 3; row++) {
+        const T a1 = R[3 * row + I1], a2 = R[3 * row + I2];
+        R[3 * row + I1] = cs * a1 + sn * a2;
+        R[3 * row + I2] = cs * a2 - sn * a1;
+    }
+}
 
 // ---------------------------------------------------------------------------
 // One evaluation of the dynamics of the env in E (state in E.q/u/act/lm,
@@ -71,10 +89,11 @@ __device__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
     }
     gsync<G>();
 
-    // ---- phase B: kinematics, one tree level at a time, lane = body ----
+    // ---- phase B: kinematics, one tree level at a time, lane = body of the level ----
     for (int lev = 0; lev < m.n_levels; lev++) {
-        if (lane < nb && m.body_level[lane] == lev) {
-            const int b = lane, p = m.body_parent[b];
+        const int lb = m.level_begin[lev] + lane;
+        if (lb < m.level_begin[lev + 1]) {
+            const int b = m.level_body[lb], p = m.body_parent[b];
             T Rp[9], R[9], r[3], V[6], A[6];
             if (p >= 0) {
                 for (int c = 0; c < 9; c++) Rp[c] = E.R[p][c];
@@ -89,49 +108,70 @@ __device__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
             for (int c = 0; c < 9; c++) R[c] = Rp[c];
             bool root_open = p < 0;
             const int ab = m.body_axis_begin[b], ae = ab + m.body_axis_count[b];
+            int dprev = -1;
+            T Sd[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
             for (int a = ab; a < ae; a++) {
-                const int d = m.axis_dof[a];
-                if (d >= 0 && (a == ab || m.axis_dof[a - 1] != d))
-                    for (int c = 0; c < 6; c++) E.S[d][c] = T(0);
-            }
-            for (int a = ab; a < ae; a++) {
-                const int d = m.axis_dof[a];
+                const int d = m.axis_dof[a], code = m.axis_code[a];
                 const T s = E.ax_s[a], ds = E.ax_ds[a], dds = E.ax_dds[a];
                 T S[6], aw[3];
                 if (m.axis_kind[a] == BIO_AXIS_TRANS) {
-                    matvec3(Rp, m.axis_vec[a], aw);
+                    if (code != 0) {
+                        const int kx = (code > 0 ? code : -code) - 1;
+                        const T sg = code > 0 ? T(1) : T(-1);
+                        if (kx == 0) axis_col<T, 0>(Rp, sg, aw);
+                        else if (kx == 1) axis_col<T, 1>(Rp, sg, aw);
+                        else axis_col<T, 2>(Rp, sg, aw);
+                    } else {
+                        matvec3(Rp, m.axis_vec[a], aw);
+                    }
                     S[0] = S[1] = S[2] = T(0); S[3] = aw[0]; S[4] = aw[1]; S[5] = aw[2];
                     for (int c = 0; c < 3; c++) r[c] += aw[c] * s;
                 } else {
                     if (root_open) { for (int c = 0; c < 3; c++) { E.O[c] = r[c]; r[c] = T(0); } root_open = false; }
-                    matvec3(R, m.axis_vec[a], aw);
+                    T sn, cs;
+                    if (code != 0) {
+                        // rotation about a coordinate axis of the current frame: two columns mix
+                        const int kx = (code > 0 ? code : -code) - 1;
+                        const T sg = code > 0 ? T(1) : T(-1);
+                        Num<T>::sincos(sg * s, &sn, &cs);
+                        if (kx == 0) { axis_col<T, 0>(R, sg, aw); rot_cols<T, 1, 2>(R, cs, sn); }
+                        else if (kx == 1) { axis_col<T, 1>(R, sg, aw); rot_cols<T, 2, 0>(R, cs, sn); }
+                        else { axis_col<T, 2>(R, sg, aw); rot_cols<T, 0, 1>(R, cs, sn); }
+                    } else {
+                        matvec3(R, m.axis_vec[a], aw);
+                        Num<T>::sincos(s, &sn, &cs);
+                        const T ax = m.axis_vec[a][0], ay = m.axis_vec[a][1], az = m.axis_vec[a][2], vv = T(1) - cs;
+                        const T K[9] = {cs + ax * ax * vv, ax * ay * vv - az * sn, ax * az * vv + ay * sn,
+                                        ay * ax * vv + az * sn, cs + ay * ay * vv, ay * az * vv - ax * sn,
+                                        az * ax * vv - ay * sn, az * ay * vv + ax * sn, cs + az * az * vv};
+                        T Rn[9];
+                        for (int i = 0; i < 3; i++)
+                            for (int j = 0; j < 3; j++)
+                                Rn[3 * i + j] = R[3 * i] * K[j] + R[3 * i + 1] * K[3 + j] + R[3 * i + 2] * K[6 + j];
+                        for (int c = 0; c < 9; c++) R[c] = Rn[c];
+                    }
                     S[0] = aw[0]; S[1] = aw[1]; S[2] = aw[2];
                     cross3(r, aw, S + 3);
-                    T sn, cs;
-                    Num<T>::sincos(s, &sn, &cs);
-                    const T ax = m.axis_vec[a][0], ay = m.axis_vec[a][1], az = m.axis_vec[a][2], vv = T(1) - cs;
-                    const T K[9] = {cs + ax * ax * vv, ax * ay * vv - az * sn, ax * az * vv + ay * sn,
-                                    ay * ax * vv + az * sn, cs + ay * ay * vv, ay * az * vv - ax * sn,
-                                    az * ax * vv - ay * sn, az * ay * vv + ax * sn, cs + az * az * vv};
-                    T Rn[9];
-                    for (int i = 0; i < 3; i++)
-                        for (int j = 0; j < 3; j++)
-                            Rn[3 * i + j] = R[3 * i] * K[j] + R[3 * i + 1] * K[3 + j] + R[3 * i + 2] * K[6 + j];
-                    for (int c = 0; c < 9; c++) R[c] = Rn[c];
                 }
                 if (d >= 0) {
+                    if (d != dprev) {
+                        if (dprev >= 0) for (int c = 0; c < 6; c++) E.S[dprev][c] = Sd[c];
+                        for (int c = 0; c < 6; c++) Sd[c] = T(0);
+                        dprev = d;
+                    }
                     const T qd = E.u[d], sd = ds * qd, acc = dds * qd * qd;
                     T c1[3], c2[3], c3[3];
                     cross3(V, S, c1); cross3(V, S + 3, c2); cross3(V + 3, S, c3);
                     for (int c = 0; c < 3; c++) {
-                        E.S[d][c] += ds * S[c];
-                        E.S[d][3 + c] += ds * S[3 + c];
+                        Sd[c] += ds * S[c];
+                        Sd[3 + c] += ds * S[3 + c];
                         A[c] += S[c] * acc + c1[c] * sd;
                         A[3 + c] += S[3 + c] * acc + (c2[c] + c3[c]) * sd;
                     }
                     for (int c = 0; c < 6; c++) V[c] += S[c] * sd;
                 }
             }
+            if (dprev >= 0) for (int c = 0; c < 6; c++) E.S[dprev][c] = Sd[c];
             if (root_open) { for (int c = 0; c < 3; c++) { E.O[c] = r[c]; r[c] = T(0); } }
             for (int c = 0; c < 9; c++) E.R[b][c] = R[c];
             for (int c = 0; c < 3; c++) E.r[b][c] = r[c];
@@ -144,12 +184,12 @@ __device__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
     if (lane < nm) {
         const int i = lane;
         int pidx[BIO_MAX_MUSCLE_PTS];
-        int np = 0;
+        int np = 0, pmov = -1;
+        T mdloc[3] = {T(0), T(0), T(0)};
         const int pb = m.mus_pt_begin[i], pe = pb + m.mus_pt_count[i];
         for (int p = pb; p < pe; p++) {
             const int kind = m.pt_kind[p], d = m.pt_dof[p], b = m.pt_body[p];
             T loc[3];
-            E.x.pt.ptq[p] = T(0);
             if (kind == BIO_PT_CONDITIONAL) {
                 const T v = E.q[d];
                 if (!(v >= m.pt_range[p][0] - T(1e-5) && v <= m.pt_range[p][1] + T(1e-5))) {
@@ -158,8 +198,9 @@ __device__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
                 }
             }
             if (kind == BIO_PT_MOVING) {
-                T d1, d2;
-                for (int c = 0; c < 3; c++) func_eval(m, m.pt_func[p][c], E.q[d], loc[c], d1, d2);
+                T d2;
+                for (int c = 0; c < 3; c++) func_eval(m, m.pt_func[p][c], E.q[d], loc[c], mdloc[c], d2);
+                pmov = p;
             } else {
                 for (int c = 0; c < 3; c++) loc[c] = m.pt_loc[p][c];
             }
@@ -215,14 +256,11 @@ __device__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
             const T f[3] = {dx * il, dy * il, dz * il};
             for (int c = 0; c < 3; c++) { E.x.pt.ptf[p0][c] += f[c]; E.x.pt.ptf[p1][c] -= f[c]; }
         }
-        // generalized force of moving points: f . R_b dloc/dq
-        for (int s = 0; s < np; s++) {
-            const int p = pidx[s];
-            if (m.pt_kind[p] != BIO_PT_MOVING) continue;
-            T dloc[3], yv, d2, dw[3];
-            for (int c = 0; c < 3; c++) func_eval(m, m.pt_func[p][c], E.q[m.pt_dof[p]], yv, dloc[c], d2);
-            matvec3(E.R[m.pt_body[p]], dloc, dw);
-            E.x.pt.ptq[p] = dot3(E.x.pt.ptf[p], dw);
+        // generalized force of the muscle's moving point (at most one per muscle): f . R_b dloc/dq
+        if (pmov >= 0) {
+            T dw[3];
+            matvec3(E.R[m.pt_body[pmov]], mdloc, dw);
+            E.x.pt.ptq[pmov] = dot3(E.x.pt.ptf[pmov], dw);
         }
     }
     // ---- phase D: lane = contact sphere | coordinate limit ----
@@ -277,12 +315,13 @@ __device__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
         for (int k = m.body_pt_begin[b]; k < m.body_pt_begin[b] + m.body_pt_count[b]; k++) {
             const int p = m.body_pt_list[k];
             const T f[3] = {E.x.pt.ptf[p][0], E.x.pt.ptf[p][1], E.x.pt.ptf[p][2]};
+            if (f[0] == T(0) && f[1] == T(0) && f[2] == T(0)) continue;   // inactive point: its ptx is stale
             T n[3];
-            cross3(E.x.pt.ptx[p], f, n);   // ptx of an inactive point is stale but its force is 0
-            for (int c = 0; c < 3; c++) { Wn[c] += (f[0] != T(0) || f[1] != T(0) || f[2] != T(0)) ? n[c] : T(0); Wf[c] += f[c]; }
+            cross3(E.x.pt.ptx[p], f, n);
+            for (int c = 0; c < 3; c++) { Wn[c] += n[c]; Wf[c] += f[c]; }
         }
         for (int s = 0; s < m.n_spheres; s++) {
-            if (m.sph_body[s] != b) continue;
+            if (m.sph_body[s] != b || E.sphF[s][1] == T(0)) continue;
             T n[3];
             cross3(E.sphx[s], E.sphF[s], n);
             for (int c = 0; c < 3; c++) { Wn[c] += n[c]; Wf[c] += E.sphF[s][c]; }
@@ -330,13 +369,13 @@ __device__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
         for (int j = 0; j < 3; j++) { IA[j] += t1[j]; IA[3 + j] = mb * A[3 + j] - t2[j]; }
         T c1[3], c2[3], c3[3];
         cross3(V, IV, c1); cross3(V + 3, IV + 3, c2); cross3(V, IV + 3, c3);
-        E.Im[b] = mb;
+        E.BI[b][0] = mb;
         for (int j = 0; j < 3; j++) {
-            E.Ih[b][j] = hh[j];
-            E.F[b][j] = IA[j] + c1[j] + c2[j] - Wn[j];
-            E.F[b][3 + j] = IA[3 + j] + c3[j] - Wf[j];
+            E.BI[b][1 + j] = hh[j];
+            E.BI[b][10 + j] = IA[j] + c1[j] + c2[j] - Wn[j];
+            E.BI[b][13 + j] = IA[3 + j] + c3[j] - Wf[j];
         }
-        for (int j = 0; j < 6; j++) E.II[b][j] = I6[j];
+        for (int j = 0; j < 6; j++) E.BI[b][4 + j] = I6[j];
     } else if (lane - nb < nd) {
         const int d = lane - nb;
         T qf = T(0);
@@ -389,48 +428,58 @@ __device__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
         }
     }
 
-    // ---- phase F: composite inertias / subtree forces, parents gather from children ----
+    // ---- phase F: composite inertias / subtree forces; task = (body of the level, value) ----
     for (int lev = m.n_levels - 2; lev >= 0; lev--) {
-        if (lane < nb && m.body_level[lane] == lev) {
-            const int b = lane;
-            for (int c_ = b + 1; c_ < nb; c_++) {
-                if (m.body_parent[c_] != b) continue;
-                E.Im[b] += E.Im[c_];
-                for (int j = 0; j < 3; j++) E.Ih[b][j] += E.Ih[c_][j];
-                for (int j = 0; j < 6; j++) { E.II[b][j] += E.II[c_][j]; E.F[b][j] += E.F[c_][j]; }
-            }
+        const int cnt = (m.level_begin[lev + 1] - m.level_begin[lev]) * 16;
+        for (int tsk = lane; tsk < cnt; tsk += G) {
+            const int b = m.level_body[m.level_begin[lev] + (tsk >> 4)], v = tsk & 15;
+            T acc = E.BI[b][v];
+            for (int k = m.child_begin[b]; k < m.child_begin[b + 1]; k++) acc += E.BI[m.child_list[k]][v];
+            E.BI[b][v] = acc;
         }
         gsync<G>();
     }
 
-    // ---- phase G: joint-space inertia entries (lane = entry), bias ----
-    if (h_imp > T(0)) {
-        // contact Jacobian columns col[s][d] = w_d x p_s + v_d for the dofs on the sphere's chain
-        for (int tsk = lane; tsk < m.n_spheres * nd; tsk += G) {
-            const int s = tsk / nd, d = tsk % nd;
-            const int last = m.body_last_dof[m.sph_body[s]];
-            T cv[3] = {T(0), T(0), T(0)};
-            if (E.sphD[s][1] > T(0) && ((m.dof_anc_mask[last] >> d) & 1u)) {
-                cross3(E.S[d], E.sphx[s], cv);
-                for (int c = 0; c < 3; c++) cv[c] += E.S[d][3 + c];
-            }
-            for (int c = 0; c < 3; c++) E.x.jac.col[s][d][c] = cv[c];
-        }
-        gsync<G>();
-    }
-    for (int e = lane; e < m.n_entries; e += G) {
-        const int i = m.ent_i[e], j = m.ent_j[e], b = m.dof_body[i];
+    // ---- phase G: I^c S per dof, contact Jacobian columns, then one lane per coupled (i,j) entry ----
+    if (lane < nd) {
+        const int i = lane, b = m.dof_body[i];
         const T* S = E.S[i];
+        const T* B = E.BI[b];
         T IS[6], t1[3], t2[3];
-        IS[0] = E.II[b][0] * S[0] + E.II[b][3] * S[1] + E.II[b][4] * S[2];
-        IS[1] = E.II[b][3] * S[0] + E.II[b][1] * S[1] + E.II[b][5] * S[2];
-        IS[2] = E.II[b][4] * S[0] + E.II[b][5] * S[1] + E.II[b][2] * S[2];
-        cross3(E.Ih[b], S + 3, t1); cross3(E.Ih[b], S, t2);
-        for (int c = 0; c < 3; c++) { IS[c] += t1[c]; IS[3 + c] = E.Im[b] * S[3 + c] - t2[c]; }
+        IS[0] = B[4] * S[0] + B[7] * S[1] + B[8] * S[2];
+        IS[1] = B[7] * S[0] + B[5] * S[1] + B[9] * S[2];
+        IS[2] = B[8] * S[0] + B[9] * S[1] + B[6] * S[2];
+        cross3(B + 1, S + 3, t1); cross3(B + 1, S, t2);
+        for (int c = 0; c < 3; c++) { E.IS[i][c] = IS[c] + t1[c]; E.IS[i][3 + c] = B[0] * S[3 + c] - t2[c]; }
+        T bi = T(0);
+        for (int c = 0; c < 6; c++) bi += S[c] * B[10 + c];
+        E.rhs[i] = E.Q[i] - bi;
+    }
+    unsigned act_mask = 0u;      // active contacts of this env (same value on every lane)
+    if (h_imp > T(0)) {
+        for (int s = 0; s < m.n_spheres; s++) if (E.sphD[s][1] > T(0)) act_mask |= 1u << s;
+        // contact Jacobian columns col[s][d] = w_d x p_s + v_d for the dofs on the sphere's chain
+        if (act_mask)
+            for (int tsk = lane; tsk < m.n_spheres * nd; tsk += G) {
+                const int s = tsk / nd, d = tsk - s * nd;
+                if (!((act_mask >> s) & 1u)) continue;
+                const int last = m.body_last_dof[m.sph_body[s]];
+                T cv[3] = {T(0), T(0), T(0)};
+                if ((m.dof_anc_mask[last] >> d) & 1u) {
+                    cross3(E.S[d], E.sphx[s], cv);
+                    for (int c = 0; c < 3; c++) cv[c] += E.S[d][3 + c];
+                }
+                for (int c = 0; c < 3; c++) E.x.jac.col[s][d][c] = cv[c];
+            }
+    }
+    gsync<G>();
+    for (int e = lane; e < m.n_entries; e += G) {
+        const int i = m.ent_i[e], j = m.ent_j[e];
         T v = T(0);
-        for (int c = 0; c < 6; c++) v += E.S[j][c] * IS[c];
+        for (int c = 0; c < 6; c++) v += E.S[j][c] * E.IS[i][c];
         if (h_imp > T(0)) {
             for (int s = 0; s < m.n_spheres; s++) {
+                if (!((act_mask >> s) & 1u)) continue;
                 const T* ci = E.x.jac.col[s][i];
                 const T* cj = E.x.jac.col[s][j];
                 v += h_imp * (E.sphD[s][0] * (ci[0] * cj[0] + ci[2] * cj[2]) + E.sphD[s][1] * ci[1] * cj[1]);
@@ -439,35 +488,48 @@ __device__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
                 for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == i) v += h_imp * E.limD[l];
         }
         E.H[i * (i + 1) / 2 + j] = v;
-        if (i == j) {
-            T bi = T(0);
-            for (int c = 0; c < 6; c++) bi += S[c] * E.F[b][c];
-            E.rhs[i] = E.Q[i] - bi;
-        }
     }
     gsync<G>();
 
-    // ---- phase H: sparse L^T D L along the tree and solve (serial, lane 0) ----
-    if (lane == 0) {
-        for (int kq = nd - 1; kq >= 0; kq--) {
-            const T dk = E.H[kq * (kq + 1) / 2 + kq];
-            for (int i = m.dof_parent[kq]; i >= 0; i = m.dof_parent[i]) {
-                const T a = E.H[kq * (kq + 1) / 2 + i] / dk;
-                for (int j = i; j >= 0; j = m.dof_parent[j]) E.H[i * (i + 1) / 2 + j] -= a * E.H[kq * (kq + 1) / 2 + j];
-                E.H[kq * (kq + 1) / 2 + i] = a;
-            }
+    // ---- phase H: sparse L^T D L along the tree, one lane per (i,j) pair of a step ----
+    for (int st = 0; st < nd; st++) {
+        const int pb = m.lt_step_begin[st], pe = m.lt_step_begin[st + 1];
+        for (int p = pb + lane; p < pe; p += G) {
+            const T hki = E.H[m.lt_ki[p]], hkj = E.H[m.lt_kj[p]], hkk = E.H[m.lt_kk[p]];
+            E.H[m.lt_ij[p]] -= (hki / hkk) * hkj;
         }
-        for (int i = nd - 1; i >= 0; i--)
-            for (int j = m.dof_parent[i]; j >= 0; j = m.dof_parent[j]) E.rhs[j] -= E.H[i * (i + 1) / 2 + j] * E.rhs[i];
-        for (int i = 0; i < nd; i++) E.rhs[i] /= E.H[i * (i + 1) / 2 + i];
-        for (int i = 0; i < nd; i++) {
+        gsync<G>();
+        // row k becomes L_ki = H_ki / H_kk (row k is not read by later steps)
+        for (int p = pb + lane; p < pe; p += G)
+            if (m.lt_diag[p]) E.H[m.lt_ki[p]] = E.H[m.lt_ki[p]] / E.H[m.lt_kk[p]];
+    }
+    gsync<G>();
+    // solve L^T D L x = rhs by tree depth: z_j = b_j - sum_{i in desc(j)} L_ij z_i (deepest first)
+    for (int dep = m.n_depths - 1; dep >= 0; dep--) {
+        if (lane < nd && m.dof_depth[lane] == dep) {
+            const int j = lane;
+            T v = E.rhs[j];
+            for (int k = m.desc_begin[j]; k < m.desc_begin[j + 1]; k++) {
+                const int i = m.desc_list[k];
+                v -= E.H[i * (i + 1) / 2 + j] * E.rhs[i];
+            }
+            E.rhs[j] = v;
+        }
+        gsync<G>();
+    }
+    if (lane < nd) E.rhs[lane] /= E.H[lane * (lane + 1) / 2 + lane];
+    gsync<G>();
+    // x_i = y_i - sum_{j in anc(i)} L_ij x_j (shallowest first)
+    for (int dep = 0; dep < m.n_depths; dep++) {
+        if (lane < nd && m.dof_depth[lane] == dep) {
+            const int i = lane;
             T v = E.rhs[i];
             for (int j = m.dof_parent[i]; j >= 0; j = m.dof_parent[j]) v -= E.H[i * (i + 1) / 2 + j] * E.rhs[j];
             E.rhs[i] = v;
             E.udot[i] = v;
         }
+        gsync<G>();
     }
-    gsync<G>();
 }
 
 // state <-> work buffer helpers (lane d < nd owns a dof, lane k < nm owns a muscle)

@@ -31,7 +31,8 @@ template <> struct Num<float> {
     static BIO_DEV void sincos(float x, float* s, float* c) { sincosf(x, s, c); }
     static BIO_DEV float fmod(float x, float y) { return fmodf(x, y); }
     static BIO_DEV float ceil(float x) { return ceilf(x); }
-    static BIO_DEV float newton_tol() { return 1e-6f; }
+    // |delta| of the normalised fibre velocity; below this the fp32 residual is rounding noise
+    static BIO_DEV float newton_tol() { return 2e-5f; }
     static constexpr int bisect_iters = 30;
 };
 template <> struct Num<double> {
@@ -74,7 +75,10 @@ BIO_DEV void func_eval(const DevModel<T>& m, int f, T x, T& y, T& d1, T& d2) {
     if (x >= m.knot_x[kb + n - 1]) {
         d1 = m.knot_c[kb + n - 1][1]; y = m.knot_c[kb + n - 1][0] + d1 * (x - m.knot_x[kb + n - 1]); d2 = T(0); return;
     }
-    int i = 0;
+    // bucketed start (host table), then at most a few forward steps
+    int bk = (int)((x - m.knot_x[kb]) * m.func_bucket_inv[f]);
+    bk = bk < 0 ? 0 : (bk > 15 ? 15 : bk);
+    int i = m.func_bucket[f][bk];
     while (i + 1 < n - 1 && x >= m.knot_x[kb + i + 1]) i++;
     const T dx = x - m.knot_x[kb + i];
     const T c0 = m.knot_c[kb + i][0], c1 = m.knot_c[kb + i][1], c2 = m.knot_c[kb + i][2], c3 = m.knot_c[kb + i][3];
@@ -96,12 +100,14 @@ BIO_DEV void curve_eval(const DevModel<T>& m, int c, T x, T& y, T& dy) {
     const T t = (x - x0) * ih;
     int i = (int)Num<T>::floor(t);
     i = i < 0 ? 0 : (i > BIO_CURVE_N - 1 ? BIO_CURVE_N - 1 : i);
-    const T s = t - T(i), s2 = s * s, s3 = s2 * s;
+    const T s = t - T(i);
     const T y0 = m.curve_tab[c][i][0], m0 = m.curve_tab[c][i][1];
     const T y1 = m.curve_tab[c][i + 1][0], m1 = m.curve_tab[c][i + 1][1];
-    y = (T(2) * s3 - T(3) * s2 + T(1)) * y0 + (s3 - T(2) * s2 + s) * m0 + (T(-2) * s3 + T(3) * s2) * y1 + (s3 - s2) * m1;
-    dy = ((T(6) * s2 - T(6) * s) * y0 + (T(3) * s2 - T(4) * s + T(1)) * m0 + (T(-6) * s2 + T(6) * s) * y1 +
-          (T(3) * s2 - T(2) * s) * m1) * ih;
+    // cubic Hermite in monomial (Horner) form: same polynomial as the basis form
+    const T dl = y1 - y0;
+    const T c2 = T(3) * dl - T(2) * m0 - m1, c3 = m0 + m1 - T(2) * dl;
+    y = y0 + s * (m0 + s * (c2 + s * c3));
+    dy = (m0 + s * (T(2) * c2 + T(3) * s * c3)) * ih;
 }
 template <typename T>
 BIO_DEV T curve_value(const DevModel<T>& m, int c, T x) { T y, d; curve_eval(m, c, x, y, d); return y; }

@@ -10,7 +10,7 @@
 namespace bio {
 
 template <typename T>
-struct DevModel {
+struct alignas(16) DevModel {
     int32_t n_bodies, n_dof, n_axes, n_muscles, n_act, n_pathpts, n_spheres, n_limits;
     int32_t n_funcs, n_knots, n_obspts, n_coords, is_torque, has_tz, max_pts_per_muscle, pad;
     T gravity[3];
@@ -92,6 +92,24 @@ struct DevModel {
     int32_t ent_i[BIO_MAX_DOF * (BIO_MAX_DOF + 1) / 2];
     int32_t ent_j[BIO_MAX_DOF * (BIO_MAX_DOF + 1) / 2];
     int32_t obs_desc[256];                   // (kind << 16) | index per observation slot
+    // spline search: 16 uniform buckets per function -> first candidate knot
+    T func_bucket_inv[BIO_MAX_FUNCS];
+    int8_t func_bucket[BIO_MAX_FUNCS][16];
+    // L^T D L schedule: step s handles k = n_dof-1-s; one lane per (i,j) pair of proper ancestors of k
+    int32_t lt_step_begin[BIO_MAX_DOF + 1];
+    uint8_t lt_ij[320], lt_ki[320], lt_kj[320], lt_kk[320], lt_diag[320];
+    // solve by tree depth: dofs of one depth are independent
+    int32_t n_depths;
+    int32_t dof_depth[BIO_MAX_DOF];
+    int32_t desc_begin[BIO_MAX_DOF + 1];
+    uint8_t desc_list[128];
+    // children of every body (composite inertia gather)
+    int32_t child_begin[BIO_MAX_BODIES + 1];
+    int32_t child_list[BIO_MAX_BODIES];
+    int32_t level_begin[BIO_MAX_BODIES + 1];  // bodies grouped by tree level
+    int32_t level_body[BIO_MAX_BODIES];
+    int32_t axis_code[BIO_MAX_AXES];          // +-(k+1): axis is +-e_k, 0: general direction
+    int32_t pad3[3];
     // curves: uniform cubic Hermite, rows (y, h*dy/dx)
     T curve_x0[BIO_N_CURVES];
     T curve_inv_h[BIO_N_CURVES];
@@ -205,6 +223,74 @@ void convert_model(const BioModelTables& s, DevModel<T>& d) {
     }
     BIO_CPI(func_kind); BIO_CPI(func_knot_begin); BIO_CPI(func_knot_count);
     BIO_CP(func_c); BIO_CP(knot_x); BIO_CP(knot_c);
+    for (int f = 0; f < s.n_funcs; f++) {
+        if (s.func_kind[f] != BIO_FUNC_SPLINE) continue;
+        const int kb = s.func_knot_begin[f], n = s.func_knot_count[f];
+        const double x0 = s.knot_x[kb], x1 = s.knot_x[kb + n - 1], bw = (x1 - x0) / 16.0;
+        d.func_bucket_inv[f] = (T)(1.0 / bw);
+        for (int b = 0; b < 16; b++) {
+            // last knot at or before the bucket start, shifted one bucket down so
+            // that rounding of the bucket index in the scalar type cannot skip a knot
+            const double xs = x0 + (b > 0 ? b - 1 : 0) * bw;
+            int i = 0;
+            while (i + 1 < n - 1 && s.knot_x[kb + i + 1] <= xs) i++;
+            d.func_bucket[f][b] = (int8_t)i;
+        }
+    }
+    {   // L^T D L schedule
+        auto tri = [](int i, int j) { return i * (i + 1) / 2 + j; };
+        int np = 0;
+        for (int st = 0; st < s.n_dof; st++) {
+            const int k = s.n_dof - 1 - st;
+            d.lt_step_begin[st] = np;
+            for (int i = k - 1; i >= 0; i--) {
+                if (!((s.dof_anc_mask[k] >> i) & 1u)) continue;
+                for (int j = i; j >= 0; j--) {
+                    if (!((s.dof_anc_mask[k] >> j) & 1u)) continue;
+                    if (np < 320) {
+                        d.lt_ij[np] = (uint8_t)tri(i, j); d.lt_ki[np] = (uint8_t)tri(k, i);
+                        d.lt_kj[np] = (uint8_t)tri(k, j); d.lt_kk[np] = (uint8_t)tri(k, k);
+                        d.lt_diag[np] = (uint8_t)(i == j);
+                    }
+                    np++;
+                }
+            }
+        }
+        d.lt_step_begin[s.n_dof] = np;
+        d.n_depths = 0;
+        for (int i = 0; i < s.n_dof; i++) {
+            int dep = 0;
+            for (int j = 0; j < i; j++) if ((s.dof_anc_mask[i] >> j) & 1u) dep++;
+            d.dof_depth[i] = dep;
+            if (dep + 1 > d.n_depths) d.n_depths = dep + 1;
+        }
+        int nl = 0;
+        for (int j = 0; j < s.n_dof; j++) {
+            d.desc_begin[j] = nl;
+            for (int i = j + 1; i < s.n_dof; i++)
+                if ((s.dof_anc_mask[i] >> j) & 1u) { if (nl < 128) d.desc_list[nl] = (uint8_t)i; nl++; }
+        }
+        d.desc_begin[s.n_dof] = nl;
+        int nc = 0;
+        for (int b = 0; b < s.n_bodies; b++) {
+            d.child_begin[b] = nc;
+            for (int c = b + 1; c < s.n_bodies; c++) if (s.body_parent[c] == b) d.child_list[nc++] = c;
+        }
+        d.child_begin[s.n_bodies] = nc;
+        int nl2 = 0;
+        for (int lev = 0; lev < d.n_levels; lev++) {
+            d.level_begin[lev] = nl2;
+            for (int b = 0; b < s.n_bodies; b++) if (d.body_level[b] == lev) d.level_body[nl2++] = b;
+        }
+        d.level_begin[d.n_levels] = nl2;
+        for (int a = 0; a < s.n_axes; a++) {
+            d.axis_code[a] = 0;
+            for (int k = 0; k < 3; k++) {
+                const double v = s.axis_vec[a][k], o1 = s.axis_vec[a][(k + 1) % 3], o2 = s.axis_vec[a][(k + 2) % 3];
+                if (o1 == 0.0 && o2 == 0.0 && (v == 1.0 || v == -1.0)) d.axis_code[a] = v > 0 ? (k + 1) : -(k + 1);
+            }
+        }
+    }
     BIO_CP(mus_fiso); BIO_CP(mus_lopt); BIO_CP(mus_lts); BIO_CP(mus_vmax); BIO_CP(mus_tact);
     BIO_CP(mus_tdeact); BIO_CP(mus_amin); BIO_CP(mus_beta); BIO_CP(mus_default_act);
     BIO_CP(mus_height); BIO_CP(mus_lm_min); BIO_CP(mus_cot_mass); BIO_CP(mus_slow_twitch);
