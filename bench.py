@@ -44,10 +44,14 @@ def _flops_per_env_step(task, env_id):
     e = d.get(env_id)
     if not e:
         return None, None
+    from bioimitation_gym_b200 import tasks
+    integ = [k for k, v in tasks.INTEGRATORS.items() if v == task.integrator][0]
+    if e["integrator"] == integ and e["substeps"] == task.n_substeps:
+        return e["flops_per_env_step"], e
+    # other scheme / substep count: scale by the number of dynamics evaluations
     rhs_per_sub = {0: 1, 1: 2, 2: 4, 3: 1}[task.integrator]
-    key = "rhs_implicit" if task.integrator == 3 else "rhs"
-    f = task.n_substeps * rhs_per_sub * e[key] + e["out"]
-    return f, e
+    evals = task.n_substeps * rhs_per_sub + 1
+    return e["flops_per_rhs_eval_incl_overheads"] * evals, e
 
 
 class ClockSampler(threading.Thread):
@@ -257,7 +261,8 @@ def main():
             pass
         fp32_peak = None
         try:
-            fp32_peak = json.load(open(os.path.join(ROOT, "profiles", "fp32_peak.json")))["fp32_tflops"]
+            v = float(env.lib.bio_measure_fp32_peak(local_rank))   # FFMA chain, measured now, untimed
+            fp32_peak = v if v > 0 else None
         except Exception:
             pass
         if flops is not None:
@@ -265,7 +270,7 @@ def main():
             peak = fp32_peak or 148 * 128 * 2 * 1.965e9 / 1e12
             roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                         "frac": achieved / peak,
-                        "peak_source": "measured FFMA microbenchmark (profiles/fp32_peak.json)" if fp32_peak
+                        "peak_source": "measured on this GPU by bio_measure_fp32_peak (FFMA chain, FMA = 2 flops)" if fp32_peak
                         else "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (no measured FP32 peak yet)",
                         "flops_per_env_step": flops, "traffic": None}
             try:

@@ -460,3 +460,48 @@ int32_t bio_obs_dim(bio_handle hh) { return hh ? ((HandleBase*)hh)->task.obs_dim
 int32_t bio_n_act(bio_handle hh) { return hh ? ((HandleBase*)hh)->model.n_act : 0; }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// FP32 FMA-chain microbenchmark: the roofline denominator of this compute-bound
+// path (MEASURED_PEAKS.json only carries HBM and bf16 tensor peaks).
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+    float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+}  // namespace
+
+extern "C" double bio_measure_fp32_peak(int32_t device) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    float* out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        fma_peak_kernel<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    return cudaGetLastError() == cudaSuccess ? best : -1.0;
+}

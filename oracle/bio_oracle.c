@@ -303,14 +303,20 @@ double orc_equilibrium_lm(const BioModelTables* m, int i, double L, double a) {
     return 0.5 * (lo + hi);
 }
 
-/* Path length / lengthening speed of muscle i; when T != NULL also applies
-   the tension to the bodies (W) and to the generalized forces (Q). */
-static void muscle_path(const BioModelTables* m, const Kin* k, const double* q, const double* u,
-                        int i, double* Lout, double* Ldot, const double* T, double W[][6], double* Q) {
+/* Path geometry of muscle i (GeometryPath without wrap objects): active
+   points, segment unit vectors, length and lengthening speed. */
+typedef struct PathGeom {
+    int np;
+    int body[8], dof[8];          /* dof >= 0: moving point governed by that coordinate */
+    double x[8][3], e[8][3], dw[8][3];
+    double L, Ld;
+} PathGeom;
+
+static void muscle_geom(const BioModelTables* m, const Kin* k, const double* q, const double* u, int i,
+                        PathGeom* g) {
     int pb = m->mus_pt_begin[i], pc = m->mus_pt_count[i];
-    double L = 0, Ld = 0;
-    int have_prev = 0, prev = -1;
-    double xp[3] = {0}, vp[3] = {0}, dloc_prev[3] = {0};
+    double vp[3] = {0, 0, 0};
+    g->np = 0; g->L = 0; g->Ld = 0;
     for (int p = pb; p < pb + pc; p++) {
         int b = m->pt_body[p], kind = m->pt_kind[p], d = m->pt_dof[p];
         double loc[3], dloc[3] = {0, 0, 0};
@@ -326,37 +332,49 @@ static void muscle_path(const BioModelTables* m, const Kin* k, const double* q, 
         } else {
             memcpy(loc, m->pt_loc[p], sizeof loc);
         }
-        double x[3], v[3], dw[3] = {0, 0, 0};
+        int n = g->np;
+        double* x = g->x[n];
+        double v[3];
         point_pos(k, b, loc, x);
         point_vel(k, b, x, v);
+        g->body[n] = b; g->dof[n] = -1;
+        g->dw[n][0] = g->dw[n][1] = g->dw[n][2] = 0;
         if (kind == BIO_PT_MOVING) {
-            matvec3(k->R[b], dloc, dw);
-            for (int c = 0; c < 3; c++) v[c] += dw[c] * u[d];
+            matvec3(k->R[b], dloc, g->dw[n]);
+            for (int c = 0; c < 3; c++) v[c] += g->dw[n][c] * u[d];
+            g->dof[n] = d;
         }
-        if (have_prev) {
-            double e[3] = {x[0] - xp[0], x[1] - xp[1], x[2] - xp[2]};
+        if (n > 0) {
+            double* e = g->e[n - 1];
+            const double* xp = g->x[n - 1];
+            for (int c = 0; c < 3; c++) e[c] = x[c] - xp[c];
             double len = sqrt(dot3(e, e));
             for (int c = 0; c < 3; c++) e[c] /= len;
-            L += len;
-            Ld += e[0] * (v[0] - vp[0]) + e[1] * (v[1] - vp[1]) + e[2] * (v[2] - vp[2]);
-            if (T) {
-                double f[3] = {*T * e[0], *T * e[1], *T * e[2]}, fn[3] = {-f[0], -f[1], -f[2]};
-                add_force(W, m->pt_body[prev], xp, f);
-                add_force(W, b, x, fn);
-                if (m->pt_kind[prev] == BIO_PT_MOVING) Q[m->pt_dof[prev]] += dot3(f, dloc_prev);
-                if (kind == BIO_PT_MOVING) Q[d] += dot3(fn, dw);
-            }
+            g->L += len;
+            g->Ld += e[0] * (v[0] - vp[0]) + e[1] * (v[1] - vp[1]) + e[2] * (v[2] - vp[2]);
         }
-        memcpy(xp, x, sizeof x); memcpy(vp, v, sizeof v); memcpy(dloc_prev, dw, sizeof dw);
-        prev = p; have_prev = 1;
+        memcpy(vp, v, sizeof v);
+        g->np = n + 1;
     }
-    *Lout = L; *Ldot = Ld;
+}
+
+/* Tension T along the path: equal and opposite forces at the ends of every
+   segment, plus the generalized force of moving points (f . R_b dloc/dq). */
+static void muscle_apply(const PathGeom* g, double T, double W[][6], double* Q) {
+    for (int s = 0; s + 1 < g->np; s++) {
+        double f[3] = {T * g->e[s][0], T * g->e[s][1], T * g->e[s][2]}, fn[3] = {-f[0], -f[1], -f[2]};
+        add_force(W, g->body[s], g->x[s], f);
+        add_force(W, g->body[s + 1], g->x[s + 1], fn);
+        if (g->dof[s] >= 0) Q[g->dof[s]] += dot3(f, g->dw[s]);
+        if (g->dof[s + 1] >= 0) Q[g->dof[s + 1]] += dot3(fn, g->dw[s + 1]);
+    }
 }
 
 void orc_path_lengths(const BioModelTables* m, const double* q, const double* u, double* L, double* Ld) {
     Kin k;
+    PathGeom g;
     kinematics(m, q, u, &k);
-    for (int i = 0; i < m->n_muscles; i++) muscle_path(m, &k, q, u, i, &L[i], &Ld[i], NULL, NULL, NULL);
+    for (int i = 0; i < m->n_muscles; i++) { muscle_geom(m, &k, q, u, i, &g); L[i] = g.L; Ld[i] = g.Ld; }
 }
 
 /* quintic smooth step (SimTK::Function::Step) */
@@ -391,12 +409,12 @@ void orc_eval_h(const BioModelTables* m, int newton_iters, const double* q, cons
 
     /* muscles */
     for (int i = 0; i < m->n_muscles; i++) {
-        double L, Ld;
+        PathGeom g;
         MusOut mo;
-        muscle_path(m, &k, q, u, i, &L, &Ld, NULL, NULL, NULL);
-        muscle_dynamics(m, i, L, act[i], lm[i], ctrl[i], newton_iters, &mo);
-        muscle_path(m, &k, q, u, i, &L, &Ld, &mo.T, W, Q);
-        o->path_len[i] = L; o->path_vel[i] = Ld;
+        muscle_geom(m, &k, q, u, i, &g);
+        muscle_dynamics(m, i, g.L, act[i], lm[i], ctrl[i], newton_iters, &mo);
+        muscle_apply(&g, mo.T, W, Q);
+        o->path_len[i] = g.L; o->path_vel[i] = g.Ld;
         o->tendon_force[i] = mo.T; o->fiber_force[i] = mo.Ffib; o->active_fiber_force[i] = mo.Fact;
         o->lmdot[i] = mo.lmdot; o->adot[i] = mo.adot;
     }

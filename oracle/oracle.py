@@ -64,7 +64,8 @@ def lib():
     if _lib is None:
         if not os.path.exists(_LIB_PATH):
             build()
-        L = ctypes.CDLL(_LIB_PATH)
+        # BIO_ORACLE_LIB: the op-counting build (oracle/count_flops.py)
+        L = ctypes.CDLL(os.environ.get("BIO_ORACLE_LIB", _LIB_PATH))
         for f in ("orc_sizeof_env", "orc_sizeof_eval", "orc_sizeof_model_tables",
                   "orc_sizeof_task_config", "orc_splitmix64", "orc_rand"):
             getattr(L, f).restype = ctypes.c_uint64

@@ -291,3 +291,45 @@ def test_errors_are_reported_not_thrown():
     with pytest.raises(backend.BioError):
         backend.VecEnv("MuscleWalkingImitation2D-v0", dict(num_envs=0))
     env.close()
+
+
+def test_single_env_classes_keep_the_reference_call_pattern():
+    """tests/test_env.py:15-26 of the reference: make, reset, step with sampled actions."""
+    from bioimitation_gym_b200 import envs
+    env = envs.make("MuscleWalkingImitation2D-v0", dict(mode="train"))
+    assert type(env).__name__ == "MuscleWalkingImitationEnv2D"
+    assert env.action_space.shape == (14,) and env.observation_space.shape == (138,)
+    assert float(env.action_space.low.min()) == 0.0 and float(env.action_space.high.max()) == 1.0
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (138,)
+    for _ in range(30):
+        obs, reward, done, info = env.step(env.action_space.sample())
+        assert obs.shape == (138,) and isinstance(reward, float) and isinstance(done, bool)
+        assert len(info["all_rewards"]) == 5
+        if done:
+            obs = env.reset()
+    d = env.reset(obs_as_dict=True)
+    assert list(d)[:4] == ["phase", "coordinate_pos", "coordinate_vel", "coordinate_acc"]
+    assert "pelvis_tx" not in d["coordinate_pos"] and len(d["muscles"]) == 14
+    env.close()
+    tq = envs.make("TorqueWalkingImitation3D-v0", dict(max_actuation=150))
+    assert tq.action_space.shape == (11,) and float(tq.action_space.high[0]) == 200.0   # model compiled with 200
+    tq.close()
+
+
+def test_large_batch_and_all_integrators_run():
+    import torch
+    from bioimitation_gym_b200 import backend
+    for integ, sub in (("rk2", 20), ("rk4", 10), ("semi_implicit_euler", 40), ("implicit_damping", 10)):
+        env = backend.VecEnv("MuscleWalkingImitation2D-v0", dict(num_envs=1000, integrator=integ, substeps=sub))
+        env.reset()
+        for _ in range(3):
+            obs, rew, done, _ = env.step(torch.rand((1000, 14), device=env.device))
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        env.close()
+    env = backend.VecEnv("MusclePalsyImitation3D-v0", dict(num_envs=3000, apply_perturbations=True))
+    env.reset()
+    for _ in range(5):
+        obs, rew, done, _ = env.step(torch.rand((3000, 22), device=env.device))
+    assert torch.isfinite(obs).all()
+    env.close()
