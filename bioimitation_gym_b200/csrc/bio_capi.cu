@@ -120,7 +120,21 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
         const bool want_coop = !(kv && strcmp(kv, "thread") == 0);
         typedef bio::CoopCls<0> C0;
         typedef bio::CoopCls<1> C1;
+        int max_anc = 0, max_mov = 0;
+        for (int i = 0; i < model->n_dof; i++) {
+            int c = 0;
+            for (int j = 0; j < i; j++) c += (model->dof_anc_mask[i] >> j) & 1u;
+            if (c > max_anc) max_anc = c;
+        }
+        for (int i = 0; i < model->n_muscles; i++) {
+            int c = 0;
+            for (int p = model->mus_pt_begin[i]; p < model->mus_pt_begin[i] + model->mus_pt_count[i]; p++)
+                c += model->pt_kind[p] == BIO_PT_MOVING;
+            if (c > max_mov) max_mov = c;
+        }
         auto fits = [&](int G, int ND, int NM, int NP, int NAX) {
+            // factorisation step: (ancestors choose 2) + ancestors pairs on G lanes x (1 | 2) rounds
+            if (max_anc * (max_anc + 1) / 2 > G * (G == 16 ? 1 : 2) || max_mov > 1) return false;
             return model->n_dof <= ND && model->n_muscles <= NM && model->n_act <= NM && model->n_pathpts <= NP &&
                    model->n_axes <= NAX && model->n_bodies + model->n_dof <= G &&
                    model->n_bodies + model->n_obspts <= G && model->n_spheres + model->n_limits <= G &&

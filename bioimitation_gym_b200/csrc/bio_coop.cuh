@@ -68,13 +68,17 @@ __device__ __forceinline__ void rot_cols(T* R, T cs, T sn) {
     }
 }
 
+}  // namespace bio
+#include "bio_coop_planar.cuh"
+namespace bio {
+
 // ---------------------------------------------------------------------------
 // One evaluation of the dynamics of the env in E (state in E.q/u/act/lm,
 // controls in E.ctrl).  Results: E.udot, E.adot, E.lmdot and, when full, the
 // read-outs for obs / reward / done.  All G lanes of the env must call this.
 // ---------------------------------------------------------------------------
 template <typename T, int CLS>
-__device__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane, const int newton_iters,
+__device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane, const int newton_iters,
                           const T ext_fx, const int ext_pt, const T h_imp, const bool full) {
     typedef CoopCls<CLS> C;
     constexpr int G = C::G;
@@ -491,45 +495,17 @@ __device__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
     }
     gsync<G>();
 
-    // ---- phase H: sparse L^T D L along the tree, one lane per (i,j) pair of a step ----
-    for (int st = 0; st < nd; st++) {
-        const int pb = m.lt_step_begin[st], pe = m.lt_step_begin[st + 1];
-        for (int p = pb + lane; p < pe; p += G) {
-            const T hki = E.H[m.lt_ki[p]], hkj = E.H[m.lt_kj[p]], hkk = E.H[m.lt_kk[p]];
-            E.H[m.lt_ij[p]] -= (hki / hkk) * hkj;
-        }
-        gsync<G>();
-        // row k becomes L_ki = H_ki / H_kk (row k is not read by later steps)
-        for (int p = pb + lane; p < pe; p += G)
-            if (m.lt_diag[p]) E.H[m.lt_ki[p]] = E.H[m.lt_ki[p]] / E.H[m.lt_kk[p]];
-    }
-    gsync<G>();
-    // solve L^T D L x = rhs by tree depth: z_j = b_j - sum_{i in desc(j)} L_ij z_i (deepest first)
-    for (int dep = m.n_depths - 1; dep >= 0; dep--) {
-        if (lane < nd && m.dof_depth[lane] == dep) {
-            const int j = lane;
-            T v = E.rhs[j];
-            for (int k = m.desc_begin[j]; k < m.desc_begin[j + 1]; k++) {
-                const int i = m.desc_list[k];
-                v -= E.H[i * (i + 1) / 2 + j] * E.rhs[i];
-            }
-            E.rhs[j] = v;
-        }
-        gsync<G>();
-    }
-    if (lane < nd) E.rhs[lane] /= E.H[lane * (lane + 1) / 2 + lane];
-    gsync<G>();
-    // x_i = y_i - sum_{j in anc(i)} L_ij x_j (shallowest first)
-    for (int dep = 0; dep < m.n_depths; dep++) {
-        if (lane < nd && m.dof_depth[lane] == dep) {
-            const int i = lane;
-            T v = E.rhs[i];
-            for (int j = m.dof_parent[i]; j >= 0; j = m.dof_parent[j]) v -= E.H[i * (i + 1) / 2 + j] * E.rhs[j];
-            E.rhs[i] = v;
-            E.udot[i] = v;
-        }
-        gsync<G>();
-    }
+    // ---- phase H: sparse L^T D L along the tree + solve (bio_coop_planar.cuh) ----
+    coop_solve<T, CLS>(m, E, lane);
+}
+
+// planar (2D) models take the specialised evaluation
+template <typename T, int CLS>
+__device__ __forceinline__ void coop_eval_any(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane,
+                                              const int newton_iters, const T ext_fx, const int ext_pt, const T h_imp,
+                                              const bool full) {
+    if (m.planar) coop_eval_planar<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
+    else coop_eval<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
 }
 
 // state <-> work buffer helpers (lane d < nd owns a dof, lane k < nm owns a muscle)
@@ -553,20 +529,20 @@ __device__ void coop_integrate(const DevModel<T>& m, const DevTask<T>& c, EnvWor
     for (int sub = 0; sub < c.n_substeps; sub++) {
         const T t = t0 + T(sub) * h;
         if (c.integrator == BIO_INT_SEMI_IMPLICIT_EULER || c.integrator == BIO_INT_IMPLICIT_DAMPING) {
-            coop_eval<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, t), ext_pt,
+            coop_eval_any<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, t), ext_pt,
                               c.integrator == BIO_INT_IMPLICIT_DAMPING ? h : T(0), false);
             if (isd) { const T un = E.u[lane] + h * E.udot[lane]; E.u[lane] = un; E.q[lane] += h * un; }
             if (ism) { E.act[lane] += h * E.adot[lane]; E.lm[lane] += h * E.lmdot[lane]; }
         } else if (c.integrator == BIO_INT_RK2_MIDPOINT) {
             const T q0 = isd ? E.q[lane] : T(0), u0 = isd ? E.u[lane] : T(0);
             const T a0 = ism ? E.act[lane] : T(0), l0 = ism ? E.lm[lane] : T(0);
-            coop_eval<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, t), ext_pt, T(0), false);
+            coop_eval_any<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, t), ext_pt, T(0), false);
             const T hh = T(0.5) * h;
             if (isd) { E.q[lane] = q0 + hh * u0; E.u[lane] = u0 + hh * E.udot[lane]; }
             if (ism) { E.act[lane] = a0 + hh * E.adot[lane]; E.lm[lane] = l0 + hh * E.lmdot[lane]; }
             coop_clamp(m, E, lane);
             gsync<G>();
-            coop_eval<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, t + hh), ext_pt, T(0), false);
+            coop_eval_any<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, t + hh), ext_pt, T(0), false);
             if (isd) { const T um = E.u[lane]; E.q[lane] = q0 + h * um; E.u[lane] = u0 + h * E.udot[lane]; }
             if (ism) { E.act[lane] = a0 + h * E.adot[lane]; E.lm[lane] = l0 + h * E.lmdot[lane]; }
         } else {  // classic RK4
@@ -576,7 +552,7 @@ __device__ void coop_integrate(const DevModel<T>& m, const DevTask<T>& c, EnvWor
             for (int r = 0; r < 4; r++) {
                 const T wgt = (r == 0 || r == 3) ? T(1) : T(2);
                 const T cn = r == 2 ? T(1) : T(0.5);
-                coop_eval<T, CLS>(m, E, lane, c.newton_iters,
+                coop_eval_any<T, CLS>(m, E, lane, c.newton_iters,
                                   perturb_force(c, seed, env, t + (r == 0 ? T(0) : (r == 3 ? h : T(0.5) * h))), ext_pt,
                                   T(0), false);
                 if (isd) { aq += wgt * E.u[lane]; au += wgt * E.udot[lane]; }
@@ -721,7 +697,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     coop_integrate<T, CLS>(m, c, E, lane, istep, seed, env);
     istep += 1;
     const int ext_pt = c.perturb ? c.perturb_obspt : -1;
-    coop_eval<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, T(istep) * c.dt), ext_pt, T(0), true);
+    coop_eval_any<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, T(istep) * c.dt), ext_pt, T(0), true);
     gsync<G>();
     T* orow = obs + (size_t)ii * c.obs_dim;
     if (valid) coop_write_obs<T, CLS>(m, c, E, lane, istep, orow);
@@ -854,7 +830,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
         ep_return = T(0);
         ep_len = 0;
         gsync<G>();
-        coop_eval<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, T(istep) * c.dt), ext_pt, T(0), true);
+        coop_eval_any<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, T(istep) * c.dt), ext_pt, T(0), true);
         gsync<G>();
         if (valid) coop_write_obs<T, CLS>(m, c, E, lane, istep, orow);
     }

@@ -97,19 +97,20 @@ struct alignas(16) DevModel {
     int8_t func_bucket[BIO_MAX_FUNCS][16];
     // L^T D L schedule: step s handles k = n_dof-1-s; one lane per (i,j) pair of proper ancestors of k
     int32_t lt_step_begin[BIO_MAX_DOF + 1];
-    uint8_t lt_ij[320], lt_ki[320], lt_kj[320], lt_kk[320], lt_diag[320];
     // solve by tree depth: dofs of one depth are independent
     int32_t n_depths;
     int32_t dof_depth[BIO_MAX_DOF];
-    int32_t desc_begin[BIO_MAX_DOF + 1];
-    uint8_t desc_list[128];
     // children of every body (composite inertia gather)
     int32_t child_begin[BIO_MAX_BODIES + 1];
     int32_t child_list[BIO_MAX_BODIES];
     int32_t level_begin[BIO_MAX_BODIES + 1];  // bodies grouped by tree level
     int32_t level_body[BIO_MAX_BODIES];
     int32_t axis_code[BIO_MAX_AXES];          // +-(k+1): axis is +-e_k, 0: general direction
-    int32_t pad3[3];
+    uint32_t lt_pack[320];                    // ij | ki<<8 | kj<<16 | i<<24 | diag<<31 per (i,j) pair
+    int32_t lt_max_pairs;                     // largest number of pairs in one step
+    int32_t planar;                           // 1: all rotations about z, translations in x/y (2D models)
+    int32_t pad3;
+    T body_z[BIO_MAX_BODIES];                 // planar models: constant z of every body origin
     // curves: uniform cubic Hermite, rows (y, h*dy/dx)
     T curve_x0[BIO_N_CURVES];
     T curve_inv_h[BIO_N_CURVES];
@@ -248,15 +249,27 @@ void convert_model(const BioModelTables& s, DevModel<T>& d) {
                 for (int j = i; j >= 0; j--) {
                     if (!((s.dof_anc_mask[k] >> j) & 1u)) continue;
                     if (np < 320) {
-                        d.lt_ij[np] = (uint8_t)tri(i, j); d.lt_ki[np] = (uint8_t)tri(k, i);
-                        d.lt_kj[np] = (uint8_t)tri(k, j); d.lt_kk[np] = (uint8_t)tri(k, k);
-                        d.lt_diag[np] = (uint8_t)(i == j);
+                        d.lt_pack[np] = (uint32_t)tri(i, j) | ((uint32_t)tri(k, i) << 8) | ((uint32_t)tri(k, j) << 16) |
+                                        ((uint32_t)i << 24) | (i == j ? 0x80000000u : 0u);
                     }
                     np++;
                 }
             }
         }
         d.lt_step_begin[s.n_dof] = np;
+        d.lt_max_pairs = 0;
+        for (int st = 0; st < s.n_dof; st++)
+            if (d.lt_step_begin[st + 1] - d.lt_step_begin[st] > d.lt_max_pairs)
+                d.lt_max_pairs = d.lt_step_begin[st + 1] - d.lt_step_begin[st];
+        // planar model: every rotation about +-z, every translation along +-x / +-y, no gravity in z
+        d.planar = s.gravity[2] == 0.0 ? 1 : 0;
+        for (int a = 0; a < s.n_axes; a++) {
+            const double ax = s.axis_vec[a][0], ay = s.axis_vec[a][1], az = s.axis_vec[a][2];
+            if (s.axis_kind[a] == BIO_AXIS_ROT) { if (!(ax == 0.0 && ay == 0.0 && (az == 1.0 || az == -1.0))) d.planar = 0; }
+            else if (!(az == 0.0 && ((ay == 0.0 && (ax == 1.0 || ax == -1.0)) || (ax == 0.0 && (ay == 1.0 || ay == -1.0))))) d.planar = 0;
+        }
+        for (int b = 0; b < s.n_bodies; b++)
+            d.body_z[b] = (T)((s.body_parent[b] >= 0 ? (double)d.body_z[s.body_parent[b]] : 0.0) + s.body_joint_loc[b][2]);
         d.n_depths = 0;
         for (int i = 0; i < s.n_dof; i++) {
             int dep = 0;
@@ -264,13 +277,6 @@ void convert_model(const BioModelTables& s, DevModel<T>& d) {
             d.dof_depth[i] = dep;
             if (dep + 1 > d.n_depths) d.n_depths = dep + 1;
         }
-        int nl = 0;
-        for (int j = 0; j < s.n_dof; j++) {
-            d.desc_begin[j] = nl;
-            for (int i = j + 1; i < s.n_dof; i++)
-                if ((s.dof_anc_mask[i] >> j) & 1u) { if (nl < 128) d.desc_list[nl] = (uint8_t)i; nl++; }
-        }
-        d.desc_begin[s.n_dof] = nl;
         int nc = 0;
         for (int b = 0; b < s.n_bodies; b++) {
             d.child_begin[b] = nc;
