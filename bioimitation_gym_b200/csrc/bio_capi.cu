@@ -135,6 +135,7 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
         auto fits = [&](int G, int ND, int NM, int NP, int NAX) {
             // factorisation step: (ancestors choose 2) + ancestors pairs on G lanes x (1 | 2) rounds
             if (max_anc * (max_anc + 1) / 2 > G * (G == 16 ? 1 : 2) || max_mov > 1) return false;
+            if (model->n_spheres * (max_anc + 1) > 64 || model->n_spheres > 8) return false;
             return model->n_dof <= ND && model->n_muscles <= NM && model->n_act <= NM && model->n_pathpts <= NP &&
                    model->n_axes <= NAX && model->n_bodies + model->n_dof <= G &&
                    model->n_bodies + model->n_obspts <= G && model->n_spheres + model->n_limits <= G &&

@@ -45,6 +45,8 @@ struct EnvWork {
     T H[C::ND * (C::ND + 1) / 2], rhs[C::ND];
     T udot[C::ND], adot[C::NM], lmdot[C::NM];
     T ffib[C::NM], fact[C::NM];
+    T vn[C::NM];                                           // Newton warm start: last normalised fibre velocity
+    T limDd[C::ND];                                        // limit damping summed per dof
     T ctrl[C::NM], curr[C::NM], lastact[C::NM];
     T com_pos[3], com_vel[3];
     T contact[2][6];
@@ -232,15 +234,21 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         curve_eval(m, 3, (L - lat) / m.mus_lts[i], ft, dtmp);
         const T ac = clampv(E.act[i], amin, T(1));
         const T afal = ac * fal;
-        T vn = T(0);
+        // Warm start from the root of the previous evaluation of this step.  The residual is
+        // monotone and sigmoid-shaped (convex for vn<0, concave for vn>0), so Newton is only
+        // guaranteed from points between 0 and the root: anything else restarts from 0.
+        T vn = E.vn[i];
+        const T e0 = (afal + fpe) * cosa - ft;    // residual at vn = 0 (f_V(0) = 1)
         for (int it = 0; it < newton_iters; it++) {
             curve_eval(m, 1, vn, fv, dfv);
             const T err = (afal * fv + fpe + beta * vn) * cosa - ft;
+            if (it == 0 && vn != T(0) && !(vn * e0 < T(0) && err * e0 > T(0))) { vn = T(0); continue; }
             const T derr = (afal * dfv + beta) * cosa;
             const T delta = -err / derr;
             vn += delta;
             if (Num<T>::abs(delta) < Num<T>::newton_tol()) break;
         }
+        E.vn[i] = vn;
         if (lmi <= lmin && vn < T(0)) vn = T(0);
         E.lmdot[i] = vn * m.mus_vmax[i] * lopt;
         const T ec = clampv(E.ctrl[i], amin, T(1));
@@ -382,8 +390,9 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         for (int j = 0; j < 6; j++) E.BI[b][4 + j] = I6[j];
     } else if (lane - nb < nd) {
         const int d = lane - nb;
-        T qf = T(0);
-        for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == d) qf += E.limf[l];
+        T qf = T(0), ld = T(0);
+        for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == d) { qf += E.limf[l]; ld += E.limD[l]; }
+        E.limDd[d] = ld;
         for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += E.x.pt.ptq[p]; }
         if (m.is_torque) for (int a = 0; a < m.n_act; a++) if (m.act_dof[a] == d) qf += E.ctrl[a];
         E.Q[d] = qf;
@@ -464,16 +473,12 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         for (int s = 0; s < m.n_spheres; s++) if (E.sphD[s][1] > T(0)) act_mask |= 1u << s;
         // contact Jacobian columns col[s][d] = w_d x p_s + v_d for the dofs on the sphere's chain
         if (act_mask)
-            for (int tsk = lane; tsk < m.n_spheres * nd; tsk += G) {
-                const int s = tsk / nd, d = tsk - s * nd;
+            for (int tsk = lane; tsk < m.jc_n; tsk += G) {      // (sphere, dof on its chain)
+                const int s = m.jc_s[tsk], d = m.jc_d[tsk];
                 if (!((act_mask >> s) & 1u)) continue;
-                const int last = m.body_last_dof[m.sph_body[s]];
-                T cv[3] = {T(0), T(0), T(0)};
-                if ((m.dof_anc_mask[last] >> d) & 1u) {
-                    cross3(E.S[d], E.sphx[s], cv);
-                    for (int c = 0; c < 3; c++) cv[c] += E.S[d][3 + c];
-                }
-                for (int c = 0; c < 3; c++) E.x.jac.col[s][d][c] = cv[c];
+                T cv[3];
+                cross3(E.S[d], E.sphx[s], cv);
+                for (int c = 0; c < 3; c++) E.x.jac.col[s][d][c] = cv[c] + E.S[d][3 + c];
             }
     }
     gsync<G>();
@@ -482,14 +487,15 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         T v = T(0);
         for (int c = 0; c < 6; c++) v += E.S[j][c] * E.IS[i][c];
         if (h_imp > T(0)) {
-            for (int s = 0; s < m.n_spheres; s++) {
-                if (!((act_mask >> s) & 1u)) continue;
+            unsigned mm = act_mask & m.ent_sph[e];               // active spheres whose chain holds i (and j)
+            while (mm) {
+                const int s = __ffs(mm) - 1;
+                mm &= mm - 1u;
                 const T* ci = E.x.jac.col[s][i];
                 const T* cj = E.x.jac.col[s][j];
                 v += h_imp * (E.sphD[s][0] * (ci[0] * cj[0] + ci[2] * cj[2]) + E.sphD[s][1] * ci[1] * cj[1]);
             }
-            if (i == j)
-                for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == i) v += h_imp * E.limD[l];
+            if (i == j) v += h_imp * E.limDd[i];
         }
         E.H[i * (i + 1) / 2 + j] = v;
     }
@@ -691,6 +697,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
         E.ctrl[lane] = clampv(c.feed_mean_action ? curr : action, m.act_min[lane], m.act_max[lane]);
     }
     hist_pos = (hist_pos + 1) % Hh;
+    if (ism) E.vn[lane] = T(0);   // every control step starts its Newton solves from 0 (results do not depend on history)
     gsync<G>();
 
     // ---- integrate one control step, evaluate at the new state ----
@@ -825,6 +832,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
         }
         if (ism) { E.act[lane] = m.mus_default_act[lane]; E.lm[lane] = c.ref_lm0[(size_t)idx * nm + lane]; }
         if (isa) E.ctrl[lane] = T(0);
+        if (ism) E.vn[lane] = T(0);
         istep = idx;
         first_next = 1;
         ep_return = T(0);

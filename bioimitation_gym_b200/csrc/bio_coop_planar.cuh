@@ -50,16 +50,22 @@ __device__ __forceinline__ void coop_solve(const DevModel<T>& m, EnvWork<T, CLS>
             if (keep_ki[it] >= 0) E.H[keep_ki[it]] = keep_a[it];   // row k is not read by later steps
     }
     gsync<G>();
-    // x_i = z_i / D_i - sum_{j in anc(i)} L_ij x_j, shallowest dofs first
-    for (int dep = 0; dep < m.n_depths; dep++) {
-        if (lane < nd && m.dof_depth[lane] == dep) {
-            const int i = lane, row = i * (i + 1) / 2;
-            T v = E.rhs[i] / E.H[row + i];
-            for (int j = m.dof_parent[i]; j >= 0; j = m.dof_parent[j]) v -= E.H[row + j] * E.udot[j];
-            E.udot[i] = v;
-        }
-        gsync<G>();
+    // L x = D^-1 z by columns: lane i keeps w_i in a register; when x_j is final (all its
+    // ancestors are < j) it is broadcast by shuffle and every descendant i subtracts L_ij x_j
+    T wv = T(0);
+    int row = 0;
+    uint32_t anc = 0u;
+    if (lane < nd) {
+        row = lane * (lane + 1) / 2;
+        wv = E.rhs[lane] / E.H[row + lane];
+        anc = m.dof_anc_mask[lane];
     }
+    for (int j = 0; j < nd - 1; j++) {
+        const T xj = __shfl_sync(0xffffffffu, wv, j, G);
+        if (lane > j && ((anc >> j) & 1u)) wv -= E.H[row + j] * xj;
+    }
+    if (lane < nd) E.udot[lane] = wv;
+    gsync<G>();
 }
 
 // planar helpers: R2 = [c -s; s c]
@@ -202,15 +208,21 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
         curve_eval(m, 3, (L - lat) / m.mus_lts[i], ft, dtmp);
         const T ac = clampv(E.act[i], amin, T(1));
         const T afal = ac * fal;
-        T vn = T(0);
+        // Warm start from the root of the previous evaluation of this step.  The residual is
+        // monotone and sigmoid-shaped (convex for vn<0, concave for vn>0), so Newton is only
+        // guaranteed from points between 0 and the root: anything else restarts from 0.
+        T vn = E.vn[i];
+        const T e0 = (afal + fpe) * cosa - ft;    // residual at vn = 0 (f_V(0) = 1)
         for (int it = 0; it < newton_iters; it++) {
             curve_eval(m, 1, vn, fv, dfv);
             const T err = (afal * fv + fpe + beta * vn) * cosa - ft;
+            if (it == 0 && vn != T(0) && !(vn * e0 < T(0) && err * e0 > T(0))) { vn = T(0); continue; }
             const T derr = (afal * dfv + beta) * cosa;
             const T delta = -err / derr;
             vn += delta;
             if (Num<T>::abs(delta) < Num<T>::newton_tol()) break;
         }
+        E.vn[i] = vn;
         if (lmi <= lmin && vn < T(0)) vn = T(0);
         E.lmdot[i] = vn * m.mus_vmax[i] * lopt;
         const T ec = clampv(E.ctrl[i], amin, T(1));
@@ -322,8 +334,9 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
         E.BI[b][6] = IAy + w * px - Wy;
     } else if (lane - nb < nd) {
         const int d = lane - nb;
-        T qf = T(0);
-        for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == d) qf += E.limf[l];
+        T qf = T(0), ld = T(0);
+        for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == d) { qf += E.limf[l]; ld += E.limD[l]; }
+        E.limDd[d] = ld;
         for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += E.x.pt.ptq[p]; }
         if (m.is_torque) for (int a = 0; a < m.n_act; a++) if (m.act_dof[a] == d) qf += E.ctrl[a];
         E.Q[d] = qf;
@@ -405,16 +418,11 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
     if (h_imp > T(0)) {
         for (int s = 0; s < m.n_spheres; s++) if (E.sphD[s][1] > T(0)) act_mask |= 1u << s;
         if (act_mask)
-            for (int tsk = lane; tsk < m.n_spheres * nd; tsk += G) {
-                const int s = tsk / nd, d = tsk - s * nd;
+            for (int tsk = lane; tsk < m.jc_n; tsk += G) {      // (sphere, dof on its chain)
+                const int s = m.jc_s[tsk], d = m.jc_d[tsk];
                 if (!((act_mask >> s) & 1u)) continue;
-                const int last = m.body_last_dof[m.sph_body[s]];
-                T cx = T(0), cy = T(0);
-                if ((m.dof_anc_mask[last] >> d) & 1u) {
-                    cx = E.S[d][1] - E.S[d][0] * E.sphx[s][1];
-                    cy = E.S[d][2] + E.S[d][0] * E.sphx[s][0];
-                }
-                E.x.jac.col[s][d][0] = cx; E.x.jac.col[s][d][1] = cy;
+                E.x.jac.col[s][d][0] = E.S[d][1] - E.S[d][0] * E.sphx[s][1];
+                E.x.jac.col[s][d][1] = E.S[d][2] + E.S[d][0] * E.sphx[s][0];
             }
     }
     gsync<G>();
@@ -422,13 +430,14 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
         const int i = m.ent_i[e], j = m.ent_j[e];
         T v = E.S[j][0] * E.IS[i][0] + E.S[j][1] * E.IS[i][1] + E.S[j][2] * E.IS[i][2];
         if (h_imp > T(0)) {
-            for (int s = 0; s < m.n_spheres; s++) {
-                if (!((act_mask >> s) & 1u)) continue;
+            unsigned mm = act_mask & m.ent_sph[e];               // active spheres whose chain holds i (and j)
+            while (mm) {
+                const int s = __ffs(mm) - 1;
+                mm &= mm - 1u;
                 v += h_imp * (E.sphD[s][0] * E.x.jac.col[s][i][0] * E.x.jac.col[s][j][0] +
                               E.sphD[s][1] * E.x.jac.col[s][i][1] * E.x.jac.col[s][j][1]);
             }
-            if (i == j)
-                for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == i) v += h_imp * E.limD[l];
+            if (i == j) v += h_imp * E.limDd[i];
         }
         E.H[i * (i + 1) / 2 + j] = v;
     }

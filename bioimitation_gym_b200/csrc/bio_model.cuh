@@ -111,6 +111,11 @@ struct alignas(16) DevModel {
     int32_t planar;                           // 1: all rotations about z, translations in x/y (2D models)
     int32_t pad3;
     T body_z[BIO_MAX_BODIES];                 // planar models: constant z of every body origin
+    // implicit damping: (sphere, dof on its chain) tasks and, per H entry, the spheres that touch it
+    int32_t jc_n;
+    int32_t pad4[3];
+    uint8_t jc_s[64], jc_d[64];
+    uint8_t ent_sph[BIO_MAX_DOF * (BIO_MAX_DOF + 1) / 2 + 8];
     // curves: uniform cubic Hermite, rows (y, h*dy/dx)
     T curve_x0[BIO_N_CURVES];
     T curve_inv_h[BIO_N_CURVES];
@@ -267,6 +272,23 @@ void convert_model(const BioModelTables& s, DevModel<T>& d) {
             const double ax = s.axis_vec[a][0], ay = s.axis_vec[a][1], az = s.axis_vec[a][2];
             if (s.axis_kind[a] == BIO_AXIS_ROT) { if (!(ax == 0.0 && ay == 0.0 && (az == 1.0 || az == -1.0))) d.planar = 0; }
             else if (!(az == 0.0 && ((ay == 0.0 && (ax == 1.0 || ax == -1.0)) || (ax == 0.0 && (ay == 1.0 || ay == -1.0))))) d.planar = 0;
+        }
+        d.jc_n = 0;
+        for (int sp = 0; sp < s.n_spheres; sp++) {
+            const int last = d.body_last_dof[s.sph_body[sp]];
+            for (int j = 0; j <= last && last >= 0; j++)
+                if ((s.dof_anc_mask[last] >> j) & 1u) {
+                    if (d.jc_n < 64) { d.jc_s[d.jc_n] = (uint8_t)sp; d.jc_d[d.jc_n] = (uint8_t)j; }
+                    d.jc_n++;
+                }
+        }
+        for (int e = 0; e < d.n_entries; e++) {
+            unsigned msk = 0;
+            for (int sp = 0; sp < s.n_spheres; sp++) {
+                const int last = d.body_last_dof[s.sph_body[sp]];
+                if (last >= 0 && ((s.dof_anc_mask[last] >> d.ent_i[e]) & 1u)) msk |= 1u << sp;  // i on the chain => j too
+            }
+            d.ent_sph[e] = (uint8_t)msk;
         }
         for (int b = 0; b < s.n_bodies; b++)
             d.body_z[b] = (T)((s.body_parent[b] >= 0 ? (double)d.body_z[s.body_parent[b]] : 0.0) + s.body_joint_loc[b][2]);

@@ -37,7 +37,7 @@ INTEGRATORS = {"semi_implicit_euler": M["BIO_INT_SEMI_IMPLICIT_EULER"],
 # 0.5 ms (DESIGN.md "Integrator" has the stability / accuracy measurements).
 DEFAULT_INTEGRATOR = "implicit_damping"
 DEFAULT_SUBSTEPS = 20
-DEFAULT_NEWTON_ITERS = 12
+DEFAULT_NEWTON_ITERS = 30      # cap; the loop stops at |delta| < tolerance (typically 2-5 iterations)
 
 
 @dataclass
