@@ -189,9 +189,12 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     // ---- phase C: lane = muscle ----
     if (lane < nm) {
         const int i = lane;
-        int pidx[BIO_MAX_MUSCLE_PTS];
-        int np = 0, pmov = -1;
+        // one streaming pass over the path points: positions, segment unit vectors and the
+        // length; ptf[p] first holds the direction sum (e_out - e_in) and is scaled by the
+        // tension once it is known (inactive points keep zero position and force)
+        int pmov = -1, prev = -1;
         T mdloc[3] = {T(0), T(0), T(0)};
+        T xp[3] = {T(0), T(0), T(0)}, ev[3] = {T(0), T(0), T(0)}, L = T(0);
         const int pb = m.mus_pt_begin[i], pe = pb + m.mus_pt_count[i];
         for (int p = pb; p < pe; p++) {
             const int kind = m.pt_kind[p], d = m.pt_dof[p], b = m.pt_body[p];
@@ -199,7 +202,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             if (kind == BIO_PT_CONDITIONAL) {
                 const T v = E.q[d];
                 if (!(v >= m.pt_range[p][0] - T(1e-5) && v <= m.pt_range[p][1] + T(1e-5))) {
-                    for (int c = 0; c < 3; c++) E.x.pt.ptf[p][c] = T(0);
+                    for (int c = 0; c < 3; c++) { E.x.pt.ptf[p][c] = T(0); E.x.pt.ptx[p][c] = T(0); }
                     continue;
                 }
             }
@@ -212,16 +215,19 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             }
             T x[3];
             matvec3(E.R[b], loc, x);
-            for (int c = 0; c < 3; c++) { x[c] += E.r[b][c]; E.x.pt.ptx[p][c] = x[c]; E.x.pt.ptf[p][c] = T(0); }
-            pidx[np++] = p;
+            for (int c = 0; c < 3; c++) { x[c] += E.r[b][c]; E.x.pt.ptx[p][c] = x[c]; }
+            if (prev >= 0) {
+                const T dx = x[0] - xp[0], dy = x[1] - xp[1], dz = x[2] - xp[2];
+                const T d2 = dx * dx + dy * dy + dz * dz;
+                const T il = Num<T>::rsqrt(d2);
+                L += d2 * il;
+                const T nv[3] = {dx * il, dy * il, dz * il};
+                for (int c = 0; c < 3; c++) { E.x.pt.ptf[prev][c] = nv[c] - ev[c]; ev[c] = nv[c]; }
+            }
+            for (int c = 0; c < 3; c++) xp[c] = x[c];
+            prev = p;
         }
-        T L = T(0);
-        for (int s = 0; s + 1 < np; s++) {
-            const T* x0 = E.x.pt.ptx[pidx[s]];
-            const T* x1 = E.x.pt.ptx[pidx[s + 1]];
-            const T dx = x1[0] - x0[0], dy = x1[1] - x0[1], dz = x1[2] - x0[2];
-            L += Num<T>::sqrt(dx * dx + dy * dy + dz * dz);
-        }
+        if (prev >= 0) for (int c = 0; c < 3; c++) E.x.pt.ptf[prev][c] = -ev[c];
         const T fiso = m.mus_fiso[i], lopt = m.mus_lopt[i], h = m.mus_height[i], beta = m.mus_beta[i];
         const T amin = m.mus_amin[i], lmin = m.mus_lm_min[i];
         const T lmi = E.lm[i];
@@ -260,14 +266,8 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             E.fact[i] = fiso * afal * fv;
             E.ffib[i] = fiso * (afal * fv + fpe + beta * vn);
         }
-        for (int s = 0; s + 1 < np; s++) {
-            const int p0 = pidx[s], p1 = pidx[s + 1];
-            const T dx = E.x.pt.ptx[p1][0] - E.x.pt.ptx[p0][0], dy = E.x.pt.ptx[p1][1] - E.x.pt.ptx[p0][1],
-                    dz = E.x.pt.ptx[p1][2] - E.x.pt.ptx[p0][2];
-            const T il = tension / Num<T>::sqrt(dx * dx + dy * dy + dz * dz);
-            const T f[3] = {dx * il, dy * il, dz * il};
-            for (int c = 0; c < 3; c++) { E.x.pt.ptf[p0][c] += f[c]; E.x.pt.ptf[p1][c] -= f[c]; }
-        }
+        for (int p = pb; p < pe; p++)
+            for (int c = 0; c < 3; c++) E.x.pt.ptf[p][c] *= tension;
         // generalized force of the muscle's moving point (at most one per muscle): f . R_b dloc/dq
         if (pmov >= 0) {
             T dw[3];
@@ -327,8 +327,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         for (int k = m.body_pt_begin[b]; k < m.body_pt_begin[b] + m.body_pt_count[b]; k++) {
             const int p = m.body_pt_list[k];
             const T f[3] = {E.x.pt.ptf[p][0], E.x.pt.ptf[p][1], E.x.pt.ptf[p][2]};
-            if (f[0] == T(0) && f[1] == T(0) && f[2] == T(0)) continue;   // inactive point: its ptx is stale
-            T n[3];
+            T n[3];                                                       // inactive points: zero force and position
             cross3(E.x.pt.ptx[p], f, n);
             for (int c = 0; c < 3; c++) { Wn[c] += n[c]; Wf[c] += f[c]; }
         }

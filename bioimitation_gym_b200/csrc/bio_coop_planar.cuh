@@ -110,36 +110,29 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
                 aw_ = T(0); ax_ = -m.gravity[0]; ay_ = -m.gravity[1];
             }
             T c = cp, s_ = sp;
-            bool root_open = p < 0;
             const int ab = m.body_axis_begin[b], ae = ab + m.body_axis_count[b];
-            int dprev = -1;
             T Sw = T(0), Sx = T(0), Sy = T(0);
             for (int a = ab; a < ae; a++) {
-                const int d = m.axis_dof[a], code = m.axis_code[a];
-                const T s = E.ax_s[a], ds = E.ax_ds[a], dds = E.ax_dds[a];
-                const T sg = code > 0 ? T(1) : T(-1);
+                const int desc = m.axis_desc[a], d = (desc >> 3) & 31;
+                const T s = E.ax_s[a];
+                const T sg = (desc & 2) ? T(-1) : T(1);
                 T kw, kx, ky;                     // this axis' motion vector
-                if (m.axis_kind[a] == BIO_AXIS_TRANS) {
-                    const int ka = (code > 0 ? code : -code) - 1;     // 0: x, 1: y
+                if (!(desc & 1)) {                // translation along x or y of the parent frame
                     kw = T(0);
-                    kx = sg * (ka == 0 ? cp : -sp);
-                    ky = sg * (ka == 0 ? sp : cp);
+                    kx = sg * ((desc & 4) ? -sp : cp);
+                    ky = sg * ((desc & 4) ? cp : sp);
                     rx += kx * s; ry += ky * s;
-                } else {
-                    if (root_open) { E.O[0] = rx; E.O[1] = ry; E.O[2] = T(0); rx = ry = T(0); root_open = false; }
+                } else {                          // rotation about +-z through the current origin
+                    if (desc & 256) { E.O[0] = rx; E.O[1] = ry; E.O[2] = T(0); rx = ry = T(0); }
                     kw = sg; kx = sg * ry; ky = -sg * rx;
                     T sn, cs;
                     Num<T>::sincos(sg * s, &sn, &cs);
                     const T cn = c * cs - s_ * sn, snn = s_ * cs + c * sn;
                     c = cn; s_ = snn;
                 }
-                if (d >= 0) {
-                    if (d != dprev) {
-                        if (dprev >= 0) { E.S[dprev][0] = Sw; E.S[dprev][1] = Sx; E.S[dprev][2] = Sy; }
-                        Sw = Sx = Sy = T(0);
-                        dprev = d;
-                    }
-                    const T qd = E.u[d], sd = ds * qd, acc = dds * qd * qd;
+                if (d != 31) {
+                    const T ds = E.ax_ds[a], qd = E.u[d], sd = ds * qd, acc = E.ax_dds[a] * qd * qd;
+                    if (desc & 512) Sw = Sx = Sy = T(0);
                     // V x S (planar): angular part 0, linear = w * (-S_vy, S_vx) + S_w * (V_vy, -V_vx)
                     const T cx = -w * ky + kw * vy, cy = w * kx - kw * vx;
                     Sw += ds * kw; Sx += ds * kx; Sy += ds * ky;
@@ -147,10 +140,10 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
                     ax_ += kx * acc + cx * sd;
                     ay_ += ky * acc + cy * sd;
                     w += kw * sd; vx += kx * sd; vy += ky * sd;
+                    if (desc & 1024) { E.S[d][0] = Sw; E.S[d][1] = Sx; E.S[d][2] = Sy; }
                 }
+                if (desc & 2048) { E.O[0] = rx; E.O[1] = ry; E.O[2] = T(0); rx = ry = T(0); }
             }
-            if (dprev >= 0) { E.S[dprev][0] = Sw; E.S[dprev][1] = Sx; E.S[dprev][2] = Sy; }
-            if (root_open) { E.O[0] = rx; E.O[1] = ry; E.O[2] = T(0); rx = ry = T(0); }
             E.R[b][0] = c; E.R[b][1] = s_;
             E.r[b][0] = rx; E.r[b][1] = ry; E.r[b][2] = m.body_z[b];
             E.V[b][0] = w; E.V[b][1] = vx; E.V[b][2] = vy;
@@ -162,9 +155,12 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
     // ---- phase C: lane = muscle (path geometry is 3-D: points keep their constant z) ----
     if (lane < nm) {
         const int i = lane;
-        int pidx[BIO_MAX_MUSCLE_PTS];
-        int np = 0, pmov = -1;
+        // one streaming pass over the path points: positions, segment unit vectors and the
+        // length; ptf[p] first holds the direction sum (e_out - e_in) and is scaled by the
+        // tension once it is known (inactive points keep zero position and force)
+        int pmov = -1, prev = -1;
         T mdloc[3] = {T(0), T(0), T(0)};
+        T xp = T(0), yp = T(0), zp = T(0), ex = T(0), ey = T(0), ez = T(0), L = T(0);
         const int pb = m.mus_pt_begin[i], pe = pb + m.mus_pt_count[i];
         for (int p = pb; p < pe; p++) {
             const int kind = m.pt_kind[p], d = m.pt_dof[p], b = m.pt_body[p];
@@ -172,7 +168,7 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
             if (kind == BIO_PT_CONDITIONAL) {
                 const T v = E.q[d];
                 if (!(v >= m.pt_range[p][0] - T(1e-5) && v <= m.pt_range[p][1] + T(1e-5))) {
-                    for (int c = 0; c < 3; c++) E.x.pt.ptf[p][c] = T(0);
+                    for (int c = 0; c < 3; c++) { E.x.pt.ptf[p][c] = T(0); E.x.pt.ptx[p][c] = T(0); }
                     continue;
                 }
             }
@@ -185,17 +181,21 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
             }
             T x, y;
             rot2(E.R[b][0], E.R[b][1], loc[0], loc[1], x, y);
-            E.x.pt.ptx[p][0] = x + E.r[b][0]; E.x.pt.ptx[p][1] = y + E.r[b][1]; E.x.pt.ptx[p][2] = loc[2] + E.r[b][2];
-            for (int c = 0; c < 3; c++) E.x.pt.ptf[p][c] = T(0);
-            pidx[np++] = p;
+            x += E.r[b][0]; y += E.r[b][1];
+            const T z = loc[2] + E.r[b][2];
+            E.x.pt.ptx[p][0] = x; E.x.pt.ptx[p][1] = y; E.x.pt.ptx[p][2] = z;
+            if (prev >= 0) {
+                const T dx = x - xp, dy = y - yp, dz = z - zp;
+                const T d2 = dx * dx + dy * dy + dz * dz;
+                const T il = Num<T>::rsqrt(d2);
+                L += d2 * il;
+                const T nx = dx * il, ny = dy * il, nz = dz * il;
+                E.x.pt.ptf[prev][0] = nx - ex; E.x.pt.ptf[prev][1] = ny - ey; E.x.pt.ptf[prev][2] = nz - ez;
+                ex = nx; ey = ny; ez = nz;
+            }
+            xp = x; yp = y; zp = z; prev = p;
         }
-        T L = T(0);
-        for (int s = 0; s + 1 < np; s++) {
-            const T* x0 = E.x.pt.ptx[pidx[s]];
-            const T* x1 = E.x.pt.ptx[pidx[s + 1]];
-            const T dx = x1[0] - x0[0], dy = x1[1] - x0[1], dz = x1[2] - x0[2];
-            L += Num<T>::sqrt(dx * dx + dy * dy + dz * dz);
-        }
+        if (prev >= 0) { E.x.pt.ptf[prev][0] = -ex; E.x.pt.ptf[prev][1] = -ey; E.x.pt.ptf[prev][2] = -ez; }
         const T fiso = m.mus_fiso[i], lopt = m.mus_lopt[i], h = m.mus_height[i], beta = m.mus_beta[i];
         const T amin = m.mus_amin[i], lmin = m.mus_lm_min[i];
         const T lmi = E.lm[i];
@@ -234,14 +234,8 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
             E.fact[i] = fiso * afal * fv;
             E.ffib[i] = fiso * (afal * fv + fpe + beta * vn);
         }
-        for (int s = 0; s + 1 < np; s++) {
-            const int p0 = pidx[s], p1 = pidx[s + 1];
-            const T dx = E.x.pt.ptx[p1][0] - E.x.pt.ptx[p0][0], dy = E.x.pt.ptx[p1][1] - E.x.pt.ptx[p0][1],
-                    dz = E.x.pt.ptx[p1][2] - E.x.pt.ptx[p0][2];
-            const T il = tension / Num<T>::sqrt(dx * dx + dy * dy + dz * dz);
-            const T f[3] = {dx * il, dy * il, dz * il};
-            for (int c = 0; c < 3; c++) { E.x.pt.ptf[p0][c] += f[c]; E.x.pt.ptf[p1][c] -= f[c]; }
-        }
+        for (int p = pb; p < pe; p++)
+            for (int c = 0; c < 3; c++) E.x.pt.ptf[p][c] *= tension;
         if (pmov >= 0) {
             const int b = m.pt_body[pmov];
             T dwx, dwy;
@@ -299,8 +293,7 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
         T Wn = T(0), Wx = T(0), Wy = T(0);
         for (int k = m.body_pt_begin[b]; k < m.body_pt_begin[b] + m.body_pt_count[b]; k++) {
             const int p = m.body_pt_list[k];
-            const T fx = E.x.pt.ptf[p][0], fy = E.x.pt.ptf[p][1];
-            if (fx == T(0) && fy == T(0) && E.x.pt.ptf[p][2] == T(0)) continue;
+            const T fx = E.x.pt.ptf[p][0], fy = E.x.pt.ptf[p][1];   // inactive points: zero force, zero position
             Wn += E.x.pt.ptx[p][0] * fy - E.x.pt.ptx[p][1] * fx;
             Wx += fx; Wy += fy;
         }

@@ -25,6 +25,7 @@ namespace bio {
 template <typename T> struct Num;
 template <> struct Num<float> {
     static BIO_DEV float sqrt(float x) { return sqrtf(x); }
+    static BIO_DEV float rsqrt(float x) { return rsqrtf(x); }
     static BIO_DEV float abs(float x) { return fabsf(x); }
     static BIO_DEV float floor(float x) { return floorf(x); }
     static BIO_DEV float exp(float x) { return expf(x); }
@@ -37,6 +38,7 @@ template <> struct Num<float> {
 };
 template <> struct Num<double> {
     static BIO_DEV double sqrt(double x) { return ::sqrt(x); }
+    static BIO_DEV double rsqrt(double x) { return 1.0 / ::sqrt(x); }
     static BIO_DEV double abs(double x) { return ::fabs(x); }
     static BIO_DEV double floor(double x) { return ::floor(x); }
     static BIO_DEV double exp(double x) { return ::exp(x); }

@@ -116,6 +116,10 @@ struct alignas(16) DevModel {
     int32_t pad4[3];
     uint8_t jc_s[64], jc_d[64];
     uint8_t ent_sph[BIO_MAX_DOF * (BIO_MAX_DOF + 1) / 2 + 8];
+    // packed per-axis descriptor (planar kinematics): bit0 rotation, bit1 negative axis, bit2 translation
+    // along y, bits3-7 dof (31: constant), bit8 first rotation of the root (fixes O), bit9 first axis of
+    // its dof, bit10 last axis of its dof, bit11 root without rotation: fix O after this (last) axis
+    int32_t axis_desc[BIO_MAX_AXES];
     // curves: uniform cubic Hermite, rows (y, h*dy/dx)
     T curve_x0[BIO_N_CURVES];
     T curve_inv_h[BIO_N_CURVES];
@@ -272,6 +276,23 @@ void convert_model(const BioModelTables& s, DevModel<T>& d) {
             const double ax = s.axis_vec[a][0], ay = s.axis_vec[a][1], az = s.axis_vec[a][2];
             if (s.axis_kind[a] == BIO_AXIS_ROT) { if (!(ax == 0.0 && ay == 0.0 && (az == 1.0 || az == -1.0))) d.planar = 0; }
             else if (!(az == 0.0 && ((ay == 0.0 && (ax == 1.0 || ax == -1.0)) || (ax == 0.0 && (ay == 1.0 || ay == -1.0))))) d.planar = 0;
+        }
+        for (int b = 0; b < s.n_bodies; b++) {
+            const int ab = s.body_axis_begin[b], ae = ab + s.body_axis_count[b];
+            bool seen_rot = false;
+            for (int a = ab; a < ae; a++) {
+                const int dof = s.axis_dof[a];
+                const bool rot = s.axis_kind[a] == BIO_AXIS_ROT;
+                const double comp = rot ? s.axis_vec[a][2] : (s.axis_vec[a][0] != 0.0 ? s.axis_vec[a][0] : s.axis_vec[a][1]);
+                int w = (rot ? 1 : 0) | (comp < 0 ? 2 : 0) | ((!rot && s.axis_vec[a][0] == 0.0) ? 4 : 0) |
+                        ((dof >= 0 ? dof : 31) << 3);
+                if (rot && !seen_rot && s.body_parent[b] < 0) w |= 1 << 8;
+                if (rot) seen_rot = true;
+                if (dof >= 0 && (a == ab || s.axis_dof[a - 1] != dof)) w |= 1 << 9;
+                if (dof >= 0 && (a == ae - 1 || s.axis_dof[a + 1] != dof)) w |= 1 << 10;
+                if (a == ae - 1 && !seen_rot && s.body_parent[b] < 0) w |= 1 << 11;
+                d.axis_desc[a] = w;
+            }
         }
         d.jc_n = 0;
         for (int sp = 0; sp < s.n_spheres; sp++) {
