@@ -13,9 +13,8 @@
 #include <string>
 #include <vector>
 
-#include "bio_coop.cuh"
+#include "bio_launch.cuh"
 
-#define COOP_BLOCK 256
 
 namespace {
 
@@ -42,6 +41,8 @@ struct HandleBase {
     unsigned long long seed = 0;
     long long env_offset = 0;
     int block = 32;
+    int n_sms = 148;
+    int coop_grid = 0;
     std::vector<void*> allocs;
     double* stats = nullptr;          // 16 doubles
     virtual ~HandleBase() {}
@@ -93,10 +94,7 @@ int pick_block(int n) {
 template <typename T>
 int set_kernel_attrs(Handle<T>* h) {
     h->smem = sizeof(bio::DevModel<T>);
-    CU(cudaFuncSetAttribute(bio::bio_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    CU(cudaFuncSetAttribute(bio::bio_reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    CU(cudaFuncSetAttribute(bio::bio_eval_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    CU(cudaFuncSetAttribute(bio::bio_lm0_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CU(bio::thread_set_smem<T>((int)h->smem));
     return 0;
 }
 
@@ -111,6 +109,8 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
     h->seed = seed;
     h->env_offset = env_offset;
     h->block = pick_block(n);
+    CU(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device));
+    if (const char* e = getenv("BIO_COOP_GRID")) h->coop_grid = atoi(e);
     if (const char* e = getenv("BIO_BLOCK")) { int b = atoi(e); if (b >= 32 && b <= 256 && b % 32 == 0) h->block = b; }
     int rc;
     if ((rc = set_kernel_attrs(h))) return rc;
@@ -144,14 +144,12 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
         const size_t base = ((sizeof(bio::DevModel<T>) + 15) / 16) * 16;
         if (want_coop && fits(C0::G, C0::ND, C0::NM, C0::NP, C0::NAX)) {
             h->coop_cls = 0;
-            h->coop_smem = base + (COOP_BLOCK / C0::G) * sizeof(bio::EnvWork<T, 0>);
-            CU(cudaFuncSetAttribute(bio::bio_coop_step_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)h->coop_smem));
+            h->coop_smem = base + (COOP_THREADS(T) / C0::G) * sizeof(bio::EnvWork<T, 0>);
+            CU((bio::coop_set_smem<T, 0>((int)h->coop_smem)));
         } else if (want_coop && fits(C1::G, C1::ND, C1::NM, C1::NP, C1::NAX)) {
             h->coop_cls = 1;
-            h->coop_smem = base + (COOP_BLOCK / C1::G) * sizeof(bio::EnvWork<T, 1>);
-            CU(cudaFuncSetAttribute(bio::bio_coop_step_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)h->coop_smem));
+            h->coop_smem = base + (COOP_THREADS(T) / C1::G) * sizeof(bio::EnvWork<T, 1>);
+            CU((bio::coop_set_smem<T, 1>((int)h->coop_smem)));
         }
     }
     // model block
@@ -181,7 +179,7 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
     h->task_d.ref_lm0 = lm0;
     if (nm > 0) {
         const int blk = 32, grid = (ref->n_rows + blk - 1) / blk;
-        bio::bio_lm0_kernel<T><<<grid, blk, h->smem>>>(h->d_model, h->task_d.ref_q, ref->n_rows, ref->n_coords, lm0);
+        bio::launch_lm0<T>(grid, blk, h->smem, h->d_model, h->task_d.ref_q, ref->n_rows, ref->n_coords, lm0);
         h->launches++;
         CU(cudaGetLastError());
     }
@@ -211,8 +209,8 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
     CU(cudaDeviceSynchronize());
     // initial reference-state reset of all envs
     const int grid = (n + h->block - 1) / h->block;
-    bio::bio_reset_kernel<T><<<grid, h->block, h->smem>>>(h->d_model, h->task_d, h->st, n, h->seed, h->env_offset,
-                                                         nullptr, nullptr, 0);
+    bio::launch_reset<T>(grid, h->block, h->smem, 0, h->d_model, h->task_d, h->st, n, h->seed, h->env_offset, nullptr,
+                         nullptr, 0);
     h->launches++;
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
@@ -240,21 +238,23 @@ int validate(const BioModelTables* m, const BioTaskConfig* t, const BioRefTables
 template <typename T>
 int step_impl(Handle<T>* h, const void* actions, void* obs, void* reward, uint8_t* done, void* terms,
               cudaStream_t s) {
-    if (h->coop_cls == 0) {
-        const int epc = COOP_BLOCK / bio::CoopCls<0>::G, grid = (h->n + epc - 1) / epc;
-        bio::bio_coop_step_kernel<T, 0><<<grid, COOP_BLOCK, h->coop_smem, s>>>(
-            h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset, (const T*)actions, (T*)obs, (T*)reward, done,
-            (T*)terms, h->stats);
-    } else if (h->coop_cls == 1) {
-        const int epc = COOP_BLOCK / bio::CoopCls<1>::G, grid = (h->n + epc - 1) / epc;
-        bio::bio_coop_step_kernel<T, 1><<<grid, COOP_BLOCK, h->coop_smem, s>>>(
-            h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset, (const T*)actions, (T*)obs, (T*)reward, done,
-            (T*)terms, h->stats);
+    if (h->coop_cls >= 0) {
+        // persistent launch: resident CTAs only, warps walk the env items round-robin over the CTAs
+        const int G = h->coop_cls == 0 ? (int)bio::CoopCls<0>::G : (int)bio::CoopCls<1>::G;
+        const int items = (h->n + (32 / G) - 1) / (32 / G);
+        const int ctas = h->n_sms * COOP_CTAS_PER_SM(T);
+        int grid = items < ctas ? items : ctas;
+        if (h->coop_grid > 0) grid = h->coop_grid;   // BIO_COOP_GRID: launch-shape experiments
+        if (h->coop_cls == 0)
+            bio::launch_coop<T, 0>(grid, h->coop_smem, s, h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset, (const T*)actions, (T*)obs, (T*)reward, done,
+                (T*)terms, h->stats);
+        else
+            bio::launch_coop<T, 1>(grid, h->coop_smem, s, h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset, (const T*)actions, (T*)obs, (T*)reward, done,
+                (T*)terms, h->stats);
     } else {
         const int grid = (h->n + h->block - 1) / h->block;
-        bio::bio_step_kernel<T><<<grid, h->block, h->smem, s>>>(h->d_model, h->task_d, h->st, h->n, h->seed,
-                                                               h->env_offset, (const T*)actions, (T*)obs, (T*)reward,
-                                                               done, (T*)terms, h->stats);
+        bio::launch_step<T>(grid, h->block, h->smem, s, h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset,
+                            (const T*)actions, (T*)obs, (T*)reward, done, (T*)terms, h->stats);
     }
     h->launches++;
     CU(cudaGetLastError());
@@ -264,8 +264,8 @@ int step_impl(Handle<T>* h, const void* actions, void* obs, void* reward, uint8_
 template <typename T>
 int reset_impl(Handle<T>* h, const uint8_t* mask, void* obs, cudaStream_t s, int bump) {
     const int grid = (h->n + h->block - 1) / h->block;
-    bio::bio_reset_kernel<T><<<grid, h->block, h->smem, s>>>(h->d_model, h->task_d, h->st, h->n, h->seed,
-                                                            h->env_offset, mask, (T*)obs, bump);
+    bio::launch_reset<T>(grid, h->block, h->smem, s, h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset, mask,
+                         (T*)obs, bump);
     h->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -276,7 +276,7 @@ int transpose(Handle<T>* h, const T* src, T* dst, int k, int to_soa, cudaStream_
     const size_t total = (size_t)h->n * k;
     if (!total) return 0;
     const int blk = 256;
-    bio::bio_transpose_kernel<T><<<(unsigned)((total + blk - 1) / blk), blk, 0, s>>>(src, dst, h->n, k, to_soa);
+    bio::launch_transpose<T>((unsigned)((total + blk - 1) / blk), blk, s, src, dst, h->n, k, to_soa);
     h->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -323,8 +323,8 @@ int eval_impl(Handle<T>* h, const void* controls, const BioDebugPtrs* o, cudaStr
     d.path_vel = (T*)o->path_vel; d.contact = (T*)o->contact; d.limit_force = (T*)o->limit_force;
     d.mass_matrix = (T*)o->mass_matrix; d.bias = (T*)o->bias;
     const int grid = (h->n + h->block - 1) / h->block;
-    bio::bio_eval_kernel<T><<<grid, h->block, h->smem, s>>>(h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset,
-                                                           (const T*)controls, d);
+    bio::launch_eval<T>(grid, h->block, h->smem, s, h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset,
+                        (const T*)controls, d);
     h->launches++;
     CU(cudaGetLastError());
     return 0;

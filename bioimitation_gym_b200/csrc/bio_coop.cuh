@@ -53,7 +53,13 @@ struct EnvWork {
     T max_limit, pad_;
 };
 
-template <int G> __device__ __forceinline__ void gsync() { __syncwarp(); }
+// The G lanes of an env are the unit of synchronisation: two envs sharing a warp (G = 16) may
+// take different branches (auto-reset of one of them), so every barrier, shuffle and ballot
+// names only the lanes of its own env.
+template <int G> __device__ __forceinline__ unsigned group_mask() {
+    return G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G));
+}
+template <int G> __device__ __forceinline__ void gsync() { __syncwarp(group_mask<G>()); }
 
 // column K of a row-major 3x3 (times a sign), and R <- R * Rot(e_K, angle) as a mix of the two other columns
 template <typename T, int K>
@@ -582,13 +588,13 @@ __device__ void coop_integrate(const DevModel<T>& m, const DevTask<T>& c, EnvWor
 template <typename T, int G>
 __device__ __forceinline__ T group_sum(T v) {
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(group_mask<G>(), v, o, G);
     return v;
 }
 template <typename T, int G>
 __device__ __forceinline__ T group_max(T v) {
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) { const T w = __shfl_xor_sync(0xffffffffu, v, o, G); v = w > v ? w : v; }
+    for (int o = G / 2; o > 0; o >>= 1) { const T w = __shfl_xor_sync(group_mask<G>(), v, o, G); v = w > v ? w : v; }
     return v;
 }
 
@@ -632,20 +638,30 @@ __device__ void coop_write_obs(const DevModel<T>& m, const DevTask<T>& c, const 
     for (int o = lane; o < c.obs_dim; o += G) orow[o] = obs_value<T, CLS>(m, c, E, istep, row_next, pel, o);
 }
 
+// Persistent launch: COOP_CTAS_PER_SM CTAs of 256 threads per SM, the model block is staged once
+// per CTA, and every warp walks the work items (one item = the 32/G envs of a warp)
+// item = blockIdx + gridDim * (warp + warps_per_cta * k), so that the items are dealt round-robin
+// over the CTAs first (4096 envs on 148 SMs: 13 or 14 busy warps per SM instead of 8 or 16).
+#define COOP_THREADS(T) 256
+#define COOP_CTAS_PER_SM(T) (sizeof(T) == 4 ? 2 : 1)
+
 template <typename T, int CLS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(COOP_THREADS(T), COOP_CTAS_PER_SM(T))
 bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, const EnvState<T> st, int n,
                      unsigned long long seed, long long env_offset, const T* __restrict__ actions,
                      T* __restrict__ obs, T* __restrict__ reward, uint8_t* __restrict__ done, T* __restrict__ terms,
                      double* __restrict__ stats) {
     typedef CoopCls<CLS> C;
     constexpr int G = C::G;
+    constexpr int EPW = 32 / G;                 // envs per warp
     extern __shared__ __align__(16) unsigned char smem[];
     const DevModel<T>& m = stage_model(gm, smem);
     EnvWork<T, CLS>* works = reinterpret_cast<EnvWork<T, CLS>*>(smem + ((sizeof(DevModel<T>) + 15) / 16) * 16);
     const int slot = threadIdx.x / G, lane = threadIdx.x % G;
-    const int envs_per_cta = blockDim.x / G;
-    const int i = blockIdx.x * envs_per_cta + slot;
+    const int warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
+    const int n_items = (n + EPW - 1) / EPW;
+    for (int item = blockIdx.x + gridDim.x * warp; item < n_items; item += gridDim.x * warps_per_cta) {
+    const int i = item * EPW + ((threadIdx.x & 31) / G);
     // all lanes of an env take the same branch; envs of a warp may differ only in i >= n
     const bool valid = i < n;
     const int ii = valid ? i : n - 1;          // out-of-range groups shadow the last env, stores are masked
@@ -663,8 +679,8 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     // ---- action pre-processing: lane = actuator ----
     T action = isa ? actions[(size_t)ii * na + lane] : T(0);
     const bool lane_nan = action != action;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (0xffffu << ((threadIdx.x & 31) / G * G));
-    const bool nan = (__ballot_sync(0xffffffffu, lane_nan) & gmask) != 0u;
+    const unsigned gmask = group_mask<G>();
+    const bool nan = __ballot_sync(gmask, lane_nan) != 0u;
     gsync<G>();   // E.q / E.u visible for the PD law
     if (nan) {
         action = T(0);
@@ -734,10 +750,10 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
                          c.ref_body_pos + ((size_t)row * c.ref_bodies + c.rew_refbody[sd][j]) * 3);
     }
     // sum of the 4 bodies of each side: butterfly over 4 lanes
-    fpart += __shfl_xor_sync(0xffffffffu, fpart, 1, G);
-    fpart += __shfl_xor_sync(0xffffffffu, fpart, 2, G);
-    const T foot_r = T(0.5) * Num<T>::exp(T(-20) * __shfl_sync(0xffffffffu, fpart, 0, G));
-    const T foot_l = T(0.5) * Num<T>::exp(T(-20) * __shfl_sync(0xffffffffu, fpart, 4, G));
+    fpart += __shfl_xor_sync(gmask, fpart, 1, G);
+    fpart += __shfl_xor_sync(gmask, fpart, 2, G);
+    const T foot_r = T(0.5) * Num<T>::exp(T(-20) * __shfl_sync(gmask, fpart, 0, G));
+    const T foot_l = T(0.5) * Num<T>::exp(T(-20) * __shfl_sync(gmask, fpart, 4, G));
     T effort, a_error = T(0);
     if (c.effort_torque) {
         const T s2 = group_sum<T, G>(isa ? curr * curr : T(0));
@@ -782,7 +798,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
         fin = isfinite(E.q[lane]) && isfinite(E.u[lane]) && isfinite(E.udot[lane]);
     }
     const T maxacc = group_max<T, G>(acc);
-    const bool finite = isfinite(rew) && ((__ballot_sync(0xffffffffu, !fin) & gmask) == 0u);
+    const bool finite = isfinite(rew) && (__ballot_sync(gmask, !fin) == 0u);
     int reason = 0;
     if (!finite) { reason = BIO_DONE_NONFINITE; rew = T(0); }
     else if (E.x.out.obs_pos[c.term_obspt][1] < c.term_height) reason = BIO_DONE_HEIGHT;
@@ -856,10 +872,9 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
             st.episode[ii] = episode;
         }
     }
-    if (stats && threadIdx.x == 0) {
-        const int rem = n - blockIdx.x * envs_per_cta;
-        atomicAdd(&stats[0], (double)(rem < envs_per_cta ? rem : envs_per_cta));
+    gsync<G>();   // the warp's work slots are reused by its next item
     }
+    if (stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[0], (double)n);
 }
 
 }  // namespace bio

@@ -61,7 +61,7 @@ __device__ __forceinline__ void coop_solve(const DevModel<T>& m, EnvWork<T, CLS>
         anc = m.dof_anc_mask[lane];
     }
     for (int j = 0; j < nd - 1; j++) {
-        const T xj = __shfl_sync(0xffffffffu, wv, j, G);
+        const T xj = __shfl_sync(group_mask<G>(), wv, j, G);
         if (lane > j && ((anc >> j) & 1u)) wv -= E.H[row + j] * xj;
     }
     if (lane < nd) E.udot[lane] = wv;

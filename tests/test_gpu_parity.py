@@ -261,6 +261,35 @@ def test_sharding_invariance():
         e.close()
 
 
+@pytest.mark.parametrize("env_id,n_act", [("MuscleWalkingImitation2D-v0", 14), ("MuscleWalkingImitation3D-v0", 22)])
+def test_persistent_launch_walks_every_env(env_id, n_act):
+    """The step kernel is a persistent launch (one CTA per SM, warps walk the env items):
+    a batch large enough that every warp takes several items, with many auto-resets hitting
+    only one of the two envs of a warp, must equal the same envs stepped in small shards
+    that need one item per warp."""
+    import torch
+    from bioimitation_gym_b200 import backend
+    n, shard = 12000, 1500
+    full = backend.VecEnv(env_id, dict(num_envs=n, seed=9))
+    parts = [backend.VecEnv(env_id, dict(num_envs=shard, seed=9, env_offset=k)) for k in range(0, n, shard)]
+    of = full.reset().clone()
+    for k, pe in enumerate(parts):
+        assert torch.equal(of[k * shard:(k + 1) * shard], pe.reset())
+    g = torch.Generator(device="cpu").manual_seed(2)
+    n_done = 0
+    for _ in range(120):
+        a = torch.rand((n, n_act), generator=g)
+        o, r, d, _ = full.step(a)
+        n_done += int(d.sum())
+        for k, pe in enumerate(parts):
+            sl = slice(k * shard, (k + 1) * shard)
+            o1, r1, d1, _ = pe.step(a[sl])
+            assert torch.equal(o[sl], o1) and torch.equal(r[sl], r1) and torch.equal(d[sl], d1)
+    assert n_done > 20           # auto-reset was exercised
+    for e in [full] + parts:
+        e.close()
+
+
 def test_host_buffer_entry_point_matches_device_path():
     import torch
     env, _ = _mk("MuscleWalkingImitation2D-v0", 256, "float32")
