@@ -26,28 +26,45 @@ template <typename T, int CLS>
 struct EnvWork {
     typedef CoopCls<CLS> C;
     T q[C::ND], u[C::ND], act[C::NM], lm[C::NM];          // state of the current evaluation
-    T ax_s[C::NAX], ax_ds[C::NAX], ax_dds[C::NAX];
     T O[4];
-    T R[BIO_MAX_BODIES][9], r[BIO_MAX_BODIES][3], V[BIO_MAX_BODIES][6], A[BIO_MAX_BODIES][6];
-    T S[C::ND][6];
+    union {
+        struct {                                           // general (spatial) evaluation, coop_eval
+            T ax_s[C::NAX], ax_ds[C::NAX], ax_dds[C::NAX];
+            T R[BIO_MAX_BODIES][9], r[BIO_MAX_BODIES][3], V[BIO_MAX_BODIES][6], A[BIO_MAX_BODIES][6];
+            T S[C::ND][6];
+            // spatial inertia about O and body force per body: [0] mass, [1..3] m*c, [4..9] I (xx yy zz xy xz yz),
+            // [10..15] force (n; f); turned into composite / subtree sums in place
+            T BI[BIO_MAX_BODIES][16];
+            T IS[C::ND][6];                                // I^c_body(i) * S_i
+            T H[C::ND * (C::ND + 1) / 2], rhs[C::ND];
+            T Q[C::ND], limDd[C::ND];
+        } g;
+        struct {                                           // planar program, coop_eval_planar
+            T ax[C::NAX][4];                               // s, ds/dq, ds/dq * qdot, d2s/dq2 * qdot^2
+            T axr[C::NAX][2];                              // cos, sin of the signed rotation angle
+            T pose[BIO_MAX_BODIES][4];                     // cos, sin, x, y (about O, ground axes)
+            T V[BIO_MAX_BODIES][4], A[BIO_MAX_BODIES][4];  // (w, vx, vy), bias acceleration likewise
+            T S[C::ND][4];                                 // motion vector of every dof
+            T bI[BIO_MAX_BODIES][12];                      // spatial inertia about O [0..5] and force [6..8] per body
+            T Qf[C::ND], Ld[C::ND];                        // generalized force and h * limit damping per dof
+            T mv[P2_MAXMOV][8];                            // moving points: location [0..2], d/dq [4..6]
+            T mq[P2_MAXMOV];                               // their generalized force
+            T brx[P2_MAXBR][20];                           // chain -> root: composite inertia, force, Schur, rhs
+            T brk[P2_MAXBR][12];                           // chain block solve kept for the back substitution
+        } p;
+    } k;
     union {
         struct { T ptx[C::NP][3], ptf[C::NP][3], ptq[C::NP]; } pt;   // phases C..E
         struct { T col[BIO_MAX_SPHERES][C::ND][3]; } jac;             // phase G (implicit damping)
         struct { T obs_pos[COOP_MAXOBS][3], obs_vel[COOP_MAXOBS][3], comp[BIO_MAX_BODIES][6]; } out;  // full eval
+        struct { T w[P2_MAXSRC][4]; } src;                            // planar program: wrench sources
     } x;
     T sphx[BIO_MAX_SPHERES][3], sphF[BIO_MAX_SPHERES][3], sphD[BIO_MAX_SPHERES][2];
     T limf[BIO_MAX_LIMITS], limD[BIO_MAX_LIMITS];
-    T Q[C::ND];
-    // spatial inertia about O and body force per body: [0] mass, [1..3] m*c, [4..9] I (xx yy zz xy xz yz),
-    // [10..15] force (n; f); turned into composite / subtree sums in place
-    T BI[BIO_MAX_BODIES][16];
-    T IS[C::ND][6];                                        // I^c_body(i) * S_i
-    T H[C::ND * (C::ND + 1) / 2], rhs[C::ND];
     T udot[C::ND], adot[C::NM], lmdot[C::NM];
     T ffib[C::NM], fact[C::NM];
     T vn[C::NM];                                           // Newton warm start: last normalised fibre velocity
-    T limDd[C::ND];                                        // limit damping summed per dof
-    T ctrl[C::NM], curr[C::NM], lastact[C::NM];
+    T ctrl[C::NM];
     T com_pos[3], com_vel[3];
     T contact[2][6];
     T max_limit, pad_;
@@ -91,13 +108,14 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     typedef CoopCls<CLS> C;
     constexpr int G = C::G;
     const int nb = m.n_bodies, nd = m.n_dof, nm = m.n_muscles;
+    auto& K = E.k.g;
 
     // ---- phase A: joint functions of the coordinates ----
     for (int a = lane; a < m.n_axes; a += G) {
         const int d = m.axis_dof[a];
         T s, ds, dds;
         func_eval(m, m.axis_func[a], d >= 0 ? E.q[d] : T(0), s, ds, dds);
-        E.ax_s[a] = s; E.ax_ds[a] = ds; E.ax_dds[a] = dds;
+        K.ax_s[a] = s; K.ax_ds[a] = ds; K.ax_dds[a] = dds;
     }
     gsync<G>();
 
@@ -108,10 +126,10 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             const int b = m.level_body[lb], p = m.body_parent[b];
             T Rp[9], R[9], r[3], V[6], A[6];
             if (p >= 0) {
-                for (int c = 0; c < 9; c++) Rp[c] = E.R[p][c];
+                for (int c = 0; c < 9; c++) Rp[c] = K.R[p][c];
                 matvec3(Rp, m.body_joint_loc[b], r);
-                for (int c = 0; c < 3; c++) r[c] += E.r[p][c];
-                for (int c = 0; c < 6; c++) { V[c] = E.V[p][c]; A[c] = E.A[p][c]; }
+                for (int c = 0; c < 3; c++) r[c] += K.r[p][c];
+                for (int c = 0; c < 6; c++) { V[c] = K.V[p][c]; A[c] = K.A[p][c]; }
             } else {
                 Rp[0] = T(1); Rp[1] = T(0); Rp[2] = T(0); Rp[3] = T(0); Rp[4] = T(1); Rp[5] = T(0);
                 Rp[6] = T(0); Rp[7] = T(0); Rp[8] = T(1);
@@ -124,7 +142,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             T Sd[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
             for (int a = ab; a < ae; a++) {
                 const int d = m.axis_dof[a], code = m.axis_code[a];
-                const T s = E.ax_s[a], ds = E.ax_ds[a], dds = E.ax_dds[a];
+                const T s = K.ax_s[a], ds = K.ax_ds[a], dds = K.ax_dds[a];
                 T S[6], aw[3];
                 if (m.axis_kind[a] == BIO_AXIS_TRANS) {
                     if (code != 0) {
@@ -167,7 +185,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
                 }
                 if (d >= 0) {
                     if (d != dprev) {
-                        if (dprev >= 0) for (int c = 0; c < 6; c++) E.S[dprev][c] = Sd[c];
+                        if (dprev >= 0) for (int c = 0; c < 6; c++) K.S[dprev][c] = Sd[c];
                         for (int c = 0; c < 6; c++) Sd[c] = T(0);
                         dprev = d;
                     }
@@ -183,11 +201,11 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
                     for (int c = 0; c < 6; c++) V[c] += S[c] * sd;
                 }
             }
-            if (dprev >= 0) for (int c = 0; c < 6; c++) E.S[dprev][c] = Sd[c];
+            if (dprev >= 0) for (int c = 0; c < 6; c++) K.S[dprev][c] = Sd[c];
             if (root_open) { for (int c = 0; c < 3; c++) { E.O[c] = r[c]; r[c] = T(0); } }
-            for (int c = 0; c < 9; c++) E.R[b][c] = R[c];
-            for (int c = 0; c < 3; c++) E.r[b][c] = r[c];
-            for (int c = 0; c < 6; c++) { E.V[b][c] = V[c]; E.A[b][c] = A[c]; }
+            for (int c = 0; c < 9; c++) K.R[b][c] = R[c];
+            for (int c = 0; c < 3; c++) K.r[b][c] = r[c];
+            for (int c = 0; c < 6; c++) { K.V[b][c] = V[c]; K.A[b][c] = A[c]; }
         }
         gsync<G>();
     }
@@ -220,8 +238,8 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
                 for (int c = 0; c < 3; c++) loc[c] = m.pt_loc[p][c];
             }
             T x[3];
-            matvec3(E.R[b], loc, x);
-            for (int c = 0; c < 3; c++) { x[c] += E.r[b][c]; E.x.pt.ptx[p][c] = x[c]; }
+            matvec3(K.R[b], loc, x);
+            for (int c = 0; c < 3; c++) { x[c] += K.r[b][c]; E.x.pt.ptx[p][c] = x[c]; }
             if (prev >= 0) {
                 const T dx = x[0] - xp[0], dy = x[1] - xp[1], dz = x[2] - xp[2];
                 const T d2 = dx * dx + dy * dy + dz * dz;
@@ -277,7 +295,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         // generalized force of the muscle's moving point (at most one per muscle): f . R_b dloc/dq
         if (pmov >= 0) {
             T dw[3];
-            matvec3(E.R[m.pt_body[pmov]], mdloc, dw);
+            matvec3(K.R[m.pt_body[pmov]], mdloc, dw);
             E.x.pt.ptq[pmov] = dot3(E.x.pt.ptf[pmov], dw);
         }
     }
@@ -285,16 +303,16 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     if (lane < m.n_spheres) {
         const int s = lane, b = m.sph_body[s];
         T xc[3];
-        matvec3(E.R[b], m.sph_loc[s], xc);
-        for (int c = 0; c < 3; c++) xc[c] += E.r[b][c];
+        matvec3(K.R[b], m.sph_loc[s], xc);
+        for (int c = 0; c < 3; c++) xc[c] += K.r[b][c];
         const T rad = m.sph_radius[s];
         const T depth = rad - (xc[1] + E.O[1]);
         T F[3] = {T(0), T(0), T(0)}, D0 = T(0), D1 = T(0);
         T p[3] = {xc[0], T(-0.5) * depth - E.O[1], xc[2]};
         if (depth > T(0)) {
             T v[3];
-            cross3(E.V[b], p, v);
-            for (int c = 0; c < 3; c++) v[c] += E.V[b][3 + c];
+            cross3(K.V[b], p, v);
+            for (int c = 0; c < 3; c++) v[c] += K.V[b][3 + c];
             const T vn = -v[1];
             const T kk = m.sph_k[s];
             const T fH = T(4.0 / 3.0) * kk * depth * Num<T>::sqrt(rad * kk * depth);
@@ -346,15 +364,15 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         if (ext_pt >= 0 && m.obs_body[ext_pt] == b) {
             T x[3], n[3];
             const T fx[3] = {ext_fx, T(0), T(0)};
-            matvec3(E.R[b], m.obs_loc[ext_pt], x);
-            for (int c = 0; c < 3; c++) x[c] += E.r[b][c];
+            matvec3(K.R[b], m.obs_loc[ext_pt], x);
+            for (int c = 0; c < 3; c++) x[c] += K.r[b][c];
             cross3(x, fx, n);
             for (int c = 0; c < 3; c++) { Wn[c] += n[c]; Wf[c] += fx[c]; }
         }
         T cpos[3];
-        matvec3(E.R[b], m.body_com[b], cpos);
-        for (int c = 0; c < 3; c++) cpos[c] += E.r[b][c];
-        const T* R = E.R[b];
+        matvec3(K.R[b], m.body_com[b], cpos);
+        for (int c = 0; c < 3; c++) cpos[c] += K.r[b][c];
+        const T* R = K.R[b];
         const T* i6 = m.body_inertia[b];
         T t[9];
         for (int r_ = 0; r_ < 3; r_++) {
@@ -372,7 +390,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         I6[5] = t[3] * R[6] + t[4] * R[7] + t[5] * R[8] - mb * cpos[1] * cpos[2];
         const T hh[3] = {mb * cpos[0], mb * cpos[1], mb * cpos[2]};
         T V[6], A[6];
-        for (int c = 0; c < 6; c++) { V[c] = E.V[b][c]; A[c] = E.A[b][c]; }
+        for (int c = 0; c < 6; c++) { V[c] = K.V[b][c]; A[c] = K.A[b][c]; }
         T IV[6], IA[6], t1[3], t2[3];
         IV[0] = I6[0] * V[0] + I6[3] * V[1] + I6[4] * V[2];
         IV[1] = I6[3] * V[0] + I6[1] * V[1] + I6[5] * V[2];
@@ -386,21 +404,21 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         for (int j = 0; j < 3; j++) { IA[j] += t1[j]; IA[3 + j] = mb * A[3 + j] - t2[j]; }
         T c1[3], c2[3], c3[3];
         cross3(V, IV, c1); cross3(V + 3, IV + 3, c2); cross3(V, IV + 3, c3);
-        E.BI[b][0] = mb;
+        K.BI[b][0] = mb;
         for (int j = 0; j < 3; j++) {
-            E.BI[b][1 + j] = hh[j];
-            E.BI[b][10 + j] = IA[j] + c1[j] + c2[j] - Wn[j];
-            E.BI[b][13 + j] = IA[3 + j] + c3[j] - Wf[j];
+            K.BI[b][1 + j] = hh[j];
+            K.BI[b][10 + j] = IA[j] + c1[j] + c2[j] - Wn[j];
+            K.BI[b][13 + j] = IA[3 + j] + c3[j] - Wf[j];
         }
-        for (int j = 0; j < 6; j++) E.BI[b][4 + j] = I6[j];
+        for (int j = 0; j < 6; j++) K.BI[b][4 + j] = I6[j];
     } else if (lane - nb < nd) {
         const int d = lane - nb;
         T qf = T(0), ld = T(0);
         for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == d) { qf += E.limf[l]; ld += E.limD[l]; }
-        E.limDd[d] = ld;
+        K.limDd[d] = ld;
         for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += E.x.pt.ptq[p]; }
         if (m.is_torque) for (int a = 0; a < m.n_act; a++) if (m.act_dof[a] == d) qf += E.ctrl[a];
-        E.Q[d] = qf;
+        K.Q[d] = qf;
     }
     gsync<G>();
 
@@ -409,17 +427,17 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         if (lane < nb) {
             const int b = lane;
             T cpos[3], vc[3];
-            matvec3(E.R[b], m.body_com[b], cpos);
-            for (int c = 0; c < 3; c++) cpos[c] += E.r[b][c];
-            cross3(E.V[b], cpos, vc);
-            for (int c = 0; c < 3; c++) { E.x.out.comp[b][c] = m.body_mass[b] * cpos[c]; E.x.out.comp[b][3 + c] = m.body_mass[b] * (vc[c] + E.V[b][3 + c]); }
+            matvec3(K.R[b], m.body_com[b], cpos);
+            for (int c = 0; c < 3; c++) cpos[c] += K.r[b][c];
+            cross3(K.V[b], cpos, vc);
+            for (int c = 0; c < 3; c++) { E.x.out.comp[b][c] = m.body_mass[b] * cpos[c]; E.x.out.comp[b][3 + c] = m.body_mass[b] * (vc[c] + K.V[b][3 + c]); }
         } else if (lane - nb < m.n_obspts) {
             const int p = lane - nb, b = m.obs_body[p];
             T x[3], v[3];
-            matvec3(E.R[b], m.obs_loc[p], x);
-            for (int c = 0; c < 3; c++) x[c] += E.r[b][c];
-            cross3(E.V[b], x, v);
-            for (int c = 0; c < 3; c++) { E.x.out.obs_pos[p][c] = x[c] + E.O[c]; E.x.out.obs_vel[p][c] = v[c] + E.V[b][3 + c]; }
+            matvec3(K.R[b], m.obs_loc[p], x);
+            for (int c = 0; c < 3; c++) x[c] += K.r[b][c];
+            cross3(K.V[b], x, v);
+            for (int c = 0; c < 3; c++) { E.x.out.obs_pos[p][c] = x[c] + E.O[c]; E.x.out.obs_vel[p][c] = v[c] + K.V[b][3 + c]; }
         }
         gsync<G>();
         if (lane < 3) {
@@ -451,9 +469,9 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         const int cnt = (m.level_begin[lev + 1] - m.level_begin[lev]) * 16;
         for (int tsk = lane; tsk < cnt; tsk += G) {
             const int b = m.level_body[m.level_begin[lev] + (tsk >> 4)], v = tsk & 15;
-            T acc = E.BI[b][v];
-            for (int k = m.child_begin[b]; k < m.child_begin[b + 1]; k++) acc += E.BI[m.child_list[k]][v];
-            E.BI[b][v] = acc;
+            T acc = K.BI[b][v];
+            for (int k = m.child_begin[b]; k < m.child_begin[b + 1]; k++) acc += K.BI[m.child_list[k]][v];
+            K.BI[b][v] = acc;
         }
         gsync<G>();
     }
@@ -461,17 +479,17 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     // ---- phase G: I^c S per dof, contact Jacobian columns, then one lane per coupled (i,j) entry ----
     if (lane < nd) {
         const int i = lane, b = m.dof_body[i];
-        const T* S = E.S[i];
-        const T* B = E.BI[b];
+        const T* S = K.S[i];
+        const T* B = K.BI[b];
         T IS[6], t1[3], t2[3];
         IS[0] = B[4] * S[0] + B[7] * S[1] + B[8] * S[2];
         IS[1] = B[7] * S[0] + B[5] * S[1] + B[9] * S[2];
         IS[2] = B[8] * S[0] + B[9] * S[1] + B[6] * S[2];
         cross3(B + 1, S + 3, t1); cross3(B + 1, S, t2);
-        for (int c = 0; c < 3; c++) { E.IS[i][c] = IS[c] + t1[c]; E.IS[i][3 + c] = B[0] * S[3 + c] - t2[c]; }
+        for (int c = 0; c < 3; c++) { K.IS[i][c] = IS[c] + t1[c]; K.IS[i][3 + c] = B[0] * S[3 + c] - t2[c]; }
         T bi = T(0);
         for (int c = 0; c < 6; c++) bi += S[c] * B[10 + c];
-        E.rhs[i] = E.Q[i] - bi;
+        K.rhs[i] = K.Q[i] - bi;
     }
     unsigned act_mask = 0u;      // active contacts of this env (same value on every lane)
     if (h_imp > T(0)) {
@@ -482,15 +500,15 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
                 const int s = m.jc_s[tsk], d = m.jc_d[tsk];
                 if (!((act_mask >> s) & 1u)) continue;
                 T cv[3];
-                cross3(E.S[d], E.sphx[s], cv);
-                for (int c = 0; c < 3; c++) E.x.jac.col[s][d][c] = cv[c] + E.S[d][3 + c];
+                cross3(K.S[d], E.sphx[s], cv);
+                for (int c = 0; c < 3; c++) E.x.jac.col[s][d][c] = cv[c] + K.S[d][3 + c];
             }
     }
     gsync<G>();
     for (int e = lane; e < m.n_entries; e += G) {
         const int i = m.ent_i[e], j = m.ent_j[e];
         T v = T(0);
-        for (int c = 0; c < 6; c++) v += E.S[j][c] * E.IS[i][c];
+        for (int c = 0; c < 6; c++) v += K.S[j][c] * K.IS[i][c];
         if (h_imp > T(0)) {
             unsigned mm = act_mask & m.ent_sph[e];               // active spheres whose chain holds i (and j)
             while (mm) {
@@ -500,9 +518,9 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
                 const T* cj = E.x.jac.col[s][j];
                 v += h_imp * (E.sphD[s][0] * (ci[0] * cj[0] + ci[2] * cj[2]) + E.sphD[s][1] * ci[1] * cj[1]);
             }
-            if (i == j) v += h_imp * E.limDd[i];
+            if (i == j) v += h_imp * K.limDd[i];
         }
-        E.H[i * (i + 1) / 2 + j] = v;
+        K.H[i * (i + 1) / 2 + j] = v;
     }
     gsync<G>();
 
@@ -515,7 +533,7 @@ template <typename T, int CLS>
 __device__ __forceinline__ void coop_eval_any(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane,
                                               const int newton_iters, const T ext_fx, const int ext_pt, const T h_imp,
                                               const bool full) {
-    if (m.planar) coop_eval_planar<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
+    if (m.prog.ok) coop_eval_planar<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
     else coop_eval<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
 }
 

@@ -1,31 +1,48 @@
-// bio_coop_planar.cuh -- joint-space solve shared by both evaluations, and the
-// evaluation specialised for PLANAR models (every rotation about z, every
-// translation in x/y: the reference's 2D gait models).
+// bio_coop_planar.cuh -- joint-space solve of the general evaluation, and the
+// evaluation of PLANAR models by the planar program (PlanarProg, bio_model.cuh).
 //
-// For such a model the dynamics are exactly those of the (w_z, v_x, v_y) part of
-// every spatial vector: moments about x / y and forces along z act on directions
-// that have no degree of freedom.  Poses are (cos, sin, x, y) with a constant z
-// per body (z still enters path lengths and the reported contact moments), spatial
-// vectors have 3 components, the spatial inertia 4.  Same formulas as coop_eval
-// otherwise; chosen at run time by DevModel::planar.
+// Planar model: every rotation about z, every translation in x/y (the reference's 2D
+// gait models).  The dynamics are those of the (w_z, v_x, v_y) part of every spatial
+// vector; the spatial inertia is a symmetric 3x3.  The tree is a root body with up to
+// three dofs that carries chains of single-dof bodies, so one lane per chain can keep a
+// whole chain in registers:
+//
+//   phase A  lane = elementary axis | moving-point function: joint functions, sin/cos
+//   phase B  lane = chain: kinematics root -> leaf (the root joint is recomputed by every
+//            chain lane instead of being exchanged)
+//   phase C  lane = muscle: path geometry as crossing segments (a segment between two
+//            points of one body does no work on the tree), tendon force, damped-equilibrium
+//            fibre velocity (Newton, warm-started), activation ODE; the muscle leaves one
+//            tension-scaled wrench per body it touches ("wrench source")
+//   phase D  lane = contact sphere | coordinate limit (spheres are wrench sources too)
+//   phase E  lane = body: gather of the wrench sources acting on the body, its spatial inertia and
+//            force (contact damping h J^T D J enters as an inertia of the foot) | lane = dof:
+//            generalized force of limits, moving points and actuators
+//   phase F  lane = chain: composite inertias, the chain's block of the joint-space matrix,
+//            its L D L^T, and the Schur complement on the root dofs
+//   phase G  lane = chain: root 3x3 solve (redundantly per lane), chain back substitution
+//
+// Same equations as the general evaluation (coop_eval) and the CPU oracle; phases talk through
+// shared memory only, so the host emulation in tests/emul can run them lane by lane.
 #pragma once
 
 namespace bio {
 
-// Sparse L^T D L of E.H along the tree with the forward substitution fused in,
-// then the back substitution by tree depth.  In: E.H (tree-coupled entries),
-// E.rhs.  Out: E.udot.
+// Sparse L^T D L of K.H along the tree with the forward substitution fused in,
+// then the back substitution by tree depth.  In: K.H (tree-coupled entries),
+// K.rhs.  Out: E.udot.  (general evaluation)
 template <typename T, int CLS>
 __device__ __forceinline__ void coop_solve(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
     constexpr int G = CoopCls<CLS>::G;
     constexpr int NIT = CLS == 0 ? 1 : 2;       // pairs per step <= G * NIT (checked at create)
+    auto& K = E.k.g;
     const int nd = m.n_dof;
     for (int st = 0; st < nd; st++) {
         const int pb = m.lt_step_begin[st], pe = m.lt_step_begin[st + 1];
         if (pb == pe) continue;                  // root-most dof: nothing to eliminate
         const int k = nd - 1 - st;
-        const T inv = T(1) / E.H[k * (k + 1) / 2 + k];
-        const T bk = E.rhs[k];                   // final z_k: every descendant step is done
+        const T inv = T(1) / K.H[k * (k + 1) / 2 + k];
+        const T bk = K.rhs[k];                   // final z_k: every descendant step is done
         T keep_a[NIT];
         int keep_ki[NIT];
 #pragma unroll
@@ -35,19 +52,19 @@ __device__ __forceinline__ void coop_solve(const DevModel<T>& m, EnvWork<T, CLS>
             if (p < pe) {
                 const uint32_t pk = m.lt_pack[p];
                 const int ij = pk & 255u, ki = (pk >> 8) & 255u, kj = (pk >> 16) & 255u;
-                const T a = E.H[ki] * inv;
-                E.H[ij] -= a * E.H[kj];
+                const T a = K.H[ki] * inv;
+                K.H[ij] -= a * K.H[kj];
                 if (pk & 0x80000000u) {          // diagonal pair (i,i): owns L_ki and the rhs update of i
                     keep_a[it] = a;
                     keep_ki[it] = ki;
-                    E.rhs[(pk >> 24) & 15u] -= a * bk;
+                    K.rhs[(pk >> 24) & 15u] -= a * bk;
                 }
             }
         }
         gsync<G>();
 #pragma unroll
         for (int it = 0; it < NIT; it++)
-            if (keep_ki[it] >= 0) E.H[keep_ki[it]] = keep_a[it];   // row k is not read by later steps
+            if (keep_ki[it] >= 0) K.H[keep_ki[it]] = keep_a[it];   // row k is not read by later steps
     }
     gsync<G>();
     // L x = D^-1 z by columns: lane i keeps w_i in a register; when x_j is final (all its
@@ -57,205 +74,257 @@ __device__ __forceinline__ void coop_solve(const DevModel<T>& m, EnvWork<T, CLS>
     uint32_t anc = 0u;
     if (lane < nd) {
         row = lane * (lane + 1) / 2;
-        wv = E.rhs[lane] / E.H[row + lane];
+        wv = K.rhs[lane] / K.H[row + lane];
         anc = m.dof_anc_mask[lane];
     }
     for (int j = 0; j < nd - 1; j++) {
         const T xj = __shfl_sync(group_mask<G>(), wv, j, G);
-        if (lane > j && ((anc >> j) & 1u)) wv -= E.H[row + j] * xj;
+        if (lane > j && ((anc >> j) & 1u)) wv -= K.H[row + j] * xj;
     }
     if (lane < nd) E.udot[lane] = wv;
     gsync<G>();
 }
 
-// planar helpers: R2 = [c -s; s c]
+// ---------------------------------------------------------------------------
+// planar program
+// ---------------------------------------------------------------------------
 template <typename T> BIO_DEV void rot2(T c, T s, T x, T y, T& ox, T& oy) { ox = c * x - s * y; oy = s * x + c * y; }
 
+// pose, velocity and bias acceleration of the frame a chain walk carries along
+template <typename T>
+struct P2Frame {
+    T c, s, rx, ry, w, vx, vy, aw, ax, ay;
+};
+
+// planar spatial inertia about O (symmetric 3x3 on (w, vx, vy)) and a spatial force
+template <typename T>
+struct P2Inertia {
+    T ww, wx, wy, xx, xy, yy, n, fx, fy;
+};
+
+// ---- phase A: joint functions of the coordinates (and the functions of moving path points) ----
 template <typename T, int CLS>
-__device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane,
-                                              const int newton_iters, const T ext_fx, const int ext_pt, const T h_imp,
-                                              const bool full) {
-    typedef CoopCls<CLS> C;
-    constexpr int G = C::G;
-    const int nb = m.n_bodies, nd = m.n_dof, nm = m.n_muscles;
-    // layout inside the general arrays:
-    //   R[b] = (c, s)   r[b] = (x, y, z_const)   V[b] = (w, vx, vy)   A[b] likewise   S[d] = (w, vx, vy)
-    //   BI[b] = (m, hx, hy, Izz, n, fx, fy)
-
-    // ---- phase A: joint functions ----
-    for (int a = lane; a < m.n_axes; a += G) {
-        const int d = m.axis_dof[a];
+BIO_DEV void p2_phase_a(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
+    constexpr int G = CoopCls<CLS>::G;
+    const PlanarProg<T>& pr = m.prog;
+    auto& K = E.k.p;
+    for (int t = lane; t < pr.n_atasks; t += G) {
+        const int d = pr.at_dof[t];
         T s, ds, dds;
-        func_eval(m, m.axis_func[a], d >= 0 ? E.q[d] : T(0), s, ds, dds);
-        E.ax_s[a] = s; E.ax_ds[a] = ds; E.ax_dds[a] = dds;
+        func_eval(m, pr.at_func[t], d >= 0 ? E.q[d] : T(0), s, ds, dds);
+        if (t < m.n_axes) {
+            const T qd = d >= 0 ? E.u[d] : T(0);
+            const int desc = m.axis_desc[t];
+            T sn = T(0), cs = T(1);
+            if (desc & 1) Num<T>::sincos((desc & 2) ? -s : s, &sn, &cs);
+            K.ax[t][0] = s; K.ax[t][1] = ds; K.ax[t][2] = ds * qd; K.ax[t][3] = dds * qd * qd;
+            K.axr[t][0] = cs; K.axr[t][1] = sn;
+        } else {
+            const int k = (t - m.n_axes) / 3, c = (t - m.n_axes) % 3;
+            K.mv[k][c] = s + pr.at_add[t];
+            K.mv[k][4 + c] = ds;
+        }
     }
-    gsync<G>();
+}
 
-    // ---- phase B: planar kinematics by tree level ----
-    for (int lev = 0; lev < m.n_levels; lev++) {
-        const int lb = m.level_begin[lev] + lane;
-        if (lb < m.level_begin[lev + 1]) {
-            const int b = m.level_body[lb], p = m.body_parent[b];
-            T cp, sp, rx, ry, w, vx, vy, aw_, ax_, ay_;
-            if (p >= 0) {
-                cp = E.R[p][0]; sp = E.R[p][1];
-                rot2(cp, sp, m.body_joint_loc[b][0], m.body_joint_loc[b][1], rx, ry);
-                rx += E.r[p][0]; ry += E.r[p][1];
-                w = E.V[p][0]; vx = E.V[p][1]; vy = E.V[p][2];
-                aw_ = E.A[p][0]; ax_ = E.A[p][1]; ay_ = E.A[p][2];
-            } else {
-                cp = T(1); sp = T(0);
-                rx = m.body_joint_loc[b][0]; ry = m.body_joint_loc[b][1];
-                w = vx = vy = T(0);
-                aw_ = T(0); ax_ = -m.gravity[0]; ay_ = -m.gravity[1];
-            }
-            T c = cp, s_ = sp;
-            const int ab = m.body_axis_begin[b], ae = ab + m.body_axis_count[b];
-            T Sw = T(0), Sx = T(0), Sy = T(0);
-            for (int a = ab; a < ae; a++) {
-                const int desc = m.axis_desc[a], d = (desc >> 3) & 31;
-                const T s = E.ax_s[a];
-                const T sg = (desc & 2) ? T(-1) : T(1);
-                T kw, kx, ky;                     // this axis' motion vector
-                if (!(desc & 1)) {                // translation along x or y of the parent frame
-                    kw = T(0);
-                    kx = sg * ((desc & 4) ? -sp : cp);
-                    ky = sg * ((desc & 4) ? cp : sp);
-                    rx += kx * s; ry += ky * s;
-                } else {                          // rotation about +-z through the current origin
-                    if (desc & 256) { E.O[0] = rx; E.O[1] = ry; E.O[2] = T(0); rx = ry = T(0); }
-                    kw = sg; kx = sg * ry; ky = -sg * rx;
-                    T sn, cs;
-                    Num<T>::sincos(sg * s, &sn, &cs);
-                    const T cn = c * cs - s_ * sn, snn = s_ * cs + c * sn;
-                    c = cn; s_ = snn;
-                }
-                if (d != 31) {
-                    const T ds = E.ax_ds[a], qd = E.u[d], sd = ds * qd, acc = E.ax_dds[a] * qd * qd;
-                    if (desc & 512) Sw = Sx = Sy = T(0);
-                    // V x S (planar): angular part 0, linear = w * (-S_vy, S_vx) + S_w * (V_vy, -V_vx)
-                    const T cx = -w * ky + kw * vy, cy = w * kx - kw * vx;
-                    Sw += ds * kw; Sx += ds * kx; Sy += ds * ky;
-                    aw_ += kw * acc;
-                    ax_ += kx * acc + cx * sd;
-                    ay_ += ky * acc + cy * sd;
-                    w += kw * sd; vx += kx * sd; vy += ky * sd;
-                    if (desc & 1024) { E.S[d][0] = Sw; E.S[d][1] = Sx; E.S[d][2] = Sy; }
-                }
-                if (desc & 2048) { E.O[0] = rx; E.O[1] = ry; E.O[2] = T(0); rx = ry = T(0); }
-            }
-            E.R[b][0] = c; E.R[b][1] = s_;
-            E.r[b][0] = rx; E.r[b][1] = ry; E.r[b][2] = m.body_z[b];
-            E.V[b][0] = w; E.V[b][1] = vx; E.V[b][2] = vy;
-            E.A[b][0] = aw_; E.A[b][1] = ax_; E.A[b][2] = ay_;
+// ---- phase B: lane l < n_branches walks the root joint and then its chain, one elementary axis
+// after the other (lane 0 publishes the root body; the other lanes only need its frame) ----
+template <typename T, int CLS>
+BIO_DEV void p2_phase_b(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
+    const PlanarProg<T>& pr = m.prog;
+    auto& K = E.k.p;
+    const int nbr = pr.n_branches > 0 ? pr.n_branches : 1;
+    if (lane >= nbr) return;
+    P2Frame<T> f;
+    f.c = T(1); f.s = T(0); f.rx = f.ry = T(0);
+    f.w = f.vx = f.vy = T(0);
+    f.aw = T(0); f.ax = -m.gravity[0]; f.ay = -m.gravity[1];
+    T cp = T(1), sp = T(0);                      // frame of the parent body: translations run along its axes
+    T Sw = T(0), Sx = T(0), Sy = T(0);
+    const int n = pr.ch_n[lane];
+    for (int i = 0; i < n; i++) {
+        const int code = pr.ch_code[lane][i];
+        const int a = code & 255, b = (code >> 8) & 15;
+        const bool own = lane == 0 || !(code & (1 << 14));
+        if (code & (1 << 12)) {                  // first axis of body b: move to its joint location
+            T jx, jy;
+            rot2(f.c, f.s, m.body_joint_loc[b][0], m.body_joint_loc[b][1], jx, jy);
+            f.rx += jx; f.ry += jy;
+            cp = f.c; sp = f.s;
         }
-        gsync<G>();
+        const int desc = m.axis_desc[a], d = (desc >> 3) & 31;
+        const T s = K.ax[a][0];
+        const T sg = (desc & 2) ? T(-1) : T(1);
+        T kw, kx, ky;                            // this axis' motion vector
+        if (!(desc & 1)) {                       // translation along x or y of the parent frame
+            kw = T(0);
+            kx = sg * ((desc & 4) ? -sp : cp);
+            ky = sg * ((desc & 4) ? cp : sp);
+            f.rx += kx * s; f.ry += ky * s;
+        } else {                                 // rotation about +-z through the current origin
+            if (desc & 256) {
+                if (own) { E.O[0] = f.rx; E.O[1] = f.ry; E.O[2] = T(0); }
+                f.rx = f.ry = T(0);
+            }
+            kw = sg; kx = sg * f.ry; ky = -sg * f.rx;
+            const T cs = K.axr[a][0], sn = K.axr[a][1];
+            const T cn = f.c * cs - f.s * sn, snn = f.s * cs + f.c * sn;
+            f.c = cn; f.s = snn;
+        }
+        if (d != 31) {
+            const T ds = K.ax[a][1], sd = K.ax[a][2], acc = K.ax[a][3];
+            if (desc & 512) Sw = Sx = Sy = T(0);
+            // V x S (planar): angular part 0, linear = w * (-S_vy, S_vx) + S_w * (V_vy, -V_vx)
+            const T cx = -f.w * ky + kw * f.vy, cy = f.w * kx - kw * f.vx;
+            Sw += ds * kw; Sx += ds * kx; Sy += ds * ky;
+            f.aw += kw * acc;
+            f.ax += kx * acc + cx * sd;
+            f.ay += ky * acc + cy * sd;
+            f.w += kw * sd; f.vx += kx * sd; f.vy += ky * sd;
+            if ((desc & 1024) && own) { K.S[d][0] = Sw; K.S[d][1] = Sx; K.S[d][2] = Sy; }
+        }
+        if (desc & 2048) {
+            if (own) { E.O[0] = f.rx; E.O[1] = f.ry; E.O[2] = T(0); }
+            f.rx = f.ry = T(0);
+        }
+        if ((code & (1 << 13)) && own) {         // last axis of body b: publish its frame
+            K.pose[b][0] = f.c; K.pose[b][1] = f.s; K.pose[b][2] = f.rx; K.pose[b][3] = f.ry;
+            K.V[b][0] = f.w; K.V[b][1] = f.vx; K.V[b][2] = f.vy;
+            K.A[b][0] = f.aw; K.A[b][1] = f.ax; K.A[b][2] = f.ay;
+        }
     }
+}
 
-    // ---- phase C: lane = muscle (path geometry is 3-D: points keep their constant z) ----
-    if (lane < nm) {
-        const int i = lane;
-        // one streaming pass over the path points: positions, segment unit vectors and the
-        // length; ptf[p] first holds the direction sum (e_out - e_in) and is scaled by the
-        // tension once it is known (inactive points keep zero position and force)
-        int pmov = -1, prev = -1;
-        T mdloc[3] = {T(0), T(0), T(0)};
-        T xp = T(0), yp = T(0), zp = T(0), ex = T(0), ey = T(0), ez = T(0), L = T(0);
-        const int pb = m.mus_pt_begin[i], pe = pb + m.mus_pt_count[i];
-        for (int p = pb; p < pe; p++) {
-            const int kind = m.pt_kind[p], d = m.pt_dof[p], b = m.pt_body[p];
-            T loc[3];
-            if (kind == BIO_PT_CONDITIONAL) {
-                const T v = E.q[d];
-                if (!(v >= m.pt_range[p][0] - T(1e-5) && v <= m.pt_range[p][1] + T(1e-5))) {
-                    for (int c = 0; c < 3; c++) { E.x.pt.ptf[p][c] = T(0); E.x.pt.ptx[p][c] = T(0); }
-                    continue;
+// ---- phase C: lane = muscle ----
+template <typename T, int CLS>
+BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane, const int newton_iters,
+                        const bool full) {
+    const PlanarProg<T>& pr = m.prog;
+    auto& K = E.k.p;
+    if (lane >= m.n_muscles) return;
+    const int i = lane;
+    // streaming pass over the active path points: length, and the wrench of every segment that
+    // crosses from one body to another (+w on the body of its first point, -w on the other)
+    T W[P2_MAXSLOT][3];
+#pragma unroll
+    for (int sl = 0; sl < P2_MAXSLOT; sl++) W[sl][0] = W[sl][1] = W[sl][2] = T(0);
+    T xp = T(0), yp = T(0), zp = T(0), ex = T(0), ey = T(0), ez = T(0), L = T(0);
+    T gx = T(0), gy = T(0), gz = T(0);           // direction sum (e_out - e_in) at the moving point
+    T mdx = T(0), mdy = T(0), mdz = T(0);        // its d(location)/dq in ground axes
+    int prev_slot = -1, mov = -1;
+    bool prev_moving = false;
+    const int pb = m.mus_pt_begin[i], pe = pb + m.mus_pt_count[i];
+    for (int p = pb; p < pe; p++) {
+        const int info = pr.pt_info[p];
+        const int b = info & 15, kind = (info >> 4) & 3, slot = (info >> 11) & 3;
+        if (kind == BIO_PT_CONDITIONAL) {
+            const T v = E.q[(info >> 6) & 31];
+            if (!(v >= m.pt_range[p][0] - T(1e-5) && v <= m.pt_range[p][1] + T(1e-5))) continue;
+        }
+        const T c = K.pose[b][0], s = K.pose[b][1];
+        T lx, ly, lz;
+        if (kind == BIO_PT_MOVING) {
+            mov = (info >> 13) & 7;
+            lx = K.mv[mov][0]; ly = K.mv[mov][1]; lz = K.mv[mov][2];
+            rot2(c, s, K.mv[mov][4], K.mv[mov][5], mdx, mdy);
+            mdz = K.mv[mov][6];
+        } else {
+            lx = pr.pt_xyz[p][0]; ly = pr.pt_xyz[p][1]; lz = pr.pt_xyz[p][2];
+        }
+        T x, y;
+        rot2(c, s, lx, ly, x, y);
+        x += K.pose[b][2]; y += K.pose[b][3];
+        const T z = lz;
+        if (prev_slot >= 0) {
+            const T dx = x - xp, dy = y - yp, dz = z - zp;
+            const T d2 = dx * dx + dy * dy + dz * dz;
+            const T il = Num<T>::rsqrt(d2);
+            L += d2 * il;
+            ex = dx * il; ey = dy * il; ez = dz * il;
+            if (prev_moving) { gx += ex; gy += ey; gz += ez; }
+            if (slot != prev_slot) {
+                const T wn = xp * ey - yp * ex;
+#pragma unroll
+                for (int sl = 0; sl < P2_MAXSLOT; sl++) {
+                    const T sgn = sl == prev_slot ? T(1) : (sl == slot ? T(-1) : T(0));
+                    W[sl][0] += sgn * wn; W[sl][1] += sgn * ex; W[sl][2] += sgn * ey;
                 }
             }
-            if (kind == BIO_PT_MOVING) {
-                T d2;
-                for (int c = 0; c < 3; c++) func_eval(m, m.pt_func[p][c], E.q[d], loc[c], mdloc[c], d2);
-                pmov = p;
-            } else {
-                for (int c = 0; c < 3; c++) loc[c] = m.pt_loc[p][c];
-            }
-            T x, y;
-            rot2(E.R[b][0], E.R[b][1], loc[0], loc[1], x, y);
-            x += E.r[b][0]; y += E.r[b][1];
-            const T z = loc[2] + E.r[b][2];
-            E.x.pt.ptx[p][0] = x; E.x.pt.ptx[p][1] = y; E.x.pt.ptx[p][2] = z;
-            if (prev >= 0) {
-                const T dx = x - xp, dy = y - yp, dz = z - zp;
-                const T d2 = dx * dx + dy * dy + dz * dz;
-                const T il = Num<T>::rsqrt(d2);
-                L += d2 * il;
-                const T nx = dx * il, ny = dy * il, nz = dz * il;
-                E.x.pt.ptf[prev][0] = nx - ex; E.x.pt.ptf[prev][1] = ny - ey; E.x.pt.ptf[prev][2] = nz - ez;
-                ex = nx; ey = ny; ez = nz;
-            }
-            xp = x; yp = y; zp = z; prev = p;
         }
-        if (prev >= 0) { E.x.pt.ptf[prev][0] = -ex; E.x.pt.ptf[prev][1] = -ey; E.x.pt.ptf[prev][2] = -ez; }
-        const T fiso = m.mus_fiso[i], lopt = m.mus_lopt[i], h = m.mus_height[i], beta = m.mus_beta[i];
-        const T amin = m.mus_amin[i], lmin = m.mus_lm_min[i];
-        const T lmi = E.lm[i];
-        const T lmc = lmi < lmin ? lmin : lmi;
-        const T lat = Num<T>::sqrt(lmc * lmc - h * h);
-        const T cosa = lat / lmc;
-        T fal, fpe, ft, fv, dfv, dtmp;
-        curve_eval(m, 0, lmc / lopt, fal, dtmp);
-        curve_eval(m, 2, lmc / lopt, fpe, dtmp);
-        curve_eval(m, 3, (L - lat) / m.mus_lts[i], ft, dtmp);
-        const T ac = clampv(E.act[i], amin, T(1));
-        const T afal = ac * fal;
-        // Warm start from the root of the previous evaluation of this step.  The residual is
-        // monotone and sigmoid-shaped (convex for vn<0, concave for vn>0), so Newton is only
-        // guaranteed from points between 0 and the root: anything else restarts from 0.
-        T vn = E.vn[i];
-        const T e0 = (afal + fpe) * cosa - ft;    // residual at vn = 0 (f_V(0) = 1)
-        for (int it = 0; it < newton_iters; it++) {
-            curve_eval(m, 1, vn, fv, dfv);
-            const T err = (afal * fv + fpe + beta * vn) * cosa - ft;
-            if (it == 0 && vn != T(0) && !(vn * e0 < T(0) && err * e0 > T(0))) { vn = T(0); continue; }
-            const T derr = (afal * dfv + beta) * cosa;
-            const T delta = -err / derr;
-            vn += delta;
-            if (Num<T>::abs(delta) < Num<T>::newton_tol()) break;
-        }
-        E.vn[i] = vn;
-        if (lmi <= lmin && vn < T(0)) vn = T(0);
-        E.lmdot[i] = vn * m.mus_vmax[i] * lopt;
-        const T ec = clampv(E.ctrl[i], amin, T(1));
-        const T tau = ec > ac ? m.mus_tact[i] * (T(0.5) + T(1.5) * ac) : m.mus_tdeact[i] / (T(0.5) + T(1.5) * ac);
-        E.adot[i] = (ec - ac) / tau;
-        const T tension = fiso * ft;
-        if (full) {
-            curve_eval(m, 1, vn, fv, dfv);
-            E.fact[i] = fiso * afal * fv;
-            E.ffib[i] = fiso * (afal * fv + fpe + beta * vn);
-        }
-        for (int p = pb; p < pe; p++)
-            for (int c = 0; c < 3; c++) E.x.pt.ptf[p][c] *= tension;
-        if (pmov >= 0) {
-            const int b = m.pt_body[pmov];
-            T dwx, dwy;
-            rot2(E.R[b][0], E.R[b][1], mdloc[0], mdloc[1], dwx, dwy);
-            E.x.pt.ptq[pmov] = E.x.pt.ptf[pmov][0] * dwx + E.x.pt.ptf[pmov][1] * dwy + E.x.pt.ptf[pmov][2] * mdloc[2];
-        }
+        prev_moving = kind == BIO_PT_MOVING;
+        if (prev_moving) { gx = -ex; gy = -ey; gz = -ez; }   // -e_in (zero when it is the first point)
+        xp = x; yp = y; zp = z; prev_slot = slot;
     }
-    // ---- phase D: lane = contact sphere | coordinate limit ----
+    const T fiso = m.mus_fiso[i], lopt = m.mus_lopt[i], h = m.mus_height[i], beta = m.mus_beta[i];
+    const T amin = m.mus_amin[i], lmin = m.mus_lm_min[i];
+    const T lmi = E.lm[i];
+    const T lmc = lmi < lmin ? lmin : lmi;
+    const T lat = Num<T>::sqrt(lmc * lmc - h * h);
+    const T cosa = lat / lmc;
+    T fal, fpe, ft, fv, dfv, dtmp;
+    curve_eval(m, 3, (L - lat) / m.mus_lts[i], ft, dtmp);
+    const T tension = fiso * ft;
+    {   // wrench sources of this muscle: one per body it touches
+        const int s0 = pr.mus_src0[i], ns = pr.mus_src0[i + 1] - s0;
+#pragma unroll
+        for (int sl = 0; sl < P2_MAXSLOT; sl++) {
+            if (sl < ns) {
+                E.x.src.w[s0 + sl][0] = tension * W[sl][0];
+                E.x.src.w[s0 + sl][1] = tension * W[sl][1];
+                E.x.src.w[s0 + sl][2] = tension * W[sl][2];
+            }
+        }
+        // generalized force of the moving point: f . R_b dloc/dq
+        if (mov >= 0) K.mq[mov] = tension * (gx * mdx + gy * mdy + gz * mdz);
+    }
+    curve_eval(m, 0, lmc / lopt, fal, dtmp);
+    curve_eval(m, 2, lmc / lopt, fpe, dtmp);
+    const T ac = clampv(E.act[i], amin, T(1));
+    const T afal = ac * fal;
+    // Warm start from the root of the previous evaluation of this step.  The residual is
+    // monotone and sigmoid-shaped (convex for vn<0, concave for vn>0), so Newton is only
+    // guaranteed from points between 0 and the root: anything else restarts from 0.
+    T vn = E.vn[i];
+    const T e0 = (afal + fpe) * cosa - ft;    // residual at vn = 0 (f_V(0) = 1)
+    for (int it = 0; it < newton_iters; it++) {
+        curve_eval(m, 1, vn, fv, dfv);
+        const T err = (afal * fv + fpe + beta * vn) * cosa - ft;
+        if (it == 0 && vn != T(0) && !(vn * e0 < T(0) && err * e0 > T(0))) { vn = T(0); continue; }
+        const T derr = (afal * dfv + beta) * cosa;
+        const T delta = -err / derr;
+        vn += delta;
+        if (Num<T>::abs(delta) < Num<T>::newton_tol()) break;
+    }
+    E.vn[i] = vn;
+    if (lmi <= lmin && vn < T(0)) vn = T(0);
+    E.lmdot[i] = vn * m.mus_vmax[i] * lopt;
+    const T ec = clampv(E.ctrl[i], amin, T(1));
+    const T tau = ec > ac ? m.mus_tact[i] * (T(0.5) + T(1.5) * ac) : m.mus_tdeact[i] / (T(0.5) + T(1.5) * ac);
+    E.adot[i] = (ec - ac) / tau;
+    if (full) {
+        curve_eval(m, 1, vn, fv, dfv);
+        E.fact[i] = fiso * afal * fv;
+        E.ffib[i] = fiso * (afal * fv + fpe + beta * vn);
+    }
+}
+
+// ---- phase D: lane = contact sphere | coordinate limit ----
+template <typename T, int CLS>
+BIO_DEV void p2_phase_d(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
+    const PlanarProg<T>& pr = m.prog;
+    auto& K = E.k.p;
     if (lane < m.n_spheres) {
         const int s = lane, b = m.sph_body[s];
         T xc, yc;
-        rot2(E.R[b][0], E.R[b][1], m.sph_loc[s][0], m.sph_loc[s][1], xc, yc);
-        xc += E.r[b][0]; yc += E.r[b][1];
-        const T zc = m.sph_loc[s][2] + E.r[b][2];
+        rot2(K.pose[b][0], K.pose[b][1], m.sph_loc[s][0], m.sph_loc[s][1], xc, yc);
+        xc += K.pose[b][2]; yc += K.pose[b][3];
+        const T zc = m.sph_loc[s][2] + m.body_z[b];
         const T rad = m.sph_radius[s];
         const T depth = rad - (yc + E.O[1]);
         T Fx = T(0), Fy = T(0), D0 = T(0), D1 = T(0);
         const T py = T(-0.5) * depth - E.O[1];
         if (depth > T(0)) {
-            const T vx = E.V[b][1] - E.V[b][0] * py, vy = E.V[b][2] + E.V[b][0] * xc;
+            const T vx = K.V[b][1] - K.V[b][0] * py, vy = K.V[b][2] + K.V[b][0] * xc;
             const T vn = -vy;
             const T kk = m.sph_k[s];
             const T fH = T(4.0 / 3.0) * kk * depth * Num<T>::sqrt(rad * kk * depth);
@@ -276,6 +345,9 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
         E.sphx[s][0] = xc; E.sphx[s][1] = py; E.sphx[s][2] = zc;
         E.sphF[s][0] = Fx; E.sphF[s][1] = Fy; E.sphF[s][2] = T(0);
         E.sphD[s][0] = D0; E.sphD[s][1] = D1;
+        E.x.src.w[pr.sph_src0 + s][0] = xc * Fy - py * Fx;
+        E.x.src.w[pr.sph_src0 + s][1] = Fx;
+        E.x.src.w[pr.sph_src0 + s][2] = Fy;
     } else if (lane - m.n_spheres < m.n_limits) {
         const int l = lane - m.n_spheres, d = m.lim_dof[l];
         const T w = m.lim_w[l], qq = E.q[d];
@@ -285,159 +357,303 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
                     m.lim_damp[l] * (sup + slo) * E.u[d];
         E.limD[l] = m.lim_damp[l] * (sup + slo);
     }
-    gsync<G>();
+}
 
-    // ---- phase E: lane = body (planar wrench, inertia, body force) | dof (generalized forces) ----
-    if (lane < nb) {
+// ---- phase E: lane b < n_bodies: gather of the wrench sources acting on body b, then its spatial
+// inertia about O and force (inertial - applied); the contact damping of its active spheres,
+// h J^T D J with J = [[-py, 1, 0], [px, 0, 1]], is part of the inertia.
+// lane n_bodies + d: generalized force on dof d from limits, moving path points and actuators ----
+template <typename T, int CLS>
+BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane, const T h_imp, const T ext_fx,
+                        const int ext_pt) {
+    const PlanarProg<T>& pr = m.prog;
+    auto& K = E.k.p;
+    if (lane < m.n_bodies) {
         const int b = lane;
         T Wn = T(0), Wx = T(0), Wy = T(0);
-        for (int k = m.body_pt_begin[b]; k < m.body_pt_begin[b] + m.body_pt_count[b]; k++) {
-            const int p = m.body_pt_list[k];
-            const T fx = E.x.pt.ptf[p][0], fy = E.x.pt.ptf[p][1];   // inactive points: zero force, zero position
-            Wn += E.x.pt.ptx[p][0] * fy - E.x.pt.ptx[p][1] * fx;
-            Wx += fx; Wy += fy;
+        for (int k = pr.inc_begin[b]; k < pr.inc_begin[b + 1]; k++) {
+            const int e = pr.inc_src[k];
+            Wn += E.x.src.w[e][0]; Wx += E.x.src.w[e][1]; Wy += E.x.src.w[e][2];
         }
-        for (int s = 0; s < m.n_spheres; s++) {
-            if (m.sph_body[s] != b || E.sphF[s][1] == T(0)) continue;
-            Wn += E.sphx[s][0] * E.sphF[s][1] - E.sphx[s][1] * E.sphF[s][0];
-            Wx += E.sphF[s][0]; Wy += E.sphF[s][1];
-        }
+        const T c = K.pose[b][0], s = K.pose[b][1];
+        T cx, cy;
+        rot2(c, s, m.body_com[b][0], m.body_com[b][1], cx, cy);
+        cx += K.pose[b][2]; cy += K.pose[b][3];
+        const T mb = m.body_mass[b];
+        const T hx = mb * cx, hy = mb * cy;
+        T Iww = m.body_inertia[b][2] + mb * (cx * cx + cy * cy), Iwx = -hy, Iwy = hx, Ixx = mb, Iyy = mb;
+        const T w = K.V[b][0], vx = K.V[b][1], vy = K.V[b][2];
+        const T aw = K.A[b][0], ax = K.A[b][1], ay = K.A[b][2];
+        const T px = mb * vx - hy * w, py = mb * vy + hx * w;
+        const T IAn = Iww * aw + hx * ay - hy * ax, IAx = mb * ax - hy * aw, IAy = mb * ay + hx * aw;
         if (ext_pt >= 0 && m.obs_body[ext_pt] == b) {
             T x, y;
-            rot2(E.R[b][0], E.R[b][1], m.obs_loc[ext_pt][0], m.obs_loc[ext_pt][1], x, y);
-            y += E.r[b][1];
+            rot2(c, s, m.obs_loc[ext_pt][0], m.obs_loc[ext_pt][1], x, y);
+            y += K.pose[b][3];
             Wn += -y * ext_fx;
             Wx += ext_fx;
         }
-        T cx, cy;
-        rot2(E.R[b][0], E.R[b][1], m.body_com[b][0], m.body_com[b][1], cx, cy);
-        cx += E.r[b][0]; cy += E.r[b][1];
-        const T mb = m.body_mass[b];
-        const T Izz = m.body_inertia[b][2] + mb * (cx * cx + cy * cy);
-        const T hx = mb * cx, hy = mb * cy;
-        const T w = E.V[b][0], vx = E.V[b][1], vy = E.V[b][2];
-        const T aw_ = E.A[b][0], ax_ = E.A[b][1], ay_ = E.A[b][2];
-        // momentum (L; p) and I*A
-        const T Lz = Izz * w + hx * vy - hy * vx, px = mb * vx - hy * w, py = mb * vy + hx * w;
-        const T IAn = Izz * aw_ + hx * ay_ - hy * ax_, IAx = mb * ax_ - hy * aw_, IAy = mb * ay_ + hx * aw_;
-        (void)Lz;
-        E.BI[b][0] = mb; E.BI[b][1] = hx; E.BI[b][2] = hy; E.BI[b][3] = Izz;
-        E.BI[b][4] = IAn + (vx * py - vy * px) - Wn;      // V x* (I V): n = v x p, f = w z x p
-        E.BI[b][5] = IAx - w * py - Wx;
-        E.BI[b][6] = IAy + w * px - Wy;
-    } else if (lane - nb < nd) {
-        const int d = lane - nb;
-        T qf = T(0), ld = T(0);
-        for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == d) { qf += E.limf[l]; ld += E.limD[l]; }
-        E.limDd[d] = ld;
-        for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += E.x.pt.ptq[p]; }
-        if (m.is_torque) for (int a = 0; a < m.n_act; a++) if (m.act_dof[a] == d) qf += E.ctrl[a];
-        E.Q[d] = qf;
-    }
-    gsync<G>();
-
-    // ---- full evaluation read-outs ----
-    if (full) {
-        if (lane < nb) {
-            const int b = lane;
-            T cx, cy;
-            rot2(E.R[b][0], E.R[b][1], m.body_com[b][0], m.body_com[b][1], cx, cy);
-            cx += E.r[b][0]; cy += E.r[b][1];
-            const T mb = m.body_mass[b];
-            E.x.out.comp[b][0] = mb * cx; E.x.out.comp[b][1] = mb * cy; E.x.out.comp[b][2] = mb * (m.body_com[b][2] + E.r[b][2]);
-            E.x.out.comp[b][3] = mb * (E.V[b][1] - E.V[b][0] * cy);
-            E.x.out.comp[b][4] = mb * (E.V[b][2] + E.V[b][0] * cx);
-            E.x.out.comp[b][5] = T(0);
-        } else if (lane - nb < m.n_obspts) {
-            const int p = lane - nb, b = m.obs_body[p];
-            T x, y;
-            rot2(E.R[b][0], E.R[b][1], m.obs_loc[p][0], m.obs_loc[p][1], x, y);
-            x += E.r[b][0]; y += E.r[b][1];
-            E.x.out.obs_pos[p][0] = x + E.O[0]; E.x.out.obs_pos[p][1] = y + E.O[1];
-            E.x.out.obs_pos[p][2] = m.obs_loc[p][2] + E.r[b][2];
-            E.x.out.obs_vel[p][0] = E.V[b][1] - E.V[b][0] * y;
-            E.x.out.obs_vel[p][1] = E.V[b][2] + E.V[b][0] * x;
-            E.x.out.obs_vel[p][2] = T(0);
-        }
-        gsync<G>();
-        if (lane < 3) {
-            T ms = T(0), ps = T(0);
-            for (int b = 0; b < nb; b++) { ms += E.x.out.comp[b][lane]; ps += E.x.out.comp[b][3 + lane]; }
-            const T im = T(1) / m.total_mass;
-            E.com_pos[lane] = ms * im + E.O[lane];
-            E.com_vel[lane] = ps * im;
-        } else if (lane < 5) {
-            const int g = lane - 3;
-            T w[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-            for (int s = 0; s < m.n_spheres; s++) {
-                if (m.sph_group[s] != g) continue;
-                const T pa[3] = {E.sphx[s][0] + E.O[0], E.sphx[s][1] + E.O[1], E.sphx[s][2]};
-                T n[3];
-                cross3(pa, E.sphF[s], n);
-                for (int c = 0; c < 3; c++) { w[c] += E.sphF[s][c]; w[3 + c] += n[c]; }
-            }
-            for (int c = 0; c < 6; c++) E.contact[g][c] = w[c];
-        } else if (lane == 5) {
-            T mx = T(0);
-            for (int l = 0; l < m.n_limits; l++) { const T a = Num<T>::abs(E.limf[l]); mx = a > mx ? a : mx; }
-            E.max_limit = mx;
-        }
-    }
-
-    // ---- phase F: composites; task = (body of the level, one of 7 values) ----
-    for (int lev = m.n_levels - 2; lev >= 0; lev--) {
-        const int cnt = (m.level_begin[lev + 1] - m.level_begin[lev]) * 8;
-        for (int tsk = lane; tsk < cnt; tsk += G) {
-            const int b = m.level_body[m.level_begin[lev] + (tsk >> 3)], v = tsk & 7;
-            if (v == 7) continue;
-            T acc = E.BI[b][v];
-            for (int k = m.child_begin[b]; k < m.child_begin[b + 1]; k++) acc += E.BI[m.child_list[k]][v];
-            E.BI[b][v] = acc;
-        }
-        gsync<G>();
-    }
-
-    // ---- phase G: I^c S per dof, contact Jacobian columns, entries ----
-    if (lane < nd) {
-        const int i = lane;
-        const T* B = E.BI[m.dof_body[i]];
-        const T sw = E.S[i][0], sx = E.S[i][1], sy = E.S[i][2];
-        E.IS[i][0] = B[3] * sw + B[1] * sy - B[2] * sx;
-        E.IS[i][1] = B[0] * sx - B[2] * sw;
-        E.IS[i][2] = B[0] * sy + B[1] * sw;
-        E.rhs[i] = E.Q[i] - (sw * B[4] + sx * B[5] + sy * B[6]);
-    }
-    unsigned act_mask = 0u;
-    if (h_imp > T(0)) {
-        for (int s = 0; s < m.n_spheres; s++) if (E.sphD[s][1] > T(0)) act_mask |= 1u << s;
-        if (act_mask)
-            for (int tsk = lane; tsk < m.jc_n; tsk += G) {      // (sphere, dof on its chain)
-                const int s = m.jc_s[tsk], d = m.jc_d[tsk];
-                if (!((act_mask >> s) & 1u)) continue;
-                E.x.jac.col[s][d][0] = E.S[d][1] - E.S[d][0] * E.sphx[s][1];
-                E.x.jac.col[s][d][1] = E.S[d][2] + E.S[d][0] * E.sphx[s][0];
-            }
-    }
-    gsync<G>();
-    for (int e = lane; e < m.n_entries; e += G) {
-        const int i = m.ent_i[e], j = m.ent_j[e];
-        T v = E.S[j][0] * E.IS[i][0] + E.S[j][1] * E.IS[i][1] + E.S[j][2] * E.IS[i][2];
+        T* o = K.bI[b];
+        o[6] = IAn + (vx * py - vy * px) - Wn;   // V x* (I V): n = v x p, f = w z x p
+        o[7] = IAx - w * py - Wx;
+        o[8] = IAy + w * px - Wy;
         if (h_imp > T(0)) {
-            unsigned mm = act_mask & m.ent_sph[e];               // active spheres whose chain holds i (and j)
-            while (mm) {
-                const int s = __ffs(mm) - 1;
-                mm &= mm - 1u;
-                v += h_imp * (E.sphD[s][0] * E.x.jac.col[s][i][0] * E.x.jac.col[s][j][0] +
-                              E.sphD[s][1] * E.x.jac.col[s][i][1] * E.x.jac.col[s][j][1]);
+            int mask = pr.body_sph_mask[b];
+            for (int sp = 0; mask; sp++, mask >>= 1) {
+                if (!(mask & 1) || !(E.sphD[sp][1] > T(0))) continue;
+                const T sx = E.sphx[sp][0], sy = E.sphx[sp][1];
+                const T d0 = h_imp * E.sphD[sp][0], d1 = h_imp * E.sphD[sp][1];
+                Iww += d0 * sy * sy + d1 * sx * sx;
+                Iwx -= d0 * sy;
+                Iwy += d1 * sx;
+                Ixx += d0;
+                Iyy += d1;
             }
-            if (i == j) v += h_imp * E.limDd[i];
         }
-        E.H[i * (i + 1) / 2 + j] = v;
+        o[0] = Iww; o[1] = Iwx; o[2] = Iwy; o[3] = Ixx; o[4] = T(0); o[5] = Iyy;
+    } else if (lane - m.n_bodies < m.n_dof) {
+        const int d = lane - m.n_bodies;
+        T qf = T(0), ld = T(0);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int l = pr.dof_lim[d][j];
+            if (l >= 0) { qf += E.limf[l]; ld += E.limD[l]; }
+            const int k = pr.dof_mov[d][j];
+            if (k >= 0) qf += K.mq[k];
+        }
+        const int a = pr.dof_act[d];
+        if (a >= 0) qf += E.ctrl[a];
+        K.Qf[d] = qf;
+        K.Ld[d] = h_imp * ld;
+    }
+}
+
+// ---- phase F: lane l < n_branches: composite inertias of the chain, its block of the joint-space
+// matrix, L D L^T, Schur complement on the root dofs ----
+template <typename T, int CLS>
+BIO_DEV void p2_phase_f(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
+    const PlanarProg<T>& pr = m.prog;
+    auto& K = E.k.p;
+    if (lane >= pr.n_branches) return;
+    const int l = lane, nb = pr.br_nb[l];
+    T Ic[P2_MAXCB][9];
+#pragma unroll
+    for (int k = 0; k < P2_MAXCB; k++) {
+        const int b = k < nb ? pr.br_body[l][k] : -1;
+#pragma unroll
+        for (int e = 0; e < 9; e++) Ic[k][e] = b >= 0 ? K.bI[b][e] : T(0);
+    }
+#pragma unroll
+    for (int k = P2_MAXCB - 2; k >= 0; k--)      // composites: suffix sums along the chain
+#pragma unroll
+        for (int e = 0; e < 9; e++) Ic[k][e] += Ic[k + 1][e];
+    T Sr[3][3];                                  // motion vectors of the root dofs
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const bool has = r < pr.root_ndof;
+        const int d = has ? pr.root_dof[r] : 0;
+        Sr[r][0] = has ? K.S[d][0] : T(0); Sr[r][1] = has ? K.S[d][1] : T(0); Sr[r][2] = has ? K.S[d][2] : T(0);
+    }
+    // chain block A (lower triangle), coupling C to the root dofs, right-hand side b
+    T Sk[P2_MAXCB][3], A[P2_MAXCB][P2_MAXCB], C[P2_MAXCB][3], bb[P2_MAXCB];
+#pragma unroll
+    for (int k = 0; k < P2_MAXCB; k++) {
+        const int d = k < nb ? pr.br_dof[l][k] : -1;
+        const bool has = d >= 0;
+        const int dd = has ? d : 0;
+        Sk[k][0] = has ? K.S[dd][0] : T(0); Sk[k][1] = has ? K.S[dd][1] : T(0); Sk[k][2] = has ? K.S[dd][2] : T(0);
+        const T ISn = Ic[k][0] * Sk[k][0] + Ic[k][1] * Sk[k][1] + Ic[k][2] * Sk[k][2];
+        const T ISx = Ic[k][1] * Sk[k][0] + Ic[k][3] * Sk[k][1] + Ic[k][4] * Sk[k][2];
+        const T ISy = Ic[k][2] * Sk[k][0] + Ic[k][4] * Sk[k][1] + Ic[k][5] * Sk[k][2];
+#pragma unroll
+        for (int j = 0; j <= k; j++) A[k][j] = Sk[j][0] * ISn + Sk[j][1] * ISx + Sk[j][2] * ISy;
+#pragma unroll
+        for (int r = 0; r < 3; r++) C[k][r] = Sr[r][0] * ISn + Sr[r][1] * ISx + Sr[r][2] * ISy;
+        bb[k] = (has ? K.Qf[dd] : T(0)) - (Sk[k][0] * Ic[k][6] + Sk[k][1] * Ic[k][7] + Sk[k][2] * Ic[k][8]);
+        A[k][k] += has ? K.Ld[dd] : T(1);        // no dof: identity row, zero coupling and rhs
+    }
+    // L D L^T of the 3x3 block, then A^-1 [C | b]
+    const T i0 = T(1) / A[0][0];
+    const T l10 = A[1][0] * i0, l20 = A[2][0] * i0;
+    const T i1 = T(1) / (A[1][1] - l10 * A[1][0]);
+    const T t21 = A[2][1] - l20 * A[1][0];
+    const T l21 = t21 * i1;
+    const T i2 = T(1) / (A[2][2] - l20 * A[2][0] - l21 * t21);
+    T X[P2_MAXCB][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const T r0 = c < 3 ? C[0][c] : bb[0], r1 = c < 3 ? C[1][c] : bb[1], r2 = c < 3 ? C[2][c] : bb[2];
+        const T y1 = r1 - l10 * r0, y2 = r2 - l20 * r0 - l21 * y1;
+        const T x2 = y2 * i2;
+        const T x1 = y1 * i1 - l21 * x2;
+        const T x0 = r0 * i0 - l10 * x1 - l20 * x2;
+        X[0][c] = x0; X[1][c] = x1; X[2][c] = x2;
+    }
+    T* o = K.brx[l];
+#pragma unroll
+    for (int e = 0; e < 9; e++) o[e] = Ic[0][e];
+    {   // Schur complement C^T A^-1 C (lower triangle) and C^T A^-1 b
+        int e = 9;
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c <= r; c++) o[e++] = C[0][r] * X[0][c] + C[1][r] * X[1][c] + C[2][r] * X[2][c];
+#pragma unroll
+        for (int r = 0; r < 3; r++) o[15 + r] = C[0][r] * X[0][3] + C[1][r] * X[1][3] + C[2][r] * X[2][3];
+    }
+#pragma unroll
+    for (int k = 0; k < P2_MAXCB; k++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) K.brk[l][4 * k + c] = X[k][c];
+}
+
+// ---- phase G: root solve (every chain lane repeats it), chain back substitution ----
+template <typename T, int CLS>
+BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
+    const PlanarProg<T>& pr = m.prog;
+    auto& K = E.k.p;
+    const int nbr = pr.n_branches > 0 ? pr.n_branches : 1;
+    if (lane >= nbr) return;
+    T a[9];
+#pragma unroll
+    for (int e = 0; e < 9; e++) a[e] = K.bI[pr.root_body][e];
+    T sch[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, g[3] = {T(0), T(0), T(0)};
+    for (int l = 0; l < pr.n_branches; l++) {
+#pragma unroll
+        for (int e = 0; e < 9; e++) a[e] += K.brx[l][e];
+#pragma unroll
+        for (int e = 0; e < 6; e++) sch[e] += K.brx[l][9 + e];
+#pragma unroll
+        for (int e = 0; e < 3; e++) g[e] += K.brx[l][15 + e];
+    }
+    T Sr[3][3], IS[3][3], H[3][3], rhs[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const bool has = r < pr.root_ndof;
+        const int d = has ? pr.root_dof[r] : 0;
+        Sr[r][0] = has ? K.S[d][0] : T(0); Sr[r][1] = has ? K.S[d][1] : T(0); Sr[r][2] = has ? K.S[d][2] : T(0);
+        IS[r][0] = a[0] * Sr[r][0] + a[1] * Sr[r][1] + a[2] * Sr[r][2];
+        IS[r][1] = a[1] * Sr[r][0] + a[3] * Sr[r][1] + a[4] * Sr[r][2];
+        IS[r][2] = a[2] * Sr[r][0] + a[4] * Sr[r][1] + a[5] * Sr[r][2];
+    }
+    {
+        int e = 0;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const bool has = r < pr.root_ndof;
+            const int d = has ? pr.root_dof[r] : 0;
+#pragma unroll
+            for (int c = 0; c <= r; c++, e++)
+                H[r][c] = Sr[c][0] * IS[r][0] + Sr[c][1] * IS[r][1] + Sr[c][2] * IS[r][2] - sch[e];
+            H[r][r] += has ? K.Ld[d] : T(1);
+            rhs[r] = (has ? K.Qf[d] : T(0)) - (Sr[r][0] * a[6] + Sr[r][1] * a[7] + Sr[r][2] * a[8]) - g[r];
+        }
+    }
+    const T i0 = T(1) / H[0][0];
+    const T l10 = H[1][0] * i0, l20 = H[2][0] * i0;
+    const T i1 = T(1) / (H[1][1] - l10 * H[1][0]);
+    const T t21 = H[2][1] - l20 * H[1][0];
+    const T l21 = t21 * i1;
+    const T i2 = T(1) / (H[2][2] - l20 * H[2][0] - l21 * t21);
+    const T y1 = rhs[1] - l10 * rhs[0], y2 = rhs[2] - l20 * rhs[0] - l21 * y1;
+    T ar[3];
+    ar[2] = y2 * i2;
+    ar[1] = y1 * i1 - l21 * ar[2];
+    ar[0] = rhs[0] * i0 - l10 * ar[1] - l20 * ar[2];
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) if (r < pr.root_ndof) E.udot[pr.root_dof[r]] = ar[r];
+    }
+    if (lane < pr.n_branches) {
+#pragma unroll
+        for (int k = 0; k < P2_MAXCB; k++) {
+            const int d = k < pr.br_nb[lane] ? pr.br_dof[lane][k] : -1;
+            if (d >= 0) {
+                const T* x = K.brk[lane] + 4 * k;
+                E.udot[d] = x[3] - (x[0] * ar[0] + x[1] * ar[1] + x[2] * ar[2]);
+            }
+        }
+    }
+}
+
+// ---- full evaluation read-outs (two steps with a barrier in between) ----
+template <typename T, int CLS>
+BIO_DEV void p2_readout_1(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
+    auto& K = E.k.p;
+    const int nb = m.n_bodies;
+    if (lane < nb) {
+        const int b = lane;
+        T cx, cy;
+        rot2(K.pose[b][0], K.pose[b][1], m.body_com[b][0], m.body_com[b][1], cx, cy);
+        cx += K.pose[b][2]; cy += K.pose[b][3];
+        const T mb = m.body_mass[b];
+        E.x.out.comp[b][0] = mb * cx; E.x.out.comp[b][1] = mb * cy; E.x.out.comp[b][2] = mb * (m.body_com[b][2] + m.body_z[b]);
+        E.x.out.comp[b][3] = mb * (K.V[b][1] - K.V[b][0] * cy);
+        E.x.out.comp[b][4] = mb * (K.V[b][2] + K.V[b][0] * cx);
+        E.x.out.comp[b][5] = T(0);
+    } else if (lane - nb < m.n_obspts) {
+        const int p = lane - nb, b = m.obs_body[p];
+        T x, y;
+        rot2(K.pose[b][0], K.pose[b][1], m.obs_loc[p][0], m.obs_loc[p][1], x, y);
+        x += K.pose[b][2]; y += K.pose[b][3];
+        E.x.out.obs_pos[p][0] = x + E.O[0]; E.x.out.obs_pos[p][1] = y + E.O[1];
+        E.x.out.obs_pos[p][2] = m.obs_loc[p][2] + m.body_z[b];
+        E.x.out.obs_vel[p][0] = K.V[b][1] - K.V[b][0] * y;
+        E.x.out.obs_vel[p][1] = K.V[b][2] + K.V[b][0] * x;
+        E.x.out.obs_vel[p][2] = T(0);
+    }
+}
+
+template <typename T, int CLS>
+BIO_DEV void p2_readout_2(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
+    const int nb = m.n_bodies;
+    if (lane < 3) {
+        T ms = T(0), ps = T(0);
+        for (int b = 0; b < nb; b++) { ms += E.x.out.comp[b][lane]; ps += E.x.out.comp[b][3 + lane]; }
+        const T im = T(1) / m.total_mass;
+        E.com_pos[lane] = ms * im + E.O[lane];
+        E.com_vel[lane] = ps * im;
+    } else if (lane < 5) {
+        const int g = lane - 3;
+        T w[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+        for (int s = 0; s < m.n_spheres; s++) {
+            if (m.sph_group[s] != g) continue;
+            const T pa[3] = {E.sphx[s][0] + E.O[0], E.sphx[s][1] + E.O[1], E.sphx[s][2]};
+            T n[3];
+            cross3(pa, E.sphF[s], n);
+            for (int c = 0; c < 3; c++) { w[c] += E.sphF[s][c]; w[3 + c] += n[c]; }
+        }
+        for (int c = 0; c < 6; c++) E.contact[g][c] = w[c];
+    } else if (lane == 5) {
+        T mx = T(0);
+        for (int l = 0; l < m.n_limits; l++) { const T a = Num<T>::abs(E.limf[l]); mx = a > mx ? a : mx; }
+        E.max_limit = mx;
+    }
+}
+
+template <typename T, int CLS>
+__device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane,
+                                              const int newton_iters, const T ext_fx, const int ext_pt, const T h_imp,
+                                              const bool full) {
+    constexpr int G = CoopCls<CLS>::G;
+    p2_phase_a<T, CLS>(m, E, lane);
+    gsync<G>();
+    p2_phase_b<T, CLS>(m, E, lane);
+    gsync<G>();
+    p2_phase_c<T, CLS>(m, E, lane, newton_iters, full);
+    p2_phase_d<T, CLS>(m, E, lane);
+    gsync<G>();
+    p2_phase_e<T, CLS>(m, E, lane, h_imp, ext_fx, ext_pt);
+    gsync<G>();
+    p2_phase_f<T, CLS>(m, E, lane);
+    gsync<G>();
+    p2_phase_g<T, CLS>(m, E, lane);
+    if (full) {
+        p2_readout_1<T, CLS>(m, E, lane);
+        gsync<G>();
+        p2_readout_2<T, CLS>(m, E, lane);
     }
     gsync<G>();
-
-    // ---- phase H ----
-    coop_solve<T, CLS>(m, E, lane);
 }
 
 }  // namespace bio

@@ -20,7 +20,7 @@
 
 namespace bio {
 
-#define BIO_DEV __device__ __forceinline__
+#define BIO_DEV __host__ __device__ __forceinline__
 
 template <typename T> struct Num;
 template <> struct Num<float> {

@@ -9,6 +9,54 @@
 
 namespace bio {
 
+// ---------------------------------------------------------------------------
+// Planar program (bio_coop_planar.cuh): host-built schedule for models whose tree is a
+// root body (<= 3 planar dofs) carrying chains of single-dof bodies (the reference's 2D gait
+// models: pelvis+torso, and femur / tibia / foot per leg).  One lane walks one chain, so the
+// kinematics, the composite inertias, the joint-space block of the chain and its elimination
+// stay in that lane's registers; muscles hand their tension-scaled unit wrenches to the bodies
+// through a list of wrench sources.
+// ---------------------------------------------------------------------------
+#define P2_MAXBR 4        // chains hanging from the root
+#define P2_MAXCB 3        // bodies per chain
+#define P2_MAXAX 3        // elementary axes per joint
+#define P2_MAXSLOT 3      // distinct bodies one muscle touches
+#define P2_MAXSRC 64      // wrench sources: (muscle, slot) pairs, then spheres
+#define P2_MAXMOV 4       // moving path points
+#define P2_MAXTASK (BIO_MAX_AXES + 3 * P2_MAXMOV)
+
+template <typename T>
+struct alignas(16) PlanarProg {
+    int32_t ok, n_branches, n_atasks, n_src;
+    int32_t root_body, root_axis_begin, root_axis_count, root_ndof;
+    int32_t root_dof[4];
+    int32_t root_sph_mask, sph_src0, pad_[2];
+    int32_t br_nb[P2_MAXBR];
+    int32_t br_body[P2_MAXBR][P2_MAXCB];
+    int32_t br_axis_begin[P2_MAXBR][P2_MAXCB];
+    int32_t br_axis_count[P2_MAXBR][P2_MAXCB];
+    int32_t br_dof[P2_MAXBR][P2_MAXCB];        // dof of the body's joint (-1: none)
+    int32_t br_sph_mask[P2_MAXBR][P2_MAXCB];   // contact spheres carried by the body
+    int32_t body_sph_mask[BIO_MAX_BODIES];     // the same per body
+    // chain walk: root axes, then the axes of the chain's bodies; code = axis | body<<8 | first-of-body<<12 |
+    // last-of-body<<13 | root-joint<<14
+    int32_t ch_n[P2_MAXBR];
+    int32_t ch_code[P2_MAXBR][(P2_MAXCB + 1) * P2_MAXAX];
+    // phase A tasks: t < n_axes: axis t; then 3 per moving point (k = (t - n_axes) / 3, component % 3)
+    int32_t at_func[P2_MAXTASK], at_dof[P2_MAXTASK];
+    T at_add[P2_MAXTASK];                      // constant added to the value (body z of a moving point)
+    // path points: location in the body frame with z already in ground axes (planar: constant)
+    T pt_xyz[BIO_MAX_PATHPTS][4];
+    int32_t pt_info[BIO_MAX_PATHPTS];          // body | kind<<4 | dof<<6 | slot<<11 | moving index<<13
+    int32_t mus_src0[BIO_MAX_MUSCLES + 1];     // first wrench source of the muscle (one per slot); [n_muscles] = end
+    int32_t mov_dof[P2_MAXMOV];
+    // generalized-force inputs per dof
+    int8_t dof_lim[BIO_MAX_DOF][2], dof_mov[BIO_MAX_DOF][2], dof_act[BIO_MAX_DOF];
+    // wrench sources acting on every body
+    int32_t inc_begin[BIO_MAX_BODIES + 1];
+    uint8_t inc_src[3 * BIO_MAX_MUSCLES + BIO_MAX_SPHERES + 8];
+};
+
 template <typename T>
 struct alignas(16) DevModel {
     int32_t n_bodies, n_dof, n_axes, n_muscles, n_act, n_pathpts, n_spheres, n_limits;
@@ -125,6 +173,7 @@ struct alignas(16) DevModel {
     T curve_inv_h[BIO_N_CURVES];
     T curve_x1[BIO_N_CURVES];
     T curve_tab[BIO_N_CURVES][BIO_CURVE_N + 1][2];
+    PlanarProg<T> prog;
 };
 
 template <typename T>
@@ -182,6 +231,8 @@ struct EnvState {
         static_assert(sizeof(s.field) == sizeof(d.field), "int field " #field); \
         memcpy(&d.field, &s.field, sizeof(d.field));                           \
     } while (0)
+
+template <typename T> void build_planar_prog(const BioModelTables& s, DevModel<T>& d);
 
 template <typename T>
 void convert_model(const BioModelTables& s, DevModel<T>& d) {
@@ -357,6 +408,160 @@ void convert_model(const BioModelTables& s, DevModel<T>& d) {
     BIO_CP(curve_x0); BIO_CP(curve_x1); BIO_CP(curve_tab);
     for (int c = 0; c < BIO_N_CURVES; c++)
         d.curve_inv_h[c] = (T)((double)BIO_CURVE_N / (s.curve_x1[c] - s.curve_x0[c]));
+    build_planar_prog(s, d);
+}
+
+// Planar program of a model (see PlanarProg); prog.ok = 0 when the model does not have the
+// root-plus-chains shape, and the general cooperative evaluation is used instead.
+template <typename T>
+void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
+    PlanarProg<T>& pr = d.prog;
+    memset(&pr, 0, sizeof(pr));
+    if (!d.planar || s.n_bodies < 1 || s.n_bodies > BIO_MAX_BODIES || s.body_parent[0] >= 0) return;
+    int n_child[BIO_MAX_BODIES] = {0}, child[BIO_MAX_BODIES];
+    for (int b = 1; b < s.n_bodies; b++) {
+        const int p = s.body_parent[b];
+        if (p < 0 || p >= b) return;                      // one root, parents first
+        if (p != 0) { if (n_child[p]) return; child[p] = b; }
+        n_child[p]++;
+    }
+    auto joint_dofs = [&](int b, int* dofs) {             // distinct dofs of the joint, in axis order
+        int n = 0;
+        for (int a = s.body_axis_begin[b]; a < s.body_axis_begin[b] + s.body_axis_count[b]; a++) {
+            const int dof = s.axis_dof[a];
+            if (dof < 0) continue;
+            bool seen = false;
+            for (int k = 0; k < n; k++) seen = seen || dofs[k] == dof;
+            if (!seen) { if (n < 4) dofs[n] = dof; n++; }
+        }
+        return n;
+    };
+    for (int b = 0; b < s.n_bodies; b++) if (s.body_axis_count[b] > P2_MAXAX) return;
+    pr.root_body = 0;
+    pr.root_axis_begin = s.body_axis_begin[0];
+    pr.root_axis_count = s.body_axis_count[0];
+    { int dofs[4] = {-1, -1, -1, -1}; pr.root_ndof = joint_dofs(0, dofs); if (pr.root_ndof > 3) return;
+      for (int k = 0; k < 4; k++) pr.root_dof[k] = k < pr.root_ndof ? dofs[k] : -1; }
+    int body_branch[BIO_MAX_BODIES], body_k[BIO_MAX_BODIES];
+    body_branch[0] = -1; body_k[0] = 0;
+    for (int b = 1; b < s.n_bodies; b++) {
+        if (s.body_parent[b] != 0) continue;
+        if (pr.n_branches >= P2_MAXBR) return;
+        const int l = pr.n_branches++;
+        int cur = b, k = 0;
+        for (;;) {
+            if (k >= P2_MAXCB) return;
+            int dofs[4] = {-1, -1, -1, -1};
+            if (joint_dofs(cur, dofs) > 1) return;
+            pr.br_body[l][k] = cur;
+            pr.br_axis_begin[l][k] = s.body_axis_begin[cur];
+            pr.br_axis_count[l][k] = s.body_axis_count[cur];
+            pr.br_dof[l][k] = dofs[0];
+            body_branch[cur] = l; body_k[cur] = k;
+            k++;
+            if (!n_child[cur]) break;
+            cur = child[cur];
+        }
+        pr.br_nb[l] = k;
+        for (; k < P2_MAXCB; k++) { pr.br_body[l][k] = -1; pr.br_dof[l][k] = -1; }
+    }
+    // contact spheres per body
+    if (s.n_spheres > BIO_MAX_SPHERES) return;
+    for (int sp = 0; sp < s.n_spheres; sp++) {
+        const int b = s.sph_body[sp];
+        if (b == 0) pr.root_sph_mask |= 1 << sp;
+        else pr.br_sph_mask[body_branch[b]][body_k[b]] |= 1 << sp;
+    }
+    for (int b = 0; b < s.n_bodies; b++) {
+        pr.body_sph_mask[b] = 0;
+        for (int sp = 0; sp < s.n_spheres; sp++) if (s.sph_body[sp] == b) pr.body_sph_mask[b] |= 1 << sp;
+    }
+    for (int l = 0; l < (pr.n_branches > 0 ? pr.n_branches : 1); l++) {
+        int n = 0;
+        auto add_joint = [&](int b, bool root) {
+            const int ab = s.body_axis_begin[b], cnt = s.body_axis_count[b];
+            for (int j = 0; j < cnt; j++)
+                pr.ch_code[l][n++] = (ab + j) | (b << 8) | (j == 0 ? 1 << 12 : 0) | (j == cnt - 1 ? 1 << 13 : 0) |
+                                     (root ? 1 << 14 : 0);
+        };
+        if (s.body_axis_count[0] < 1) return;             // every body needs at least one axis slot
+        add_joint(0, true);
+        for (int k = 0; k < pr.br_nb[l] && pr.n_branches > 0; k++) {
+            if (s.body_axis_count[pr.br_body[l][k]] < 1) return;
+            add_joint(pr.br_body[l][k], false);
+        }
+        pr.ch_n[l] = n;
+    }
+    // phase A tasks
+    int n_mov = 0, mov_of_pt[BIO_MAX_PATHPTS];
+    for (int a = 0; a < s.n_axes; a++) { pr.at_func[a] = s.axis_func[a]; pr.at_dof[a] = s.axis_dof[a]; pr.at_add[a] = T(0); }
+    for (int p = 0; p < s.n_pathpts; p++) {
+        mov_of_pt[p] = -1;
+        if (s.pt_kind[p] != BIO_PT_MOVING) continue;
+        if (n_mov >= P2_MAXMOV) return;
+        for (int c = 0; c < 3; c++) {
+            const int t = s.n_axes + 3 * n_mov + c;
+            pr.at_func[t] = s.pt_func[p][c];
+            pr.at_dof[t] = s.pt_dof[p];
+            pr.at_add[t] = c == 2 ? d.body_z[s.pt_body[p]] : T(0);
+        }
+        pr.mov_dof[n_mov] = s.pt_dof[p];
+        mov_of_pt[p] = n_mov++;
+    }
+    pr.n_atasks = s.n_axes + 3 * n_mov;
+    // path points, muscle slots and wrench sources
+    int n_src = 0;
+    int src_body[P2_MAXSRC];
+    for (int i = 0; i < s.n_muscles; i++) {
+        int slot_body[P2_MAXSLOT], n_slot = 0, n_moving = 0;
+        pr.mus_src0[i] = n_src;
+        for (int p = s.mus_pt_begin[i]; p < s.mus_pt_begin[i] + s.mus_pt_count[i]; p++) {
+            const int b = s.pt_body[p];
+            int slot = -1;
+            for (int k = 0; k < n_slot; k++) if (slot_body[k] == b) slot = k;
+            if (slot < 0) { if (n_slot >= P2_MAXSLOT) return; slot = n_slot; slot_body[n_slot++] = b; }
+            if (s.pt_kind[p] == BIO_PT_MOVING) n_moving++;
+            const int dof = s.pt_dof[p] >= 0 ? s.pt_dof[p] : 31;
+            pr.pt_info[p] = b | (s.pt_kind[p] << 4) | (dof << 6) | (slot << 11) | ((mov_of_pt[p] >= 0 ? mov_of_pt[p] : 0) << 13);
+            pr.pt_xyz[p][0] = (T)s.pt_loc[p][0];
+            pr.pt_xyz[p][1] = (T)s.pt_loc[p][1];
+            pr.pt_xyz[p][2] = (T)(s.pt_loc[p][2] + (double)d.body_z[b]);
+            pr.pt_xyz[p][3] = T(0);
+        }
+        if (n_moving > 1) return;
+        for (int k = 0; k < n_slot; k++) { if (n_src >= P2_MAXSRC) return; src_body[n_src++] = slot_body[k]; }
+    }
+    pr.mus_src0[s.n_muscles] = n_src;
+    pr.sph_src0 = n_src;
+    for (int sp = 0; sp < s.n_spheres; sp++) { if (n_src >= P2_MAXSRC) return; src_body[n_src++] = s.sph_body[sp]; }
+    pr.n_src = n_src;
+    {
+        int k = 0;
+        for (int b = 0; b < s.n_bodies; b++) {
+            pr.inc_begin[b] = k;
+            for (int e = 0; e < n_src; e++)
+                if (src_body[e] == b) { if (k >= (int)sizeof(pr.inc_src)) return; pr.inc_src[k++] = (uint8_t)e; }
+        }
+        for (int b = s.n_bodies; b <= BIO_MAX_BODIES; b++) pr.inc_begin[b] = k;
+    }
+    // per-dof generalized-force inputs
+    for (int dd = 0; dd < BIO_MAX_DOF; dd++) { pr.dof_lim[dd][0] = pr.dof_lim[dd][1] = pr.dof_mov[dd][0] = pr.dof_mov[dd][1] = pr.dof_act[dd] = -1; }
+    for (int l = 0; l < s.n_limits; l++) {
+        const int dd = s.lim_dof[l];
+        if (pr.dof_lim[dd][0] < 0) pr.dof_lim[dd][0] = (int8_t)l; else if (pr.dof_lim[dd][1] < 0) pr.dof_lim[dd][1] = (int8_t)l; else return;
+    }
+    for (int k = 0; k < n_mov; k++) {
+        const int dd = pr.mov_dof[k];
+        if (pr.dof_mov[dd][0] < 0) pr.dof_mov[dd][0] = (int8_t)k; else if (pr.dof_mov[dd][1] < 0) pr.dof_mov[dd][1] = (int8_t)k; else return;
+    }
+    if (s.is_torque)
+        for (int a = 0; a < s.n_act; a++) {
+            const int dd = s.act_dof[a];
+            if (dd < 0) continue;
+            if (pr.dof_act[dd] >= 0) return;
+            pr.dof_act[dd] = (int8_t)a;
+        }
+    pr.ok = 1;
 }
 
 // Observation layout as a descriptor per slot (same order as write_obs in
