@@ -117,7 +117,8 @@ BIO_DEV void p2_phase_a(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
             const int desc = m.axis_desc[t];
             T sn = T(0), cs = T(1);
             if (desc & 1) Num<T>::sincos((desc & 2) ? -s : s, &sn, &cs);
-            K.ax[t][0] = s; K.ax[t][1] = ds; K.ax[t][2] = ds * qd; K.ax[t][3] = dds * qd * qd;
+            K.ax[t][0] = (desc & 1) ? T(0) : s;          // displacement along the axis (translations only)
+            K.ax[t][1] = ds; K.ax[t][2] = ds * qd; K.ax[t][3] = dds * qd * qd;
             K.axr[t][0] = cs; K.axr[t][1] = sn;
         } else {
             const int k = (t - m.n_axes) / 3, c = (t - m.n_axes) % 3;
@@ -128,69 +129,64 @@ BIO_DEV void p2_phase_a(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
 }
 
 // ---- phase B: lane l < n_branches walks the root joint and then its chain, one elementary axis
-// after the other (lane 0 publishes the root body; the other lanes only need its frame) ----
+// per step (lane 0 publishes the root body; the other lanes only need its frame).  Every step is the
+// same arithmetic: a translation has cos = 1, sin = 0 and a displacement, a rotation has no
+// displacement, a constant axis has zero rates (exact no-ops) ----
 template <typename T, int CLS>
 BIO_DEV void p2_phase_b(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
     const PlanarProg<T>& pr = m.prog;
     auto& K = E.k.p;
     const int nbr = pr.n_branches > 0 ? pr.n_branches : 1;
     if (lane >= nbr) return;
-    P2Frame<T> f;
-    f.c = T(1); f.s = T(0); f.rx = f.ry = T(0);
-    f.w = f.vx = f.vy = T(0);
-    f.aw = T(0); f.ax = -m.gravity[0]; f.ay = -m.gravity[1];
+    T c = T(1), s = T(0), rx = T(0), ry = T(0);
+    T w = T(0), vx = T(0), vy = T(0);
+    T aw = T(0), ax = -m.gravity[0], ay = -m.gravity[1];
     T cp = T(1), sp = T(0);                      // frame of the parent body: translations run along its axes
     T Sw = T(0), Sx = T(0), Sy = T(0);
     const int n = pr.ch_n[lane];
+#pragma unroll 2
     for (int i = 0; i < n; i++) {
         const int code = pr.ch_code[lane][i];
-        const int a = code & 255, b = (code >> 8) & 15;
-        const bool own = lane == 0 || !(code & (1 << 14));
-        if (code & (1 << 12)) {                  // first axis of body b: move to its joint location
-            T jx, jy;
-            rot2(f.c, f.s, m.body_joint_loc[b][0], m.body_joint_loc[b][1], jx, jy);
-            f.rx += jx; f.ry += jy;
-            cp = f.c; sp = f.s;
+        const int a = code & 255;
+        const T jx = pr.ch_j[lane][i][0], jy = pr.ch_j[lane][i][1];
+        const T rw = pr.ax_k[a][0], tA = pr.ax_k[a][1], tB = pr.ax_k[a][2];
+        const T st = K.ax[a][0], ds = K.ax[a][1], sd = K.ax[a][2], acc = K.ax[a][3];
+        const T cs = K.axr[a][0], sn = K.axr[a][1];
+        const bool own = lane == 0 || !(code & P2_F_ROOT);
+        // first axis of a body: move to its joint location (zero otherwise)
+        rx += c * jx - s * jy; ry += s * jx + c * jy;
+        if (code & P2_F_FIRST) { cp = c; sp = s; }
+        if (code & P2_F_OPRE) {
+            if (own) { E.O[0] = rx; E.O[1] = ry; E.O[2] = T(0); }
+            rx = ry = T(0);
         }
-        const int desc = m.axis_desc[a], d = (desc >> 3) & 31;
-        const T s = K.ax[a][0];
-        const T sg = (desc & 2) ? T(-1) : T(1);
-        T kw, kx, ky;                            // this axis' motion vector
-        if (!(desc & 1)) {                       // translation along x or y of the parent frame
-            kw = T(0);
-            kx = sg * ((desc & 4) ? -sp : cp);
-            ky = sg * ((desc & 4) ? cp : sp);
-            f.rx += kx * s; f.ry += ky * s;
-        } else {                                 // rotation about +-z through the current origin
-            if (desc & 256) {
-                if (own) { E.O[0] = f.rx; E.O[1] = f.ry; E.O[2] = T(0); }
-                f.rx = f.ry = T(0);
-            }
-            kw = sg; kx = sg * f.ry; ky = -sg * f.rx;
-            const T cs = K.axr[a][0], sn = K.axr[a][1];
-            const T cn = f.c * cs - f.s * sn, snn = f.s * cs + f.c * sn;
-            f.c = cn; f.s = snn;
+        // motion vector of the axis: translation along x / y of the parent frame, or rotation about
+        // +-z through the current origin
+        const T kx = tA * cp + tB * sp + rw * ry, ky = tA * sp - tB * cp - rw * rx;
+        rx += kx * st; ry += ky * st;
+        const T cn = c * cs - s * sn, snn = s * cs + c * sn;
+        c = cn; s = snn;
+        // V x S (planar): angular part 0, linear = w * (-S_vy, S_vx) + S_w * (V_vy, -V_vx)
+        const T cx = -w * ky + rw * vy, cy = w * kx - rw * vx;
+        if (code & P2_F_SRESET) Sw = Sx = Sy = T(0);
+        Sw += ds * rw; Sx += ds * kx; Sy += ds * ky;
+        aw += rw * acc;
+        ax += kx * acc + cx * sd;
+        ay += ky * acc + cy * sd;
+        w += rw * sd; vx += kx * sd; vy += ky * sd;
+        if ((code & P2_F_SPUB) && own) {
+            const int d = (code >> 12) & 31;
+            K.S[d][0] = Sw; K.S[d][1] = Sx; K.S[d][2] = Sy;
         }
-        if (d != 31) {
-            const T ds = K.ax[a][1], sd = K.ax[a][2], acc = K.ax[a][3];
-            if (desc & 512) Sw = Sx = Sy = T(0);
-            // V x S (planar): angular part 0, linear = w * (-S_vy, S_vx) + S_w * (V_vy, -V_vx)
-            const T cx = -f.w * ky + kw * f.vy, cy = f.w * kx - kw * f.vx;
-            Sw += ds * kw; Sx += ds * kx; Sy += ds * ky;
-            f.aw += kw * acc;
-            f.ax += kx * acc + cx * sd;
-            f.ay += ky * acc + cy * sd;
-            f.w += kw * sd; f.vx += kx * sd; f.vy += ky * sd;
-            if ((desc & 1024) && own) { K.S[d][0] = Sw; K.S[d][1] = Sx; K.S[d][2] = Sy; }
+        if (code & P2_F_OPOST) {
+            if (own) { E.O[0] = rx; E.O[1] = ry; E.O[2] = T(0); }
+            rx = ry = T(0);
         }
-        if (desc & 2048) {
-            if (own) { E.O[0] = f.rx; E.O[1] = f.ry; E.O[2] = T(0); }
-            f.rx = f.ry = T(0);
-        }
-        if ((code & (1 << 13)) && own) {         // last axis of body b: publish its frame
-            K.pose[b][0] = f.c; K.pose[b][1] = f.s; K.pose[b][2] = f.rx; K.pose[b][3] = f.ry;
-            K.V[b][0] = f.w; K.V[b][1] = f.vx; K.V[b][2] = f.vy;
-            K.A[b][0] = f.aw; K.A[b][1] = f.ax; K.A[b][2] = f.ay;
+        if ((code & P2_F_LAST) && own) {         // last axis of its body: publish the frame
+            const int b = (code >> 8) & 15;
+            K.pose[b][0] = c; K.pose[b][1] = s; K.pose[b][2] = rx; K.pose[b][3] = ry;
+            K.V[b][0] = w; K.V[b][1] = vx; K.V[b][2] = vy;
+            K.A[b][0] = aw; K.A[b][1] = ax; K.A[b][2] = ay;
         }
     }
 }
@@ -259,10 +255,10 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     const T amin = m.mus_amin[i], lmin = m.mus_lm_min[i];
     const T lmi = E.lm[i];
     const T lmc = lmi < lmin ? lmin : lmi;
-    const T lat = Num<T>::sqrt(lmc * lmc - h * h);
-    const T cosa = lat / lmc;
+    const T lat = Num<T>::sqrt_pos(lmc * lmc - h * h);
+    const T cosa = Num<T>::div(lat, lmc);
     T fal, fpe, ft, fv, dfv, dtmp;
-    curve_eval(m, 3, (L - lat) / m.mus_lts[i], ft, dtmp);
+    curve_eval(m, 3, Num<T>::div(L - lat, m.mus_lts[i]), ft, dtmp);
     const T tension = fiso * ft;
     {   // wrench sources of this muscle: one per body it touches
         const int s0 = pr.mus_src0[i], ns = pr.mus_src0[i + 1] - s0;
@@ -277,8 +273,9 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         // generalized force of the moving point: f . R_b dloc/dq
         if (mov >= 0) K.mq[mov] = tension * (gx * mdx + gy * mdy + gz * mdz);
     }
-    curve_eval(m, 0, lmc / lopt, fal, dtmp);
-    curve_eval(m, 2, lmc / lopt, fpe, dtmp);
+    const T lnorm = Num<T>::div(lmc, lopt);
+    curve_eval(m, 0, lnorm, fal, dtmp);
+    curve_eval(m, 2, lnorm, fpe, dtmp);
     const T ac = clampv(E.act[i], amin, T(1));
     const T afal = ac * fal;
     // Warm start from the root of the previous evaluation of this step.  The residual is
@@ -291,7 +288,7 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         const T err = (afal * fv + fpe + beta * vn) * cosa - ft;
         if (it == 0 && vn != T(0) && !(vn * e0 < T(0) && err * e0 > T(0))) { vn = T(0); continue; }
         const T derr = (afal * dfv + beta) * cosa;
-        const T delta = -err / derr;
+        const T delta = -Num<T>::div(err, derr);
         vn += delta;
         if (Num<T>::abs(delta) < Num<T>::newton_tol()) break;
     }
@@ -299,8 +296,8 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     if (lmi <= lmin && vn < T(0)) vn = T(0);
     E.lmdot[i] = vn * m.mus_vmax[i] * lopt;
     const T ec = clampv(E.ctrl[i], amin, T(1));
-    const T tau = ec > ac ? m.mus_tact[i] * (T(0.5) + T(1.5) * ac) : m.mus_tdeact[i] / (T(0.5) + T(1.5) * ac);
-    E.adot[i] = (ec - ac) / tau;
+    const T tau = ec > ac ? m.mus_tact[i] * (T(0.5) + T(1.5) * ac) : Num<T>::div(m.mus_tdeact[i], T(0.5) + T(1.5) * ac);
+    E.adot[i] = Num<T>::div(ec - ac, tau);
     if (full) {
         curve_eval(m, 1, vn, fv, dfv);
         E.fact[i] = fiso * afal * fv;
@@ -327,18 +324,18 @@ BIO_DEV void p2_phase_d(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
             const T vx = K.V[b][1] - K.V[b][0] * py, vy = K.V[b][2] + K.V[b][0] * xc;
             const T vn = -vy;
             const T kk = m.sph_k[s];
-            const T fH = T(4.0 / 3.0) * kk * depth * Num<T>::sqrt(rad * kk * depth);
+            const T fH = T(4.0 / 3.0) * kk * depth * Num<T>::sqrt_pos(rad * kk * depth);
             const T f = fH * (T(1) + T(1.5) * m.sph_c[s] * vn);
             if (f > T(0)) {
                 Fy = f;
                 const T vs = Num<T>::abs(vx);
-                const T vrel = vs / m.sph_vt[s];
-                const T strib = m.sph_ud[s] + T(2) * (m.sph_us[s] - m.sph_ud[s]) / (T(1) + vrel * vrel);
+                const T vrel = Num<T>::div(vs, m.sph_vt[s]);
+                const T strib = m.sph_ud[s] + Num<T>::div(T(2) * (m.sph_us[s] - m.sph_ud[s]), T(1) + vrel * vrel);
                 if (vs != T(0)) {
                     const T ff = f * ((vrel < T(1) ? vrel : T(1)) * strib + m.sph_uv[s] * vs);
-                    Fx = -ff * vx / vs;
+                    Fx = -Num<T>::div(ff * vx, vs);
                 }
-                D0 = f * ((vrel < T(1) ? T(1) / m.sph_vt[s] : T(1) / vs) * strib + m.sph_uv[s]);
+                D0 = f * (Num<T>::rcp(vrel < T(1) ? m.sph_vt[s] : vs) * strib + m.sph_uv[s]);
                 D1 = T(1.5) * m.sph_c[s] * fH;
             }
         }
@@ -351,8 +348,8 @@ BIO_DEV void p2_phase_d(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     } else if (lane - m.n_spheres < m.n_limits) {
         const int l = lane - m.n_spheres, d = m.lim_dof[l];
         const T w = m.lim_w[l], qq = E.q[d];
-        const T sup = step5((qq - m.lim_qup[l]) / w);
-        const T slo = T(1) - step5((qq - (m.lim_qlo[l] - w)) / w);
+        const T sup = step5(Num<T>::div(qq - m.lim_qup[l], w));
+        const T slo = T(1) - step5(Num<T>::div(qq - (m.lim_qlo[l] - w), w));
         E.limf[l] = -m.lim_kup[l] * sup * (qq - m.lim_qup[l]) + m.lim_klo[l] * slo * (m.lim_qlo[l] - qq) -
                     m.lim_damp[l] * (sup + slo) * E.u[d];
         E.limD[l] = m.lim_damp[l] * (sup + slo);
@@ -473,12 +470,12 @@ BIO_DEV void p2_phase_f(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         A[k][k] += has ? K.Ld[dd] : T(1);        // no dof: identity row, zero coupling and rhs
     }
     // L D L^T of the 3x3 block, then A^-1 [C | b]
-    const T i0 = T(1) / A[0][0];
+    const T i0 = Num<T>::rcp(A[0][0]);
     const T l10 = A[1][0] * i0, l20 = A[2][0] * i0;
-    const T i1 = T(1) / (A[1][1] - l10 * A[1][0]);
+    const T i1 = Num<T>::rcp(A[1][1] - l10 * A[1][0]);
     const T t21 = A[2][1] - l20 * A[1][0];
     const T l21 = t21 * i1;
-    const T i2 = T(1) / (A[2][2] - l20 * A[2][0] - l21 * t21);
+    const T i2 = Num<T>::rcp(A[2][2] - l20 * A[2][0] - l21 * t21);
     T X[P2_MAXCB][4];
 #pragma unroll
     for (int c = 0; c < 4; c++) {
@@ -549,12 +546,12 @@ BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
             rhs[r] = (has ? K.Qf[d] : T(0)) - (Sr[r][0] * a[6] + Sr[r][1] * a[7] + Sr[r][2] * a[8]) - g[r];
         }
     }
-    const T i0 = T(1) / H[0][0];
+    const T i0 = Num<T>::rcp(H[0][0]);
     const T l10 = H[1][0] * i0, l20 = H[2][0] * i0;
-    const T i1 = T(1) / (H[1][1] - l10 * H[1][0]);
+    const T i1 = Num<T>::rcp(H[1][1] - l10 * H[1][0]);
     const T t21 = H[2][1] - l20 * H[1][0];
     const T l21 = t21 * i1;
-    const T i2 = T(1) / (H[2][2] - l20 * H[2][0] - l21 * t21);
+    const T i2 = Num<T>::rcp(H[2][2] - l20 * H[2][0] - l21 * t21);
     const T y1 = rhs[1] - l10 * rhs[0], y2 = rhs[2] - l20 * rhs[0] - l21 * y1;
     T ar[3];
     ar[2] = y2 * i2;

@@ -26,6 +26,18 @@ template <typename T> struct Num;
 template <> struct Num<float> {
     static BIO_DEV float sqrt(float x) { return sqrtf(x); }
     static BIO_DEV float rsqrt(float x) { return rsqrtf(x); }
+    // fp32 production build: quotient / reciprocal / square root of a positive number from the
+    // special-function unit (<= 2 ulp) instead of the IEEE sequences with their slow-path calls;
+    // the host emulation keeps plain arithmetic
+#ifdef __CUDA_ARCH__
+    static BIO_DEV float div(float a, float b) { return __fdividef(a, b); }
+    static BIO_DEV float rcp(float b) { return __frcp_rn(b); }
+    static BIO_DEV float sqrt_pos(float x) { return x * rsqrtf(x); }
+#else
+    static BIO_DEV float div(float a, float b) { return a / b; }
+    static BIO_DEV float rcp(float b) { return 1.0f / b; }
+    static BIO_DEV float sqrt_pos(float x) { return sqrtf(x); }
+#endif
     static BIO_DEV float abs(float x) { return fabsf(x); }
     static BIO_DEV float floor(float x) { return floorf(x); }
     static BIO_DEV float exp(float x) { return expf(x); }
@@ -39,6 +51,9 @@ template <> struct Num<float> {
 template <> struct Num<double> {
     static BIO_DEV double sqrt(double x) { return ::sqrt(x); }
     static BIO_DEV double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+    static BIO_DEV double div(double a, double b) { return a / b; }
+    static BIO_DEV double rcp(double b) { return 1.0 / b; }
+    static BIO_DEV double sqrt_pos(double x) { return ::sqrt(x); }
     static BIO_DEV double abs(double x) { return ::fabs(x); }
     static BIO_DEV double floor(double x) { return ::floor(x); }
     static BIO_DEV double exp(double x) { return ::exp(x); }
@@ -89,27 +104,25 @@ BIO_DEV void func_eval(const DevModel<T>& m, int f, T x, T& y, T& d1, T& d2) {
     d2 = T(2) * c2 + T(6) * dx * c3;
 }
 
-// Tabulated Millard curve: value and slope.
+// Tabulated Millard curve: value and slope.  Outside the table the curve continues linearly with
+// the end slope; written without branches: the cubic is evaluated at the clamped abscissa and the
+// overshoot is added along its slope there.
 template <typename T>
 BIO_DEV void curve_eval(const DevModel<T>& m, int c, T x, T& y, T& dy) {
-    const T x0 = m.curve_x0[c], ih = m.curve_inv_h[c];
-    if (x < x0) { dy = m.curve_tab[c][0][1] * ih; y = m.curve_tab[c][0][0] + dy * (x - x0); return; }
-    if (x > m.curve_x1[c]) {
-        dy = m.curve_tab[c][BIO_CURVE_N][1] * ih;
-        y = m.curve_tab[c][BIO_CURVE_N][0] + dy * (x - m.curve_x1[c]);
-        return;
-    }
-    const T t = (x - x0) * ih;
-    int i = (int)Num<T>::floor(t);
-    i = i < 0 ? 0 : (i > BIO_CURVE_N - 1 ? BIO_CURVE_N - 1 : i);
-    const T s = t - T(i);
+    const T ih = m.curve_inv_h[c];
+    const T t = (x - m.curve_x0[c]) * ih;
+    const T tc = t < T(0) ? T(0) : (t > T(BIO_CURVE_N) ? T(BIO_CURVE_N) : t);
+    int i = (int)tc;
+    i = i > BIO_CURVE_N - 1 ? BIO_CURVE_N - 1 : i;
+    const T s = tc - T(i);
     const T y0 = m.curve_tab[c][i][0], m0 = m.curve_tab[c][i][1];
     const T y1 = m.curve_tab[c][i + 1][0], m1 = m.curve_tab[c][i + 1][1];
     // cubic Hermite in monomial (Horner) form: same polynomial as the basis form
     const T dl = y1 - y0;
     const T c2 = T(3) * dl - T(2) * m0 - m1, c3 = m0 + m1 - T(2) * dl;
-    y = y0 + s * (m0 + s * (c2 + s * c3));
-    dy = (m0 + s * (T(2) * c2 + T(3) * s * c3)) * ih;
+    const T dyt = m0 + s * (T(2) * c2 + T(3) * s * c3);
+    y = y0 + s * (m0 + s * (c2 + s * c3)) + dyt * (t - tc);
+    dy = dyt * ih;
 }
 template <typename T>
 BIO_DEV T curve_value(const DevModel<T>& m, int c, T x) { T y, d; curve_eval(m, c, x, y, d); return y; }

@@ -24,6 +24,13 @@ namespace bio {
 #define P2_MAXSRC 64      // wrench sources: (muscle, slot) pairs, then spheres
 #define P2_MAXMOV 4       // moving path points
 #define P2_MAXTASK (BIO_MAX_AXES + 3 * P2_MAXMOV)
+#define P2_F_FIRST (1 << 17)     // first axis of its body
+#define P2_F_LAST (1 << 18)      // last axis of its body: publish the body frame
+#define P2_F_ROOT (1 << 19)      // axis of the root joint (recomputed by every chain lane, published by lane 0)
+#define P2_F_SRESET (1 << 20)    // first axis of its dof
+#define P2_F_SPUB (1 << 21)      // last axis of its dof: publish the motion vector
+#define P2_F_OPRE (1 << 22)      // first rotation of the root: the origin O is fixed before this axis
+#define P2_F_OPOST (1 << 23)     // root without rotation: O is fixed after this (last) axis
 
 template <typename T>
 struct alignas(16) PlanarProg {
@@ -38,10 +45,13 @@ struct alignas(16) PlanarProg {
     int32_t br_dof[P2_MAXBR][P2_MAXCB];        // dof of the body's joint (-1: none)
     int32_t br_sph_mask[P2_MAXBR][P2_MAXCB];   // contact spheres carried by the body
     int32_t body_sph_mask[BIO_MAX_BODIES];     // the same per body
-    // chain walk: root axes, then the axes of the chain's bodies; code = axis | body<<8 | first-of-body<<12 |
-    // last-of-body<<13 | root-joint<<14
+    // chain walk: root axes, then the axes of the chain's bodies, one step per elementary axis:
+    // code = axis | body<<8 | dof<<12 | flags (P2_F_*); ch_j = joint location on the first axis of a
+    // body (else 0); ax_k = (rw, tA, tB): motion vector (rw, tA*cp + tB*sp + rw*ry, tA*sp - tB*cp - rw*rx)
     int32_t ch_n[P2_MAXBR];
     int32_t ch_code[P2_MAXBR][(P2_MAXCB + 1) * P2_MAXAX];
+    T ch_j[P2_MAXBR][(P2_MAXCB + 1) * P2_MAXAX][2];
+    T ax_k[BIO_MAX_AXES][4];
     // phase A tasks: t < n_axes: axis t; then 3 per moving point (k = (t - n_axes) / 3, component % 3)
     int32_t at_func[P2_MAXTASK], at_dof[P2_MAXTASK];
     T at_add[P2_MAXTASK];                      // constant added to the value (body z of a moving point)
@@ -476,13 +486,28 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         pr.body_sph_mask[b] = 0;
         for (int sp = 0; sp < s.n_spheres; sp++) if (s.sph_body[sp] == b) pr.body_sph_mask[b] |= 1 << sp;
     }
+    for (int a = 0; a < s.n_axes; a++) {
+        const int desc = d.axis_desc[a];
+        const T sg = (desc & 2) ? T(-1) : T(1);
+        pr.ax_k[a][0] = (desc & 1) ? sg : T(0);
+        pr.ax_k[a][1] = (!(desc & 1) && !(desc & 4)) ? sg : T(0);
+        pr.ax_k[a][2] = (!(desc & 1) && (desc & 4)) ? -sg : T(0);
+        pr.ax_k[a][3] = T(0);
+    }
     for (int l = 0; l < (pr.n_branches > 0 ? pr.n_branches : 1); l++) {
         int n = 0;
         auto add_joint = [&](int b, bool root) {
             const int ab = s.body_axis_begin[b], cnt = s.body_axis_count[b];
-            for (int j = 0; j < cnt; j++)
-                pr.ch_code[l][n++] = (ab + j) | (b << 8) | (j == 0 ? 1 << 12 : 0) | (j == cnt - 1 ? 1 << 13 : 0) |
-                                     (root ? 1 << 14 : 0);
+            for (int j = 0; j < cnt; j++) {
+                const int a = ab + j, desc = d.axis_desc[a], dof = (desc >> 3) & 31;
+                pr.ch_code[l][n] = a | (b << 8) | (dof << 12) | (j == 0 ? P2_F_FIRST : 0) | (j == cnt - 1 ? P2_F_LAST : 0) |
+                                   (root ? P2_F_ROOT : 0) | ((desc & 512) ? P2_F_SRESET : 0) |
+                                   ((desc & 1024) ? P2_F_SPUB : 0) | ((desc & 256) ? P2_F_OPRE : 0) |
+                                   ((desc & 2048) ? P2_F_OPOST : 0);
+                pr.ch_j[l][n][0] = j == 0 ? (T)s.body_joint_loc[b][0] : T(0);
+                pr.ch_j[l][n][1] = j == 0 ? (T)s.body_joint_loc[b][1] : T(0);
+                n++;
+            }
         };
         if (s.body_axis_count[0] < 1) return;             // every body needs at least one axis slot
         add_joint(0, true);
