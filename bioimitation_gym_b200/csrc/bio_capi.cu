@@ -43,6 +43,7 @@ struct HandleBase {
     int block = 32;
     int n_sms = 148;
     int coop_grid = 0;
+    int coop_ctas = 1;            // resident CTAs of the cooperative kernel per SM (occupancy query)
     std::vector<void*> allocs;
     double* stats = nullptr;          // 16 doubles
     virtual ~HandleBase() {}
@@ -146,10 +147,12 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
             h->coop_cls = 0;
             h->coop_smem = base + (COOP_THREADS(T) / C0::G) * sizeof(bio::EnvWork<T, 0>);
             CU((bio::coop_set_smem<T, 0>((int)h->coop_smem)));
+            h->coop_ctas = bio::coop_ctas_per_sm<T, 0>((int)h->coop_smem);
         } else if (want_coop && fits(C1::G, C1::ND, C1::NM, C1::NP, C1::NAX)) {
             h->coop_cls = 1;
             h->coop_smem = base + (COOP_THREADS(T) / C1::G) * sizeof(bio::EnvWork<T, 1>);
             CU((bio::coop_set_smem<T, 1>((int)h->coop_smem)));
+            h->coop_ctas = bio::coop_ctas_per_sm<T, 1>((int)h->coop_smem);
         }
     }
     // model block
@@ -242,7 +245,7 @@ int step_impl(Handle<T>* h, const void* actions, void* obs, void* reward, uint8_
         // persistent launch: resident CTAs only, warps walk the env items round-robin over the CTAs
         const int G = h->coop_cls == 0 ? (int)bio::CoopCls<0>::G : (int)bio::CoopCls<1>::G;
         const int items = (h->n + (32 / G) - 1) / (32 / G);
-        const int ctas = h->n_sms * COOP_CTAS_PER_SM(T);
+        const int ctas = h->n_sms * (h->coop_ctas > 0 ? h->coop_ctas : 1);
         int grid = items < ctas ? items : ctas;
         if (h->coop_grid > 0) grid = h->coop_grid;   // BIO_COOP_GRID: launch-shape experiments
         if (h->coop_cls == 0)

@@ -23,10 +23,10 @@ template <> struct CoopCls<1> { enum { G = 32, ND = 16, NM = 24, NP = 80, NAX = 
 #define COOP_MAXOBS 12
 
 template <typename T, int CLS>
-struct EnvWork {
+struct alignas(16) EnvWork {
     typedef CoopCls<CLS> C;
     T q[C::ND], u[C::ND], act[C::NM], lm[C::NM];          // state of the current evaluation
-    T O[4];
+    alignas(16) T O[4];
     union {
         struct {                                           // general (spatial) evaluation, coop_eval
             T ax_s[C::NAX], ax_ds[C::NAX], ax_dds[C::NAX];
@@ -40,24 +40,24 @@ struct EnvWork {
             T Q[C::ND], limDd[C::ND];
         } g;
         struct {                                           // planar program, coop_eval_planar
-            T ax[C::NAX][4];                               // s, ds/dq, ds/dq * qdot, d2s/dq2 * qdot^2
-            T axr[C::NAX][2];                              // cos, sin of the signed rotation angle
-            T pose[BIO_MAX_BODIES][4];                     // cos, sin, x, y (about O, ground axes)
-            T V[BIO_MAX_BODIES][4], A[BIO_MAX_BODIES][4];  // (w, vx, vy), bias acceleration likewise
-            T S[C::ND][4];                                 // motion vector of every dof
-            T bI[BIO_MAX_BODIES][12];                      // spatial inertia about O [0..5] and force [6..8] per body
+            alignas(16) T ax[C::NAX][4];                   // displacement, ds/dq, ds/dq * qdot, d2s/dq2 * qdot^2
+            alignas(16) T axr[C::NAX][2];                  // cos, sin of the signed rotation angle
+            alignas(16) T pose[BIO_MAX_BODIES][4];         // cos, sin, x, y (about O, ground axes)
+            alignas(16) T V[BIO_MAX_BODIES][4], A[BIO_MAX_BODIES][4];  // (w, vx, vy), bias acceleration likewise
+            alignas(16) T S[C::ND][4];                     // motion vector of every dof
+            alignas(16) T bI[BIO_MAX_BODIES][12];          // spatial inertia about O [0..5] and force [6..8] per body
             T Qf[C::ND], Ld[C::ND];                        // generalized force and h * limit damping per dof
-            T mv[P2_MAXMOV][8];                            // moving points: location [0..2], d/dq [4..6]
+            alignas(16) T mv[P2_MAXMOV][8];                            // moving points: location [0..2], d/dq [4..6]
             T mq[P2_MAXMOV];                               // their generalized force
-            T brx[P2_MAXBR][20];                           // chain -> root: composite inertia, force, Schur, rhs
-            T brk[P2_MAXBR][12];                           // chain block solve kept for the back substitution
+            alignas(16) T brx[P2_MAXBR][20];                           // chain -> root: composite inertia, force, Schur, rhs
+            alignas(16) T brk[P2_MAXBR][12];                           // chain block solve kept for the back substitution
         } p;
     } k;
     union {
         struct { T ptx[C::NP][3], ptf[C::NP][3], ptq[C::NP]; } pt;   // phases C..E
         struct { T col[BIO_MAX_SPHERES][C::ND][3]; } jac;             // phase G (implicit damping)
         struct { T obs_pos[COOP_MAXOBS][3], obs_vel[COOP_MAXOBS][3], comp[BIO_MAX_BODIES][6]; } out;  // full eval
-        struct { T w[P2_MAXSRC][4]; } src;                            // planar program: wrench sources
+        struct { alignas(16) T w[P2_MAXSRC][4]; } src;                            // planar program: wrench sources
     } x;
     T sphx[BIO_MAX_SPHERES][3], sphF[BIO_MAX_SPHERES][3], sphD[BIO_MAX_SPHERES][2];
     T limf[BIO_MAX_LIMITS], limD[BIO_MAX_LIMITS];

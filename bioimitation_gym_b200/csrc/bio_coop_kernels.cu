@@ -14,6 +14,15 @@ cudaError_t coop_set_smem<BIO_T, BIO_CLS>(int smem) {
 }
 
 template <>
+int coop_ctas_per_sm<BIO_T, BIO_CLS>(int smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bio_coop_step_kernel<BIO_T, BIO_CLS>, COOP_THREADS(BIO_T),
+                                                      (size_t)smem) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+template <>
 void launch_coop<BIO_T, BIO_CLS>(int grid, size_t smem, cudaStream_t s, const DevModel<BIO_T>* gm,
                                  const DevTask<BIO_T>& c, const EnvState<BIO_T>& st, int n, unsigned long long seed,
                                  long long env_offset, const BIO_T* actions, BIO_T* obs, BIO_T* reward, uint8_t* done,

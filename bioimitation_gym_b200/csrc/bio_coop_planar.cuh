@@ -117,9 +117,9 @@ BIO_DEV void p2_phase_a(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
             const int desc = m.axis_desc[t];
             T sn = T(0), cs = T(1);
             if (desc & 1) Num<T>::sincos((desc & 2) ? -s : s, &sn, &cs);
-            K.ax[t][0] = (desc & 1) ? T(0) : s;          // displacement along the axis (translations only)
-            K.ax[t][1] = ds; K.ax[t][2] = ds * qd; K.ax[t][3] = dds * qd * qd;
-            K.axr[t][0] = cs; K.axr[t][1] = sn;
+            // displacement along the axis (translations only), rates
+            st4(K.ax[t], (desc & 1) ? T(0) : s, ds, ds * qd, dds * qd * qd);
+            st2(K.axr[t], cs, sn);
         } else {
             const int k = (t - m.n_axes) / 3, c = (t - m.n_axes) % 3;
             K.mv[k][c] = s + pr.at_add[t];
@@ -148,18 +148,18 @@ BIO_DEV void p2_phase_b(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     for (int i = 0; i < n; i++) {
         const int code = pr.ch_code[lane][i];
         const int a = code & 255;
-        const T jx = pr.ch_j[lane][i][0], jy = pr.ch_j[lane][i][1];
-        const T rw = pr.ax_k[a][0], tA = pr.ax_k[a][1], tB = pr.ax_k[a][2];
-        const T st = K.ax[a][0], ds = K.ax[a][1], sd = K.ax[a][2], acc = K.ax[a][3];
-        const T cs = K.axr[a][0], sn = K.axr[a][1];
-        const bool own = lane == 0 || !(code & P2_F_ROOT);
+        T jx, jy, rw, tA, tB, t3, st, ds, sd, acc, cs, sn;
+        ld2(pr.ch_j[lane][i], jx, jy);
+        ld4(pr.ax_k[a], rw, tA, tB, t3);
+        ld4(K.ax[a], st, ds, sd, acc);
+        ld2(K.axr[a], cs, sn);
         // first axis of a body: move to its joint location (zero otherwise)
         rx += c * jx - s * jy; ry += s * jx + c * jy;
-        if (code & P2_F_FIRST) { cp = c; sp = s; }
-        if (code & P2_F_OPRE) {
-            if (own) { E.O[0] = rx; E.O[1] = ry; E.O[2] = T(0); }
-            rx = ry = T(0);
-        }
+        const bool first = (code & P2_F_FIRST) != 0, opre = (code & P2_F_OPRE) != 0, opost = (code & P2_F_OPOST) != 0;
+        cp = first ? c : cp; sp = first ? s : sp;
+        // the chain lanes repeat the root joint and store the same values
+        if (opre) st4(E.O, rx, ry, T(0), T(0));
+        rx = opre ? T(0) : rx; ry = opre ? T(0) : ry;
         // motion vector of the axis: translation along x / y of the parent frame, or rotation about
         // +-z through the current origin
         const T kx = tA * cp + tB * sp + rw * ry, ky = tA * sp - tB * cp - rw * rx;
@@ -168,25 +168,20 @@ BIO_DEV void p2_phase_b(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         c = cn; s = snn;
         // V x S (planar): angular part 0, linear = w * (-S_vy, S_vx) + S_w * (V_vy, -V_vx)
         const T cx = -w * ky + rw * vy, cy = w * kx - rw * vx;
-        if (code & P2_F_SRESET) Sw = Sx = Sy = T(0);
-        Sw += ds * rw; Sx += ds * kx; Sy += ds * ky;
+        const T keep = (code & P2_F_SRESET) ? T(0) : T(1);
+        Sw = keep * Sw + ds * rw; Sx = keep * Sx + ds * kx; Sy = keep * Sy + ds * ky;
         aw += rw * acc;
         ax += kx * acc + cx * sd;
         ay += ky * acc + cy * sd;
         w += rw * sd; vx += kx * sd; vy += ky * sd;
-        if ((code & P2_F_SPUB) && own) {
-            const int d = (code >> 12) & 31;
-            K.S[d][0] = Sw; K.S[d][1] = Sx; K.S[d][2] = Sy;
-        }
-        if (code & P2_F_OPOST) {
-            if (own) { E.O[0] = rx; E.O[1] = ry; E.O[2] = T(0); }
-            rx = ry = T(0);
-        }
-        if ((code & P2_F_LAST) && own) {         // last axis of its body: publish the frame
+        if (code & P2_F_SPUB) st4(K.S[(code >> 12) & 31], Sw, Sx, Sy, T(0));
+        if (opost) st4(E.O, rx, ry, T(0), T(0));
+        rx = opost ? T(0) : rx; ry = opost ? T(0) : ry;
+        if (code & P2_F_LAST) {                  // last axis of its body: publish the frame
             const int b = (code >> 8) & 15;
-            K.pose[b][0] = c; K.pose[b][1] = s; K.pose[b][2] = rx; K.pose[b][3] = ry;
-            K.V[b][0] = w; K.V[b][1] = vx; K.V[b][2] = vy;
-            K.A[b][0] = aw; K.A[b][1] = ax; K.A[b][2] = ay;
+            st4(K.pose[b], c, s, rx, ry);
+            st4(K.V[b], w, vx, vy, T(0));
+            st4(K.A[b], aw, ax, ay, T(0));
         }
     }
 }
@@ -217,19 +212,20 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
             const T v = E.q[(info >> 6) & 31];
             if (!(v >= m.pt_range[p][0] - T(1e-5) && v <= m.pt_range[p][1] + T(1e-5))) continue;
         }
-        const T c = K.pose[b][0], s = K.pose[b][1];
-        T lx, ly, lz;
+        T c, s, ox, oy, lx, ly, lz, l3;
+        ld4(K.pose[b], c, s, ox, oy);
         if (kind == BIO_PT_MOVING) {
+            T dlx, dly, dl3;
             mov = (info >> 13) & 7;
-            lx = K.mv[mov][0]; ly = K.mv[mov][1]; lz = K.mv[mov][2];
-            rot2(c, s, K.mv[mov][4], K.mv[mov][5], mdx, mdy);
-            mdz = K.mv[mov][6];
+            ld4(K.mv[mov], lx, ly, lz, l3);
+            ld4(K.mv[mov] + 4, dlx, dly, mdz, dl3);
+            rot2(c, s, dlx, dly, mdx, mdy);
         } else {
-            lx = pr.pt_xyz[p][0]; ly = pr.pt_xyz[p][1]; lz = pr.pt_xyz[p][2];
+            ld4(pr.pt_xyz[p], lx, ly, lz, l3);
         }
         T x, y;
         rot2(c, s, lx, ly, x, y);
-        x += K.pose[b][2]; y += K.pose[b][3];
+        x += ox; y += oy;
         const T z = lz;
         if (prev_slot >= 0) {
             const T dx = x - xp, dy = y - yp, dz = z - zp;
@@ -265,9 +261,7 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
 #pragma unroll
         for (int sl = 0; sl < P2_MAXSLOT; sl++) {
             if (sl < ns) {
-                E.x.src.w[s0 + sl][0] = tension * W[sl][0];
-                E.x.src.w[s0 + sl][1] = tension * W[sl][1];
-                E.x.src.w[s0 + sl][2] = tension * W[sl][2];
+                st4(E.x.src.w[s0 + sl], tension * W[sl][0], tension * W[sl][1], tension * W[sl][2], T(0));
             }
         }
         // generalized force of the moving point: f . R_b dloc/dq
@@ -312,16 +306,19 @@ BIO_DEV void p2_phase_d(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     auto& K = E.k.p;
     if (lane < m.n_spheres) {
         const int s = lane, b = m.sph_body[s];
-        T xc, yc;
-        rot2(K.pose[b][0], K.pose[b][1], m.sph_loc[s][0], m.sph_loc[s][1], xc, yc);
-        xc += K.pose[b][2]; yc += K.pose[b][3];
+        T xc, yc, pc, ps, pox, poy;
+        ld4(K.pose[b], pc, ps, pox, poy);
+        rot2(pc, ps, m.sph_loc[s][0], m.sph_loc[s][1], xc, yc);
+        xc += pox; yc += poy;
         const T zc = m.sph_loc[s][2] + m.body_z[b];
         const T rad = m.sph_radius[s];
         const T depth = rad - (yc + E.O[1]);
         T Fx = T(0), Fy = T(0), D0 = T(0), D1 = T(0);
         const T py = T(-0.5) * depth - E.O[1];
         if (depth > T(0)) {
-            const T vx = K.V[b][1] - K.V[b][0] * py, vy = K.V[b][2] + K.V[b][0] * xc;
+            T bw, bvx, bvy, b3;
+            ld4(K.V[b], bw, bvx, bvy, b3);
+            const T vx = bvx - bw * py, vy = bvy + bw * xc;
             const T vn = -vy;
             const T kk = m.sph_k[s];
             const T fH = T(4.0 / 3.0) * kk * depth * Num<T>::sqrt_pos(rad * kk * depth);
@@ -342,9 +339,7 @@ BIO_DEV void p2_phase_d(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         E.sphx[s][0] = xc; E.sphx[s][1] = py; E.sphx[s][2] = zc;
         E.sphF[s][0] = Fx; E.sphF[s][1] = Fy; E.sphF[s][2] = T(0);
         E.sphD[s][0] = D0; E.sphD[s][1] = D1;
-        E.x.src.w[pr.sph_src0 + s][0] = xc * Fy - py * Fx;
-        E.x.src.w[pr.sph_src0 + s][1] = Fx;
-        E.x.src.w[pr.sph_src0 + s][2] = Fy;
+        st4(E.x.src.w[pr.sph_src0 + s], xc * Fy - py * Fx, Fx, Fy, T(0));
     } else if (lane - m.n_spheres < m.n_limits) {
         const int l = lane - m.n_spheres, d = m.lim_dof[l];
         const T w = m.lim_w[l], qq = E.q[d];
@@ -369,30 +364,32 @@ BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         const int b = lane;
         T Wn = T(0), Wx = T(0), Wy = T(0);
         for (int k = pr.inc_begin[b]; k < pr.inc_begin[b + 1]; k++) {
-            const int e = pr.inc_src[k];
-            Wn += E.x.src.w[e][0]; Wx += E.x.src.w[e][1]; Wy += E.x.src.w[e][2];
+            T s0, s1, s2, s3;
+            ld4(E.x.src.w[pr.inc_src[k]], s0, s1, s2, s3);
+            Wn += s0; Wx += s1; Wy += s2;
         }
-        const T c = K.pose[b][0], s = K.pose[b][1];
-        T cx, cy;
+        T c, s, ox, oy, cx, cy;
+        ld4(K.pose[b], c, s, ox, oy);
         rot2(c, s, m.body_com[b][0], m.body_com[b][1], cx, cy);
-        cx += K.pose[b][2]; cy += K.pose[b][3];
+        cx += ox; cy += oy;
         const T mb = m.body_mass[b];
         const T hx = mb * cx, hy = mb * cy;
         T Iww = m.body_inertia[b][2] + mb * (cx * cx + cy * cy), Iwx = -hy, Iwy = hx, Ixx = mb, Iyy = mb;
-        const T w = K.V[b][0], vx = K.V[b][1], vy = K.V[b][2];
-        const T aw = K.A[b][0], ax = K.A[b][1], ay = K.A[b][2];
+        T w, vx, vy, aw, ax, ay, pad3;
+        ld4(K.V[b], w, vx, vy, pad3);
+        ld4(K.A[b], aw, ax, ay, pad3);
         const T px = mb * vx - hy * w, py = mb * vy + hx * w;
         const T IAn = Iww * aw + hx * ay - hy * ax, IAx = mb * ax - hy * aw, IAy = mb * ay + hx * aw;
         if (ext_pt >= 0 && m.obs_body[ext_pt] == b) {
             T x, y;
             rot2(c, s, m.obs_loc[ext_pt][0], m.obs_loc[ext_pt][1], x, y);
-            y += K.pose[b][3];
+            y += oy;
             Wn += -y * ext_fx;
             Wx += ext_fx;
         }
         T* o = K.bI[b];
-        o[6] = IAn + (vx * py - vy * px) - Wn;   // V x* (I V): n = v x p, f = w z x p
-        o[7] = IAx - w * py - Wx;
+        const T fn = IAn + (vx * py - vy * px) - Wn;   // V x* (I V): n = v x p, f = w z x p
+        const T ffx = IAx - w * py - Wx;
         o[8] = IAy + w * px - Wy;
         if (h_imp > T(0)) {
             int mask = pr.body_sph_mask[b];
@@ -407,7 +404,8 @@ BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
                 Iyy += d1;
             }
         }
-        o[0] = Iww; o[1] = Iwx; o[2] = Iwy; o[3] = Ixx; o[4] = T(0); o[5] = Iyy;
+        st4(o, Iww, Iwx, Iwy, Ixx);
+        st4(o + 4, T(0), Iyy, fn, ffx);
     } else if (lane - m.n_bodies < m.n_dof) {
         const int d = lane - m.n_bodies;
         T qf = T(0), ld = T(0);
@@ -437,8 +435,14 @@ BIO_DEV void p2_phase_f(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
 #pragma unroll
     for (int k = 0; k < P2_MAXCB; k++) {
         const int b = k < nb ? pr.br_body[l][k] : -1;
+        if (b >= 0) {
+            ld4(K.bI[b], Ic[k][0], Ic[k][1], Ic[k][2], Ic[k][3]);
+            ld4(K.bI[b] + 4, Ic[k][4], Ic[k][5], Ic[k][6], Ic[k][7]);
+            Ic[k][8] = K.bI[b][8];
+        } else {
 #pragma unroll
-        for (int e = 0; e < 9; e++) Ic[k][e] = b >= 0 ? K.bI[b][e] : T(0);
+            for (int e = 0; e < 9; e++) Ic[k][e] = T(0);
+        }
     }
 #pragma unroll
     for (int k = P2_MAXCB - 2; k >= 0; k--)      // composites: suffix sums along the chain
@@ -449,7 +453,9 @@ BIO_DEV void p2_phase_f(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     for (int r = 0; r < 3; r++) {
         const bool has = r < pr.root_ndof;
         const int d = has ? pr.root_dof[r] : 0;
-        Sr[r][0] = has ? K.S[d][0] : T(0); Sr[r][1] = has ? K.S[d][1] : T(0); Sr[r][2] = has ? K.S[d][2] : T(0);
+        T s3;
+        ld4(K.S[d], Sr[r][0], Sr[r][1], Sr[r][2], s3);
+        if (!has) Sr[r][0] = Sr[r][1] = Sr[r][2] = T(0);
     }
     // chain block A (lower triangle), coupling C to the root dofs, right-hand side b
     T Sk[P2_MAXCB][3], A[P2_MAXCB][P2_MAXCB], C[P2_MAXCB][3], bb[P2_MAXCB];
@@ -458,7 +464,9 @@ BIO_DEV void p2_phase_f(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         const int d = k < nb ? pr.br_dof[l][k] : -1;
         const bool has = d >= 0;
         const int dd = has ? d : 0;
-        Sk[k][0] = has ? K.S[dd][0] : T(0); Sk[k][1] = has ? K.S[dd][1] : T(0); Sk[k][2] = has ? K.S[dd][2] : T(0);
+        T s3;
+        ld4(K.S[dd], Sk[k][0], Sk[k][1], Sk[k][2], s3);
+        if (!has) Sk[k][0] = Sk[k][1] = Sk[k][2] = T(0);
         const T ISn = Ic[k][0] * Sk[k][0] + Ic[k][1] * Sk[k][1] + Ic[k][2] * Sk[k][2];
         const T ISx = Ic[k][1] * Sk[k][0] + Ic[k][3] * Sk[k][1] + Ic[k][4] * Sk[k][2];
         const T ISy = Ic[k][2] * Sk[k][0] + Ic[k][4] * Sk[k][1] + Ic[k][5] * Sk[k][2];
@@ -486,7 +494,7 @@ BIO_DEV void p2_phase_f(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         const T x0 = r0 * i0 - l10 * x1 - l20 * x2;
         X[0][c] = x0; X[1][c] = x1; X[2][c] = x2;
     }
-    T* o = K.brx[l];
+    T o[20];
 #pragma unroll
     for (int e = 0; e < 9; e++) o[e] = Ic[0][e];
     {   // Schur complement C^T A^-1 C (lower triangle) and C^T A^-1 b
@@ -497,11 +505,12 @@ BIO_DEV void p2_phase_f(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
             for (int c = 0; c <= r; c++) o[e++] = C[0][r] * X[0][c] + C[1][r] * X[1][c] + C[2][r] * X[2][c];
 #pragma unroll
         for (int r = 0; r < 3; r++) o[15 + r] = C[0][r] * X[0][3] + C[1][r] * X[1][3] + C[2][r] * X[2][3];
+        o[18] = o[19] = T(0);
     }
 #pragma unroll
-    for (int k = 0; k < P2_MAXCB; k++)
+    for (int e = 0; e < 20; e += 4) st4(K.brx[l] + e, o[e], o[e + 1], o[e + 2], o[e + 3]);
 #pragma unroll
-        for (int c = 0; c < 4; c++) K.brk[l][4 * k + c] = X[k][c];
+    for (int k = 0; k < P2_MAXCB; k++) st4(K.brk[l] + 4 * k, X[k][0], X[k][1], X[k][2], X[k][3]);
 }
 
 // ---- phase G: root solve (every chain lane repeats it), chain back substitution ----
@@ -512,23 +521,29 @@ BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     const int nbr = pr.n_branches > 0 ? pr.n_branches : 1;
     if (lane >= nbr) return;
     T a[9];
-#pragma unroll
-    for (int e = 0; e < 9; e++) a[e] = K.bI[pr.root_body][e];
+    ld4(K.bI[pr.root_body], a[0], a[1], a[2], a[3]);
+    ld4(K.bI[pr.root_body] + 4, a[4], a[5], a[6], a[7]);
+    a[8] = K.bI[pr.root_body][8];
     T sch[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, g[3] = {T(0), T(0), T(0)};
     for (int l = 0; l < pr.n_branches; l++) {
+        T v[20];
 #pragma unroll
-        for (int e = 0; e < 9; e++) a[e] += K.brx[l][e];
+        for (int e = 0; e < 20; e += 4) ld4(K.brx[l] + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
 #pragma unroll
-        for (int e = 0; e < 6; e++) sch[e] += K.brx[l][9 + e];
+        for (int e = 0; e < 9; e++) a[e] += v[e];
 #pragma unroll
-        for (int e = 0; e < 3; e++) g[e] += K.brx[l][15 + e];
+        for (int e = 0; e < 6; e++) sch[e] += v[9 + e];
+#pragma unroll
+        for (int e = 0; e < 3; e++) g[e] += v[15 + e];
     }
     T Sr[3][3], IS[3][3], H[3][3], rhs[3];
 #pragma unroll
     for (int r = 0; r < 3; r++) {
         const bool has = r < pr.root_ndof;
         const int d = has ? pr.root_dof[r] : 0;
-        Sr[r][0] = has ? K.S[d][0] : T(0); Sr[r][1] = has ? K.S[d][1] : T(0); Sr[r][2] = has ? K.S[d][2] : T(0);
+        T s3;
+        ld4(K.S[d], Sr[r][0], Sr[r][1], Sr[r][2], s3);
+        if (!has) Sr[r][0] = Sr[r][1] = Sr[r][2] = T(0);
         IS[r][0] = a[0] * Sr[r][0] + a[1] * Sr[r][1] + a[2] * Sr[r][2];
         IS[r][1] = a[1] * Sr[r][0] + a[3] * Sr[r][1] + a[4] * Sr[r][2];
         IS[r][2] = a[2] * Sr[r][0] + a[4] * Sr[r][1] + a[5] * Sr[r][2];
@@ -566,8 +581,9 @@ BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         for (int k = 0; k < P2_MAXCB; k++) {
             const int d = k < pr.br_nb[lane] ? pr.br_dof[lane][k] : -1;
             if (d >= 0) {
-                const T* x = K.brk[lane] + 4 * k;
-                E.udot[d] = x[3] - (x[0] * ar[0] + x[1] * ar[1] + x[2] * ar[2]);
+                T x0, x1, x2, x3;
+                ld4(K.brk[lane] + 4 * k, x0, x1, x2, x3);
+                E.udot[d] = x3 - (x0 * ar[0] + x1 * ar[1] + x2 * ar[2]);
             }
         }
     }

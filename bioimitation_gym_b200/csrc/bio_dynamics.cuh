@@ -79,6 +79,44 @@ template <typename T> BIO_DEV void matvec3(const T* R, const T* v, T* o) {
 }
 template <typename T> BIO_DEV T clampv(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
+// 4 / 2 consecutive scalars as one shared-memory transaction (16-byte aligned arrays of the work
+// buffer and of the model block); plain element access on the host
+template <typename T> BIO_DEV void ld4(const T* p, T& a, T& b, T& c, T& d) {
+#ifdef __CUDA_ARCH__
+    if (sizeof(T) == 4) { const float4 v = *reinterpret_cast<const float4*>(p); a = v.x; b = v.y; c = v.z; d = v.w; }
+    else {
+        const double2 v = *reinterpret_cast<const double2*>(p), w = *reinterpret_cast<const double2*>(p + 2);
+        a = v.x; b = v.y; c = w.x; d = w.y;
+    }
+#else
+    a = p[0]; b = p[1]; c = p[2]; d = p[3];
+#endif
+}
+template <typename T> BIO_DEV void st4(T* p, T a, T b, T c, T d) {
+#ifdef __CUDA_ARCH__
+    if (sizeof(T) == 4) *reinterpret_cast<float4*>(p) = make_float4((float)a, (float)b, (float)c, (float)d);
+    else { *reinterpret_cast<double2*>(p) = make_double2(a, b); *reinterpret_cast<double2*>(p + 2) = make_double2(c, d); }
+#else
+    p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+#endif
+}
+template <typename T> BIO_DEV void ld2(const T* p, T& a, T& b) {
+#ifdef __CUDA_ARCH__
+    if (sizeof(T) == 4) { const float2 v = *reinterpret_cast<const float2*>(p); a = v.x; b = v.y; }
+    else { const double2 v = *reinterpret_cast<const double2*>(p); a = v.x; b = v.y; }
+#else
+    a = p[0]; b = p[1];
+#endif
+}
+template <typename T> BIO_DEV void st2(T* p, T a, T b) {
+#ifdef __CUDA_ARCH__
+    if (sizeof(T) == 4) *reinterpret_cast<float2*>(p) = make_float2((float)a, (float)b);
+    else *reinterpret_cast<double2*>(p) = make_double2(a, b);
+#else
+    p[0] = a; p[1] = b;
+#endif
+}
+
 // OpenSim Function of one coordinate: value and first/second derivative.
 template <typename T>
 BIO_DEV void func_eval(const DevModel<T>& m, int f, T x, T& y, T& d1, T& d2) {

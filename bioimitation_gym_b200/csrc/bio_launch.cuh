@@ -30,6 +30,7 @@ template <typename T>
 void launch_transpose(unsigned grid, int block, cudaStream_t s, const T* src, T* dst, int n, int k, int to_soa);
 
 template <typename T, int CLS> cudaError_t coop_set_smem(int smem);
+template <typename T, int CLS> int coop_ctas_per_sm(int smem);   // resident CTAs per SM at this shared-memory size
 template <typename T, int CLS>
 void launch_coop(int grid, size_t smem, cudaStream_t s, const DevModel<T>* gm, const DevTask<T>& c,
                  const EnvState<T>& st, int n, unsigned long long seed, long long env_offset, const T* actions, T* obs,

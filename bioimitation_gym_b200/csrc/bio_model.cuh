@@ -50,13 +50,13 @@ struct alignas(16) PlanarProg {
     // body (else 0); ax_k = (rw, tA, tB): motion vector (rw, tA*cp + tB*sp + rw*ry, tA*sp - tB*cp - rw*rx)
     int32_t ch_n[P2_MAXBR];
     int32_t ch_code[P2_MAXBR][(P2_MAXCB + 1) * P2_MAXAX];
-    T ch_j[P2_MAXBR][(P2_MAXCB + 1) * P2_MAXAX][2];
-    T ax_k[BIO_MAX_AXES][4];
+    alignas(16) T ch_j[P2_MAXBR][(P2_MAXCB + 1) * P2_MAXAX][2];
+    alignas(16) T ax_k[BIO_MAX_AXES][4];
     // phase A tasks: t < n_axes: axis t; then 3 per moving point (k = (t - n_axes) / 3, component % 3)
     int32_t at_func[P2_MAXTASK], at_dof[P2_MAXTASK];
     T at_add[P2_MAXTASK];                      // constant added to the value (body z of a moving point)
     // path points: location in the body frame with z already in ground axes (planar: constant)
-    T pt_xyz[BIO_MAX_PATHPTS][4];
+    alignas(16) T pt_xyz[BIO_MAX_PATHPTS][4];
     int32_t pt_info[BIO_MAX_PATHPTS];          // body | kind<<4 | dof<<6 | slot<<11 | moving index<<13
     int32_t mus_src0[BIO_MAX_MUSCLES + 1];     // first wrench source of the muscle (one per slot); [n_muscles] = end
     int32_t mov_dof[P2_MAXMOV];

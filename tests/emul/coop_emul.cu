@@ -61,3 +61,14 @@ extern "C" int emul_planar_eval(const BioModelTables* s, int precision, int newt
         return run<float>(s, newton_iters, q, u, act, lm, ctrl, h_imp, ext_fx, ext_pt, udot, adot, lmdot, misc);
     return run<double>(s, newton_iters, q, u, act, lm, ctrl, h_imp, ext_fx, ext_pt, udot, adot, lmdot, misc);
 }
+
+// sizes that decide how many CTAs fit on an SM (bytes): model block and per-env work buffer
+extern "C" void emul_sizes(int64_t* out) {
+    out[0] = (int64_t)sizeof(bio::DevModel<float>);
+    out[1] = (int64_t)sizeof(bio::EnvWork<float, 0>);
+    out[2] = (int64_t)sizeof(bio::EnvWork<float, 1>);
+    out[3] = (int64_t)sizeof(bio::DevModel<double>);
+    out[4] = (int64_t)sizeof(bio::EnvWork<double, 0>);
+    out[5] = (int64_t)sizeof(bio::EnvWork<double, 1>);
+    out[6] = (int64_t)sizeof(bio::PlanarProg<float>);
+}
