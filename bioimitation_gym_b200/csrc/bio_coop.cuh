@@ -264,19 +264,20 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         curve_eval(m, 3, (L - lat) / m.mus_lts[i], ft, dtmp);
         const T ac = clampv(E.act[i], amin, T(1));
         const T afal = ac * fal;
-        // Warm start from the root of the previous evaluation of this step.  The residual is
-        // monotone and sigmoid-shaped (convex for vn<0, concave for vn>0), so Newton is only
-        // guaranteed from points between 0 and the root: anything else restarts from 0.
+        // Newton on the damped-equilibrium residual, warm-started from the root of the previous
+        // evaluation of this step.  The residual is increasing in vn, convex for vn < 0 and concave
+        // for vn > 0, so Newton converges monotonically from 0 and from any point between 0 and the
+        // root; an iterate that would cross 0 is put on 0 (globally convergent).
         T vn = E.vn[i];
-        const T e0 = (afal + fpe) * cosa - ft;    // residual at vn = 0 (f_V(0) = 1)
         for (int it = 0; it < newton_iters; it++) {
             curve_eval(m, 1, vn, fv, dfv);
             const T err = (afal * fv + fpe + beta * vn) * cosa - ft;
-            if (it == 0 && vn != T(0) && !(vn * e0 < T(0) && err * e0 > T(0))) { vn = T(0); continue; }
             const T derr = (afal * dfv + beta) * cosa;
-            const T delta = -err / derr;
-            vn += delta;
-            if (Num<T>::abs(delta) < Num<T>::newton_tol()) break;
+            const T delta = -Num<T>::div(err, derr);
+            const T vnew = vn + delta;
+            const bool crossed = vnew * vn < T(0);
+            vn = crossed ? T(0) : vnew;
+            if (!crossed && Num<T>::abs(delta) < Num<T>::newton_tol()) break;
         }
         E.vn[i] = vn;
         if (lmi <= lmin && vn < T(0)) vn = T(0);

@@ -200,8 +200,8 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
 #pragma unroll
     for (int sl = 0; sl < P2_MAXSLOT; sl++) W[sl][0] = W[sl][1] = W[sl][2] = T(0);
     T xp = T(0), yp = T(0), zp = T(0), ex = T(0), ey = T(0), ez = T(0), L = T(0);
-    T gx = T(0), gy = T(0), gz = T(0);           // direction sum (e_out - e_in) at the moving point
-    T mdx = T(0), mdy = T(0), mdz = T(0);        // its d(location)/dq in ground axes
+    T mdx = T(0), mdy = T(0), mdz = T(0);        // moving point: d(location)/dq in ground axes
+    T mqu = T(0);                                // and (e_out - e_in) . d(location)/dq
     int prev_slot = -1, mov = -1;
     bool prev_moving = false;
     const int pb = m.mus_pt_begin[i], pe = pb + m.mus_pt_count[i];
@@ -233,7 +233,9 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
             const T il = Num<T>::rsqrt(d2);
             L += d2 * il;
             ex = dx * il; ey = dy * il; ez = dz * il;
-            if (prev_moving) { gx += ex; gy += ey; gz += ez; }
+            // the segment pulls its first point along +e and its second along -e
+            const T msg = (prev_moving ? T(1) : T(0)) - (kind == BIO_PT_MOVING ? T(1) : T(0));
+            mqu += msg * (ex * mdx + ey * mdy + ez * mdz);
             if (slot != prev_slot) {
                 const T wn = xp * ey - yp * ex;
 #pragma unroll
@@ -244,7 +246,6 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
             }
         }
         prev_moving = kind == BIO_PT_MOVING;
-        if (prev_moving) { gx = -ex; gy = -ey; gz = -ez; }   // -e_in (zero when it is the first point)
         xp = x; yp = y; zp = z; prev_slot = slot;
     }
     const T fiso = m.mus_fiso[i], lopt = m.mus_lopt[i], h = m.mus_height[i], beta = m.mus_beta[i];
@@ -265,26 +266,27 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
             }
         }
         // generalized force of the moving point: f . R_b dloc/dq
-        if (mov >= 0) K.mq[mov] = tension * (gx * mdx + gy * mdy + gz * mdz);
+        if (mov >= 0) K.mq[mov] = tension * mqu;
     }
     const T lnorm = Num<T>::div(lmc, lopt);
     curve_eval(m, 0, lnorm, fal, dtmp);
     curve_eval(m, 2, lnorm, fpe, dtmp);
     const T ac = clampv(E.act[i], amin, T(1));
     const T afal = ac * fal;
-    // Warm start from the root of the previous evaluation of this step.  The residual is
-    // monotone and sigmoid-shaped (convex for vn<0, concave for vn>0), so Newton is only
-    // guaranteed from points between 0 and the root: anything else restarts from 0.
+    // Newton on the damped-equilibrium residual, warm-started from the root of the previous
+    // evaluation of this step.  The residual is increasing in vn, convex for vn < 0 and concave for
+    // vn > 0, so Newton converges monotonically from 0 and from any point between 0 and the root;
+    // an iterate that would cross 0 is put on 0, which makes the iteration globally convergent.
     T vn = E.vn[i];
-    const T e0 = (afal + fpe) * cosa - ft;    // residual at vn = 0 (f_V(0) = 1)
     for (int it = 0; it < newton_iters; it++) {
         curve_eval(m, 1, vn, fv, dfv);
         const T err = (afal * fv + fpe + beta * vn) * cosa - ft;
-        if (it == 0 && vn != T(0) && !(vn * e0 < T(0) && err * e0 > T(0))) { vn = T(0); continue; }
         const T derr = (afal * dfv + beta) * cosa;
         const T delta = -Num<T>::div(err, derr);
-        vn += delta;
-        if (Num<T>::abs(delta) < Num<T>::newton_tol()) break;
+        const T vnew = vn + delta;
+        const bool crossed = vnew * vn < T(0);
+        vn = crossed ? T(0) : vnew;
+        if (!crossed && Num<T>::abs(delta) < Num<T>::newton_tol()) break;
     }
     E.vn[i] = vn;
     if (lmi <= lmin && vn < T(0)) vn = T(0);

@@ -12,8 +12,8 @@ namespace {
 
 template <typename T>
 int run(const BioModelTables* s, int newton_iters, const double* q, const double* u, const double* act,
-        const double* lm, const double* ctrl, double h_imp, double ext_fx, int ext_pt, double* udot, double* adot,
-        double* lmdot, double* misc) {
+        const double* lm, const double* ctrl, const double* vn0, double h_imp, double ext_fx, int ext_pt, double* udot,
+        double* adot, double* lmdot, double* misc) {
     using namespace bio;
     typedef EnvWork<T, 0> Work;
     constexpr int G = CoopCls<0>::G;
@@ -24,7 +24,7 @@ int run(const BioModelTables* s, int newton_iters, const double* q, const double
     Work* E = new Work();
     memset(E, 0, sizeof(Work));
     for (int i = 0; i < s->n_dof; i++) { E->q[i] = (T)q[i]; E->u[i] = (T)u[i]; }
-    for (int i = 0; i < s->n_muscles; i++) { E->act[i] = (T)act[i]; E->lm[i] = (T)lm[i]; }
+    for (int i = 0; i < s->n_muscles; i++) { E->act[i] = (T)act[i]; E->lm[i] = (T)lm[i]; E->vn[i] = vn0 ? (T)vn0[i] : T(0); }
     for (int i = 0; i < s->n_act; i++) E->ctrl[i] = (T)ctrl[i];
     for (int l = 0; l < G; l++) p2_phase_a<T, 0>(*m, *E, l);
     for (int l = 0; l < G; l++) p2_phase_b<T, 0>(*m, *E, l);
@@ -55,11 +55,11 @@ int run(const BioModelTables* s, int newton_iters, const double* q, const double
 
 extern "C" int emul_planar_eval(const BioModelTables* s, int precision, int newton_iters, const double* q,
                                 const double* u, const double* act, const double* lm, const double* ctrl,
-                                double h_imp, double ext_fx, int ext_pt, double* udot, double* adot, double* lmdot,
+                                const double* vn0, double h_imp, double ext_fx, int ext_pt, double* udot, double* adot, double* lmdot,
                                 double* misc) {
     if (precision == BIO_PREC_F32)
-        return run<float>(s, newton_iters, q, u, act, lm, ctrl, h_imp, ext_fx, ext_pt, udot, adot, lmdot, misc);
-    return run<double>(s, newton_iters, q, u, act, lm, ctrl, h_imp, ext_fx, ext_pt, udot, adot, lmdot, misc);
+        return run<float>(s, newton_iters, q, u, act, lm, ctrl, vn0, h_imp, ext_fx, ext_pt, udot, adot, lmdot, misc);
+    return run<double>(s, newton_iters, q, u, act, lm, ctrl, vn0, h_imp, ext_fx, ext_pt, udot, adot, lmdot, misc);
 }
 
 // sizes that decide how many CTAs fit on an SM (bytes): model block and per-env work buffer

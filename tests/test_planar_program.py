@@ -42,12 +42,13 @@ def _pad(x, n):
     return out
 
 
-def _emul(L, t, q, u, act, lm, ctrl, prec=1, h_imp=0.0, ext_fx=0.0, ext_pt=-1):
+def _emul(L, t, q, u, act, lm, ctrl, prec=1, h_imp=0.0, ext_fx=0.0, ext_pt=-1, vn0=None, iters=30):
     nd, nm = t.n_dof, t.n_muscles
     udot, adot, lmdot, misc = np.zeros(16), np.zeros(24), np.zeros(24), np.zeros(256)
     q_, u_, a_, l_, c_ = _pad(q, 16), _pad(u, 16), _pad(act, 24), _pad(lm, 24), _pad(ctrl, 24)
-    rc = L.emul_planar_eval(ctypes.byref(t), prec, 20, _p(q_), _p(u_), _p(a_), _p(l_), _p(c_),
-                            ctypes.c_double(h_imp), ctypes.c_double(ext_fx), ext_pt, _p(udot), _p(adot),
+    v_ = _pad(vn0, 24) if vn0 is not None else None
+    rc = L.emul_planar_eval(ctypes.byref(t), prec, iters, _p(q_), _p(u_), _p(a_), _p(l_), _p(c_),
+                            _p(v_) if v_ is not None else None, ctypes.c_double(h_imp), ctypes.c_double(ext_fx), ext_pt, _p(udot), _p(adot),
                             _p(lmdot), _p(misc))
     assert rc == 0, "the model does not match the planar program (rc %d)" % rc
     return dict(udot=udot[:nd], adot=adot[:nm], lmdot=lmdot[:nm], com_pos=misc[0:3], com_vel=misc[3:6],
@@ -106,11 +107,30 @@ def test_emulated_implicit_damping_and_perturbation(emul_lib, oracle_lib, models
     assert worst32 < 3e-2
 
 
+def test_warm_started_newton_finds_the_same_root(emul_lib, oracle_lib, models):
+    """Any warm start of the fibre-velocity Newton iteration (the kernel keeps the root of the
+    previous substep) must end on the root the oracle finds from zero."""
+    orc = oracle_lib
+    t = models["2d_muscle"].tables
+    g = np.load(os.path.join(HERE, "golden", "config1_muscle_walking_2d.npz"))
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for k in range(0, g["q"].shape[0], 9):
+        q, u, act, lm = g["q"][k], g["u"][k], g["act"][k], g["lm"][k]
+        ctrl = np.clip(g["action"][k], 0, 1)
+        o = orc.eval_dynamics(t, q, u, act, lm, ctrl, newton_iters=60)
+        for scale in (1e-14, 1e-6, 1e-3, 0.1, 1.0, 5.0):
+            e = _emul(emul_lib, t, q, u, act, lm, ctrl, vn0=rng.uniform(-scale, scale, t.n_muscles), iters=30)
+            worst = max(worst, float(np.max(np.abs(o["lmdot"] - e["lmdot"]) / np.maximum(np.abs(o["lmdot"]), 1e-2))))
+    print("warm-started Newton, worst relative fibre-velocity difference %.2e" % worst)
+    assert worst < 1e-8
+
+
 def test_program_rejects_models_it_does_not_cover(emul_lib, models):
     t = models["3d_muscle"].tables
     udot, adot, lmdot, misc = np.zeros(16), np.zeros(24), np.zeros(24), np.zeros(256)
     z16, z24 = np.zeros(16), np.zeros(24)
-    rc = emul_lib.emul_planar_eval(ctypes.byref(t), 1, 5, _p(z16), _p(z16), _p(z24), _p(z24), _p(z24),
+    rc = emul_lib.emul_planar_eval(ctypes.byref(t), 1, 5, _p(z16), _p(z16), _p(z24), _p(z24), _p(z24), None,
                                    ctypes.c_double(0.0), ctypes.c_double(0.0), -1, _p(udot), _p(adot), _p(lmdot),
                                    _p(misc))
     assert rc == -1
