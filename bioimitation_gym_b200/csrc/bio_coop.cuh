@@ -66,6 +66,7 @@ struct alignas(16) EnvWork {
     T vn[C::NM];                                           // Newton warm start: last normalised fibre velocity
     T ctrl[C::NM];
     T com_pos[3], com_vel[3];
+    int8_t knot_hint[P2_MAXTASK];                          // planar program: last spline interval per phase-A task
     T contact[2][6];
     T max_limit, pad_;
 };
@@ -732,6 +733,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     }
     hist_pos = (hist_pos + 1) % Hh;
     if (ism) E.vn[lane] = T(0);   // every control step starts its Newton solves from 0 (results do not depend on history)
+    for (int t = lane; t < P2_MAXTASK; t += G) E.knot_hint[t] = 0;   // spline search hints (any start gives the same interval)
     gsync<G>();
 
     // ---- integrate one control step, evaluate at the new state ----

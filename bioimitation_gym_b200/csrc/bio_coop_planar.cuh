@@ -111,7 +111,7 @@ BIO_DEV void p2_phase_a(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     for (int t = lane; t < pr.n_atasks; t += G) {
         const int d = pr.at_dof[t];
         T s, ds, dds;
-        func_eval(m, pr.at_func[t], d >= 0 ? E.q[d] : T(0), s, ds, dds);
+        func_eval(m, pr.at_func[t], d >= 0 ? E.q[d] : T(0), s, ds, dds, &E.knot_hint[t]);
         if (t < m.n_axes) {
             const T qd = d >= 0 ? E.u[d] : T(0);
             const int desc = m.axis_desc[t];
@@ -365,6 +365,7 @@ BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     if (lane < m.n_bodies) {
         const int b = lane;
         T Wn = T(0), Wx = T(0), Wy = T(0);
+#pragma unroll 4
         for (int k = pr.inc_begin[b]; k < pr.inc_begin[b + 1]; k++) {
             T s0, s1, s2, s3;
             ld4(E.x.src.w[pr.inc_src[k]], s0, s1, s2, s3);
@@ -395,8 +396,10 @@ BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         o[8] = IAy + w * px - Wy;
         if (h_imp > T(0)) {
             int mask = pr.body_sph_mask[b];
-            for (int sp = 0; mask; sp++, mask >>= 1) {
-                if (!(mask & 1) || !(E.sphD[sp][1] > T(0))) continue;
+            while (mask) {
+                const int sp = lowest_bit(mask);
+                mask &= mask - 1;
+                if (!(E.sphD[sp][1] > T(0))) continue;
                 const T sx = E.sphx[sp][0], sy = E.sphx[sp][1];
                 const T d0 = h_imp * E.sphD[sp][0], d1 = h_imp * E.sphD[sp][1];
                 Iww += d0 * sy * sy + d1 * sx * sx;

@@ -117,9 +117,20 @@ template <typename T> BIO_DEV void st2(T* p, T a, T b) {
 #endif
 }
 
-// OpenSim Function of one coordinate: value and first/second derivative.
+// index of the lowest set bit (mask != 0)
+BIO_DEV int lowest_bit(int mask) {
+#ifdef __CUDA_ARCH__
+    return __ffs(mask) - 1;
+#else
+    return __builtin_ctz((unsigned)mask);
+#endif
+}
+
+// OpenSim Function of one coordinate: value and first/second derivative.  hint (optional): spline
+// interval of the previous evaluation of this function; the search starts there (the coordinates
+// move little between substeps) and the interval found is written back.
 template <typename T>
-BIO_DEV void func_eval(const DevModel<T>& m, int f, T x, T& y, T& d1, T& d2) {
+BIO_DEV void func_eval(const DevModel<T>& m, int f, T x, T& y, T& d1, T& d2, int8_t* hint = nullptr) {
     const int kind = m.func_kind[f];
     if (kind == BIO_FUNC_CONST) { y = m.func_c[f][0]; d1 = T(0); d2 = T(0); return; }
     if (kind == BIO_FUNC_LINEAR) { y = m.func_c[f][0] * x + m.func_c[f][1]; d1 = m.func_c[f][0]; d2 = T(0); return; }
@@ -130,11 +141,19 @@ BIO_DEV void func_eval(const DevModel<T>& m, int f, T x, T& y, T& d1, T& d2) {
     if (x >= m.knot_x[kb + n - 1]) {
         d1 = m.knot_c[kb + n - 1][1]; y = m.knot_c[kb + n - 1][0] + d1 * (x - m.knot_x[kb + n - 1]); d2 = T(0); return;
     }
-    // bucketed start (host table), then at most a few forward steps
-    int bk = (int)((x - m.knot_x[kb]) * m.func_bucket_inv[f]);
-    bk = bk < 0 ? 0 : (bk > 15 ? 15 : bk);
-    int i = m.func_bucket[f][bk];
+    int i;
+    if (hint) {
+        i = *hint;
+        i = i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
+        while (i > 0 && x < m.knot_x[kb + i]) i--;
+    } else {
+        // bucketed start (host table), then at most a few forward steps
+        int bk = (int)((x - m.knot_x[kb]) * m.func_bucket_inv[f]);
+        bk = bk < 0 ? 0 : (bk > 15 ? 15 : bk);
+        i = m.func_bucket[f][bk];
+    }
     while (i + 1 < n - 1 && x >= m.knot_x[kb + i + 1]) i++;
+    if (hint) *hint = (int8_t)i;
     const T dx = x - m.knot_x[kb + i];
     const T c0 = m.knot_c[kb + i][0], c1 = m.knot_c[kb + i][1], c2 = m.knot_c[kb + i][2], c3 = m.knot_c[kb + i][3];
     y = c0 + dx * (c1 + dx * (c2 + dx * c3));
