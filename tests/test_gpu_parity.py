@@ -362,3 +362,26 @@ def test_large_batch_and_all_integrators_run():
         obs, rew, done, _ = env.step(torch.rand((3000, 22), device=env.device))
     assert torch.isfinite(obs).all()
     env.close()
+
+
+def test_trajectory_recorder_writes_state_storage(tmp_path):
+    """save_simulation (opensim_wrapper.py:334-338): the recorded states of one env as an
+    OpenSim states storage that reads back to what get_state returned."""
+    import torch
+    from bioimitation_gym_b200 import backend, refmotion
+    from bioimitation_gym_b200.rollout import TrajectoryRecorder
+    env = backend.VecEnv("MuscleWalkingImitation2D-v0", dict(num_envs=8, dtype="float64", seed=2, auto_reset=False))
+    rec = TrajectoryRecorder(env, [3])
+    env.reset()
+    rec.record()
+    g = torch.Generator().manual_seed(0)
+    for _ in range(5):
+        env.step(torch.rand((8, 14), generator=g, dtype=torch.float64))
+        rec.record()
+    path = rec.save_simulation(str(tmp_path))
+    labels, data, _ = refmotion.read_storage(path)
+    assert data.shape == (6, 1 + 2 * env.n_dof + 2 * env.n_muscles)
+    st = env.get_state()
+    assert np.allclose(data[-1, 1:1 + 2 * env.n_dof:2], st["q"][3].cpu().numpy(), atol=1e-7)
+    assert np.allclose(np.diff(data[:, 0]), 0.01, atol=1e-9)
+    env.close()

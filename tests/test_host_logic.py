@@ -374,3 +374,42 @@ def test_reference_tables_are_consistent(models):
     # the stance foot touches the ground (Hertz penetration of a few mm .. cm)
     low = min(refmotion.sphere_bottoms(cm, ref["q"][r, dof_cols]).min() for r in range(0, 364, 10))
     assert -0.06 < low < 0.005
+
+
+def test_device_replay_buffer_matches_reference_semantics():
+    """Ring buffer with the reference's field names (replay_buffer.py:9-74, dataset.py:46-66),
+    batch inserts, mask = 0 on real episode ends, uniform sampling."""
+    import torch
+    from bioimitation_gym_b200.rollout import Batch, DeviceReplayBuffer
+    buf = DeviceReplayBuffer(obs_dim=3, action_dim=2, capacity=10, device="cpu")
+    obs = torch.arange(12, dtype=torch.float32).reshape(4, 3)
+    act = torch.ones(4, 2)
+    rew = torch.tensor([1.0, 2.0, 3.0, 4.0])
+    done = torch.tensor([0, 1, 0, 1], dtype=torch.uint8)
+    tl = torch.tensor([0, 0, 0, 1], dtype=torch.uint8)
+    buf.insert_step(obs, act, rew, done, obs + 100, time_limit_done=tl)
+    assert len(buf) == 4 and buf.insert_index == 4
+    assert buf.masks[:4].tolist() == [1.0, 0.0, 1.0, 1.0] and buf.dones_float[:4].tolist() == [0.0, 1.0, 0.0, 1.0]
+    buf.insert_step(obs, act, rew, done, obs + 100)
+    buf.insert_step(obs, act, rew, done, obs + 100)           # wraps around
+    assert len(buf) == 10 and buf.insert_index == 2
+    assert torch.equal(buf.observations[0], obs[2]) and torch.equal(buf.observations[1], obs[3])
+    buf.insert(obs[0].numpy(), act[0].numpy(), 5.0, 1.0, 0.0, obs[1].numpy())   # single transition, reference signature
+    assert buf.insert_index == 3 and float(buf.rewards[2]) == 5.0
+    b = buf.sample(32, generator=torch.Generator().manual_seed(0))
+    assert isinstance(b, Batch) and b.observations.shape == (32, 3) and b.masks.shape == (32,)
+    assert torch.allclose(b.next_observations[b.rewards != 5.0] - b.observations[b.rewards != 5.0], torch.tensor(100.0))
+
+
+def test_state_storage_labels_and_file_round_trip(tmp_path, models):
+    from bioimitation_gym_b200 import refmotion
+    from bioimitation_gym_b200.rollout import state_labels
+    cm = models["2d_muscle"]
+    labels = state_labels(cm)
+    assert labels[0] == "time" and len(labels) == 1 + 2 * cm.tables.n_dof + 2 * cm.tables.n_muscles
+    assert "pelvis_tilt/value" in labels and "pelvis_tilt/speed" in labels
+    data = np.random.default_rng(0).normal(size=(5, len(labels)))
+    path = str(tmp_path / "simulation_States.sto")
+    refmotion.write_storage(path, "simulation_States", labels, data)
+    got_labels, got, in_deg = refmotion.read_storage(path)
+    assert got_labels == labels and not in_deg and np.allclose(got, data, atol=1e-7)
