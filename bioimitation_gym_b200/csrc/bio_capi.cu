@@ -232,6 +232,8 @@ int validate(const BioModelTables* m, const BioTaskConfig* t, const BioRefTables
         if (m->mus_pt_count[i] > BIO_MAX_MUSCLE_PTS) return fail(-1, "muscle with too many path points");
     if (t->horizon < 1 || t->horizon > BIO_MAX_HORIZON) return fail(-1, "horizon out of range");
     if (t->n_substeps < 1) return fail(-1, "n_substeps must be >= 1");
+    if (t->integrator == BIO_INT_ADAPTIVE_RKM)
+        return fail(-1, "adaptive_rkm is the CPU-baseline scheme of the oracle; the CUDA path runs fixed-step schemes");
     if (t->integrator < 0 || t->integrator > BIO_INT_IMPLICIT_DAMPING) return fail(-1, "unknown integrator");
     if (r->n_coords != m->n_coords) return fail(-1, "reference tables have a different coordinate count");
     if (r->n_rows < 2 || !r->q || !r->u || !r->body_pos || !r->com_pos) return fail(-1, "bad reference tables");

@@ -30,7 +30,8 @@ DEFAULT_BACKEND_CONFIG: Dict[str, Any] = dict(
 
 INTEGRATORS = {"semi_implicit_euler": M["BIO_INT_SEMI_IMPLICIT_EULER"],
                "rk2": M["BIO_INT_RK2_MIDPOINT"], "rk4": M["BIO_INT_RK4"],
-               "implicit_damping": M["BIO_INT_IMPLICIT_DAMPING"]}
+               "implicit_damping": M["BIO_INT_IMPLICIT_DAMPING"],
+               "adaptive_rkm": M["BIO_INT_ADAPTIVE_RKM"]}
 # Stated fixed-step scheme replacing OpenSim's adaptive Manager integrator
 # (opensim_wrapper.py:287-301): semi-implicit Euler with the dissipative
 # contact / limit forces linearly implicit in the speeds, h = 0.01 s / 20 =

@@ -652,10 +652,81 @@ static void post_clamp(const BioModelTables* m, OrcEnv* e) {
     }
 }
 
+/* Error-controlled Runge-Kutta-Merson over one control step: the stand-in for the reference's
+   opensim.Manager default integrator at its accuracy of 1e-3 (muscle_walking_imitation_env2D.py:41-42,
+   opensim_wrapper.py:287-301).  CPU baseline only ("restated reference algorithm, not OpenSim"); the
+   number of right-hand-side evaluations is returned for the report. */
+#define ORC_ADAPTIVE_ACCURACY 1e-3
+static void pack_state(const BioModelTables* m, const OrcEnv* e, double* y) {
+    int nd = m->n_dof, nm = m->n_muscles;
+    for (int i = 0; i < nd; i++) { y[i] = e->q[i]; y[nd + i] = e->u[i]; }
+    for (int i = 0; i < nm; i++) { y[2 * nd + i] = e->act[i]; y[2 * nd + nm + i] = e->lm[i]; }
+}
+static void unpack_state(const BioModelTables* m, const double* y, OrcEnv* e) {
+    int nd = m->n_dof, nm = m->n_muscles;
+    for (int i = 0; i < nd; i++) { e->q[i] = y[i]; e->u[i] = y[nd + i]; }
+    for (int i = 0; i < nm; i++) { e->act[i] = y[2 * nd + i]; e->lm[i] = y[2 * nd + nm + i]; }
+}
+static void rhs_packed(const BioModelTables* m, const BioTaskConfig* c, const double* y, const double* ctrl, double t,
+                       uint64_t seed, uint64_t env, double* dy) {
+    int nd = m->n_dof, nm = m->n_muscles;
+    OrcEnv st;
+    OrcEval ev;
+    unpack_state(m, y, &st);
+    post_clamp(m, &st);
+    eval_env(m, c, st.q, st.u, st.act, st.lm, ctrl, t, seed, env, &ev);
+    for (int i = 0; i < nd; i++) { dy[i] = st.u[i]; dy[nd + i] = ev.udot[i]; }
+    for (int i = 0; i < nm; i++) { dy[2 * nd + i] = ev.adot[i]; dy[2 * nd + nm + i] = ev.lmdot[i]; }
+}
+int orc_last_adaptive_evals = 0;
+static void integrate_adaptive(const BioModelTables* m, const BioTaskConfig* c, OrcEnv* e, const double* ctrl,
+                               uint64_t seed, uint64_t env) {
+    enum { NY = 2 * MAXD + 2 * MAXM };
+    int n = 2 * m->n_dof + 2 * m->n_muscles, evals = 0;
+    double y[NY], k1[NY], k2[NY], k3[NY], k4[NY], k5[NY], yt[NY];
+    double t = e->istep * c->dt, tend = t + c->dt, h = c->dt / 4;
+    pack_state(m, e, y);
+    while (tend - t > 1e-12 && evals < 20000) {
+        if (h > tend - t) h = tend - t;
+        rhs_packed(m, c, y, ctrl, t, seed, env, k1);
+        for (int i = 0; i < n; i++) yt[i] = y[i] + h / 3 * k1[i];
+        rhs_packed(m, c, yt, ctrl, t + h / 3, seed, env, k2);
+        for (int i = 0; i < n; i++) yt[i] = y[i] + h / 6 * (k1[i] + k2[i]);
+        rhs_packed(m, c, yt, ctrl, t + h / 3, seed, env, k3);
+        for (int i = 0; i < n; i++) yt[i] = y[i] + h / 8 * (k1[i] + 3 * k3[i]);
+        rhs_packed(m, c, yt, ctrl, t + h / 2, seed, env, k4);
+        for (int i = 0; i < n; i++) yt[i] = y[i] + h * (0.5 * k1[i] - 1.5 * k3[i] + 2 * k4[i]);
+        rhs_packed(m, c, yt, ctrl, t + h, seed, env, k5);
+        evals += 5;
+        double err = 0;
+        for (int i = 0; i < n; i++) {
+            double ei = fabs(h / 30 * (2 * k1[i] - 9 * k3[i] + 8 * k4[i] - k5[i]));
+            double sc = fabs(y[i]) > 0.1 ? fabs(y[i]) : 0.1;     /* relative, with a floor for states near zero */
+            if (ei / sc > err) err = ei / sc;
+        }
+        if (err <= ORC_ADAPTIVE_ACCURACY || h < 1e-7) {
+            for (int i = 0; i < n; i++) y[i] += h / 6 * (k1[i] + 4 * k4[i] + k5[i]);
+            t += h;
+            OrcEnv st = *e;
+            unpack_state(m, y, &st);
+            post_clamp(m, &st);
+            pack_state(m, &st, y);
+        }
+        double fac = err > 0 ? 0.9 * pow(ORC_ADAPTIVE_ACCURACY / err, 0.25) : 4.0;
+        if (fac < 0.2) fac = 0.2;
+        if (fac > 4.0) fac = 4.0;
+        h *= fac;
+    }
+    unpack_state(m, y, e);
+    post_clamp(m, e);
+    orc_last_adaptive_evals = evals;
+}
+
 /* Advance one env by dt with n_substeps fixed steps of the stated scheme. */
 static void integrate(const BioModelTables* m, const BioTaskConfig* c, OrcEnv* e, const double* ctrl,
                       uint64_t seed, uint64_t env) {
     int nd = m->n_dof, nm = m->n_muscles;
+    if (c->integrator == BIO_INT_ADAPTIVE_RKM) { integrate_adaptive(m, c, e, ctrl, seed, env); return; }
     double h = c->dt / c->n_substeps;
     double t0 = e->istep * c->dt;
     OrcEval ev;

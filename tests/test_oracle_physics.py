@@ -359,3 +359,23 @@ def test_simm_spline_interpolates_knots(oracle_lib, models):
         x0 = t.knot_x[kb]
         a = oracle_lib.func_eval(t, f, x0 - 0.5)
         assert abs(a[0] - (t.knot_c[kb][0] - 0.5 * t.knot_c[kb][1])) < 1e-12 and a[2] == 0.0
+
+
+def test_adaptive_baseline_integrator_tracks_fine_fixed_step(oracle_lib):
+    """The CPU-baseline scheme (error-controlled Runge-Kutta-Merson, accuracy 1e-3: stand-in for the
+    reference's default opensim.Manager integrator) against RK4 with h = 50 us over 10 control steps."""
+    from bioimitation_gym_b200 import registry, tasks
+    orc = oracle_lib
+    out = {}
+    for name, cfg in (("adaptive", dict(integrator="adaptive_rkm")), ("fine", dict(integrator="rk4", substeps=200))):
+        full = tasks.merged_config(dict(num_envs=4, seed=0, **cfg))
+        spec, cm, ref, task = registry.build_env_tables("MuscleWalkingImitation2D-v0", full, None, None)
+        rt = orc.RefTables(ref["q"], ref["u"], ref["body_pos"], ref["com_pos"])
+        env = orc.OracleVecEnv(cm.tables, task, rt, 4, seed=0)
+        env.reset()
+        rng = np.random.default_rng(0)
+        for _ in range(10):
+            env.step(rng.uniform(0, 1, (4, 14)))
+        out[name] = env.get_state()
+    assert np.max(np.abs(out["adaptive"]["q"] - out["fine"]["q"])) < 5e-3
+    assert np.max(np.abs(out["adaptive"]["act"] - out["fine"]["act"])) < 5e-3
