@@ -35,7 +35,10 @@ struct alignas(16) EnvWork {
             // spatial inertia about O and body force per body: [0] mass, [1..3] m*c, [4..9] I (xx yy zz xy xz yz),
             // [10..15] force (n; f); turned into composite / subtree sums in place
             T BI[BIO_MAX_BODIES][16];
-            T IS[C::ND][6];                                // I^c_body(i) * S_i
+            union {
+                T IS[C::ND][6];                            // I^c_body(i) * S_i (phase G on)
+                T mv[8][6];                                // moving path points: location [0..2], d/dq [3..5] (phases A..C)
+            };
             T H[C::ND * (C::ND + 1) / 2], rhs[C::ND];
             T Q[C::ND], limDd[C::ND];
         } g;
@@ -111,12 +114,20 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     const int nb = m.n_bodies, nd = m.n_dof, nm = m.n_muscles;
     auto& K = E.k.g;
 
-    // ---- phase A: joint functions of the coordinates ----
-    for (int a = lane; a < m.n_axes; a += G) {
-        const int d = m.axis_dof[a];
+    // ---- phase A: joint functions of the coordinates, and the location functions of moving path
+    // points (task n_axes + 3 k + c: component c of moving point k); the spline interval of the
+    // previous evaluation is the search hint ----
+    for (int a = lane; a < m.n_axes + 3 * m.n_moving; a += G) {
         T s, ds, dds;
-        func_eval(m, m.axis_func[a], d >= 0 ? E.q[d] : T(0), s, ds, dds);
-        K.ax_s[a] = s; K.ax_ds[a] = ds; K.ax_dds[a] = dds;
+        if (a < m.n_axes) {
+            const int d = m.axis_dof[a];
+            func_eval(m, m.axis_func[a], d >= 0 ? E.q[d] : T(0), s, ds, dds, a < P2_MAXTASK ? &E.knot_hint[a] : nullptr);
+            K.ax_s[a] = s; K.ax_ds[a] = ds; K.ax_dds[a] = dds;
+        } else {
+            const int k = (a - m.n_axes) / 3, c = (a - m.n_axes) % 3, p = m.moving_pt[k];
+            func_eval(m, m.pt_func[p][c], E.q[m.pt_dof[p]], s, ds, dds, a < P2_MAXTASK ? &E.knot_hint[a] : nullptr);
+            K.mv[k][c] = s; K.mv[k][3 + c] = ds;
+        }
     }
     gsync<G>();
 
@@ -232,8 +243,8 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
                 }
             }
             if (kind == BIO_PT_MOVING) {
-                T d2;
-                for (int c = 0; c < 3; c++) func_eval(m, m.pt_func[p][c], E.q[d], loc[c], mdloc[c], d2);
+                const int mk = m.pt_mov[p];
+                for (int c = 0; c < 3; c++) { loc[c] = K.mv[mk][c]; mdloc[c] = K.mv[mk][3 + c]; }
                 pmov = p;
             } else {
                 for (int c = 0; c < 3; c++) loc[c] = m.pt_loc[p][c];
@@ -257,12 +268,13 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         const T amin = m.mus_amin[i], lmin = m.mus_lm_min[i];
         const T lmi = E.lm[i];
         const T lmc = lmi < lmin ? lmin : lmi;
-        const T lat = Num<T>::sqrt(lmc * lmc - h * h);
-        const T cosa = lat / lmc;
+        const T lat = Num<T>::sqrt_pos(lmc * lmc - h * h);
+        const T cosa = Num<T>::div(lat, lmc);
         T fal, fpe, ft, fv, dfv, dtmp;
-        curve_eval(m, 0, lmc / lopt, fal, dtmp);
-        curve_eval(m, 2, lmc / lopt, fpe, dtmp);
-        curve_eval(m, 3, (L - lat) / m.mus_lts[i], ft, dtmp);
+        const T lnorm = Num<T>::div(lmc, lopt);
+        curve_eval(m, 0, lnorm, fal, dtmp);
+        curve_eval(m, 2, lnorm, fpe, dtmp);
+        curve_eval(m, 3, Num<T>::div(L - lat, m.mus_lts[i]), ft, dtmp);
         const T ac = clampv(E.act[i], amin, T(1));
         const T afal = ac * fal;
         // Newton on the damped-equilibrium residual, warm-started from the root of the previous
@@ -284,8 +296,8 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         if (lmi <= lmin && vn < T(0)) vn = T(0);
         E.lmdot[i] = vn * m.mus_vmax[i] * lopt;
         const T ec = clampv(E.ctrl[i], amin, T(1));
-        const T tau = ec > ac ? m.mus_tact[i] * (T(0.5) + T(1.5) * ac) : m.mus_tdeact[i] / (T(0.5) + T(1.5) * ac);
-        E.adot[i] = (ec - ac) / tau;
+        const T tau = ec > ac ? m.mus_tact[i] * (T(0.5) + T(1.5) * ac) : Num<T>::div(m.mus_tdeact[i], T(0.5) + T(1.5) * ac);
+        E.adot[i] = Num<T>::div(ec - ac, tau);
         const T tension = fiso * ft;
         if (full) {
             curve_eval(m, 1, vn, fv, dfv);
@@ -317,19 +329,20 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             for (int c = 0; c < 3; c++) v[c] += K.V[b][3 + c];
             const T vn = -v[1];
             const T kk = m.sph_k[s];
-            const T fH = T(4.0 / 3.0) * kk * depth * Num<T>::sqrt(rad * kk * depth);
+            const T fH = T(4.0 / 3.0) * kk * depth * Num<T>::sqrt_pos(rad * kk * depth);
             const T f = fH * (T(1) + T(1.5) * m.sph_c[s] * vn);
             if (f > T(0)) {
                 F[1] = f;
                 const T vs = Num<T>::sqrt(v[0] * v[0] + v[2] * v[2]);
-                const T vrel = vs / m.sph_vt[s];
-                const T strib = m.sph_ud[s] + T(2) * (m.sph_us[s] - m.sph_ud[s]) / (T(1) + vrel * vrel);
+                const T vrel = Num<T>::div(vs, m.sph_vt[s]);
+                const T strib = m.sph_ud[s] + Num<T>::div(T(2) * (m.sph_us[s] - m.sph_ud[s]), T(1) + vrel * vrel);
                 if (vs != T(0)) {
                     const T ff = f * ((vrel < T(1) ? vrel : T(1)) * strib + m.sph_uv[s] * vs);
-                    F[0] = -ff * v[0] / vs;
-                    F[2] = -ff * v[2] / vs;
+                    const T fs = -Num<T>::div(ff, vs);
+                    F[0] = fs * v[0];
+                    F[2] = fs * v[2];
                 }
-                D0 = f * ((vrel < T(1) ? T(1) / m.sph_vt[s] : T(1) / vs) * strib + m.sph_uv[s]);
+                D0 = f * (Num<T>::rcp(vrel < T(1) ? m.sph_vt[s] : vs) * strib + m.sph_uv[s]);
                 D1 = T(1.5) * m.sph_c[s] * fH;
             }
         }
@@ -338,8 +351,8 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     } else if (lane - m.n_spheres < m.n_limits) {
         const int l = lane - m.n_spheres, d = m.lim_dof[l];
         const T w = m.lim_w[l], qq = E.q[d];
-        const T sup = step5((qq - m.lim_qup[l]) / w);
-        const T slo = T(1) - step5((qq - (m.lim_qlo[l] - w)) / w);
+        const T sup = step5(Num<T>::div(qq - m.lim_qup[l], w));
+        const T slo = T(1) - step5(Num<T>::div(qq - (m.lim_qlo[l] - w), w));
         E.limf[l] = -m.lim_kup[l] * sup * (qq - m.lim_qup[l]) + m.lim_klo[l] * slo * (m.lim_qlo[l] - qq) -
                     m.lim_damp[l] * (sup + slo) * E.u[d];
         E.limD[l] = m.lim_damp[l] * (sup + slo);

@@ -41,7 +41,7 @@ __device__ __forceinline__ void coop_solve(const DevModel<T>& m, EnvWork<T, CLS>
         const int pb = m.lt_step_begin[st], pe = m.lt_step_begin[st + 1];
         if (pb == pe) continue;                  // root-most dof: nothing to eliminate
         const int k = nd - 1 - st;
-        const T inv = T(1) / K.H[k * (k + 1) / 2 + k];
+        const T inv = Num<T>::rcp(K.H[k * (k + 1) / 2 + k]);
         const T bk = K.rhs[k];                   // final z_k: every descendant step is done
         T keep_a[NIT];
         int keep_ki[NIT];
@@ -74,7 +74,7 @@ __device__ __forceinline__ void coop_solve(const DevModel<T>& m, EnvWork<T, CLS>
     uint32_t anc = 0u;
     if (lane < nd) {
         row = lane * (lane + 1) / 2;
-        wv = K.rhs[lane] / K.H[row + lane];
+        wv = Num<T>::div(K.rhs[lane], K.H[row + lane]);
         anc = m.dof_anc_mask[lane];
     }
     for (int j = 0; j < nd - 1; j++) {

@@ -147,6 +147,7 @@ struct alignas(16) DevModel {
     int32_t body_pt_count[BIO_MAX_BODIES];
     int32_t body_pt_list[BIO_MAX_PATHPTS];
     int32_t moving_pt[8];
+    int8_t pt_mov[BIO_MAX_PATHPTS];          // index of a moving path point in moving_pt (-1: not moving)
     int32_t ent_i[BIO_MAX_DOF * (BIO_MAX_DOF + 1) / 2];
     int32_t ent_j[BIO_MAX_DOF * (BIO_MAX_DOF + 1) / 2];
     int32_t obs_desc[256];                   // (kind << 16) | index per observation slot
@@ -285,8 +286,9 @@ void convert_model(const BioModelTables& s, DevModel<T>& d) {
             d.body_pt_count[b] = k - d.body_pt_begin[b];
         }
         d.n_moving = 0;
+        for (int p = 0; p < BIO_MAX_PATHPTS; p++) d.pt_mov[p] = -1;
         for (int p = 0; p < s.n_pathpts; p++)
-            if (s.pt_kind[p] == BIO_PT_MOVING && d.n_moving < 8) d.moving_pt[d.n_moving++] = p;
+            if (s.pt_kind[p] == BIO_PT_MOVING && d.n_moving < 8) { d.pt_mov[p] = (int8_t)d.n_moving; d.moving_pt[d.n_moving++] = p; }
         d.n_entries = 0;
         for (int i = 0; i < s.n_dof; i++)
             for (int j = 0; j <= i; j++)

@@ -126,6 +126,16 @@ def test_warm_started_newton_finds_the_same_root(emul_lib, oracle_lib, models):
     assert worst < 1e-8
 
 
+def test_two_ctas_of_the_2d_kernel_fit_one_sm(emul_lib):
+    """Shared-memory budget of the fp32 / 2D instantiation: model block + 16 per-env work buffers per
+    CTA, two CTAs (16 warps) per SM.  228 KB per SM, 1 KB reserved per CTA."""
+    out = np.zeros(8, dtype=np.int64)
+    emul_lib.emul_sizes(_p(out))
+    model, work = int(out[0]), int(out[1])
+    cta = (model + 15) // 16 * 16 + 16 * work
+    assert cta <= (233472 - 2 * 1024) // 2, "2D fp32 CTA needs %d B of shared memory: only one CTA per SM" % cta
+
+
 def test_program_rejects_models_it_does_not_cover(emul_lib, models):
     t = models["3d_muscle"].tables
     udot, adot, lmdot, misc = np.zeros(16), np.zeros(24), np.zeros(24), np.zeros(256)
