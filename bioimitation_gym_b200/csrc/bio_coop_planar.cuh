@@ -90,18 +90,6 @@ __device__ __forceinline__ void coop_solve(const DevModel<T>& m, EnvWork<T, CLS>
 // ---------------------------------------------------------------------------
 template <typename T> BIO_DEV void rot2(T c, T s, T x, T y, T& ox, T& oy) { ox = c * x - s * y; oy = s * x + c * y; }
 
-// pose, velocity and bias acceleration of the frame a chain walk carries along
-template <typename T>
-struct P2Frame {
-    T c, s, rx, ry, w, vx, vy, aw, ax, ay;
-};
-
-// planar spatial inertia about O (symmetric 3x3 on (w, vx, vy)) and a spatial force
-template <typename T>
-struct P2Inertia {
-    T ww, wx, wy, xx, xy, yy, n, fx, fy;
-};
-
 // ---- phase A: joint functions of the coordinates (and the functions of moving path points) ----
 template <typename T, int CLS>
 BIO_DEV void p2_phase_a(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
@@ -178,6 +166,102 @@ BIO_DEV void p2_phase_b(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         if (opost) st4(E.O, rx, ry, T(0), T(0));
         rx = opost ? T(0) : rx; ry = opost ? T(0) : ry;
         if (code & P2_F_LAST) {                  // last axis of its body: publish the frame
+            const int b = (code >> 8) & 15;
+            st4(K.pose[b], c, s, rx, ry);
+            st4(K.V[b], w, vx, vy, T(0));
+            st4(K.A[b], aw, ax, ay, T(0));
+        }
+    }
+}
+
+// ---- phase B as warp scans: lane = (chain, step), 8 steps per chain.  The walk above is a chain of
+// associative updates, so every quantity is a prefix over the steps of a chain:
+//   orientation   product of unit complex numbers (cos, sin)
+//   position      sum of the displacements (joint offsets turned by the orientation before the step,
+//                 translations along the parent frame), started at the step that fixes the origin O
+//   velocity      sum of motion vector * rate;  bias acceleration: sum of motion vector * d2s/dq2 q'^2
+//                 + (velocity before the step) x (motion vector) * rate
+// 3 shuffle rounds per prefix instead of 8 dependent steps.  Same results as the serial walk up to the
+// association order of the sums. ----
+template <typename T>
+__device__ __forceinline__ T shfl_up8(const unsigned mask, const T v, const int off) { return __shfl_up_sync(mask, v, off, 8); }
+template <typename T>
+__device__ __forceinline__ T shfl_at8(const unsigned mask, const T v, const int src) { return __shfl_sync(mask, v, src, 8); }
+
+template <typename T, int CLS>
+__device__ __forceinline__ void p2_phase_b_scan(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
+    constexpr int G = CoopCls<CLS>::G;
+    const PlanarProg<T>& pr = m.prog;
+    auto& K = E.k.p;
+    const unsigned mask = group_mask<G>();
+    const int l = lane >> 3, i = lane & 7;
+    const bool live = l < pr.n_branches && i < pr.ch_n[l];
+    int code = 0, sc = i;
+    T jx = T(0), jy = T(0), rw = T(0), tA = T(0), tB = T(0), t3, st = T(0), ds = T(0), sd = T(0), acc = T(0);
+    T c = T(1), s = T(0);
+    if (l < pr.n_branches) sc = pr.ch_scan[l][i];
+    if (live) {
+        code = pr.ch_code[l][i];
+        const int a = code & 255;
+        ld2(pr.ch_j[l][i], jx, jy);
+        ld4(pr.ax_k[a], rw, tA, tB, t3);
+        ld4(K.ax[a], st, ds, sd, acc);
+        ld2(K.axr[a], c, s);
+    }
+    const int first = sc & 15, o_step = (sc >> 4) & 15, in_dof = (sc >> 8) & 3;
+    // orientation after every step (inclusive prefix product) and before it
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+        const T pc = shfl_up8(mask, c, off), ps = shfl_up8(mask, s, off);
+        if (i >= off) { const T cn = c * pc - s * ps, sn = s * pc + c * ps; c = cn; s = sn; }
+    }
+    T ce = shfl_up8(mask, c, 1), se = shfl_up8(mask, s, 1);
+    if (i == 0) { ce = T(1); se = T(0); }
+    // frame of the parent body = orientation before the first step of this step's body
+    const T cp = shfl_at8(mask, ce, first), sp = shfl_at8(mask, se, first);
+    // displacement of the step; steps up to the one that fixes O build O, the later ones the position about O
+    const T tx = tA * cp + tB * sp, ty = tA * sp - tB * cp;
+    const T dx = ce * jx - se * jy + tx * st, dy = se * jx + ce * jy + ty * st;
+    T rx = i > o_step ? dx : T(0), ry = i > o_step ? dy : T(0);
+    T ox = i > o_step ? T(0) : dx, oy = i > o_step ? T(0) : dy;
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+        const T a0 = shfl_up8(mask, rx, off), a1 = shfl_up8(mask, ry, off);
+        const T a2 = shfl_up8(mask, ox, off), a3 = shfl_up8(mask, oy, off);
+        if (i >= off) { rx += a0; ry += a1; ox += a2; oy += a3; }
+    }
+    // motion vector (a rotation turns about the current origin; its own displacement is zero)
+    const T kx = tx + rw * ry, ky = ty - rw * rx;
+    // velocity after / before the step
+    T w = rw * sd, vx = kx * sd, vy = ky * sd;
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+        const T a0 = shfl_up8(mask, w, off), a1 = shfl_up8(mask, vx, off), a2 = shfl_up8(mask, vy, off);
+        if (i >= off) { w += a0; vx += a1; vy += a2; }
+    }
+    const T we = w - rw * sd, vxe = vx - kx * sd, vye = vy - ky * sd;
+    // bias acceleration: V x S (planar): angular part 0, linear = w * (-S_vy, S_vx) + S_w * (V_vy, -V_vx)
+    const T cx = -we * ky + rw * vye, cy = we * kx - rw * vxe;
+    T aw = rw * acc, ax = kx * acc + cx * sd, ay = ky * acc + cy * sd;
+    if (i == 0) { ax -= m.gravity[0]; ay -= m.gravity[1]; }
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+        const T a0 = shfl_up8(mask, aw, off), a1 = shfl_up8(mask, ax, off), a2 = shfl_up8(mask, ay, off);
+        if (i >= off) { aw += a0; ax += a1; ay += a2; }
+    }
+    // motion vector of the dof: sum over its (<= 3, consecutive) axes
+    T Sw = ds * rw, Sx = ds * kx, Sy = ds * ky;
+    {
+        const T p1w = shfl_up8(mask, Sw, 1), p1x = shfl_up8(mask, Sx, 1), p1y = shfl_up8(mask, Sy, 1);
+        const T p2w = shfl_up8(mask, Sw, 2), p2x = shfl_up8(mask, Sx, 2), p2y = shfl_up8(mask, Sy, 2);
+        if (in_dof >= 1) { Sw += p1w; Sx += p1x; Sy += p1y; }
+        if (in_dof >= 2) { Sw += p2w; Sx += p2x; Sy += p2y; }
+    }
+    // publish (the chains repeat the root joint and store the same values)
+    if (live) {
+        if (code & P2_F_SPUB) st4(K.S[(code >> 12) & 31], Sw, Sx, Sy, T(0));
+        if (i == o_step) st4(E.O, ox, oy, T(0), T(0));
+        if (code & P2_F_LAST) {
             const int b = (code >> 8) & 15;
             st4(K.pose[b], c, s, rx, ry);
             st4(K.V[b], w, vx, vy, T(0));
@@ -656,7 +740,8 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
     constexpr int G = CoopCls<CLS>::G;
     p2_phase_a<T, CLS>(m, E, lane);
     gsync<G>();
-    p2_phase_b<T, CLS>(m, E, lane);
+    if (m.prog.scan_ok && G == 16) p2_phase_b_scan<T, CLS>(m, E, lane);
+    else p2_phase_b<T, CLS>(m, E, lane);
     gsync<G>();
     p2_phase_c<T, CLS>(m, E, lane, newton_iters, full);
     p2_phase_d<T, CLS>(m, E, lane);

@@ -35,20 +35,17 @@ namespace bio {
 template <typename T>
 struct alignas(16) PlanarProg {
     int32_t ok, n_branches, n_atasks, n_src;
-    int32_t root_body, root_axis_begin, root_axis_count, root_ndof;
+    int32_t root_body, root_ndof, sph_src0, scan_ok;   // scan_ok: chain walk as warp scans (<= 2 chains of <= 8 steps)
     int32_t root_dof[4];
-    int32_t root_sph_mask, sph_src0, pad_[2];
     int32_t br_nb[P2_MAXBR];
     int32_t br_body[P2_MAXBR][P2_MAXCB];
-    int32_t br_axis_begin[P2_MAXBR][P2_MAXCB];
-    int32_t br_axis_count[P2_MAXBR][P2_MAXCB];
     int32_t br_dof[P2_MAXBR][P2_MAXCB];        // dof of the body's joint (-1: none)
-    int32_t br_sph_mask[P2_MAXBR][P2_MAXCB];   // contact spheres carried by the body
-    int32_t body_sph_mask[BIO_MAX_BODIES];     // the same per body
+    int32_t body_sph_mask[BIO_MAX_BODIES];     // contact spheres carried by the body
     // chain walk: root axes, then the axes of the chain's bodies, one step per elementary axis:
     // code = axis | body<<8 | dof<<12 | flags (P2_F_*); ch_j = joint location on the first axis of a
     // body (else 0); ax_k = (rw, tA, tB): motion vector (rw, tA*cp + tB*sp + rw*ry, tA*sp - tB*cp - rw*rx)
     int32_t ch_n[P2_MAXBR];
+    int32_t ch_scan[P2_MAXBR][8];              // scan form: first step of the body | O step<<4 | axes before it in its dof<<8
     int32_t ch_code[P2_MAXBR][(P2_MAXCB + 1) * P2_MAXAX];
     alignas(16) T ch_j[P2_MAXBR][(P2_MAXCB + 1) * P2_MAXAX][2];
     alignas(16) T ax_k[BIO_MAX_AXES][4];
@@ -450,12 +447,8 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     };
     for (int b = 0; b < s.n_bodies; b++) if (s.body_axis_count[b] > P2_MAXAX) return;
     pr.root_body = 0;
-    pr.root_axis_begin = s.body_axis_begin[0];
-    pr.root_axis_count = s.body_axis_count[0];
     { int dofs[4] = {-1, -1, -1, -1}; pr.root_ndof = joint_dofs(0, dofs); if (pr.root_ndof > 3) return;
       for (int k = 0; k < 4; k++) pr.root_dof[k] = k < pr.root_ndof ? dofs[k] : -1; }
-    int body_branch[BIO_MAX_BODIES], body_k[BIO_MAX_BODIES];
-    body_branch[0] = -1; body_k[0] = 0;
     for (int b = 1; b < s.n_bodies; b++) {
         if (s.body_parent[b] != 0) continue;
         if (pr.n_branches >= P2_MAXBR) return;
@@ -466,10 +459,7 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
             int dofs[4] = {-1, -1, -1, -1};
             if (joint_dofs(cur, dofs) > 1) return;
             pr.br_body[l][k] = cur;
-            pr.br_axis_begin[l][k] = s.body_axis_begin[cur];
-            pr.br_axis_count[l][k] = s.body_axis_count[cur];
             pr.br_dof[l][k] = dofs[0];
-            body_branch[cur] = l; body_k[cur] = k;
             k++;
             if (!n_child[cur]) break;
             cur = child[cur];
@@ -477,13 +467,7 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         pr.br_nb[l] = k;
         for (; k < P2_MAXCB; k++) { pr.br_body[l][k] = -1; pr.br_dof[l][k] = -1; }
     }
-    // contact spheres per body
     if (s.n_spheres > BIO_MAX_SPHERES) return;
-    for (int sp = 0; sp < s.n_spheres; sp++) {
-        const int b = s.sph_body[sp];
-        if (b == 0) pr.root_sph_mask |= 1 << sp;
-        else pr.br_sph_mask[body_branch[b]][body_k[b]] |= 1 << sp;
-    }
     for (int b = 0; b < s.n_bodies; b++) {
         pr.body_sph_mask[b] = 0;
         for (int sp = 0; sp < s.n_spheres; sp++) if (s.sph_body[sp] == b) pr.body_sph_mask[b] |= 1 << sp;
@@ -518,6 +502,23 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
             add_joint(pr.br_body[l][k], false);
         }
         pr.ch_n[l] = n;
+    }
+    // scan form of the chain walk: lane = (chain, step), 8 steps per chain
+    pr.scan_ok = pr.n_branches >= 1 && pr.n_branches <= 2;
+    for (int l = 0; l < pr.n_branches && pr.scan_ok; l++) {
+        if (pr.ch_n[l] > 8) { pr.scan_ok = 0; break; }
+        int o_step = -1, first = 0, in_dof = 0;
+        for (int i = 0; i < pr.ch_n[l]; i++)
+            if (pr.ch_code[l][i] & (P2_F_OPRE | P2_F_OPOST)) o_step = i;
+        if (o_step < 0) { pr.scan_ok = 0; break; }
+        for (int i = 0; i < 8; i++) {
+            if (i >= pr.ch_n[l]) { pr.ch_scan[l][i] = i | (o_step << 4); continue; }
+            const int code = pr.ch_code[l][i];
+            if (code & P2_F_FIRST) first = i;
+            in_dof = (code & P2_F_SRESET) || ((code >> 12) & 31) == 31 ? 0 : in_dof + 1;
+            if (in_dof > 2) pr.scan_ok = 0;
+            pr.ch_scan[l][i] = first | (o_step << 4) | (in_dof << 8);
+        }
     }
     // phase A tasks
     int n_mov = 0, mov_of_pt[BIO_MAX_PATHPTS];
