@@ -99,6 +99,7 @@ __device__ __forceinline__ void rot_cols(T* R, T cs, T sn) {
 
 }  // namespace bio
 #include "bio_coop_planar.cuh"
+#include "bio_coop_spatial.cuh"
 namespace bio {
 
 // ---------------------------------------------------------------------------
@@ -131,7 +132,12 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     }
     gsync<G>();
 
-    // ---- phase B: kinematics, one tree level at a time, lane = body of the level ----
+    // ---- phase B: kinematics; root-plus-chains models on a full warp: prefix scans over the steps of
+    // every chain (bio_coop_spatial.cuh), else one tree level at a time, lane = body of the level ----
+    if (G == 32 && m.prog.chain_ok) {
+        if constexpr (G == 32) p3_phase_b_scan<T, CLS>(m, E, lane);
+        gsync<G>();
+    } else
     for (int lev = 0; lev < m.n_levels; lev++) {
         const int lb = m.level_begin[lev] + lane;
         if (lb < m.level_begin[lev + 1]) {

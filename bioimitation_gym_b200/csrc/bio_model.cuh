@@ -17,7 +17,8 @@ namespace bio {
 // stay in that lane's registers; muscles hand their tension-scaled unit wrenches to the bodies
 // through a list of wrench sources.
 // ---------------------------------------------------------------------------
-#define P2_MAXBR 4        // chains hanging from the root
+#define P2_MAXBR 2        // chains hanging from the root
+#define P2_MAXSTEP 16     // elementary axes on the walk root joint -> leaf of one chain
 #define P2_MAXCB 3        // bodies per chain
 #define P2_MAXAX 3        // elementary axes per joint
 #define P2_MAXSLOT 3      // distinct bodies one muscle touches
@@ -31,11 +32,13 @@ namespace bio {
 #define P2_F_SPUB (1 << 21)      // last axis of its dof: publish the motion vector
 #define P2_F_OPRE (1 << 22)      // first rotation of the root: the origin O is fixed before this axis
 #define P2_F_OPOST (1 << 23)     // root without rotation: O is fixed after this (last) axis
+#define P2_F_ROT (1 << 24)       // rotation axis (else translation)
 
 template <typename T>
 struct alignas(16) PlanarProg {
     int32_t ok, n_branches, n_atasks, n_src;
-    int32_t root_body, root_ndof, sph_src0, scan_ok;   // scan_ok: chain walk as warp scans (<= 2 chains of <= 8 steps)
+    int32_t root_body, root_ndof, sph_src0, scan_ok;   // scan_ok: planar chain walk as warp scans (<= 8 steps per chain)
+    int32_t chain_ok, pad_[3];                         // chain lists valid (any model: root + <= 2 chains of <= 16 steps)
     int32_t root_dof[4];
     int32_t br_nb[P2_MAXBR];
     int32_t br_body[P2_MAXBR][P2_MAXCB];
@@ -45,9 +48,9 @@ struct alignas(16) PlanarProg {
     // code = axis | body<<8 | dof<<12 | flags (P2_F_*); ch_j = joint location on the first axis of a
     // body (else 0); ax_k = (rw, tA, tB): motion vector (rw, tA*cp + tB*sp + rw*ry, tA*sp - tB*cp - rw*rx)
     int32_t ch_n[P2_MAXBR];
-    int32_t ch_scan[P2_MAXBR][8];              // scan form: first step of the body | O step<<4 | axes before it in its dof<<8
-    int32_t ch_code[P2_MAXBR][(P2_MAXCB + 1) * P2_MAXAX];
-    alignas(16) T ch_j[P2_MAXBR][(P2_MAXCB + 1) * P2_MAXAX][2];
+    int32_t ch_scan[P2_MAXBR][P2_MAXSTEP];     // scan form: first step of the body | O step<<4 | axes before it in its dof<<8
+    int32_t ch_code[P2_MAXBR][P2_MAXSTEP];
+    alignas(16) T ch_j[P2_MAXBR][P2_MAXSTEP][4];
     alignas(16) T ax_k[BIO_MAX_AXES][4];
     // phase A tasks: t < n_axes: axis t; then 3 per moving point (k = (t - n_axes) / 3, component % 3)
     int32_t at_func[P2_MAXTASK], at_dof[P2_MAXTASK];
@@ -426,7 +429,10 @@ template <typename T>
 void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     PlanarProg<T>& pr = d.prog;
     memset(&pr, 0, sizeof(pr));
-    if (!d.planar || s.n_bodies < 1 || s.n_bodies > BIO_MAX_BODIES || s.body_parent[0] >= 0) return;
+    // ---- stage 1 (any model): root body 0 carrying <= P2_MAXBR unbranched chains; the walk root joint ->
+    // leaf of every chain as a list of elementary-axis steps (used by the planar program and by the scan
+    // form of the spatial kinematics) ----
+    if (s.n_bodies < 1 || s.n_bodies > BIO_MAX_BODIES || s.body_parent[0] >= 0) return;
     int n_child[BIO_MAX_BODIES] = {0}, child[BIO_MAX_BODIES];
     for (int b = 1; b < s.n_bodies; b++) {
         const int p = s.body_parent[b];
@@ -434,6 +440,54 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         if (p != 0) { if (n_child[p]) return; child[p] = b; }
         n_child[p]++;
     }
+    int chain_body[P2_MAXBR][BIO_MAX_BODIES], chain_nb[P2_MAXBR] = {0};
+    for (int b = 1; b < s.n_bodies; b++) {
+        if (s.body_parent[b] != 0) continue;
+        if (pr.n_branches >= P2_MAXBR) { pr.n_branches = 0; return; }
+        const int l = pr.n_branches++;
+        for (int cur = b;; cur = child[cur]) {
+            chain_body[l][chain_nb[l]++] = cur;
+            if (!n_child[cur]) break;
+        }
+    }
+    pr.root_body = 0;
+    pr.chain_ok = 1;
+    for (int l = 0; l < (pr.n_branches > 0 ? pr.n_branches : 1); l++) {
+        int n = 0;
+        auto add_joint = [&](int b, bool root) {
+            const int ab = s.body_axis_begin[b], cnt = s.body_axis_count[b];
+            if (cnt < 1) pr.chain_ok = 0;                 // every body needs at least one step to publish its frame
+            for (int j = 0; j < cnt; j++) {
+                if (n >= P2_MAXSTEP) { pr.chain_ok = 0; return; }
+                const int a = ab + j, desc = d.axis_desc[a], dof = (desc >> 3) & 31;
+                pr.ch_code[l][n] = a | (b << 8) | (dof << 12) | (j == 0 ? P2_F_FIRST : 0) | (j == cnt - 1 ? P2_F_LAST : 0) |
+                                   (root ? P2_F_ROOT : 0) | ((desc & 512) ? P2_F_SRESET : 0) |
+                                   ((desc & 1024) ? P2_F_SPUB : 0) | ((desc & 256) ? P2_F_OPRE : 0) |
+                                   ((desc & 2048) ? P2_F_OPOST : 0) | (s.axis_kind[a] == BIO_AXIS_ROT ? P2_F_ROT : 0);
+                for (int c = 0; c < 3; c++) pr.ch_j[l][n][c] = j == 0 ? (T)s.body_joint_loc[b][c] : T(0);
+                pr.ch_j[l][n][3] = T(0);
+                n++;
+            }
+        };
+        add_joint(0, true);
+        for (int k = 0; k < chain_nb[l] && pr.n_branches > 0; k++) add_joint(chain_body[l][k], false);
+        pr.ch_n[l] = n;
+        int o_step = -1, first = 0, in_dof = 0;
+        for (int i = 0; i < n; i++)
+            if (pr.ch_code[l][i] & (P2_F_OPRE | P2_F_OPOST)) o_step = i;
+        if (o_step < 0) { pr.chain_ok = 0; o_step = 0; }
+        for (int i = 0; i < P2_MAXSTEP; i++) {
+            if (i >= n) { pr.ch_scan[l][i] = (i & 15) | (o_step << 4); continue; }
+            const int code = pr.ch_code[l][i];
+            if (code & P2_F_FIRST) first = i;
+            in_dof = (code & P2_F_SRESET) || ((code >> 12) & 31) == 31 ? 0 : in_dof + 1;
+            if (in_dof > 2) pr.chain_ok = 0;
+            pr.ch_scan[l][i] = first | (o_step << 4) | (in_dof << 8);
+        }
+    }
+    if (!pr.chain_ok) return;
+    // ---- stage 2 (planar models): the planar program ----
+    if (!d.planar) return;
     auto joint_dofs = [&](int b, int* dofs) {             // distinct dofs of the joint, in axis order
         int n = 0;
         for (int a = s.body_axis_begin[b]; a < s.body_axis_begin[b] + s.body_axis_count[b]; a++) {
@@ -445,27 +499,17 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         }
         return n;
     };
-    for (int b = 0; b < s.n_bodies; b++) if (s.body_axis_count[b] > P2_MAXAX) return;
-    pr.root_body = 0;
     { int dofs[4] = {-1, -1, -1, -1}; pr.root_ndof = joint_dofs(0, dofs); if (pr.root_ndof > 3) return;
       for (int k = 0; k < 4; k++) pr.root_dof[k] = k < pr.root_ndof ? dofs[k] : -1; }
-    for (int b = 1; b < s.n_bodies; b++) {
-        if (s.body_parent[b] != 0) continue;
-        if (pr.n_branches >= P2_MAXBR) return;
-        const int l = pr.n_branches++;
-        int cur = b, k = 0;
-        for (;;) {
-            if (k >= P2_MAXCB) return;
+    for (int l = 0; l < pr.n_branches; l++) {
+        if (chain_nb[l] > P2_MAXCB) return;
+        for (int k = 0; k < P2_MAXCB; k++) {
             int dofs[4] = {-1, -1, -1, -1};
-            if (joint_dofs(cur, dofs) > 1) return;
-            pr.br_body[l][k] = cur;
-            pr.br_dof[l][k] = dofs[0];
-            k++;
-            if (!n_child[cur]) break;
-            cur = child[cur];
+            if (k < chain_nb[l] && joint_dofs(chain_body[l][k], dofs) > 1) return;
+            pr.br_body[l][k] = k < chain_nb[l] ? chain_body[l][k] : -1;
+            pr.br_dof[l][k] = k < chain_nb[l] ? dofs[0] : -1;
         }
-        pr.br_nb[l] = k;
-        for (; k < P2_MAXCB; k++) { pr.br_body[l][k] = -1; pr.br_dof[l][k] = -1; }
+        pr.br_nb[l] = chain_nb[l];
     }
     if (s.n_spheres > BIO_MAX_SPHERES) return;
     for (int b = 0; b < s.n_bodies; b++) {
@@ -480,46 +524,8 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         pr.ax_k[a][2] = (!(desc & 1) && (desc & 4)) ? -sg : T(0);
         pr.ax_k[a][3] = T(0);
     }
-    for (int l = 0; l < (pr.n_branches > 0 ? pr.n_branches : 1); l++) {
-        int n = 0;
-        auto add_joint = [&](int b, bool root) {
-            const int ab = s.body_axis_begin[b], cnt = s.body_axis_count[b];
-            for (int j = 0; j < cnt; j++) {
-                const int a = ab + j, desc = d.axis_desc[a], dof = (desc >> 3) & 31;
-                pr.ch_code[l][n] = a | (b << 8) | (dof << 12) | (j == 0 ? P2_F_FIRST : 0) | (j == cnt - 1 ? P2_F_LAST : 0) |
-                                   (root ? P2_F_ROOT : 0) | ((desc & 512) ? P2_F_SRESET : 0) |
-                                   ((desc & 1024) ? P2_F_SPUB : 0) | ((desc & 256) ? P2_F_OPRE : 0) |
-                                   ((desc & 2048) ? P2_F_OPOST : 0);
-                pr.ch_j[l][n][0] = j == 0 ? (T)s.body_joint_loc[b][0] : T(0);
-                pr.ch_j[l][n][1] = j == 0 ? (T)s.body_joint_loc[b][1] : T(0);
-                n++;
-            }
-        };
-        if (s.body_axis_count[0] < 1) return;             // every body needs at least one axis slot
-        add_joint(0, true);
-        for (int k = 0; k < pr.br_nb[l] && pr.n_branches > 0; k++) {
-            if (s.body_axis_count[pr.br_body[l][k]] < 1) return;
-            add_joint(pr.br_body[l][k], false);
-        }
-        pr.ch_n[l] = n;
-    }
-    // scan form of the chain walk: lane = (chain, step), 8 steps per chain
-    pr.scan_ok = pr.n_branches >= 1 && pr.n_branches <= 2;
-    for (int l = 0; l < pr.n_branches && pr.scan_ok; l++) {
-        if (pr.ch_n[l] > 8) { pr.scan_ok = 0; break; }
-        int o_step = -1, first = 0, in_dof = 0;
-        for (int i = 0; i < pr.ch_n[l]; i++)
-            if (pr.ch_code[l][i] & (P2_F_OPRE | P2_F_OPOST)) o_step = i;
-        if (o_step < 0) { pr.scan_ok = 0; break; }
-        for (int i = 0; i < 8; i++) {
-            if (i >= pr.ch_n[l]) { pr.ch_scan[l][i] = i | (o_step << 4); continue; }
-            const int code = pr.ch_code[l][i];
-            if (code & P2_F_FIRST) first = i;
-            in_dof = (code & P2_F_SRESET) || ((code >> 12) & 31) == 31 ? 0 : in_dof + 1;
-            if (in_dof > 2) pr.scan_ok = 0;
-            pr.ch_scan[l][i] = first | (o_step << 4) | (in_dof << 8);
-        }
-    }
+    pr.scan_ok = pr.n_branches >= 1;
+    for (int l = 0; l < pr.n_branches; l++) if (pr.ch_n[l] > 8) pr.scan_ok = 0;
     // phase A tasks
     int n_mov = 0, mov_of_pt[BIO_MAX_PATHPTS];
     for (int a = 0; a < s.n_axes; a++) { pr.at_func[a] = s.axis_func[a]; pr.at_dof[a] = s.axis_dof[a]; pr.at_add[a] = T(0); }
