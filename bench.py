@@ -194,12 +194,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(args.warmup):
-        env.step(pool[k % len(pool)])
-    barrier()
+    # clocks / throttle reasons are sampled from the warm-up to the end of the end-to-end loop (the timed
+    # region alone lasts tens of milliseconds, less than one nvidia-smi poll)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for k in range(args.warmup):
+        env.step(pool[k % len(pool)])
+    barrier()
     launches0 = env.launch_count
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
