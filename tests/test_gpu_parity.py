@@ -385,3 +385,68 @@ def test_trajectory_recorder_writes_state_storage(tmp_path):
     assert np.allclose(data[-1, 1:1 + 2 * env.n_dof:2], st["q"][3].cpu().numpy(), atol=1e-7)
     assert np.allclose(np.diff(data[:, 0]), 0.01, atol=1e-9)
     env.close()
+
+
+@pytest.mark.parametrize("env_id", ["MuscleWalkingImitation2D-v0", "MuscleWalkingImitation3D-v0"])
+def test_perturbation_force_parity_fp64(env_id):
+    """apply_perturbations=True (piecewise-constant +-50 N on the torso, muscle_walking_imitation_env2D.py:83-100):
+    the force sequence is keyed by (seed, env, knot) on both sides; 150 free-running steps in fp64."""
+    import torch
+    n = 32
+    env, cpu = _mk(env_id, n, "float64", seed=5, apply_perturbations=True)
+    assert env.task.perturb == 1
+    rng = np.random.default_rng(3)
+    env.reset()
+    cpu.reset()
+    worst = 0.0
+    for k in range(150):
+        a = _actions(env, rng, n)
+        obs, rew, done, info = env.step(torch.as_tensor(a, dtype=env.dtype, device=env.device))
+        oc, rc, dc, tc, _ = cpu.step(a)
+        assert (done.cpu().numpy() == dc).all(), "done mismatch at step %d" % k
+        worst = max(worst, np.max(_rel(_np(obs), oc, 100.0)), np.max(np.abs(_np(rew) - rc)))
+    print(env_id, "perturbed, fp64 150 steps: worst obs/reward difference %.2e" % worst)
+    assert worst < 1e-4
+    env.close()
+
+
+def test_statistical_parity_fp32_batch():
+    """over a batch, the fp32 production build and the fp64 oracle end episodes for the
+    same reasons at the same rate: episodes finished, mean episode length and done-reason histogram of
+    2048 envs x 160 steps (iid uniform excitations, auto-reset) within 2 % of each other."""
+    import os
+    import torch
+    n, steps = 2048, 160
+    env, _ = _mk("MuscleWalkingImitation2D-v0", n, "float32", seed=21)
+    from oracle import oracle as orc
+    ref = orc.RefTables(env.ref["q"], env.ref["u"], env.ref["body_pos"], env.ref["com_pos"])
+    cpu = orc.OracleVecEnv(env.cm.tables, env.task, ref, n, seed=21, threads=min(16, os.cpu_count() or 1))
+    rng = np.random.default_rng(8)
+    env.reset()
+    cpu.reset()
+    env.stats(reset=True)
+    hist = np.zeros(8)
+    ep_cpu = 0
+    len_sum_cpu = 0
+    ep_len = np.zeros(n, dtype=np.int64)
+    for k in range(steps):
+        a = rng.uniform(0, 1, (n, 14))
+        env.step(torch.as_tensor(a, dtype=env.dtype, device=env.device))
+        _, _, dc, _, reasons = cpu.step(a)
+        ep_len += 1
+        fin = dc.astype(bool)
+        ep_cpu += int(fin.sum())
+        len_sum_cpu += int(ep_len[fin].sum())
+        ep_len[fin] = 0
+        for bit in range(6):
+            hist[bit] += int(((reasons >> bit) & 1)[fin].sum())
+    st = env.stats().cpu().numpy()
+    ep_gpu, len_gpu = st[1], st[3] / max(st[1], 1)
+    len_cpu = len_sum_cpu / max(ep_cpu, 1)
+    print("episodes gpu %d cpu %d, mean length gpu %.2f cpu %.2f, done reasons gpu %s cpu %s"
+          % (ep_gpu, ep_cpu, len_gpu, len_cpu, st[4:10].astype(int).tolist(), hist[:6].astype(int).tolist()))
+    assert ep_cpu > 1000
+    assert abs(ep_gpu - ep_cpu) <= 0.02 * ep_cpu
+    assert abs(len_gpu - len_cpu) <= 0.02 * len_cpu
+    assert np.all(np.abs(st[4:10] - hist[:6]) <= 0.02 * ep_cpu + 2)
+    env.close()
