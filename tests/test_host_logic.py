@@ -413,3 +413,36 @@ def test_state_storage_labels_and_file_round_trip(tmp_path, models):
     refmotion.write_storage(path, "simulation_States", labels, data)
     got_labels, got, in_deg = refmotion.read_storage(path)
     assert got_labels == labels and not in_deg and np.allclose(got, data, atol=1e-7)
+
+
+def test_rllib_vector_env_adapter_interface():
+    """vector_reset / reset_at / vector_step over a stand-in backend (no GPU, no ray)."""
+    import torch
+    from bioimitation_gym_b200.rllib_adapter import BioVectorEnv
+
+    class Fake:
+        num_envs, obs_dim, n_act = 3, 4, 2
+        action_low, action_high = np.zeros(2), np.ones(2)
+
+        def __init__(self):
+            self.t = 0
+
+        def reset(self):
+            return torch.zeros(3, 4)
+
+        def step(self, a):
+            self.t += 1
+            assert tuple(a.shape) == (3, 2)
+            done = torch.tensor([0, 1, 0], dtype=torch.uint8)
+            return torch.full((3, 4), float(self.t)), torch.arange(3.0), done, {"all_rewards": torch.ones(3, 5)}
+
+        def close(self):
+            pass
+
+    v = BioVectorEnv("MuscleWalkingImitation2D-v0", backend_env=Fake())
+    obs = v.vector_reset()
+    assert len(obs) == 3 and obs[0].shape == (4,)
+    o, r, d, info = v.vector_step([[0.1, 0.2]] * 3)
+    assert len(o) == 3 and r == [0.0, 1.0, 2.0] and d == [False, True, False] and len(info[1]["all_rewards"]) == 5
+    assert np.array_equal(v.reset_at(1), o[1])          # the finished env already holds its next episode's first obs
+    assert v.action_space.shape == (2,) and v.observation_space.shape == (4,) and v.get_sub_environments() == []
