@@ -366,16 +366,36 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     gsync<G>();
 
     // ---- phase E: lane = body (wrench gather, inertia, body force) | dof (generalized forces) ----
+    // wrench of the path points on every body: on a full warp four lanes share the point list of a
+    // body (the pelvis carries a third of all points), quad butterfly, then the body lane fetches the sum
+    T Wn[3] = {T(0), T(0), T(0)}, Wf[3] = {T(0), T(0), T(0)};
+    if (nm > 0) {
+        constexpr int PARTS = G == 32 ? 4 : 1;
+        const int gb = lane / PARTS, part = lane % PARTS;
+        if (gb < nb)
+            for (int k = m.body_pt_begin[gb] + part; k < m.body_pt_begin[gb] + m.body_pt_count[gb]; k += PARTS) {
+                const int p = m.body_pt_list[k];
+                const T f[3] = {E.x.pt.ptf[p][0], E.x.pt.ptf[p][1], E.x.pt.ptf[p][2]};
+                T n[3];                                                   // inactive points: zero force and position
+                cross3(E.x.pt.ptx[p], f, n);
+                for (int c = 0; c < 3; c++) { Wn[c] += n[c]; Wf[c] += f[c]; }
+            }
+        if (PARTS > 1) {
+            const unsigned mask = group_mask<G>();
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                Wn[c] += __shfl_xor_sync(mask, Wn[c], 1, G); Wn[c] += __shfl_xor_sync(mask, Wn[c], 2, G);
+                Wf[c] += __shfl_xor_sync(mask, Wf[c], 1, G); Wf[c] += __shfl_xor_sync(mask, Wf[c], 2, G);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                Wn[c] = __shfl_sync(mask, Wn[c], (lane * PARTS) & (G - 1), G);
+                Wf[c] = __shfl_sync(mask, Wf[c], (lane * PARTS) & (G - 1), G);
+            }
+        }
+    }
     if (lane < nb) {
         const int b = lane;
-        T Wn[3] = {T(0), T(0), T(0)}, Wf[3] = {T(0), T(0), T(0)};
-        for (int k = m.body_pt_begin[b]; k < m.body_pt_begin[b] + m.body_pt_count[b]; k++) {
-            const int p = m.body_pt_list[k];
-            const T f[3] = {E.x.pt.ptf[p][0], E.x.pt.ptf[p][1], E.x.pt.ptf[p][2]};
-            T n[3];                                                       // inactive points: zero force and position
-            cross3(E.x.pt.ptx[p], f, n);
-            for (int c = 0; c < 3; c++) { Wn[c] += n[c]; Wf[c] += f[c]; }
-        }
         for (int s = 0; s < m.n_spheres; s++) {
             if (m.sph_body[s] != b || E.sphF[s][1] == T(0)) continue;
             T n[3];
