@@ -97,19 +97,19 @@ BIO_DEV void p2_phase_a(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     const PlanarProg<T>& pr = m.prog;
     auto& K = E.k.p;
     for (int t = lane; t < pr.n_atasks; t += G) {
-        const int d = pr.at_dof[t];
+        const int d = pr.at_dof[t], dst = pr.at_dst[t];
         T s, ds, dds;
         func_eval(m, pr.at_func[t], d >= 0 ? E.q[d] : T(0), s, ds, dds, &E.knot_hint[t]);
-        if (t < m.n_axes) {
+        if (dst < 64) {
             const T qd = d >= 0 ? E.u[d] : T(0);
-            const int desc = m.axis_desc[t];
+            const int desc = m.axis_desc[dst];
             T sn = T(0), cs = T(1);
             if (desc & 1) Num<T>::sincos((desc & 2) ? -s : s, &sn, &cs);
             // displacement along the axis (translations only), rates
-            st4(K.ax[t], (desc & 1) ? T(0) : s, ds, ds * qd, dds * qd * qd);
-            st2(K.axr[t], cs, sn);
+            st4(K.ax[dst], (desc & 1) ? T(0) : s, ds, ds * qd, dds * qd * qd);
+            st2(K.axr[dst], cs, sn);
         } else {
-            const int k = (t - m.n_axes) / 3, c = (t - m.n_axes) % 3;
+            const int k = (dst - 64) / 3, c = (dst - 64) % 3;
             K.mv[k][c] = s + pr.at_add[t];
             K.mv[k][4 + c] = ds;
         }

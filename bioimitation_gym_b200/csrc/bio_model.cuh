@@ -5,6 +5,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <utility>
+
 #include "../../include/bio_b200.h"
 
 namespace bio {
@@ -52,8 +54,9 @@ struct alignas(16) PlanarProg {
     int32_t ch_code[P2_MAXBR][P2_MAXSTEP];
     alignas(16) T ch_j[P2_MAXBR][P2_MAXSTEP][4];
     alignas(16) T ax_k[BIO_MAX_AXES][4];
-    // phase A tasks: t < n_axes: axis t; then 3 per moving point (k = (t - n_axes) / 3, component % 3)
-    int32_t at_func[P2_MAXTASK], at_dof[P2_MAXTASK];
+    // phase A tasks, splines first (the lanes of the last round then only see cheap functions):
+    // at_dst < 64: elementary axis at_dst; else component (at_dst - 64) % 3 of moving point (at_dst - 64) / 3
+    int32_t at_func[P2_MAXTASK], at_dof[P2_MAXTASK], at_dst[P2_MAXTASK];
     T at_add[P2_MAXTASK];                      // constant added to the value (body z of a moving point)
     // path points: location in the body frame with z already in ground axes (planar: constant)
     alignas(16) T pt_xyz[BIO_MAX_PATHPTS][4];
@@ -528,7 +531,7 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     for (int l = 0; l < pr.n_branches; l++) if (pr.ch_n[l] > 8) pr.scan_ok = 0;
     // phase A tasks
     int n_mov = 0, mov_of_pt[BIO_MAX_PATHPTS];
-    for (int a = 0; a < s.n_axes; a++) { pr.at_func[a] = s.axis_func[a]; pr.at_dof[a] = s.axis_dof[a]; pr.at_add[a] = T(0); }
+    for (int a = 0; a < s.n_axes; a++) { pr.at_func[a] = s.axis_func[a]; pr.at_dof[a] = s.axis_dof[a]; pr.at_add[a] = T(0); pr.at_dst[a] = a; }
     for (int p = 0; p < s.n_pathpts; p++) {
         mov_of_pt[p] = -1;
         if (s.pt_kind[p] != BIO_PT_MOVING) continue;
@@ -538,11 +541,18 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
             pr.at_func[t] = s.pt_func[p][c];
             pr.at_dof[t] = s.pt_dof[p];
             pr.at_add[t] = c == 2 ? d.body_z[s.pt_body[p]] : T(0);
+            pr.at_dst[t] = 64 + 3 * n_mov + c;
         }
         pr.mov_dof[n_mov] = s.pt_dof[p];
         mov_of_pt[p] = n_mov++;
     }
     pr.n_atasks = s.n_axes + 3 * n_mov;
+    for (int i = 1; i < pr.n_atasks; i++)                 // stable insertion sort: splines first
+        for (int j = i; j > 0 && s.func_kind[pr.at_func[j]] == BIO_FUNC_SPLINE &&
+                        s.func_kind[pr.at_func[j - 1]] != BIO_FUNC_SPLINE; j--) {
+            std::swap(pr.at_func[j], pr.at_func[j - 1]); std::swap(pr.at_dof[j], pr.at_dof[j - 1]);
+            std::swap(pr.at_add[j], pr.at_add[j - 1]); std::swap(pr.at_dst[j], pr.at_dst[j - 1]);
+        }
     // path points, muscle slots and wrench sources
     int n_src = 0;
     int src_body[P2_MAXSRC];
