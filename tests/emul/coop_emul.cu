@@ -72,3 +72,14 @@ extern "C" void emul_sizes(int64_t* out) {
     out[5] = (int64_t)sizeof(bio::EnvWork<double, 1>);
     out[6] = (int64_t)sizeof(bio::PlanarProg<float>);
 }
+
+// which fast paths the host-built program enables for a model: ok (planar program), scan_ok (planar
+// kinematics as warp scans), chain_ok (chain lists: spatial kinematics as warp scans), n_branches,
+// steps of chain 0 / 1, phase-A tasks, wrench sources
+extern "C" void emul_prog_info(const BioModelTables* s, int32_t* out) {
+    bio::DevModel<float>* m = new bio::DevModel<float>();
+    bio::convert_model(*s, *m);
+    out[0] = m->prog.ok; out[1] = m->prog.scan_ok; out[2] = m->prog.chain_ok; out[3] = m->prog.n_branches;
+    out[4] = m->prog.ch_n[0]; out[5] = m->prog.ch_n[1]; out[6] = m->prog.n_atasks; out[7] = m->prog.n_src;
+    delete m;
+}

@@ -136,6 +136,22 @@ def test_two_ctas_of_the_2d_kernel_fit_one_sm(emul_lib):
     assert cta <= (233472 - 2 * 1024) // 2, "2D fp32 CTA needs %d B of shared memory: only one CTA per SM" % cta
 
 
+def test_fast_paths_are_enabled_for_the_shipped_models(emul_lib, models):
+    """Guards the host-built program: every 2D model of the reference gets the planar program with scan
+    kinematics, every 3D model gets the chain lists (spatial scan kinematics); a silent fallback to the
+    general path would only show up as a slower benchmark."""
+    for key, cm in models.items():
+        out = np.zeros(8, dtype=np.int32)
+        emul_lib.emul_prog_info(ctypes.byref(cm.tables), _p(out))
+        ok, scan_ok, chain_ok, n_br, n0, n1, n_tasks, n_src = out.tolist()
+        assert chain_ok == 1 and n_br >= 1, key
+        if key.startswith("2d"):
+            assert ok == 1 and scan_ok == 1 and n_br == 2 and 1 <= n0 <= 8 and 1 <= n1 <= 8, (key, out)
+            assert n_src >= cm.tables.n_spheres + cm.tables.n_muscles
+        else:
+            assert ok == 0 and max(n0, n1) <= 16, (key, out)
+
+
 def test_program_rejects_models_it_does_not_cover(emul_lib, models):
     t = models["3d_muscle"].tables
     udot, adot, lmdot, misc = np.zeros(16), np.zeros(24), np.zeros(24), np.zeros(256)
