@@ -55,42 +55,71 @@ def _flops_per_env_step(task, env_id):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the run: NVML polled every 2 ms (the timed region lasts tens
+    of milliseconds), nvidia-smi every 100 ms when NVML cannot be loaded.  With CUDA_VISIBLE_DEVICES set
+    the NVML index is the visible device's entry of that list."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index=0):
         super().__init__(daemon=True)
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            index = int(vis.split(",")[index]) if vis else index
+        except (ValueError, IndexError):
+            pass
         self.index = index
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self.stop_flag = False
+        self.source = "nvml"
 
-    def run(self):
+    def _nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        bits = [(pynvml.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                (pynvml.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (pynvml.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        while not self.stop_flag:
+            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            self.mx.append(mx)
+            r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            for bit, name in bits:
+                if r & bit:
+                    self.reasons.add(name)
+            time.sleep(0.002)
+
+    def _smi(self):
+        self.source = "nvidia-smi"
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                r = [x.strip() for x in out.strip().split(",")]
+                self.sm.append(float(r[0]))
+                self.mx.append(float(r[1]))
+                for nm, v in zip(self.NAMES, r[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
             except Exception:
                 pass
             time.sleep(0.1)
 
+    def run(self):
+        try:
+            self._nvml()
+        except Exception:
+            self._smi()
+
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 6:
-                continue
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
+        if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)), "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": self.source}
 
 
 def cpu_arm(env_id, n_envs, steps, warmup, budget_s, threads, integrator=None):
