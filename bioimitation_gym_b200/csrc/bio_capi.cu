@@ -115,6 +115,24 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
     if (const char* e = getenv("BIO_BLOCK")) { int b = atoi(e); if (b >= 32 && b <= 256 && b % 32 == 0) h->block = b; }
     int rc;
     if ((rc = set_kernel_attrs(h))) return rc;
+    bool prog_ok = false;
+    int prog_src = 0;
+    // model block
+    {
+        bio::DevModel<T>* hm = new bio::DevModel<T>();
+        bio::convert_model(*model, *hm);
+        if (bio::build_obs_desc(*model, *task, *hm) != task->obs_dim) {
+            delete hm;
+            return fail(-1, "obs_dim of the task config does not match the observation layout");
+        }
+        rc = dev_alloc(h, (unsigned char**)&h->d_model, sizeof(bio::DevModel<T>));
+        if (rc) { delete hm; return rc; }
+        cudaError_t e = cudaMemcpy(h->d_model, hm, sizeof(bio::DevModel<T>), cudaMemcpyHostToDevice);
+        prog_ok = hm->prog.ok != 0;
+        prog_src = hm->prog.n_src;
+        delete hm;
+        CU(e);
+    }
     // cooperative kernel: size class by model, BIO_KERNEL=thread forces the thread-per-env kernel
     {
         const char* kv = getenv("BIO_KERNEL");
@@ -143,7 +161,8 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
                    model->n_obspts <= COOP_MAXOBS && model->n_coords <= 2 * G && task->n_pd <= G;
         };
         const size_t base = ((sizeof(bio::DevModel<T>) + 15) / 16) * 16;
-        if (want_coop && fits(C0::G, C0::ND, C0::NM, C0::NP, C0::NAX)) {
+        // class 0 (half-warp per env) runs the planar program only
+        if (want_coop && prog_ok && prog_src <= P2_MAXSRC && fits(C0::G, C0::ND, C0::NM, C0::NP, C0::NAX)) {
             h->coop_cls = 0;
             h->coop_smem = base + (COOP_THREADS(T) / C0::G) * sizeof(bio::EnvWork<T, 0>);
             CU((bio::coop_set_smem<T, 0>((int)h->coop_smem)));
@@ -154,20 +173,6 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
             CU((bio::coop_set_smem<T, 1>((int)h->coop_smem)));
             h->coop_ctas = bio::coop_ctas_per_sm<T, 1>((int)h->coop_smem);
         }
-    }
-    // model block
-    {
-        bio::DevModel<T>* hm = new bio::DevModel<T>();
-        bio::convert_model(*model, *hm);
-        if (bio::build_obs_desc(*model, *task, *hm) != task->obs_dim) {
-            delete hm;
-            return fail(-1, "obs_dim of the task config does not match the observation layout");
-        }
-        rc = dev_alloc(h, (unsigned char**)&h->d_model, sizeof(bio::DevModel<T>));
-        if (rc) { delete hm; return rc; }
-        cudaError_t e = cudaMemcpy(h->d_model, hm, sizeof(bio::DevModel<T>), cudaMemcpyHostToDevice);
-        delete hm;
-        CU(e);
     }
     bio::convert_task(*task, h->task_d);
     const int nd = model->n_dof, nm = model->n_muscles, na = model->n_act;

@@ -22,46 +22,68 @@ template <> struct CoopCls<1> { enum { G = 32, ND = 16, NM = 24, NP = 80, NAX = 
 
 #define COOP_MAXOBS 12
 
-template <typename T, int CLS>
-struct alignas(16) EnvWork {
-    typedef CoopCls<CLS> C;
-    T q[C::ND], u[C::ND], act[C::NM], lm[C::NM];          // state of the current evaluation
-    alignas(16) T O[4];
+// working arrays of the general (spatial) evaluation, coop_eval
+template <typename T, typename C>
+struct WorkGeneral {
+    T ax_s[C::NAX], ax_ds[C::NAX], ax_dds[C::NAX];
+    T R[BIO_MAX_BODIES][9], r[BIO_MAX_BODIES][3], V[BIO_MAX_BODIES][6], A[BIO_MAX_BODIES][6];
+    T S[C::ND][6];
+    // spatial inertia about O and body force per body: [0] mass, [1..3] m*c, [4..9] I (xx yy zz xy xz yz),
+    // [10..15] force (n; f); turned into composite / subtree sums in place
+    T BI[BIO_MAX_BODIES][16];
     union {
-        struct {                                           // general (spatial) evaluation, coop_eval
-            T ax_s[C::NAX], ax_ds[C::NAX], ax_dds[C::NAX];
-            T R[BIO_MAX_BODIES][9], r[BIO_MAX_BODIES][3], V[BIO_MAX_BODIES][6], A[BIO_MAX_BODIES][6];
-            T S[C::ND][6];
-            // spatial inertia about O and body force per body: [0] mass, [1..3] m*c, [4..9] I (xx yy zz xy xz yz),
-            // [10..15] force (n; f); turned into composite / subtree sums in place
-            T BI[BIO_MAX_BODIES][16];
-            union {
-                T IS[C::ND][6];                            // I^c_body(i) * S_i (phase G on)
-                T mv[8][6];                                // moving path points: location [0..2], d/dq [3..5] (phases A..C)
-            };
-            T H[C::ND * (C::ND + 1) / 2], rhs[C::ND];
-            T Q[C::ND], limDd[C::ND];
-        } g;
-        struct {                                           // planar program, coop_eval_planar
-            alignas(16) T ax[C::NAX][4];                   // displacement, ds/dq, ds/dq * qdot, d2s/dq2 * qdot^2
-            alignas(16) T axr[C::NAX][2];                  // cos, sin of the signed rotation angle
-            alignas(16) T pose[BIO_MAX_BODIES][4];         // cos, sin, x, y (about O, ground axes)
-            alignas(16) T V[BIO_MAX_BODIES][4], A[BIO_MAX_BODIES][4];  // (w, vx, vy), bias acceleration likewise
-            alignas(16) T S[C::ND][4];                     // motion vector of every dof
-            alignas(16) T bI[BIO_MAX_BODIES][12];          // spatial inertia about O [0..5] and force [6..8] per body
-            T Qf[C::ND], Ld[C::ND];                        // generalized force and h * limit damping per dof
-            alignas(16) T mv[P2_MAXMOV][8];                            // moving points: location [0..2], d/dq [4..6]
-            T mq[P2_MAXMOV];                               // their generalized force
-            alignas(16) T brx[P2_MAXBR][20];                           // chain -> root: composite inertia, force, Schur, rhs
-            alignas(16) T brk[P2_MAXBR][12];                           // chain block solve kept for the back substitution
-        } p;
-    } k;
+        T IS[C::ND][6];                            // I^c_body(i) * S_i (phase G on)
+        T mv[8][6];                                // moving path points: location [0..2], d/dq [3..5] (phases A..C)
+    };
+    T H[C::ND * (C::ND + 1) / 2], rhs[C::ND];
+    T Q[C::ND], limDd[C::ND];
+};
+
+// working arrays of the planar program, coop_eval_planar
+template <typename T, typename C>
+struct WorkPlanar {
+    alignas(16) T ax[C::NAX][4];                   // displacement, ds/dq, ds/dq * qdot, d2s/dq2 * qdot^2
+    alignas(16) T axr[C::NAX][2];                  // cos, sin of the signed rotation angle
+    alignas(16) T pose[BIO_MAX_BODIES][4];         // cos, sin, x, y (about O, ground axes)
+    alignas(16) T V[BIO_MAX_BODIES][4], A[BIO_MAX_BODIES][4];  // (w, vx, vy), bias acceleration likewise
+    alignas(16) T S[C::ND][4];                     // motion vector of every dof
+    alignas(16) T bI[BIO_MAX_BODIES][12];          // spatial inertia about O [0..5] and force [6..8] per body
+    T Qf[C::ND], Ld[C::ND];                        // generalized force and h * limit damping per dof
+    alignas(16) T mv[P2_MAXMOV][8];                // moving points: location [0..2], d/dq [4..6]
+    T mq[P2_MAXMOV];                               // their generalized force
+    alignas(16) T brx[P2_MAXBR][20];               // chain -> root: composite inertia, force, Schur, rhs
+    alignas(16) T brk[P2_MAXBR][12];               // chain block solve kept for the back substitution
+};
+
+template <typename T, typename C>
+struct WorkReadout { T obs_pos[COOP_MAXOBS][3], obs_vel[COOP_MAXOBS][3], comp[BIO_MAX_BODIES][6]; };   // full evaluation
+template <typename T>
+struct WorkSources { alignas(16) T w[P2_MAXSRC][4]; };                                                 // planar program
+
+// Size class 0 (half-warp per env) runs the planar program only, so its buffer holds no arrays of the
+// general evaluation; class 1 (warp per env) keeps both.
+template <typename T, int CLS> struct WorkUnions;
+template <typename T> struct WorkUnions<T, 0> {
+    typedef CoopCls<0> C;
+    struct { WorkPlanar<T, C> p; } k;
+    union { WorkReadout<T, C> out; WorkSources<T> src; } x;
+};
+template <typename T> struct WorkUnions<T, 1> {
+    typedef CoopCls<1> C;
+    union { WorkGeneral<T, C> g; WorkPlanar<T, C> p; } k;
     union {
         struct { T ptx[C::NP][3], ptf[C::NP][3], ptq[C::NP]; } pt;   // phases C..E
         struct { T col[BIO_MAX_SPHERES][C::ND][3]; } jac;             // phase G (implicit damping)
-        struct { T obs_pos[COOP_MAXOBS][3], obs_vel[COOP_MAXOBS][3], comp[BIO_MAX_BODIES][6]; } out;  // full eval
-        struct { alignas(16) T w[P2_MAXSRC][4]; } src;                            // planar program: wrench sources
+        WorkReadout<T, C> out;
+        WorkSources<T> src;
     } x;
+};
+
+template <typename T, int CLS>
+struct alignas(16) EnvWorkBody : WorkUnions<T, CLS> {
+    typedef CoopCls<CLS> C;
+    T q[C::ND], u[C::ND], act[C::NM], lm[C::NM];          // state of the current evaluation
+    alignas(16) T O[4];
     T sphx[BIO_MAX_SPHERES][3], sphF[BIO_MAX_SPHERES][3], sphD[BIO_MAX_SPHERES][2];
     T limf[BIO_MAX_LIMITS], limD[BIO_MAX_LIMITS];
     T udot[C::ND], adot[C::NM], lmdot[C::NM];
@@ -69,9 +91,18 @@ struct alignas(16) EnvWork {
     T vn[C::NM];                                           // Newton warm start: last normalised fibre velocity
     T ctrl[C::NM];
     T com_pos[3], com_vel[3];
-    int8_t knot_hint[P2_MAXTASK];                          // planar program: last spline interval per phase-A task
+    int8_t knot_hint[P2_MAXTASK];                          // last spline interval per phase-A task
     T contact[2][6];
-    T max_limit, pad_;
+    T max_limit;
+};
+
+// Two envs share a warp in class 0 and touch the same fields at the same time: the buffer size is
+// an odd multiple of 64 bytes, so that the second env's copy starts 16 banks away from the first's.
+template <typename T, int CLS>
+struct alignas(16) EnvWork : EnvWorkBody<T, CLS> {
+    static constexpr size_t raw = sizeof(EnvWorkBody<T, CLS>);
+    static constexpr size_t want = CLS == 0 ? (((raw + 63) / 64) | 1) * 64 : ((raw + 15) / 16) * 16 + 16;
+    unsigned char bank_pad[want - raw > 0 ? want - raw : 128];
 };
 
 // The G lanes of an env are the unit of synchronisation: two envs sharing a warp (G = 16) may
@@ -569,13 +600,18 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     coop_solve<T, CLS>(m, E, lane);
 }
 
-// planar (2D) models take the specialised evaluation
+// planar (2D) models take the planar program; size class 0 holds nothing else (bio_create puts a model
+// there only when the host could build the program)
 template <typename T, int CLS>
 __device__ __forceinline__ void coop_eval_any(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane,
                                               const int newton_iters, const T ext_fx, const int ext_pt, const T h_imp,
                                               const bool full) {
-    if (m.prog.ok) coop_eval_planar<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
-    else coop_eval<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
+    if constexpr (CLS == 0) {
+        coop_eval_planar<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
+    } else {
+        if (m.prog.ok) coop_eval_planar<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
+        else coop_eval<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
+    }
 }
 
 // state <-> work buffer helpers (lane d < nd owns a dof, lane k < nm owns a muscle)
