@@ -733,12 +733,13 @@ __device__ void coop_write_obs(const DevModel<T>& m, const DevTask<T>& c, const 
     for (int o = lane; o < c.obs_dim; o += G) orow[o] = obs_value<T, CLS>(m, c, E, istep, row_next, pel, o);
 }
 
-// Persistent launch: COOP_CTAS_PER_SM CTAs of 256 threads per SM, the model block is staged once
-// per CTA, and every warp walks the work items (one item = the 32/G envs of a warp)
-// item = blockIdx + gridDim * (warp + warps_per_cta * k), so that the items are dealt round-robin
-// over the CTAs first (4096 envs on 148 SMs: 13 or 14 busy warps per SM instead of 8 or 16).
-#define COOP_THREADS(T) 256
-#define COOP_CTAS_PER_SM(T) (sizeof(T) == 4 ? 2 : 1)
+// Persistent launch: one CTA per SM (fp32: 512 threads = 16 warps at 128 registers; fp64: 256), the model
+// block is staged once per SM, and every warp walks the work items (one item = the 32/G envs of a warp)
+// item = blockIdx + gridDim * (warp + warps_per_cta * k), so that the items are dealt round-robin over
+// the SMs first.  4096 envs on 148 SMs: warps 0..13 of every SM are busy, i.e. 4,4,3,3 warps on the four
+// schedulers (two CTAs of 8 warps left 4,4,4,2 and staged the model twice; measured 5 % slower).
+#define COOP_THREADS(T) (sizeof(T) == 4 ? 512 : 256)
+#define COOP_CTAS_PER_SM(T) 1
 
 template <typename T, int CLS>
 __global__ void __launch_bounds__(COOP_THREADS(T), COOP_CTAS_PER_SM(T))
