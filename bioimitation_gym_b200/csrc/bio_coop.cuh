@@ -36,6 +36,7 @@ struct WorkGeneral {
         T mv[8][6];                                // moving path points: location [0..2], d/dq [3..5] (phases A..C)
     };
     T H[C::ND * (C::ND + 1) / 2], rhs[C::ND];
+    T Lw[C::ND * (C::ND + 1) / 2];                 // factor L of L^T D L (kept apart from H: no write-after-read barrier)
     T Q[C::ND], limDd[C::ND];
 };
 

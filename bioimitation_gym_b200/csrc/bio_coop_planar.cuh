@@ -43,11 +43,8 @@ __device__ __forceinline__ void coop_solve(const DevModel<T>& m, EnvWork<T, CLS>
         const int k = nd - 1 - st;
         const T inv = Num<T>::rcp(K.H[k * (k + 1) / 2 + k]);
         const T bk = K.rhs[k];                   // final z_k: every descendant step is done
-        T keep_a[NIT];
-        int keep_ki[NIT];
 #pragma unroll
         for (int it = 0; it < NIT; it++) {
-            keep_ki[it] = -1;
             const int p = pb + lane + it * G;
             if (p < pe) {
                 const uint32_t pk = m.lt_pack[p];
@@ -55,18 +52,13 @@ __device__ __forceinline__ void coop_solve(const DevModel<T>& m, EnvWork<T, CLS>
                 const T a = K.H[ki] * inv;
                 K.H[ij] -= a * K.H[kj];
                 if (pk & 0x80000000u) {          // diagonal pair (i,i): owns L_ki and the rhs update of i
-                    keep_a[it] = a;
-                    keep_ki[it] = ki;
+                    K.Lw[ki] = a;
                     K.rhs[(pk >> 24) & 15u] -= a * bk;
                 }
             }
         }
         gsync<G>();
-#pragma unroll
-        for (int it = 0; it < NIT; it++)
-            if (keep_ki[it] >= 0) K.H[keep_ki[it]] = keep_a[it];   // row k is not read by later steps
     }
-    gsync<G>();
     // L x = D^-1 z by columns: lane i keeps w_i in a register; when x_j is final (all its
     // ancestors are < j) it is broadcast by shuffle and every descendant i subtracts L_ij x_j
     T wv = T(0);
@@ -79,7 +71,7 @@ __device__ __forceinline__ void coop_solve(const DevModel<T>& m, EnvWork<T, CLS>
     }
     for (int j = 0; j < nd - 1; j++) {
         const T xj = __shfl_sync(group_mask<G>(), wv, j, G);
-        if (lane > j && ((anc >> j) & 1u)) wv -= K.H[row + j] * xj;
+        if (lane > j && ((anc >> j) & 1u)) wv -= K.Lw[row + j] * xj;
     }
     if (lane < nd) E.udot[lane] = wv;
     gsync<G>();
