@@ -44,6 +44,7 @@ struct HandleBase {
     int n_sms = 148;
     int coop_grid = 0;
     int coop_ctas = 1;            // resident CTAs of the cooperative kernel per SM (occupancy query)
+    int coop_threads = 256;       // launch shape of the cooperative kernel
     std::vector<void*> allocs;
     double* stats = nullptr;          // 16 doubles
     virtual ~HandleBase() {}
@@ -161,18 +162,31 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
                    model->n_obspts <= COOP_MAXOBS && model->n_coords <= 2 * G && task->n_pd <= G;
         };
         const size_t base = ((sizeof(bio::DevModel<T>) + 15) / 16) * 16;
+        // launch shape by the number of item rounds per SM (see COOP_THREADS_LO / _HI in bio_coop.cuh)
+        auto pick_threads = [&](int G) {
+            const int lo = COOP_THREADS_LO(T), hi = COOP_THREADS_HI(T);
+            if (const char* e = getenv("BIO_COOP_THREADS")) { const int v = atoi(e); if (v == lo || v == hi) return v; }
+            const long items = (n + (32 / G) - 1) / (32 / G);
+            const long ipsm = (items + h->n_sms - 1) / h->n_sms;
+            const double cost_lo = (double)((ipsm + lo / 32 - 1) / (lo / 32));
+            const double cost_hi = (double)((ipsm + hi / 32 - 1) / (hi / 32)) * COOP_SHAPE_COST;
+            return cost_hi < cost_lo ? hi : lo;
+        };
         // class 0 (half-warp per env) runs the planar program only
         if (want_coop && prog_ok && prog_src <= P2_MAXSRC && fits(C0::G, C0::ND, C0::NM, C0::NP, C0::NAX)) {
             h->coop_cls = 0;
-            h->coop_smem = base + (COOP_THREADS(T) / C0::G) * sizeof(bio::EnvWork<T, 0>);
-            CU((bio::coop_set_smem<T, 0>((int)h->coop_smem)));
-            h->coop_ctas = bio::coop_ctas_per_sm<T, 0>((int)h->coop_smem);
+            h->coop_threads = pick_threads(C0::G);
+            h->coop_smem = base + (h->coop_threads / C0::G) * sizeof(bio::EnvWork<T, 0>);
+            CU((bio::coop_set_smem<T, 0>(h->coop_threads, (int)h->coop_smem)));
+            h->coop_ctas = bio::coop_ctas_per_sm<T, 0>(h->coop_threads, (int)h->coop_smem);
         } else if (want_coop && fits(C1::G, C1::ND, C1::NM, C1::NP, C1::NAX)) {
             h->coop_cls = 1;
-            h->coop_smem = base + (COOP_THREADS(T) / C1::G) * sizeof(bio::EnvWork<T, 1>);
-            CU((bio::coop_set_smem<T, 1>((int)h->coop_smem)));
-            h->coop_ctas = bio::coop_ctas_per_sm<T, 1>((int)h->coop_smem);
+            h->coop_threads = pick_threads(C1::G);
+            h->coop_smem = base + (h->coop_threads / C1::G) * sizeof(bio::EnvWork<T, 1>);
+            CU((bio::coop_set_smem<T, 1>(h->coop_threads, (int)h->coop_smem)));
+            h->coop_ctas = bio::coop_ctas_per_sm<T, 1>(h->coop_threads, (int)h->coop_smem);
         }
+        if (h->coop_cls >= 0 && h->coop_ctas < 1) return fail(-2, "the cooperative step kernel does not fit an SM");
     }
     bio::convert_task(*task, h->task_d);
     const int nd = model->n_dof, nm = model->n_muscles, na = model->n_act;
@@ -256,10 +270,10 @@ int step_impl(Handle<T>* h, const void* actions, void* obs, void* reward, uint8_
         int grid = items < ctas ? items : ctas;
         if (h->coop_grid > 0) grid = h->coop_grid;   // BIO_COOP_GRID: launch-shape experiments
         if (h->coop_cls == 0)
-            bio::launch_coop<T, 0>(grid, h->coop_smem, s, h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset, (const T*)actions, (T*)obs, (T*)reward, done,
+            bio::launch_coop<T, 0>(h->coop_threads, grid, h->coop_smem, s, h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset, (const T*)actions, (T*)obs, (T*)reward, done,
                 (T*)terms, h->stats);
         else
-            bio::launch_coop<T, 1>(grid, h->coop_smem, s, h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset, (const T*)actions, (T*)obs, (T*)reward, done,
+            bio::launch_coop<T, 1>(h->coop_threads, grid, h->coop_smem, s, h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset, (const T*)actions, (T*)obs, (T*)reward, done,
                 (T*)terms, h->stats);
     } else {
         const int grid = (h->n + h->block - 1) / h->block;

@@ -734,16 +734,21 @@ __device__ void coop_write_obs(const DevModel<T>& m, const DevTask<T>& c, const 
     for (int o = lane; o < c.obs_dim; o += G) orow[o] = obs_value<T, CLS>(m, c, E, istep, row_next, pel, o);
 }
 
-// Persistent launch: one CTA per SM (fp32: 512 threads = 16 warps at 128 registers; fp64: 256), the model
-// block is staged once per SM, and every warp walks the work items (one item = the 32/G envs of a warp)
-// item = blockIdx + gridDim * (warp + warps_per_cta * k), so that the items are dealt round-robin over
-// the SMs first.  4096 envs on 148 SMs: warps 0..13 of every SM are busy, i.e. 4,4,3,3 warps on the four
-// schedulers (two CTAs of 8 warps left 4,4,4,2 and staged the model twice; measured 5 % slower).
-#define COOP_THREADS(T) (sizeof(T) == 4 ? 512 : 256)
-#define COOP_CTAS_PER_SM(T) 1
+// Persistent launch: one CTA per SM, the model block is staged once per SM, and every warp walks the work
+// items (one item = the 32/G envs of a warp) item = blockIdx + gridDim * (warp + warps_per_cta * k), so
+// that the items are dealt round-robin over the SMs first.  Two launch shapes per fp32 instantiation:
+//   512 threads = 16 warps at 128 registers: least latency per item.  4096 envs on 148 SMs: warps 0..13
+//       of every SM are busy, i.e. 4,4,3,3 warps on the four schedulers (two CTAs of 8 warps left 4,4,4,2
+//       and staged the model twice; measured 5 % slower).
+//   640 threads = 20 warps at 96 registers: more items in flight for batches of several items per warp
+//       (measured: 2D 16384 envs +18 %, 131072 envs +7 %; 3D 8192 envs +13 %; 4096 envs -3 %).
+// bio_create picks by the number of item rounds per SM (COOP_SHAPE_COST); fp64 runs 256 threads.
+#define COOP_THREADS_LO(T) (sizeof(T) == 4 ? 512 : 256)
+#define COOP_THREADS_HI(T) (sizeof(T) == 4 ? 640 : 256)
+#define COOP_SHAPE_COST 1.17      // time of one round of items with the HI shape relative to the LO shape
 
-template <typename T, int CLS>
-__global__ void __launch_bounds__(COOP_THREADS(T), COOP_CTAS_PER_SM(T))
+template <typename T, int CLS, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, const EnvState<T> st, int n,
                      unsigned long long seed, long long env_offset, const T* __restrict__ actions,
                      T* __restrict__ obs, T* __restrict__ reward, uint8_t* __restrict__ done, T* __restrict__ terms,

@@ -29,10 +29,11 @@ void launch_eval(int grid, int block, size_t smem, cudaStream_t s, const DevMode
 template <typename T>
 void launch_transpose(unsigned grid, int block, cudaStream_t s, const T* src, T* dst, int n, int k, int to_soa);
 
-template <typename T, int CLS> cudaError_t coop_set_smem(int smem);
-template <typename T, int CLS> int coop_ctas_per_sm(int smem);   // resident CTAs per SM at this shared-memory size
+// cooperative kernel, launch shape `threads` (COOP_THREADS_LO / COOP_THREADS_HI)
+template <typename T, int CLS> cudaError_t coop_set_smem(int threads, int smem);
+template <typename T, int CLS> int coop_ctas_per_sm(int threads, int smem);   // resident CTAs per SM at this shared-memory size
 template <typename T, int CLS>
-void launch_coop(int grid, size_t smem, cudaStream_t s, const DevModel<T>* gm, const DevTask<T>& c,
+void launch_coop(int threads, int grid, size_t smem, cudaStream_t s, const DevModel<T>* gm, const DevTask<T>& c,
                  const EnvState<T>& st, int n, unsigned long long seed, long long env_offset, const T* actions, T* obs,
                  T* reward, uint8_t* done, T* terms, double* stats);
 
