@@ -745,7 +745,7 @@ __device__ void coop_write_obs(const DevModel<T>& m, const DevTask<T>& c, const 
 // bio_create picks by the number of item rounds per SM (COOP_SHAPE_COST); fp64 runs 256 threads.
 #define COOP_THREADS_LO(T) (sizeof(T) == 4 ? 512 : 256)
 #define COOP_THREADS_HI(T) (sizeof(T) == 4 ? 640 : 256)
-#define COOP_SHAPE_COST 1.17      // time of one round of items with the HI shape relative to the LO shape
+#define COOP_SHAPE_COST 1.12      // time of one round of items with the HI shape relative to the LO shape
 
 template <typename T, int CLS, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
