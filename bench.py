@@ -199,11 +199,22 @@ def main():
     import torch.distributed as dist
     from bioimitation_gym_b200 import backend, tasks
 
+    torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
+        # NCCL writes its version banner to stdout when the communicator is created: keep stdout to the one
+        # JSON line by pointing fd 1 at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     dev = torch.device("cuda", local_rank)
     N = args.envs_per_gpu
     cfg = dict(num_envs=N, device=local_rank, dtype=args.dtype, seed=1234, env_offset=rank * N)
