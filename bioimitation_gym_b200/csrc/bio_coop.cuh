@@ -52,8 +52,8 @@ struct WorkPlanar {
     T Qf[C::ND], Ld[C::ND];                        // generalized force and h * limit damping per dof
     alignas(16) T mv[P2_MAXMOV][8];                // moving points: location [0..2], d/dq [4..6]
     T mq[P2_MAXMOV];                               // their generalized force
-    alignas(16) T brx[P2_MAXBR][20];               // chain -> root: composite inertia, force, Schur, rhs
-    alignas(16) T brk[P2_MAXBR][12];               // chain block solve kept for the back substitution
+    alignas(16) T brx[P2_MAXBR][12];               // chain -> root: articulated inertia [0..5] and force [6..8] of its first body
+    alignas(16) T brk[P2_MAXBR][12];               // per chain dof: U / D [0..2], u / D [3], kept for the way back
 };
 
 template <typename T, typename C>

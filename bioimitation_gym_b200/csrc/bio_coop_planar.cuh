@@ -18,9 +18,9 @@
 //   phase E  lane = body: gather of the wrench sources acting on the body, its spatial inertia and
 //            force (contact damping h J^T D J enters as an inertia of the foot) | lane = dof:
 //            generalized force of limits, moving points and actuators
-//   phase F  lane = chain: composite inertias, the chain's block of the joint-space matrix,
-//            its L D L^T, and the Schur complement on the root dofs
-//   phase G  lane = chain: root 3x3 solve (redundantly per lane), chain back substitution
+//   phase F  lane = chain: articulated-body pass leaf -> root (the chain's L^T D L and its Schur
+//            complement on the root dofs, one dof at a time)
+//   phase G  lane = chain: root 3x3 solve (redundantly per lane), accelerations back down the chain
 //
 // Same equations as the general evaluation (coop_eval) and the CPU oracle; phases talk through
 // shared memory only, so the host emulation in tests/emul can run them lane by lane.
@@ -504,97 +504,53 @@ BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     }
 }
 
-// ---- phase F: lane l < n_branches: composite inertias of the chain, its block of the joint-space
-// matrix, L D L^T, Schur complement on the root dofs ----
+// ---- phase F: lane l < n_branches: articulated-body pass leaf -> root of the chain.  Every spatial
+// quantity is expressed in ground axes about the common point O, so handing an inertia or a force to the
+// parent is a plain sum.  Per body (from the leaf): I^A = I + I^a(child), p^A = p + p^a(child); with its dof
+// (motion vector S, generalized force Q, implicit damping Ld on the diagonal):
+//   U = I^A S,  D = S.U + Ld,  u = Q - S.p^A,  I^a = I^A - U U^T / D,  p^a = p^A + U u / D
+// (the L^T D L elimination of the chain block and its Schur complement on the root, one dof at a time).
+// The chain hands (I^a, p^a) of its first body to the root and keeps (U / D, u / D) for the way back. ----
 template <typename T, int CLS>
 BIO_DEV void p2_phase_f(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
     const PlanarProg<T>& pr = m.prog;
     auto& K = E.k.p;
     if (lane >= pr.n_branches) return;
     const int l = lane, nb = pr.br_nb[l];
-    T Ic[P2_MAXCB][9];
+    T Ia[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, pa[3] = {T(0), T(0), T(0)};
 #pragma unroll
-    for (int k = 0; k < P2_MAXCB; k++) {
+    for (int k = P2_MAXCB - 1; k >= 0; k--) {
         const int b = k < nb ? pr.br_body[l][k] : -1;
+        const int d = k < nb ? pr.br_dof[l][k] : -1;
         if (b >= 0) {
-            ld4(K.bI[b], Ic[k][0], Ic[k][1], Ic[k][2], Ic[k][3]);
-            ld4(K.bI[b] + 4, Ic[k][4], Ic[k][5], Ic[k][6], Ic[k][7]);
-            Ic[k][8] = K.bI[b][8];
-        } else {
-#pragma unroll
-            for (int e = 0; e < 9; e++) Ic[k][e] = T(0);
+            T v0, v1, v2, v3, v4, v5, v6, v7;
+            ld4(K.bI[b], v0, v1, v2, v3);
+            ld4(K.bI[b] + 4, v4, v5, v6, v7);
+            Ia[0] += v0; Ia[1] += v1; Ia[2] += v2; Ia[3] += v3; Ia[4] += v4; Ia[5] += v5;
+            pa[0] += v6; pa[1] += v7; pa[2] += K.bI[b][8];
+        }
+        if (d >= 0) {
+            T S0, S1, S2, s3;
+            ld4(K.S[d], S0, S1, S2, s3);
+            const T U0 = Ia[0] * S0 + Ia[1] * S1 + Ia[2] * S2;
+            const T U1 = Ia[1] * S0 + Ia[3] * S1 + Ia[4] * S2;
+            const T U2 = Ia[2] * S0 + Ia[4] * S1 + Ia[5] * S2;
+            const T Dinv = Num<T>::rcp(S0 * U0 + S1 * U1 + S2 * U2 + K.Ld[d]);
+            const T ud = (K.Qf[d] - (S0 * pa[0] + S1 * pa[1] + S2 * pa[2])) * Dinv;
+            const T W0 = U0 * Dinv, W1 = U1 * Dinv, W2 = U2 * Dinv;
+            Ia[0] -= U0 * W0; Ia[1] -= U0 * W1; Ia[2] -= U0 * W2;
+            Ia[3] -= U1 * W1; Ia[4] -= U1 * W2; Ia[5] -= U2 * W2;
+            pa[0] += U0 * ud; pa[1] += U1 * ud; pa[2] += U2 * ud;
+            st4(K.brk[l] + 4 * k, W0, W1, W2, ud);
         }
     }
-#pragma unroll
-    for (int k = P2_MAXCB - 2; k >= 0; k--)      // composites: suffix sums along the chain
-#pragma unroll
-        for (int e = 0; e < 9; e++) Ic[k][e] += Ic[k + 1][e];
-    T Sr[3][3];                                  // motion vectors of the root dofs
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-        const bool has = r < pr.root_ndof;
-        const int d = has ? pr.root_dof[r] : 0;
-        T s3;
-        ld4(K.S[d], Sr[r][0], Sr[r][1], Sr[r][2], s3);
-        if (!has) Sr[r][0] = Sr[r][1] = Sr[r][2] = T(0);
-    }
-    // chain block A (lower triangle), coupling C to the root dofs, right-hand side b
-    T Sk[P2_MAXCB][3], A[P2_MAXCB][P2_MAXCB], C[P2_MAXCB][3], bb[P2_MAXCB];
-#pragma unroll
-    for (int k = 0; k < P2_MAXCB; k++) {
-        const int d = k < nb ? pr.br_dof[l][k] : -1;
-        const bool has = d >= 0;
-        const int dd = has ? d : 0;
-        T s3;
-        ld4(K.S[dd], Sk[k][0], Sk[k][1], Sk[k][2], s3);
-        if (!has) Sk[k][0] = Sk[k][1] = Sk[k][2] = T(0);
-        const T ISn = Ic[k][0] * Sk[k][0] + Ic[k][1] * Sk[k][1] + Ic[k][2] * Sk[k][2];
-        const T ISx = Ic[k][1] * Sk[k][0] + Ic[k][3] * Sk[k][1] + Ic[k][4] * Sk[k][2];
-        const T ISy = Ic[k][2] * Sk[k][0] + Ic[k][4] * Sk[k][1] + Ic[k][5] * Sk[k][2];
-#pragma unroll
-        for (int j = 0; j <= k; j++) A[k][j] = Sk[j][0] * ISn + Sk[j][1] * ISx + Sk[j][2] * ISy;
-#pragma unroll
-        for (int r = 0; r < 3; r++) C[k][r] = Sr[r][0] * ISn + Sr[r][1] * ISx + Sr[r][2] * ISy;
-        bb[k] = (has ? K.Qf[dd] : T(0)) - (Sk[k][0] * Ic[k][6] + Sk[k][1] * Ic[k][7] + Sk[k][2] * Ic[k][8]);
-        A[k][k] += has ? K.Ld[dd] : T(1);        // no dof: identity row, zero coupling and rhs
-    }
-    // L D L^T of the 3x3 block, then A^-1 [C | b]
-    const T i0 = Num<T>::rcp(A[0][0]);
-    const T l10 = A[1][0] * i0, l20 = A[2][0] * i0;
-    const T i1 = Num<T>::rcp(A[1][1] - l10 * A[1][0]);
-    const T t21 = A[2][1] - l20 * A[1][0];
-    const T l21 = t21 * i1;
-    const T i2 = Num<T>::rcp(A[2][2] - l20 * A[2][0] - l21 * t21);
-    T X[P2_MAXCB][4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        const T r0 = c < 3 ? C[0][c] : bb[0], r1 = c < 3 ? C[1][c] : bb[1], r2 = c < 3 ? C[2][c] : bb[2];
-        const T y1 = r1 - l10 * r0, y2 = r2 - l20 * r0 - l21 * y1;
-        const T x2 = y2 * i2;
-        const T x1 = y1 * i1 - l21 * x2;
-        const T x0 = r0 * i0 - l10 * x1 - l20 * x2;
-        X[0][c] = x0; X[1][c] = x1; X[2][c] = x2;
-    }
-    T o[20];
-#pragma unroll
-    for (int e = 0; e < 9; e++) o[e] = Ic[0][e];
-    {   // Schur complement C^T A^-1 C (lower triangle) and C^T A^-1 b
-        int e = 9;
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int c = 0; c <= r; c++) o[e++] = C[0][r] * X[0][c] + C[1][r] * X[1][c] + C[2][r] * X[2][c];
-#pragma unroll
-        for (int r = 0; r < 3; r++) o[15 + r] = C[0][r] * X[0][3] + C[1][r] * X[1][3] + C[2][r] * X[2][3];
-        o[18] = o[19] = T(0);
-    }
-#pragma unroll
-    for (int e = 0; e < 20; e += 4) st4(K.brx[l] + e, o[e], o[e + 1], o[e + 2], o[e + 3]);
-#pragma unroll
-    for (int k = 0; k < P2_MAXCB; k++) st4(K.brk[l] + 4 * k, X[k][0], X[k][1], X[k][2], X[k][3]);
+    st4(K.brx[l], Ia[0], Ia[1], Ia[2], Ia[3]);
+    st4(K.brx[l] + 4, Ia[4], Ia[5], pa[0], pa[1]);
+    K.brx[l][8] = pa[2];
 }
 
-// ---- phase G: root solve (every chain lane repeats it), chain back substitution ----
+// ---- phase G: root solve on the articulated inertia (every chain lane repeats it), then the chain's way
+// back: qdd = u / D - (U / D) . a(parent),  a(body) = a(parent) + S qdd ----
 template <typename T, int CLS>
 BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
     const PlanarProg<T>& pr = m.prog;
@@ -605,17 +561,13 @@ BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     ld4(K.bI[pr.root_body], a[0], a[1], a[2], a[3]);
     ld4(K.bI[pr.root_body] + 4, a[4], a[5], a[6], a[7]);
     a[8] = K.bI[pr.root_body][8];
-    T sch[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, g[3] = {T(0), T(0), T(0)};
     for (int l = 0; l < pr.n_branches; l++) {
-        T v[20];
+        T v[8];
+        ld4(K.brx[l], v[0], v[1], v[2], v[3]);
+        ld4(K.brx[l] + 4, v[4], v[5], v[6], v[7]);
 #pragma unroll
-        for (int e = 0; e < 20; e += 4) ld4(K.brx[l] + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
-#pragma unroll
-        for (int e = 0; e < 9; e++) a[e] += v[e];
-#pragma unroll
-        for (int e = 0; e < 6; e++) sch[e] += v[9 + e];
-#pragma unroll
-        for (int e = 0; e < 3; e++) g[e] += v[15 + e];
+        for (int e = 0; e < 8; e++) a[e] += v[e];
+        a[8] += K.brx[l][8];
     }
     T Sr[3][3], IS[3][3], H[3][3], rhs[3];
 #pragma unroll
@@ -629,18 +581,14 @@ BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         IS[r][1] = a[1] * Sr[r][0] + a[3] * Sr[r][1] + a[4] * Sr[r][2];
         IS[r][2] = a[2] * Sr[r][0] + a[4] * Sr[r][1] + a[5] * Sr[r][2];
     }
-    {
-        int e = 0;
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
-            const bool has = r < pr.root_ndof;
-            const int d = has ? pr.root_dof[r] : 0;
+    for (int r = 0; r < 3; r++) {
+        const bool has = r < pr.root_ndof;
+        const int d = has ? pr.root_dof[r] : 0;
 #pragma unroll
-            for (int c = 0; c <= r; c++, e++)
-                H[r][c] = Sr[c][0] * IS[r][0] + Sr[c][1] * IS[r][1] + Sr[c][2] * IS[r][2] - sch[e];
-            H[r][r] += has ? K.Ld[d] : T(1);
-            rhs[r] = (has ? K.Qf[d] : T(0)) - (Sr[r][0] * a[6] + Sr[r][1] * a[7] + Sr[r][2] * a[8]) - g[r];
-        }
+        for (int c = 0; c <= r; c++) H[r][c] = Sr[c][0] * IS[r][0] + Sr[c][1] * IS[r][1] + Sr[c][2] * IS[r][2];
+        H[r][r] += has ? K.Ld[d] : T(1);         // no dof: identity row, zero right-hand side
+        rhs[r] = (has ? K.Qf[d] : T(0)) - (Sr[r][0] * a[6] + Sr[r][1] * a[7] + Sr[r][2] * a[8]);
     }
     const T i0 = Num<T>::rcp(H[0][0]);
     const T l10 = H[1][0] * i0, l20 = H[2][0] * i0;
@@ -658,13 +606,20 @@ BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         for (int r = 0; r < 3; r++) if (r < pr.root_ndof) E.udot[pr.root_dof[r]] = ar[r];
     }
     if (lane < pr.n_branches) {
+        // acceleration of the parent body beyond its bias term
+        T a0 = Sr[0][0] * ar[0] + Sr[1][0] * ar[1] + Sr[2][0] * ar[2];
+        T a1 = Sr[0][1] * ar[0] + Sr[1][1] * ar[1] + Sr[2][1] * ar[2];
+        T a2 = Sr[0][2] * ar[0] + Sr[1][2] * ar[1] + Sr[2][2] * ar[2];
 #pragma unroll
         for (int k = 0; k < P2_MAXCB; k++) {
             const int d = k < pr.br_nb[lane] ? pr.br_dof[lane][k] : -1;
             if (d >= 0) {
-                T x0, x1, x2, x3;
-                ld4(K.brk[lane] + 4 * k, x0, x1, x2, x3);
-                E.udot[d] = x3 - (x0 * ar[0] + x1 * ar[1] + x2 * ar[2]);
+                T W0, W1, W2, ud, S0, S1, S2, s3;
+                ld4(K.brk[lane] + 4 * k, W0, W1, W2, ud);
+                ld4(K.S[d], S0, S1, S2, s3);
+                const T qdd = ud - (W0 * a0 + W1 * a1 + W2 * a2);
+                E.udot[d] = qdd;
+                a0 += S0 * qdd; a1 += S1 * qdd; a2 += S2 * qdd;
             }
         }
     }
