@@ -270,15 +270,74 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     auto& K = E.k.p;
     if (lane >= m.n_muscles) return;
     const int i = lane;
-    // streaming pass over the active path points: length, and the wrench of every segment that
-    // crosses from one body to another (+w on the body of its first point, -w on the other)
+    // path geometry: length, and the wrench of every segment that crosses from one body to another
+    // (+w on the body of its first point, -w on the other); compiled form, else a streaming pass over the
+    // active path points
     T W[P2_MAXSLOT][3];
 #pragma unroll
     for (int sl = 0; sl < P2_MAXSLOT; sl++) W[sl][0] = W[sl][1] = W[sl][2] = T(0);
     T xp = T(0), yp = T(0), zp = T(0), ex = T(0), ey = T(0), ez = T(0), L = T(0);
     T mdx = T(0), mdy = T(0), mdz = T(0);        // moving point: d(location)/dq in ground axes
     T mqu = T(0);                                // and (e_out - e_in) . d(location)/dq
-    int prev_slot = -1, mov = -1;
+    int mov = -1;
+    if (pr.path_ok) {
+        // compiled path: variant from the muscle's conditional points, constant length of the variant, then
+        // its live segments (same count on every lane: no divergence between muscles)
+        int var = 0;
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const int p = pr.mc_cond[i][cc];
+            if (p >= 0) {
+                const T v = E.q[(pr.pt_info[p] >> 6) & 31];
+                if (v >= m.pt_range[p][0] - T(1e-5) && v <= m.pt_range[p][1] + T(1e-5)) var |= 1 << cc;
+            }
+        }
+        L = pr.mc_len0[i][var];
+        for (int j = 0; j < pr.mc_nlive; j++) {
+            const uint32_t seg = pr.mc_seg[i][var][j];
+            if (!(seg >> 31)) continue;
+            T pxy[2][3];
+            int slot2[2];
+            bool mv2[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int p = (seg >> (8 * e)) & 255u;
+                const int info = pr.pt_info[p];
+                const int b = info & 15;
+                T c, s, ox, oy, lx, ly, lz, l3;
+                ld4(K.pose[b], c, s, ox, oy);
+                mv2[e] = ((info >> 4) & 3) == BIO_PT_MOVING;
+                if (mv2[e]) {
+                    T dlx, dly, dl3;
+                    mov = (info >> 13) & 7;
+                    ld4(K.mv[mov], lx, ly, lz, l3);
+                    ld4(K.mv[mov] + 4, dlx, dly, mdz, dl3);
+                    rot2(c, s, dlx, dly, mdx, mdy);
+                } else {
+                    ld4(pr.pt_xyz[p], lx, ly, lz, l3);
+                }
+                rot2(c, s, lx, ly, pxy[e][0], pxy[e][1]);
+                pxy[e][0] += ox; pxy[e][1] += oy; pxy[e][2] = lz;
+                slot2[e] = (info >> 11) & 3;
+            }
+            const T dx = pxy[1][0] - pxy[0][0], dy = pxy[1][1] - pxy[0][1], dz = pxy[1][2] - pxy[0][2];
+            const T d2 = dx * dx + dy * dy + dz * dz;
+            const T il = Num<T>::rsqrt(d2);
+            L += d2 * il;
+            ex = dx * il; ey = dy * il; ez = dz * il;
+            const T msg = (mv2[0] ? T(1) : T(0)) - (mv2[1] ? T(1) : T(0));
+            mqu += msg * (ex * mdx + ey * mdy + ez * mdz);
+            if (slot2[0] != slot2[1]) {
+                const T wn = pxy[0][0] * ey - pxy[0][1] * ex;
+#pragma unroll
+                for (int sl = 0; sl < P2_MAXSLOT; sl++) {
+                    const T sgn = sl == slot2[0] ? T(1) : (sl == slot2[1] ? T(-1) : T(0));
+                    W[sl][0] += sgn * wn; W[sl][1] += sgn * ex; W[sl][2] += sgn * ey;
+                }
+            }
+        }
+    } else {
+    int prev_slot = -1;
     bool prev_moving = false;
     const int pb = m.mus_pt_begin[i], pe = pb + m.mus_pt_count[i];
     for (int p = pb; p < pe; p++) {
@@ -323,6 +382,7 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         }
         prev_moving = kind == BIO_PT_MOVING;
         xp = x; yp = y; zp = z; prev_slot = slot;
+    }
     }
     const T fiso = m.mus_fiso[i], lopt = m.mus_lopt[i], h = m.mus_height[i], beta = m.mus_beta[i];
     const T amin = m.mus_amin[i], lmin = m.mus_lm_min[i];

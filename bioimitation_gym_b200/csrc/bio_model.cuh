@@ -3,6 +3,7 @@
 // shared memory once per CTA; all warps read it with uniform (broadcast)
 // addresses.
 #pragma once
+#include <math.h>
 #include <stdint.h>
 
 #include <utility>
@@ -27,6 +28,8 @@ namespace bio {
 #define P2_MAXSRC 64      // wrench sources: (muscle, slot) pairs, then spheres
 #define P2_MAXMOV 4       // moving path points
 #define P2_MAXTASK (BIO_MAX_AXES + 3 * P2_MAXMOV)
+#define P2_MAXVAR 4       // variants of a muscle path: on/off states of its (<= 2) conditional points
+#define P2_MAXLIVE 2      // live segments of a variant (they cross bodies or touch a moving point)
 #define P2_F_FIRST (1 << 17)     // first axis of its body
 #define P2_F_LAST (1 << 18)      // last axis of its body: publish the body frame
 #define P2_F_ROOT (1 << 19)      // axis of the root joint (recomputed by every chain lane, published by lane 0)
@@ -63,6 +66,13 @@ struct alignas(16) PlanarProg {
     int32_t pt_info[BIO_MAX_PATHPTS];          // body | kind<<4 | dof<<6 | slot<<11 | moving index<<13
     int32_t mus_src0[BIO_MAX_MUSCLES + 1];     // first wrench source of the muscle (one per slot); [n_muscles] = end
     int32_t mov_dof[P2_MAXMOV];
+    // compiled paths: a segment between two fixed points of one body has a constant length and does no work on
+    // the tree, so per variant (state of the muscle's conditional points) the path is a constant length plus
+    // its live segments: mc_seg = first point | second point << 8 | 1 << 31
+    int32_t path_ok, mc_nlive, mc_pad_[2];     // path_ok: every muscle has this form; mc_nlive: most live segments of any variant
+    int32_t mc_cond[BIO_MAX_MUSCLES][2];       // conditional points of the muscle (-1: none)
+    uint32_t mc_seg[BIO_MAX_MUSCLES][P2_MAXVAR][P2_MAXLIVE];
+    T mc_len0[BIO_MAX_MUSCLES][P2_MAXVAR];
     // generalized-force inputs per dof
     int8_t dof_lim[BIO_MAX_DOF][2], dof_mov[BIO_MAX_DOF][2], dof_act[BIO_MAX_DOF];
     // wrench sources acting on every body
@@ -576,6 +586,43 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         for (int k = 0; k < n_slot; k++) { if (n_src >= P2_MAXSRC) return; src_body[n_src++] = slot_body[k]; }
     }
     pr.mus_src0[s.n_muscles] = n_src;
+    // compiled paths (see PlanarProg::mc_seg); any muscle that does not fit leaves path_ok = 0 and phase C
+    // streams over the path points instead
+    pr.path_ok = 1;
+    pr.mc_nlive = 0;
+    for (int i = 0; i < s.n_muscles && pr.path_ok; i++) {
+        const int pb = s.mus_pt_begin[i], pe = pb + s.mus_pt_count[i];
+        int n_cond = 0;
+        pr.mc_cond[i][0] = pr.mc_cond[i][1] = -1;
+        for (int p = pb; p < pe; p++)
+            if (s.pt_kind[p] == BIO_PT_CONDITIONAL) { if (n_cond >= 2) { pr.path_ok = 0; break; } pr.mc_cond[i][n_cond++] = p; }
+        if (pe > 255) pr.path_ok = 0;
+        for (int var = 0; var < P2_MAXVAR && pr.path_ok; var++) {
+            double len0 = 0.0;
+            int n_live = 0, prev = -1;
+            for (int l = 0; l < P2_MAXLIVE; l++) pr.mc_seg[i][var][l] = 0u;
+            for (int p = pb; p < pe; p++) {
+                if (s.pt_kind[p] == BIO_PT_CONDITIONAL) {
+                    const int c = pr.mc_cond[i][0] == p ? 0 : 1;
+                    if (!((var >> c) & 1)) continue;
+                }
+                if (prev >= 0) {
+                    const bool fixed = s.pt_kind[p] != BIO_PT_MOVING && s.pt_kind[prev] != BIO_PT_MOVING;
+                    if (fixed && s.pt_body[p] == s.pt_body[prev]) {
+                        double d2 = 0.0;
+                        for (int c = 0; c < 3; c++) { const double dd = s.pt_loc[p][c] - s.pt_loc[prev][c]; d2 += dd * dd; }
+                        len0 += sqrt(d2);
+                    } else {
+                        if (n_live >= P2_MAXLIVE) { pr.path_ok = 0; break; }
+                        pr.mc_seg[i][var][n_live++] = (uint32_t)prev | ((uint32_t)p << 8) | 0x80000000u;
+                    }
+                }
+                prev = p;
+            }
+            pr.mc_len0[i][var] = (T)len0;
+            if (n_live > pr.mc_nlive) pr.mc_nlive = n_live;
+        }
+    }
     pr.sph_src0 = n_src;
     for (int sp = 0; sp < s.n_spheres; sp++) { if (n_src >= P2_MAXSRC) return; src_body[n_src++] = s.sph_body[sp]; }
     pr.n_src = n_src;
