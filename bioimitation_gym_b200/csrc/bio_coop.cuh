@@ -725,11 +725,9 @@ template <typename T, int CLS>
 __device__ void coop_write_obs(const DevModel<T>& m, const DevTask<T>& c, const EnvWork<T, CLS>& E, int lane, int istep,
                                T* orow) {
     constexpr int G = CoopCls<CLS>::G;
-    T pel[3] = {T(0), T(0), T(0)};
-    for (int i = 0; i < m.n_coords; i++) {
-        const int pt = m.coord_pelvis_trans[i];
-        if (pt) pel[pt - 1] = E.q[m.coord_dof[i]];
-    }
+    T pel[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) pel[k] = m.pel_dof[k] >= 0 ? E.q[m.pel_dof[k]] : T(0);
     const int row_next = ref_row(c, istep + 1);
     for (int o = lane; o < c.obs_dim; o += G) orow[o] = obs_value<T, CLS>(m, c, E, istep, row_next, pel, o);
 }
@@ -800,7 +798,9 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     if (isa) {
         if (first) {
             last_action = action;
-            if (valid) for (int hh = 0; hh < Hh; hh++) st.history[((size_t)hh * na + lane) * n + ii] = action;
+            if (valid)
+#pragma unroll 1
+                for (int hh = 0; hh < Hh; hh++) st.history[((size_t)hh * na + lane) * n + ii] = action;
         } else {
             last_action = st.last_action[(size_t)lane * n + ii];
         }
@@ -809,6 +809,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     if (isa) {
         if (valid) st.history[((size_t)hist_pos * na + lane) * n + ii] = action;
         T sum = T(0);
+#pragma unroll 1
         for (int hh = 0; hh < Hh; hh++) sum += (hh == hist_pos) ? action : st.history[((size_t)hh * na + lane) * n + ii];
         curr = sum / T(Hh);
         E.ctrl[lane] = clampv(c.feed_mean_action ? curr : action, m.act_min[lane], m.act_max[lane]);
@@ -837,11 +838,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
         qpart += dd * dd;
     }
     const T qerr = group_sum<T, G>(qpart) / T(m.n_coords);
-    T px = T(0), py = T(0);
-    for (int k = 0; k < m.n_coords; k++) {
-        if (m.coord_pelvis_trans[k] == 1) px = E.q[m.coord_dof[k]];
-        if (m.coord_pelvis_trans[k] == 2) py = E.q[m.coord_dof[k]];
-    }
+    const T px = m.pel_dof[0] >= 0 ? E.q[m.pel_dof[0]] : T(0), py = m.pel_dof[1] >= 0 ? E.q[m.pel_dof[1]] : T(0);
     const T com_err = body_mse(E.com_pos, c.ref_com_pos + (size_t)row * 3);
     const T position_r = Num<T>::exp(T(-30) * qerr);
     const T com_r = Num<T>::exp(T(-20) * com_err);

@@ -621,13 +621,16 @@ BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     ld4(K.bI[pr.root_body], a[0], a[1], a[2], a[3]);
     ld4(K.bI[pr.root_body] + 4, a[4], a[5], a[6], a[7]);
     a[8] = K.bI[pr.root_body][8];
-    for (int l = 0; l < pr.n_branches; l++) {
-        T v[8];
-        ld4(K.brx[l], v[0], v[1], v[2], v[3]);
-        ld4(K.brx[l] + 4, v[4], v[5], v[6], v[7]);
 #pragma unroll
-        for (int e = 0; e < 8; e++) a[e] += v[e];
-        a[8] += K.brx[l][8];
+    for (int l = 0; l < P2_MAXBR; l++) {
+        if (l < pr.n_branches) {
+            T v[8];
+            ld4(K.brx[l], v[0], v[1], v[2], v[3]);
+            ld4(K.brx[l] + 4, v[4], v[5], v[6], v[7]);
+#pragma unroll
+            for (int e = 0; e < 8; e++) a[e] += v[e];
+            a[8] += K.brx[l][8];
+        }
     }
     T Sr[3][3], IS[3][3], H[3][3], rhs[3];
 #pragma unroll
@@ -718,6 +721,7 @@ BIO_DEV void p2_readout_2(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
     const int nb = m.n_bodies;
     if (lane < 3) {
         T ms = T(0), ps = T(0);
+#pragma unroll 1
         for (int b = 0; b < nb; b++) { ms += E.x.out.comp[b][lane]; ps += E.x.out.comp[b][3 + lane]; }
         const T im = T(1) / m.total_mass;
         E.com_pos[lane] = ms * im + E.O[lane];
@@ -725,6 +729,7 @@ BIO_DEV void p2_readout_2(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
     } else if (lane < 5) {
         const int g = lane - 3;
         T w[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+#pragma unroll 1
         for (int s = 0; s < m.n_spheres; s++) {
             if (m.sph_group[s] != g) continue;
             const T pa[3] = {E.sphx[s][0] + E.O[0], E.sphx[s][1] + E.O[1], E.sphx[s][2]};
@@ -735,6 +740,7 @@ BIO_DEV void p2_readout_2(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
         for (int c = 0; c < 6; c++) E.contact[g][c] = w[c];
     } else if (lane == 5) {
         T mx = T(0);
+#pragma unroll 1
         for (int l = 0; l < m.n_limits; l++) { const T a = Num<T>::abs(E.limf[l]); mx = a > mx ? a : mx; }
         E.max_limit = mx;
     }

@@ -22,6 +22,24 @@ namespace bio {
 
 #define BIO_DEV __host__ __device__ __forceinline__
 
+// sin and cos of a float to fp32 rounding level for |x| up to a few hundred radians (joint angles): two-term
+// Cody-Waite reduction by pi/2, then the single-precision minimax polynomials on [-pi/4, pi/4] (Cephes
+// coefficients).  Replaces sincosf, whose large-argument path costs three times the instructions.
+static __host__ __device__ __forceinline__ void sincos_f32(float x, float* sn, float* cs) {
+    const float k = rintf(x * 0.636619772f);
+    float r = fmaf(k, -1.57079637e+0f, x);
+    r = fmaf(k, 4.37113883e-8f, r);
+    const float z = r * r;
+    const float ps = fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f);
+    const float sr = fmaf(r * z, ps, r);
+    const float pc = fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f);
+    const float cr = fmaf(z * z, pc, fmaf(-0.5f, z, 1.0f));
+    const int n = (int)k;
+    const float s0 = (n & 1) ? cr : sr, c0 = (n & 1) ? sr : cr;
+    *sn = (n & 2) ? -s0 : s0;
+    *cs = ((n + 1) & 2) ? -c0 : c0;
+}
+
 template <typename T> struct Num;
 template <> struct Num<float> {
     static BIO_DEV float sqrt(float x) { return sqrtf(x); }
@@ -31,7 +49,7 @@ template <> struct Num<float> {
     // the host emulation keeps plain arithmetic
 #ifdef __CUDA_ARCH__
     static BIO_DEV float div(float a, float b) { return __fdividef(a, b); }
-    static BIO_DEV float rcp(float b) { return __frcp_rn(b); }
+    static BIO_DEV float rcp(float b) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return r; }
     static BIO_DEV float sqrt_pos(float x) { return x * rsqrtf(x); }
 #else
     static BIO_DEV float div(float a, float b) { return a / b; }
@@ -41,7 +59,7 @@ template <> struct Num<float> {
     static BIO_DEV float abs(float x) { return fabsf(x); }
     static BIO_DEV float floor(float x) { return floorf(x); }
     static BIO_DEV float exp(float x) { return expf(x); }
-    static BIO_DEV void sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+    static BIO_DEV void sincos(float x, float* s, float* c) { sincos_f32(x, s, c); }
     static BIO_DEV float fmod(float x, float y) { return fmodf(x, y); }
     static BIO_DEV float ceil(float x) { return ceilf(x); }
     // Newton on the normalised fibre velocity stops once a correction is below this; the iteration converges

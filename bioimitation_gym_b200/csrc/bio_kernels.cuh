@@ -42,15 +42,20 @@ __device__ const DevModel<T>& stage_model(const DevModel<T>* gm, unsigned char* 
 // perturbation force at time t (env2D.py:83-100): 100 knots over 10 s,
 // piecewise constant, +-F where fmod(t_knot, 2) > thresh
 template <typename T>
-__device__ T perturb_force(const DevTask<T>& c, unsigned long long seed, unsigned long long env, T t) {
-    if (!c.perturb) return T(0);
+__device__ __noinline__ T perturb_force_on(T force, T thresh, int negative_only, unsigned long long seed,
+                                           unsigned long long env, T t) {
     const double dtk = 10.0 / 99.0;
     int kidx = (int)ceil((double)t / dtk - 1e-12);
     kidx = kidx < 0 ? 0 : (kidx > 99 ? 99 : kidx);
     const double tk = kidx * dtk;
-    if (!(fmod(tk, 2.0) > (double)c.perturb_thresh)) return T(0);
-    if (c.perturb_negative_only) return -c.perturb_force;
-    return (bio_rand(seed, env, (unsigned long long)kidx, 7) & 1ull) ? c.perturb_force : -c.perturb_force;
+    if (!(fmod(tk, 2.0) > (double)thresh)) return T(0);
+    if (negative_only) return -force;
+    return (bio_rand(seed, env, (unsigned long long)kidx, 7) & 1ull) ? force : -force;
+}
+template <typename T>
+__device__ __forceinline__ T perturb_force(const DevTask<T>& c, unsigned long long seed, unsigned long long env, T t) {
+    // the fp64 knot arithmetic stays out of line (scalars only: the task block stays in the parameter space)
+    return c.perturb ? perturb_force_on<T>(c.perturb_force, c.perturb_thresh, c.perturb_negative_only, seed, env, t) : T(0);
 }
 
 template <typename T>

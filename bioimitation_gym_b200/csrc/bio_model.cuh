@@ -152,6 +152,7 @@ struct alignas(16) DevModel {
     T obs_loc[BIO_MAX_OBSPTS][3];
     int32_t coord_dof[BIO_MAX_COORDS];
     int32_t coord_pelvis_trans[BIO_MAX_COORDS];
+    int32_t pel_dof[4];                      // dof of pelvis_tx / ty / tz (-1: none), from coord_pelvis_trans
     T coord_const[BIO_MAX_COORDS];
     // schedules of the cooperative kernel (bio_coop.cuh), built by convert_model
     int32_t n_levels, n_moving, n_entries, pad2;
@@ -267,6 +268,9 @@ void convert_model(const BioModelTables& s, DevModel<T>& d) {
     d.is_torque = s.is_torque;
     d.has_tz = 0;
     for (int i = 0; i < s.n_coords; i++) if (s.coord_pelvis_trans[i] == 3) d.has_tz = 1;
+    for (int k = 0; k < 4; k++) d.pel_dof[k] = -1;
+    for (int i = 0; i < s.n_coords; i++)
+        if (s.coord_pelvis_trans[i] >= 1 && s.coord_pelvis_trans[i] <= 3) d.pel_dof[s.coord_pelvis_trans[i] - 1] = s.coord_dof[i];
     d.max_pts_per_muscle = 0;
     for (int i = 0; i < s.n_muscles; i++)
         if (s.mus_pt_count[i] > d.max_pts_per_muscle) d.max_pts_per_muscle = s.mus_pt_count[i];

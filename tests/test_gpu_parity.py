@@ -311,6 +311,37 @@ def test_host_buffer_entry_point_matches_device_path():
     env2.close()
 
 
+def test_host_entry_point_with_page_locked_buffers_matches_device_path():
+    """Page-locked host buffers are read / written by the kernel in place (no staging copies): same results
+    as the device path, with a mix of pinned and pageable buffers falling back to the staged copies."""
+    import torch
+    n = 300                                    # odd tail: the last warp holds one env
+    env, _ = _mk("MuscleWalkingImitation2D-v0", n, "float32")
+    env2, _ = _mk("MuscleWalkingImitation2D-v0", n, "float32")
+    env3, _ = _mk("MuscleWalkingImitation2D-v0", n, "float32")
+    env.reset(); env2.reset(); env3.reset()
+    pin = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt).pin_memory()
+    a_p, o_p, r_p, d_p, t_p = pin(n, 14), pin(n, env.obs_dim), pin(n), pin(n, dt=torch.uint8), pin(n, 5)
+    o3 = np.zeros((n, env.obs_dim), dtype=np.float32)      # pageable observation buffer, pinned others
+    rng = np.random.default_rng(5)
+    n_done = 0
+    for _ in range(40):
+        a = rng.uniform(0, 1, (n, 14)).astype(np.float32)
+        a_p.copy_(torch.as_tensor(a))
+        o, r, d, info = env.step(torch.as_tensor(a))
+        env2.step_host(a_p.numpy(), o_p.numpy(), r_p.numpy(), d_p.numpy(), t_p.numpy())
+        assert np.array_equal(o.cpu().numpy(), o_p.numpy()) and np.array_equal(r.cpu().numpy(), r_p.numpy())
+        assert np.array_equal(d.cpu().numpy(), d_p.numpy())
+        assert np.array_equal(info["all_rewards"].cpu().numpy(), t_p.numpy())
+        r3, d3, t3 = pin(n), pin(n, dt=torch.uint8), pin(n, 5)
+        env3.step_host(a_p.numpy(), o3, r3.numpy(), d3.numpy(), t3.numpy())
+        assert np.array_equal(o3, o_p.numpy()) and np.array_equal(r3.numpy(), r_p.numpy())
+        n_done += int(d_p.sum())
+    assert n_done > 0
+    for e in (env, env2, env3):
+        e.close()
+
+
 def test_errors_are_reported_not_thrown():
     import torch
     from bioimitation_gym_b200 import backend
