@@ -51,6 +51,7 @@ struct WorkPlanar {
     alignas(16) T bI[BIO_MAX_BODIES][12];          // spatial inertia about O [0..5] and force [6..8] per body
     T Qf[C::ND], Ld[C::ND];                        // generalized force and h * limit damping per dof
     alignas(16) T mv[P2_MAXMOV][8];                // moving points: location [0..2], d/dq [4..6]
+    alignas(16) T sphI[BIO_MAX_SPHERES][8];        // h * contact damping of a sphere as an inertia about O: ww wx wy xx yy
     T mq[P2_MAXMOV];                               // their generalized force
     alignas(16) T brx[P2_MAXBR][12];               // chain -> root: articulated inertia [0..5] and force [6..8] of its first body
     alignas(16) T brk[P2_MAXBR][12];               // per chain dof: U / D [0..2], u / D [3], kept for the way back
@@ -639,7 +640,13 @@ __device__ void coop_integrate(const DevModel<T>& m, const DevTask<T>& c, EnvWor
             coop_eval_any<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, t), ext_pt,
                               c.integrator == BIO_INT_IMPLICIT_DAMPING ? h : T(0), false);
             if (isd) { const T un = E.u[lane] + h * E.udot[lane]; E.u[lane] = un; E.q[lane] += h * un; }
-            if (ism) { E.act[lane] += h * E.adot[lane]; E.lm[lane] += h * E.lmdot[lane]; }
+            if (ism) {                           // explicit Euler with the clamps of coop_clamp
+                const T lmn = E.lm[lane] + h * E.lmdot[lane], lmin = m.mus_lm_min[lane];
+                E.act[lane] = clampv(E.act[lane] + h * E.adot[lane], m.mus_amin[lane], T(1));
+                E.lm[lane] = lmn < lmin ? lmin : lmn;
+            }
+            gsync<G>();
+            continue;
         } else if (c.integrator == BIO_INT_RK2_MIDPOINT) {
             const T q0 = isd ? E.q[lane] : T(0), u0 = isd ? E.u[lane] : T(0);
             const T a0 = ism ? E.act[lane] : T(0), l0 = ism ? E.lm[lane] : T(0);
@@ -825,8 +832,12 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     const int ext_pt = c.perturb ? c.perturb_obspt : -1;
     coop_eval_any<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, T(istep) * c.dt), ext_pt, T(0), true);
     gsync<G>();
-    T* orow = obs + (size_t)ii * c.obs_dim;
-    if (valid) coop_write_obs<T, CLS>(m, c, E, lane, istep, orow);
+    // Size class 0: the observation rows of the warp's two envs are adjacent in memory; they are staged in the
+    // (now idle) planar work arrays and written by the whole warp at the end, 16 bytes per lane (full 128-byte
+    // lines for a caller's page-locked host buffer).  Size class 1: a warp writes its one row directly.
+    static_assert(CLS != 0 || sizeof(E.k.p) >= 256 * sizeof(T), "observation stage does not fit the planar work arrays");
+    T* orow = CLS == 0 ? reinterpret_cast<T*>(&E.k.p) : obs + (size_t)ii * c.obs_dim;
+    if (valid || CLS == 0) coop_write_obs<T, CLS>(m, c, E, lane, istep, orow);
 
     // ---- reward (env2D.py:267-358): lane-parallel partial sums ----
     const int row = ref_row(c, istep);
@@ -955,7 +966,28 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
         gsync<G>();
         coop_eval_any<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, T(istep) * c.dt), ext_pt, T(0), true);
         gsync<G>();
-        if (valid) coop_write_obs<T, CLS>(m, c, E, lane, istep, orow);
+        if (valid || CLS == 0) coop_write_obs<T, CLS>(m, c, E, lane, istep, orow);
+    }
+    if constexpr (CLS == 0) {
+        __syncwarp();                          // both envs of the warp have staged their final observation
+        const int wl = threadIdx.x & 31, od = c.obs_dim;
+        const int i0 = item * EPW;
+        const int total = od * (i0 + 1 < n ? 2 : 1);
+        const T* s0 = reinterpret_cast<const T*>(&works[(threadIdx.x >> 5) * EPW].k.p);
+        const T* s1 = reinterpret_cast<const T*>(&works[(threadIdx.x >> 5) * EPW + 1].k.p);
+        T* base = obs + (size_t)i0 * od;
+        if (sizeof(T) == 4 && (reinterpret_cast<size_t>(base) & 15) == 0) {
+            for (int v = wl; 4 * v < total; v += 32) {
+                T x[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) { const int k = 4 * v + j; x[j] = k < od ? s0[k] : (k < total ? s1[k - od] : T(0)); }
+                if (4 * v + 3 < total) st4(base + 4 * v, x[0], x[1], x[2], x[3]);
+                else for (int j = 0; 4 * v + j < total; j++) base[4 * v + j] = x[j];
+            }
+        } else {
+            for (int k = wl; k < total; k += 32) base[k] = k < od ? s0[k] : s1[k - od];
+        }
+        __syncwarp();
     }
     // ---- write back ----
     if (valid) {

@@ -91,6 +91,24 @@ BIO_DEV void p2_phase_a(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     for (int t = lane; t < pr.n_atasks; t += G) {
         const int d = pr.at_dof[t], dst = pr.at_dst[t];
         T s, ds, dds;
+        if (t >= G && pr.a2_cheap) {
+            // tasks past the first round are constants / linear functions of translations and moving points
+            // (host order: splines, rotations, the rest): no spline search, no sin / cos
+            const int f = pr.at_func[t];
+            const T c0 = m.func_c[f][0];
+            const bool lin = m.func_kind[f] == BIO_FUNC_LINEAR;
+            s = lin ? c0 * (d >= 0 ? E.q[d] : T(0)) + m.func_c[f][1] : c0;
+            ds = lin ? c0 : T(0);
+            if (dst < 64) {
+                st4(K.ax[dst], s, ds, ds * (d >= 0 ? E.u[d] : T(0)), T(0));
+                st2(K.axr[dst], T(1), T(0));
+            } else {
+                const int k = (dst - 64) / 3, c = (dst - 64) % 3;
+                K.mv[k][c] = s + pr.at_add[t];
+                K.mv[k][4 + c] = ds;
+            }
+            continue;
+        }
         func_eval(m, pr.at_func[t], d >= 0 ? E.q[d] : T(0), s, ds, dds, &E.knot_hint[t]);
         if (dst < 64) {
             const T qd = d >= 0 ? E.u[d] : T(0);
@@ -439,7 +457,7 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
 
 // ---- phase D: lane = contact sphere | coordinate limit ----
 template <typename T, int CLS>
-BIO_DEV void p2_phase_d(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
+BIO_DEV void p2_phase_d(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane, const T h_imp) {
     const PlanarProg<T>& pr = m.prog;
     auto& K = E.k.p;
     if (lane < m.n_spheres) {
@@ -478,6 +496,10 @@ BIO_DEV void p2_phase_d(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         E.sphF[s][0] = Fx; E.sphF[s][1] = Fy; E.sphF[s][2] = T(0);
         E.sphD[s][0] = D0; E.sphD[s][1] = D1;
         st4(E.x.src.w[pr.sph_src0 + s], xc * Fy - py * Fx, Fx, Fy, T(0));
+        // implicit contact damping h J^T D J, J = [[-py, 1, 0], [xc, 0, 1]], as an inertia of the sphere's body
+        const T d0 = h_imp * D0, d1 = h_imp * D1;
+        st4(K.sphI[s], d0 * py * py + d1 * xc * xc, -d0 * py, d1 * xc, d0);
+        K.sphI[s][4] = d1;
     } else if (lane - m.n_spheres < m.n_limits) {
         const int l = lane - m.n_spheres, d = m.lim_dof[l];
         const T w = m.lim_w[l], qq = E.q[d];
@@ -532,17 +554,12 @@ BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         o[8] = IAy + w * px - Wy;
         if (h_imp > T(0)) {
             int mask = pr.body_sph_mask[b];
-            while (mask) {
+            while (mask) {                       // zero for a sphere out of contact
                 const int sp = lowest_bit(mask);
                 mask &= mask - 1;
-                if (!(E.sphD[sp][1] > T(0))) continue;
-                const T sx = E.sphx[sp][0], sy = E.sphx[sp][1];
-                const T d0 = h_imp * E.sphD[sp][0], d1 = h_imp * E.sphD[sp][1];
-                Iww += d0 * sy * sy + d1 * sx * sx;
-                Iwx -= d0 * sy;
-                Iwy += d1 * sx;
-                Ixx += d0;
-                Iyy += d1;
+                T a0, a1, a2, a3;
+                ld4(K.sphI[sp], a0, a1, a2, a3);
+                Iww += a0; Iwx += a1; Iwy += a2; Ixx += a3; Iyy += K.sphI[sp][4];
             }
         }
         st4(o, Iww, Iwx, Iwy, Ixx);
@@ -757,7 +774,7 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
     else p2_phase_b<T, CLS>(m, E, lane);
     gsync<G>();
     p2_phase_c<T, CLS>(m, E, lane, newton_iters, full);
-    p2_phase_d<T, CLS>(m, E, lane);
+    p2_phase_d<T, CLS>(m, E, lane, h_imp);
     gsync<G>();
     p2_phase_e<T, CLS>(m, E, lane, h_imp, ext_fx, ext_pt);
     gsync<G>();

@@ -69,7 +69,7 @@ struct alignas(16) PlanarProg {
     // compiled paths: a segment between two fixed points of one body has a constant length and does no work on
     // the tree, so per variant (state of the muscle's conditional points) the path is a constant length plus
     // its live segments: mc_seg = first point | second point << 8 | 1 << 31
-    int32_t path_ok, mc_nlive, mc_pad_[2];     // path_ok: every muscle has this form; mc_nlive: most live segments of any variant
+    int32_t path_ok, mc_nlive, a2_cheap, mc_pad_;   // a2_cheap: phase-A tasks past the first 16 are constants / linear translations     // path_ok: every muscle has this form; mc_nlive: most live segments of any variant
     int32_t mc_cond[BIO_MAX_MUSCLES][2];       // conditional points of the muscle (-1: none)
     uint32_t mc_seg[BIO_MAX_MUSCLES][P2_MAXVAR][P2_MAXLIVE];
     T mc_len0[BIO_MAX_MUSCLES][P2_MAXVAR];
@@ -561,12 +561,20 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         mov_of_pt[p] = n_mov++;
     }
     pr.n_atasks = s.n_axes + 3 * n_mov;
-    for (int i = 1; i < pr.n_atasks; i++)                 // stable insertion sort: splines first
-        for (int j = i; j > 0 && s.func_kind[pr.at_func[j]] == BIO_FUNC_SPLINE &&
-                        s.func_kind[pr.at_func[j - 1]] != BIO_FUNC_SPLINE; j--) {
-            std::swap(pr.at_func[j], pr.at_func[j - 1]); std::swap(pr.at_dof[j], pr.at_dof[j - 1]);
-            std::swap(pr.at_add[j], pr.at_add[j - 1]); std::swap(pr.at_dst[j], pr.at_dst[j - 1]);
-        }
+    {   // stable insertion sort by cost: splines, then rotations (sin / cos), then the rest
+        auto rank = [&](int t) {
+            if (s.func_kind[pr.at_func[t]] == BIO_FUNC_SPLINE) return 0;
+            if (pr.at_dst[t] < 64 && (d.axis_desc[pr.at_dst[t]] & 1)) return 1;
+            return s.func_kind[pr.at_func[t]] == BIO_FUNC_LINEAR ? 2 : 3;
+        };
+        for (int i = 1; i < pr.n_atasks; i++)
+            for (int j = i; j > 0 && rank(j) < rank(j - 1); j--) {
+                std::swap(pr.at_func[j], pr.at_func[j - 1]); std::swap(pr.at_dof[j], pr.at_dof[j - 1]);
+                std::swap(pr.at_add[j], pr.at_add[j - 1]); std::swap(pr.at_dst[j], pr.at_dst[j - 1]);
+            }
+        pr.a2_cheap = 1;
+        for (int t = 16; t < pr.n_atasks; t++) if (rank(t) < 2) pr.a2_cheap = 0;
+    }
     // path points, muscle slots and wrench sources
     int n_src = 0;
     int src_body[P2_MAXSRC];

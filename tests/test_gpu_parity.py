@@ -325,7 +325,7 @@ def test_host_entry_point_with_page_locked_buffers_matches_device_path():
     o3 = np.zeros((n, env.obs_dim), dtype=np.float32)      # pageable observation buffer, pinned others
     rng = np.random.default_rng(5)
     n_done = 0
-    for _ in range(40):
+    for _ in range(150):
         a = rng.uniform(0, 1, (n, 14)).astype(np.float32)
         a_p.copy_(torch.as_tensor(a))
         o, r, d, info = env.step(torch.as_tensor(a))
