@@ -4,6 +4,7 @@
 // addresses.
 #pragma once
 #include <math.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include <utility>
@@ -326,6 +327,13 @@ void convert_model(const BioModelTables& s, DevModel<T>& d) {
             while (i + 1 < n - 1 && s.knot_x[kb + i + 1] <= xs) i++;
             d.func_bucket[f][b] = (int8_t)i;
         }
+        // a spline whose pieces are all the same constant (the z of the reference's moving path points) is
+        // evaluated as a Constant: same value and zero derivatives, no knot search
+        bool flat = true;
+        for (int i = 0; i < n; i++)
+            flat = flat && s.knot_c[kb + i][0] == s.knot_c[kb][0] && s.knot_c[kb + i][1] == 0.0 &&
+                   s.knot_c[kb + i][2] == 0.0 && s.knot_c[kb + i][3] == 0.0;
+        if (flat) { d.func_kind[f] = BIO_FUNC_CONST; d.func_c[f][0] = (T)s.knot_c[kb][0]; d.func_c[f][1] = T(0); }
     }
     {   // L^T D L schedule
         auto tri = [](int i, int j) { return i * (i + 1) / 2 + j; };
@@ -563,9 +571,9 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     pr.n_atasks = s.n_axes + 3 * n_mov;
     {   // stable insertion sort by cost: splines, then rotations (sin / cos), then the rest
         auto rank = [&](int t) {
-            if (s.func_kind[pr.at_func[t]] == BIO_FUNC_SPLINE) return 0;
+            if (d.func_kind[pr.at_func[t]] == BIO_FUNC_SPLINE) return 0;
             if (pr.at_dst[t] < 64 && (d.axis_desc[pr.at_dst[t]] & 1)) return 1;
-            return s.func_kind[pr.at_func[t]] == BIO_FUNC_LINEAR ? 2 : 3;
+            return d.func_kind[pr.at_func[t]] == BIO_FUNC_LINEAR ? 2 : 3;
         };
         for (int i = 1; i < pr.n_atasks; i++)
             for (int j = i; j > 0 && rank(j) < rank(j - 1); j--) {
@@ -602,6 +610,7 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     // streams over the path points instead
     pr.path_ok = 1;
     pr.mc_nlive = 0;
+    { const char* z = getenv("BIO_PLANAR_STREAM_PATHS"); if (z && z[0] == '1') pr.path_ok = 0; }   // tests: take the fallback
     for (int i = 0; i < s.n_muscles && pr.path_ok; i++) {
         const int pb = s.mus_pt_begin[i], pe = pb + s.mus_pt_count[i];
         int n_cond = 0;

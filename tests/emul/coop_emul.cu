@@ -81,5 +81,6 @@ extern "C" void emul_prog_info(const BioModelTables* s, int32_t* out) {
     bio::convert_model(*s, *m);
     out[0] = m->prog.ok; out[1] = m->prog.scan_ok; out[2] = m->prog.chain_ok; out[3] = m->prog.n_branches;
     out[4] = m->prog.ch_n[0]; out[5] = m->prog.ch_n[1]; out[6] = m->prog.n_atasks; out[7] = m->prog.n_src;
+    out[8] = m->prog.path_ok; out[9] = m->prog.mc_nlive; out[10] = m->prog.a2_cheap;
     delete m;
 }

@@ -107,6 +107,32 @@ def test_emulated_implicit_damping_and_perturbation(emul_lib, oracle_lib, models
     assert worst32 < 3e-2
 
 
+def test_streamed_and_compiled_muscle_paths_agree(emul_lib, oracle_lib, models, monkeypatch):
+    """Phase C has two forms of the path geometry: the compiled one (constant length + live segments per
+    variant of the conditional points) and the streaming pass over the path points that any model falls back
+    to.  BIO_PLANAR_STREAM_PATHS=1 makes the host program take the fallback: both must match the oracle, also
+    at coordinates on either side of every conditional point's range."""
+    orc = oracle_lib
+    t = models["2d_muscle"].tables
+    g = np.load(os.path.join(HERE, "golden", "config1_muscle_walking_2d.npz"))
+    rng = np.random.default_rng(11)
+    for mode in ("0", "1"):
+        monkeypatch.setenv("BIO_PLANAR_STREAM_PATHS", mode)
+        worst = 0.0
+        for k in range(0, g["q"].shape[0], 11):
+            q, u, act, lm = g["q"][k].copy(), g["u"][k], g["act"][k], g["lm"][k]
+            if k % 2:                       # sweep hip / knee angles across the conditional ranges
+                q[3:] = rng.uniform(-2.7, 1.6, q.size - 3)
+            ctrl = np.clip(g["action"][k], 0, 1)
+            o = orc.eval_dynamics(t, q, u, act, lm, ctrl)
+            e = _emul(emul_lib, t, q, u, act, lm, ctrl)
+            for name, scale in (("udot", 1.0), ("lmdot", 1e-2), ("fiber_force", 1.0)):
+                a, b = np.asarray(o[name]), np.asarray(e[name])
+                worst = max(worst, float(np.max(np.abs(a - b) / np.maximum(np.abs(a), scale))))
+        print("stream paths = %s: worst relative difference %.2e" % (mode, worst))
+        assert worst < 1e-8
+
+
 def test_warm_started_newton_finds_the_same_root(emul_lib, oracle_lib, models):
     """Any warm start of the fibre-velocity Newton iteration (the kernel keeps the root of the
     previous substep) must end on the root the oracle finds from zero."""
@@ -141,13 +167,15 @@ def test_fast_paths_are_enabled_for_the_shipped_models(emul_lib, models):
     kinematics, every 3D model gets the chain lists (spatial scan kinematics); a silent fallback to the
     general path would only show up as a slower benchmark."""
     for key, cm in models.items():
-        out = np.zeros(8, dtype=np.int32)
+        out = np.zeros(16, dtype=np.int32)
         emul_lib.emul_prog_info(ctypes.byref(cm.tables), _p(out))
-        ok, scan_ok, chain_ok, n_br, n0, n1, n_tasks, n_src = out.tolist()
+        ok, scan_ok, chain_ok, n_br, n0, n1, n_tasks, n_src, path_ok, n_live, a2_cheap = out.tolist()[:11]
         assert chain_ok == 1 and n_br >= 1, key
         if key.startswith("2d"):
             assert ok == 1 and scan_ok == 1 and n_br == 2 and 1 <= n0 <= 8 and 1 <= n1 <= 8, (key, out)
             assert n_src >= cm.tables.n_spheres + cm.tables.n_muscles
+            # compiled muscle paths (one live segment per muscle in the 2D gait models), cheap second round of phase A
+            assert path_ok == 1 and n_live <= 1 and a2_cheap == 1, (key, out)
         else:
             assert ok == 0 and max(n0, n1) <= 16, (key, out)
 
