@@ -782,6 +782,12 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     int istep = st.istep[ii];
     int hist_pos = st.hist_pos[ii];
     const bool first = st.first[ii] != 0;
+    if (lane == 0) {   // bookkeeping read after the last evaluation: into L2 now
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(st.old_px + ii));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(st.ep_return + ii));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(st.ep_len + ii));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(st.episode + ii));
+    }
 
     // ---- action pre-processing: lane = actuator ----
     T action = isa ? actions[(size_t)ii * na + lane] : T(0);
@@ -802,22 +808,23 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
         action = tau;
     }
     T last_action = T(0), curr = T(0);
-    if (isa) {
-        if (first) {
-            last_action = action;
-            if (valid)
-#pragma unroll 1
-                for (int hh = 0; hh < Hh; hh++) st.history[((size_t)hh * na + lane) * n + ii] = action;
-        } else {
-            last_action = st.last_action[(size_t)lane * n + ii];
-        }
-    }
     if (first) hist_pos = 0;
     if (isa) {
-        if (valid) st.history[((size_t)hist_pos * na + lane) * n + ii] = action;
+        // the loads of the action history (and of the previous mean action) are issued together: one memory
+        // round trip instead of one per entry
+        T hv[BIO_MAX_HORIZON];
+#pragma unroll
+        for (int hh = 0; hh < BIO_MAX_HORIZON; hh++)
+            hv[hh] = (hh < Hh && !first) ? st.history[((size_t)hh * na + lane) * n + ii] : action;
+        last_action = first ? action : st.last_action[(size_t)lane * n + ii];
         T sum = T(0);
-#pragma unroll 1
-        for (int hh = 0; hh < Hh; hh++) sum += (hh == hist_pos) ? action : st.history[((size_t)hh * na + lane) * n + ii];
+#pragma unroll
+        for (int hh = 0; hh < BIO_MAX_HORIZON; hh++) {
+            if (hh < Hh) {
+                sum += hh == hist_pos ? action : hv[hh];
+                if (valid && (first || hh == hist_pos)) st.history[((size_t)hh * na + lane) * n + ii] = action;
+            }
+        }
         curr = sum / T(Hh);
         E.ctrl[lane] = clampv(c.feed_mean_action ? curr : action, m.act_min[lane], m.act_max[lane]);
     }

@@ -89,38 +89,45 @@ BIO_DEV void p2_phase_a(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     const PlanarProg<T>& pr = m.prog;
     auto& K = E.k.p;
     for (int t = lane; t < pr.n_atasks; t += G) {
-        const int d = pr.at_dof[t], dst = pr.at_dst[t];
-        T s, ds, dds;
-        if (t >= G && pr.a2_cheap) {
-            // tasks past the first round are constants / linear functions of translations and moving points
-            // (host order: splines, rotations, the rest): no spline search, no sin / cos
-            const int f = pr.at_func[t];
-            const T c0 = m.func_c[f][0];
-            const bool lin = m.func_kind[f] == BIO_FUNC_LINEAR;
-            s = lin ? c0 * (d >= 0 ? E.q[d] : T(0)) + m.func_c[f][1] : c0;
+        // one packed descriptor per task (PlanarProg::at_i4 / at_f4): the loads below do not wait on each other
+        const int4 ti = *reinterpret_cast<const int4*>(pr.at_i4[t]);
+        T c0, c1, add, f3;
+        ld4(pr.at_f4[t], c0, c1, add, f3);
+        const int kind = ti.x & 3, dst = ti.x >> 8, d = ti.y;
+        const T x = d >= 0 ? E.q[d] : T(0), qd = d >= 0 ? E.u[d] : T(0);
+        T s, ds, dds = T(0);
+        if (kind == BIO_FUNC_SPLINE) {
+            // SimmSpline: cubic piece of the interval [knot i, knot i + 1), straight lines beyond the end knots;
+            // the interval of the previous evaluation is the search hint (the coordinates move little)
+            const int kb = ti.z, n = ti.w;
+            int i = E.knot_hint[t];
+            i = i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
+            while (i > 0 && x < m.knot_x[kb + i]) i--;
+            while (i + 1 < n - 1 && x >= m.knot_x[kb + i + 1]) i++;
+            E.knot_hint[t] = (int8_t)i;
+            const bool below = x <= c0, above = x >= c1;
+            i = above ? n - 1 : (below ? 0 : i);
+            T k0, k1, k2, k3;
+            ld4(m.knot_c[kb + i], k0, k1, k2, k3);
+            if (below || above) { k2 = T(0); k3 = T(0); }
+            const T dx = x - m.knot_x[kb + i];
+            s = k0 + dx * (k1 + dx * (k2 + dx * k3));
+            ds = k1 + dx * (T(2) * k2 + T(3) * dx * k3);
+            dds = T(2) * k2 + T(6) * dx * k3;
+        } else {
+            const bool lin = kind == BIO_FUNC_LINEAR;
+            s = lin ? c0 * x + c1 : c0;
             ds = lin ? c0 : T(0);
-            if (dst < 64) {
-                st4(K.ax[dst], s, ds, ds * (d >= 0 ? E.u[d] : T(0)), T(0));
-                st2(K.axr[dst], T(1), T(0));
-            } else {
-                const int k = (dst - 64) / 3, c = (dst - 64) % 3;
-                K.mv[k][c] = s + pr.at_add[t];
-                K.mv[k][4 + c] = ds;
-            }
-            continue;
         }
-        func_eval(m, pr.at_func[t], d >= 0 ? E.q[d] : T(0), s, ds, dds, &E.knot_hint[t]);
         if (dst < 64) {
-            const T qd = d >= 0 ? E.u[d] : T(0);
-            const int desc = m.axis_desc[dst];
             T sn = T(0), cs = T(1);
-            if (desc & 1) Num<T>::sincos((desc & 2) ? -s : s, &sn, &cs);
+            if (ti.x & 4) Num<T>::sincos((ti.x & 8) ? -s : s, &sn, &cs);
             // displacement along the axis (translations only), rates
-            st4(K.ax[dst], (desc & 1) ? T(0) : s, ds, ds * qd, dds * qd * qd);
+            st4(K.ax[dst], (ti.x & 4) ? T(0) : s, ds, ds * qd, dds * qd * qd);
             st2(K.axr[dst], cs, sn);
         } else {
             const int k = (dst - 64) / 3, c = (dst - 64) % 3;
-            K.mv[k][c] = s + pr.at_add[t];
+            K.mv[k][c] = s + add;
             K.mv[k][4 + c] = ds;
         }
     }
@@ -763,23 +770,44 @@ BIO_DEV void p2_readout_2(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
     }
 }
 
+// -DBIO_PHASE_CLOCK (profiling build, tools/phase_clock.sh): thread 0 of CTA 0 accumulates the cycles of every
+// phase of its env and prints them after each full evaluation
+#ifdef BIO_PHASE_CLOCK
+#include <stdio.h>
+#define P2_CLK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); s_clk[k] += t_ - t_prev; t_prev = t_; } } while (0)
+#else
+#define P2_CLK(k) do { } while (0)
+#endif
+
 template <typename T, int CLS>
 __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane,
                                               const int newton_iters, const T ext_fx, const int ext_pt, const T h_imp,
                                               const bool full) {
     constexpr int G = CoopCls<CLS>::G;
+#ifdef BIO_PHASE_CLOCK
+    __shared__ long long s_clk[12];
+    __shared__ long long s_last;
+    long long t_prev = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0 && s_last != 0) s_clk[9] += t_prev - s_last;   // between evaluations
+#endif
     p2_phase_a<T, CLS>(m, E, lane);
     gsync<G>();
+    P2_CLK(0);
     if (m.prog.scan_ok && G == 16) p2_phase_b_scan<T, CLS>(m, E, lane);
     else p2_phase_b<T, CLS>(m, E, lane);
     gsync<G>();
+    P2_CLK(1);
     p2_phase_c<T, CLS>(m, E, lane, newton_iters, full);
+    P2_CLK(2);
     p2_phase_d<T, CLS>(m, E, lane, h_imp);
     gsync<G>();
+    P2_CLK(3);
     p2_phase_e<T, CLS>(m, E, lane, h_imp, ext_fx, ext_pt);
     gsync<G>();
+    P2_CLK(4);
     p2_phase_f<T, CLS>(m, E, lane);
     gsync<G>();
+    P2_CLK(5);
     p2_phase_g<T, CLS>(m, E, lane);
     if (full) {
         p2_readout_1<T, CLS>(m, E, lane);
@@ -787,6 +815,20 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
         p2_readout_2<T, CLS>(m, E, lane);
     }
     gsync<G>();
+    P2_CLK(6);
+#ifdef BIO_PHASE_CLOCK
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        s_clk[10] += 1;
+        if (full) {
+            printf("phase cycles over %lld evaluations: A %lld B %lld C %lld D %lld E %lld F %lld G(+readout) %lld between %lld\n",
+                   s_clk[10], s_clk[0], s_clk[1], s_clk[2], s_clk[3], s_clk[4], s_clk[5], s_clk[6], s_clk[9]);
+            for (int k = 0; k < 12; k++) s_clk[k] = 0;
+            s_last = 0;
+        } else {
+            s_last = clock64();
+        }
+    }
+#endif
 }
 
 }  // namespace bio

@@ -62,6 +62,11 @@ struct alignas(16) PlanarProg {
     // at_dst < 64: elementary axis at_dst; else component (at_dst - 64) % 3 of moving point (at_dst - 64) / 3
     int32_t at_func[P2_MAXTASK], at_dof[P2_MAXTASK], at_dst[P2_MAXTASK];
     T at_add[P2_MAXTASK];                      // constant added to the value (body z of a moving point)
+    // the same tasks packed for one 16-byte read each: at_i4 = kind | rotation << 2 | negated angle << 3 | dst << 8,
+    // dof (-1: none), first knot, knot count;  at_f4 = Constant / LinearFunction coefficients c0, c1 (spline: first
+    // and last knot abscissa), at_add, 0
+    alignas(16) int32_t at_i4[P2_MAXTASK][4];
+    alignas(16) T at_f4[P2_MAXTASK][4];
     // path points: location in the body frame with z already in ground axes (planar: constant)
     alignas(16) T pt_xyz[BIO_MAX_PATHPTS][4];
     int32_t pt_info[BIO_MAX_PATHPTS];          // body | kind<<4 | dof<<6 | slot<<11 | moving index<<13
@@ -107,7 +112,7 @@ struct alignas(16) DevModel {
     int32_t func_knot_count[BIO_MAX_FUNCS];
     T func_c[BIO_MAX_FUNCS][2];
     T knot_x[BIO_MAX_KNOTS];
-    T knot_c[BIO_MAX_KNOTS][4];
+    alignas(16) T knot_c[BIO_MAX_KNOTS][4];
     T mus_fiso[BIO_MAX_MUSCLES];
     T mus_lopt[BIO_MAX_MUSCLES];
     T mus_lts[BIO_MAX_MUSCLES];
@@ -582,6 +587,19 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
             }
         pr.a2_cheap = 1;
         for (int t = 16; t < pr.n_atasks; t++) if (rank(t) < 2) pr.a2_cheap = 0;
+        for (int t = 0; t < pr.n_atasks; t++) {
+            const int f = pr.at_func[t], kind = d.func_kind[f], dst = pr.at_dst[t];
+            const int desc = dst < 64 ? d.axis_desc[dst] : 0;
+            const int kb = s.func_knot_begin[f], n = s.func_knot_count[f];
+            pr.at_i4[t][0] = kind | ((desc & 1) << 2) | (((desc >> 1) & 1) << 3) | (dst << 8);
+            pr.at_i4[t][1] = pr.at_dof[t];
+            pr.at_i4[t][2] = kind == BIO_FUNC_SPLINE ? kb : 0;
+            pr.at_i4[t][3] = kind == BIO_FUNC_SPLINE ? n : 0;
+            pr.at_f4[t][0] = kind == BIO_FUNC_SPLINE ? (T)s.knot_x[kb] : d.func_c[f][0];
+            pr.at_f4[t][1] = kind == BIO_FUNC_SPLINE ? (T)s.knot_x[kb + n - 1] : d.func_c[f][1];
+            pr.at_f4[t][2] = pr.at_add[t];
+            pr.at_f4[t][3] = T(0);
+        }
     }
     // path points, muscle slots and wrench sources
     int n_src = 0;
