@@ -107,13 +107,17 @@ struct alignas(16) EnvWork : EnvWorkBody<T, CLS> {
     unsigned char bank_pad[want - raw > 0 ? want - raw : 128];
 };
 
-// The G lanes of an env are the unit of synchronisation: two envs sharing a warp (G = 16) may
-// take different branches (auto-reset of one of them), so every barrier, shuffle and ballot
-// names only the lanes of its own env.
-template <int G> __device__ __forceinline__ unsigned group_mask() {
-    return G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G));
+// Two envs sharing a warp (G = 16) run in lockstep: every branch that contains a barrier, shuffle or ballot is
+// taken by the whole warp (an auto-reset of one env makes the other repeat its evaluation, see the step
+// kernel), so all of them name the full warp with a compile-time mask -- a run-time mask costs a MATCH/REDUX/
+// VOTE/branch sequence in front of every shuffle group.  Shuffles stay inside the env through their width;
+// ballots are cut to the env's lanes by group_ballot.
+template <int G> __device__ __forceinline__ unsigned group_mask() { return 0xffffffffu; }
+template <int G> __device__ __forceinline__ void gsync() { __syncwarp(); }
+template <int G> __device__ __forceinline__ unsigned group_ballot(bool pred) {
+    const unsigned b = __ballot_sync(0xffffffffu, pred);
+    return G == 32 ? b : (b >> ((threadIdx.x & 31) / G * G)) & ((1u << (G & 31)) - 1u);
 }
-template <int G> __device__ __forceinline__ void gsync() { __syncwarp(group_mask<G>()); }
 
 // column K of a row-major 3x3 (times a sign), and R <- R * Rot(e_K, angle) as a mix of the two other columns
 template <typename T, int K>
@@ -739,6 +743,34 @@ __device__ void coop_write_obs(const DevModel<T>& m, const DevTask<T>& c, const 
     for (int o = lane; o < c.obs_dim; o += G) orow[o] = obs_value<T, CLS>(m, c, E, istep, row_next, pel, o);
 }
 
+// Size class 0: the observation rows of the warp's two envs (adjacent in memory) are staged in the planar
+// work arrays of their envs, idle after the evaluation; the whole warp writes them, 16 bytes per lane, so that
+// a caller's page-locked host buffer receives full lines.  rows: bit e set = row of env e of the warp.
+template <typename T, int CLS>
+__device__ __forceinline__ void coop_flush_obs(EnvWork<T, CLS>* works, T* __restrict__ obs, int od, int i0, int n,
+                                               unsigned rows) {
+    constexpr int EPW = 32 / CoopCls<CLS>::G;
+    __syncwarp();                              // the staged rows are complete
+    const int wl = threadIdx.x & 31;
+    if (i0 + 1 >= n) rows &= 1u;
+    const T* s0 = reinterpret_cast<const T*>(&works[(threadIdx.x >> 5) * EPW].k.p);
+    const T* s1 = reinterpret_cast<const T*>(&works[(threadIdx.x >> 5) * EPW + (EPW > 1 ? 1 : 0)].k.p);
+    T* base = obs + (size_t)i0 * od;
+    const int lo = (rows & 1u) ? 0 : od, hi = (rows & 2u) ? 2 * od : od;     // floats [lo, hi) of the two-row block
+    if (sizeof(T) == 4 && (reinterpret_cast<size_t>(base) & 15) == 0) {
+        for (int v = wl + (lo >> 2); 4 * v < hi; v += 32) {
+            T x[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const int k = 4 * v + j; x[j] = k < od ? s0[k] : (k < 2 * od ? s1[k - od] : T(0)); }
+            if (4 * v >= lo && 4 * v + 3 < hi) st4(base + 4 * v, x[0], x[1], x[2], x[3]);
+            else for (int j = 0; j < 4; j++) { const int k = 4 * v + j; if (k >= lo && k < hi) base[k] = x[j]; }
+        }
+    } else {
+        for (int k = lo + wl; k < hi; k += 32) base[k] = k < od ? s0[k] : s1[k - od];
+    }
+    __syncwarp();
+}
+
 // Persistent launch: one CTA per SM, the model block is staged once per SM, and every warp walks the work
 // items (one item = the 32/G envs of a warp) item = blockIdx + gridDim * (warp + warps_per_cta * k), so
 // that the items are dealt round-robin over the SMs first.  Two launch shapes per fp32 instantiation:
@@ -793,7 +825,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     T action = isa ? actions[(size_t)ii * na + lane] : T(0);
     const bool lane_nan = action != action;
     const unsigned gmask = group_mask<G>();
-    const bool nan = __ballot_sync(gmask, lane_nan) != 0u;
+    const bool nan = group_ballot<G>(lane_nan) != 0u;
     gsync<G>();   // E.q / E.u visible for the PD law
     if (nan) {
         action = T(0);
@@ -916,7 +948,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
         fin = isfinite(E.q[lane]) && isfinite(E.u[lane]) && isfinite(E.udot[lane]);
     }
     const T maxacc = group_max<T, G>(acc);
-    const bool finite = isfinite(rew) && (__ballot_sync(gmask, !fin) == 0u);
+    const bool finite = isfinite(rew) && (group_ballot<G>(!fin) == 0u);
     int reason = 0;
     if (!finite) { reason = BIO_DONE_NONFINITE; rew = T(0); }
     else if (E.x.out.obs_pos[c.term_obspt][1] < c.term_height) reason = BIO_DONE_HEIGHT;
@@ -951,50 +983,42 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
         }
     }
     gsync<G>();   // everyone is done with E.x.out before a reset overwrites it
-    if (reason && c.auto_reset) {
-        episode += 1;
-        int idx = 0;
-        if (!c.test_mode && c.reset_max_index > 0)
-            idx = (int)(bio_rand(seed, env, (unsigned long long)episode, 1) % (unsigned long long)(c.reset_max_index + 1));
-        idx = idx > c.ref_rows - 1 ? c.ref_rows - 1 : idx;
-        for (int k = lane; k < m.n_coords; k += G) {
-            const int d = m.coord_dof[k];
-            if (d < 0) continue;
-            E.q[d] = c.ref_q[(size_t)idx * c.ref_coords + k];
-            E.u[d] = c.ref_u[(size_t)idx * c.ref_coords + k];
+    // Size class 0: both staged rows go out now (the whole warp writes: 16 bytes per lane)
+    if constexpr (CLS == 0) coop_flush_obs<T, CLS>(works, obs, c.obs_dim, item * EPW, n, 3u);
+    // Auto-reset.  The branch is taken by the whole warp (see group_mask): when only one of its two envs
+    // resets, the other one repeats the evaluation of its current state and drops the results.
+    const bool do_reset = reason != 0 && c.auto_reset;
+    const unsigned reset_bits = __ballot_sync(0xffffffffu, do_reset);
+    if (reset_bits) {
+        if (do_reset) {
+            episode += 1;
+            int idx = 0;
+            if (!c.test_mode && c.reset_max_index > 0)
+                idx = (int)(bio_rand(seed, env, (unsigned long long)episode, 1) % (unsigned long long)(c.reset_max_index + 1));
+            idx = idx > c.ref_rows - 1 ? c.ref_rows - 1 : idx;
+            for (int k = lane; k < m.n_coords; k += G) {
+                const int d = m.coord_dof[k];
+                if (d < 0) continue;
+                E.q[d] = c.ref_q[(size_t)idx * c.ref_coords + k];
+                E.u[d] = c.ref_u[(size_t)idx * c.ref_coords + k];
+            }
+            if (ism) { E.act[lane] = m.mus_default_act[lane]; E.lm[lane] = c.ref_lm0[(size_t)idx * nm + lane]; }
+            if (isa) E.ctrl[lane] = T(0);
+            if (ism) E.vn[lane] = T(0);
+            istep = idx;
+            first_next = 1;
+            ep_return = T(0);
+            ep_len = 0;
         }
-        if (ism) { E.act[lane] = m.mus_default_act[lane]; E.lm[lane] = c.ref_lm0[(size_t)idx * nm + lane]; }
-        if (isa) E.ctrl[lane] = T(0);
-        if (ism) E.vn[lane] = T(0);
-        istep = idx;
-        first_next = 1;
-        ep_return = T(0);
-        ep_len = 0;
         gsync<G>();
         coop_eval_any<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, T(istep) * c.dt), ext_pt, T(0), true);
         gsync<G>();
-        if (valid || CLS == 0) coop_write_obs<T, CLS>(m, c, E, lane, istep, orow);
-    }
-    if constexpr (CLS == 0) {
-        __syncwarp();                          // both envs of the warp have staged their final observation
-        const int wl = threadIdx.x & 31, od = c.obs_dim;
-        const int i0 = item * EPW;
-        const int total = od * (i0 + 1 < n ? 2 : 1);
-        const T* s0 = reinterpret_cast<const T*>(&works[(threadIdx.x >> 5) * EPW].k.p);
-        const T* s1 = reinterpret_cast<const T*>(&works[(threadIdx.x >> 5) * EPW + 1].k.p);
-        T* base = obs + (size_t)i0 * od;
-        if (sizeof(T) == 4 && (reinterpret_cast<size_t>(base) & 15) == 0) {
-            for (int v = wl; 4 * v < total; v += 32) {
-                T x[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) { const int k = 4 * v + j; x[j] = k < od ? s0[k] : (k < total ? s1[k - od] : T(0)); }
-                if (4 * v + 3 < total) st4(base + 4 * v, x[0], x[1], x[2], x[3]);
-                else for (int j = 0; 4 * v + j < total; j++) base[4 * v + j] = x[j];
-            }
-        } else {
-            for (int k = wl; k < total; k += 32) base[k] = k < od ? s0[k] : s1[k - od];
+        if (do_reset && (valid || CLS == 0)) coop_write_obs<T, CLS>(m, c, E, lane, istep, orow);
+        if constexpr (CLS == 0) {
+            // rows of the envs that were reset (bit e: env e of the warp)
+            const unsigned rows = ((reset_bits & 0xffffu) ? 1u : 0u) | ((reset_bits >> 16) ? 2u : 0u);
+            coop_flush_obs<T, CLS>(works, obs, c.obs_dim, item * EPW, n, rows);
         }
-        __syncwarp();
     }
     // ---- write back ----
     if (valid) {
