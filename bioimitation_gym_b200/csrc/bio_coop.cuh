@@ -492,10 +492,21 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     } else if (lane - nb < nd) {
         const int d = lane - nb;
         T qf = T(0), ld = T(0);
-        for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == d) { qf += E.limf[l]; ld += E.limD[l]; }
+        if (m.gdof_ok) {                         // host lists: the (<= 2) limits / moving points and the actuator of the dof
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int l = m.gdof_lim[d][j], p = m.gdof_movpt[d][j];
+                if (l >= 0) { qf += E.limf[l]; ld += E.limD[l]; }
+                if (p >= 0) qf += E.x.pt.ptq[p];
+            }
+            const int a = m.gdof_act[d];
+            if (a >= 0) qf += E.ctrl[a];
+        } else {
+            for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == d) { qf += E.limf[l]; ld += E.limD[l]; }
+            for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += E.x.pt.ptq[p]; }
+            if (m.is_torque) for (int a = 0; a < m.n_act; a++) if (m.act_dof[a] == d) qf += E.ctrl[a];
+        }
         K.limDd[d] = ld;
-        for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += E.x.pt.ptq[p]; }
-        if (m.is_torque) for (int a = 0; a < m.n_act; a++) if (m.act_dof[a] == d) qf += E.ctrl[a];
         K.Q[d] = qf;
     }
     gsync<G>();

@@ -159,6 +159,10 @@ struct alignas(16) DevModel {
     int32_t coord_dof[BIO_MAX_COORDS];
     int32_t coord_pelvis_trans[BIO_MAX_COORDS];
     int32_t pel_dof[4];                      // dof of pelvis_tx / ty / tz (-1: none), from coord_pelvis_trans
+    // generalized-force inputs of every dof for the general evaluation: limits, moving path points (point
+    // index) and the actuator acting on it (-1: none); gdof_ok = 0: more than two per dof, scan the lists instead
+    int32_t gdof_ok, gdof_pad_[3];
+    int8_t gdof_lim[BIO_MAX_DOF][2], gdof_movpt[BIO_MAX_DOF][2], gdof_act[BIO_MAX_DOF];
     T coord_const[BIO_MAX_COORDS];
     // schedules of the cooperative kernel (bio_coop.cuh), built by convert_model
     int32_t n_levels, n_moving, n_entries, pad2;
@@ -274,6 +278,17 @@ void convert_model(const BioModelTables& s, DevModel<T>& d) {
     d.is_torque = s.is_torque;
     d.has_tz = 0;
     for (int i = 0; i < s.n_coords; i++) if (s.coord_pelvis_trans[i] == 3) d.has_tz = 1;
+    d.gdof_ok = 1;
+    for (int dd = 0; dd < BIO_MAX_DOF; dd++) { d.gdof_lim[dd][0] = d.gdof_lim[dd][1] = d.gdof_movpt[dd][0] = d.gdof_movpt[dd][1] = d.gdof_act[dd] = -1; }
+    auto gput = [&](int8_t* two, int v) { if (two[0] < 0) two[0] = (int8_t)v; else if (two[1] < 0) two[1] = (int8_t)v; else d.gdof_ok = 0; };
+    for (int l = 0; l < s.n_limits; l++) gput(d.gdof_lim[s.lim_dof[l]], l);
+    for (int p = 0; p < s.n_pathpts && p < 128; p++) if (s.pt_kind[p] == BIO_PT_MOVING && s.pt_dof[p] >= 0) gput(d.gdof_movpt[s.pt_dof[p]], p);
+    if (s.is_torque)
+        for (int a = 0; a < s.n_act; a++) {
+            if (s.act_dof[a] < 0) continue;
+            if (d.gdof_act[s.act_dof[a]] >= 0) d.gdof_ok = 0;
+            d.gdof_act[s.act_dof[a]] = (int8_t)a;
+        }
     for (int k = 0; k < 4; k++) d.pel_dof[k] = -1;
     for (int i = 0; i < s.n_coords; i++)
         if (s.coord_pelvis_trans[i] >= 1 && s.coord_pelvis_trans[i] <= 3) d.pel_dof[s.coord_pelvis_trans[i] - 1] = s.coord_dof[i];

@@ -18,6 +18,13 @@ def main():
     print("%d launches, %.1f us total" % (len(rows), s / 1e3))
     for k, v in tot.most_common():
         print("%6.2f%%  %9.1f us  %4d x  %s" % (100 * v / s, v / 1e3, cnt[k], k))
+    # the step loop of bench.py launches the step kernel (timed) and, between steps and untimed, the L2 flush
+    # (FillFunctor<unsigned char>); everything else is set-up (reset, equilibrium table, action pool) or the
+    # FP32-peak microbenchmark that runs after the loop
+    step = sum(v for k, v in tot.items() if "step_kernel" in k)
+    own = sum(v for k, v in tot.items() if k.startswith("bio::"))
+    print("share of the step kernel in the launches of this library (bio::*): %.1f %%" % (100 * step / max(own, 1e-9)))
+    print("timed region of bench.py = the step-kernel launches only (one per control step)")
 
 
 if __name__ == "__main__":

@@ -14,7 +14,7 @@ for n in (296, 4096):
     env = backend.VecEnv("MuscleWalkingImitation2D-v0", dict(num_envs=n, seed=1)); env.reset()
     a = torch.rand((n, env.n_act), device=env.device)
     for _ in range(3): env.step(a)
-    torch.cuda.synchronize(); print("----", n, "envs (last line = one control step)", flush=True)
+    torch.cuda.synchronize(); print("---- above:", n, "envs (last line = one control step)", flush=True)
     env.close()
-PY' 2>&1 | grep -E "^----|phase cycles" | awk '/^----/{if(last)print last; print; last=""} /phase cycles/{last=$0} END{print last}'
+PY' 2>&1 | grep -E "^----|phase cycles" | awk '/^----/{if(last)print last; print; last=""} /phase cycles/{last=$0}'
 python -c "import __graft_entry__ as g; g.build(force=True)"
