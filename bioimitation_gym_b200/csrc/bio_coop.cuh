@@ -38,6 +38,7 @@ struct WorkGeneral {
     T H[C::ND * (C::ND + 1) / 2], rhs[C::ND];
     T Lw[C::ND * (C::ND + 1) / 2];                 // factor L of L^T D L (kept apart from H: no write-after-read barrier)
     T Q[C::ND], limDd[C::ND];
+    T mq[8];                                       // generalized force of the moving path points (compiled paths)
 };
 
 // working arrays of the planar program, coop_eval_planar
@@ -61,6 +62,8 @@ template <typename T, typename C>
 struct WorkReadout { T obs_pos[COOP_MAXOBS][3], obs_vel[COOP_MAXOBS][3], comp[BIO_MAX_BODIES][6]; };   // full evaluation
 template <typename T>
 struct WorkSources { alignas(16) T w[P2_MAXSRC][4]; };                                                 // planar program
+template <typename T>
+struct WorkSources6 { alignas(16) T w[P2_MAXSRC][8]; };      // general evaluation, compiled paths: moment about O [0..2], force [3..5]
 
 // Size class 0 (half-warp per env) runs the planar program only, so its buffer holds no arrays of the
 // general evaluation; class 1 (warp per env) keeps both.
@@ -78,6 +81,7 @@ template <typename T> struct WorkUnions<T, 1> {
         struct { T col[BIO_MAX_SPHERES][C::ND][3]; } jac;             // phase G (implicit damping)
         WorkReadout<T, C> out;
         WorkSources<T> src;
+        WorkSources6<T> src6;
     } x;
 };
 
@@ -268,13 +272,83 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     // ---- phase C: lane = muscle ----
     if (lane < nm) {
         const int i = lane;
+        const PlanarProg<T>& pr = m.prog;
+        const bool compiled = pr.gpath_ok != 0;
+        T L = T(0);
+        int pmov = -1;
+        T mdloc[3] = {T(0), T(0), T(0)};
+        const int pb = m.mus_pt_begin[i], pe = pb + m.mus_pt_count[i];
+        // compiled paths (PlanarProg::mc_seg): constant length of the variant selected by the conditional points
+        // plus its live segments; a live segment that crosses bodies leaves +-(x cross e, e) on the two bodies
+        T Wv[P2_MAXSLOT][6];
+        T mqu = T(0);
+        int mov = -1;
+        if (compiled) {
+#pragma unroll
+            for (int sl = 0; sl < P2_MAXSLOT; sl++)
+#pragma unroll
+                for (int c = 0; c < 6; c++) Wv[sl][c] = T(0);
+            int var = 0;
+#pragma unroll
+            for (int cc = 0; cc < 2; cc++) {
+                const int p = pr.mc_cond[i][cc];
+                if (p >= 0) {
+                    const T v = E.q[(pr.pt_info[p] >> 6) & 31];
+                    if (v >= m.pt_range[p][0] - T(1e-5) && v <= m.pt_range[p][1] + T(1e-5)) var |= 1 << cc;
+                }
+            }
+            L = pr.mc_len0[i][var];
+            T mdw[3] = {T(0), T(0), T(0)};           // moving point: R_b d(location)/dq
+            for (int j = 0; j < pr.mc_nlive; j++) {
+                const uint32_t seg = pr.mc_seg[i][var][j];
+                if (!(seg >> 31)) continue;
+                T xe[2][3];
+                int slot2[2];
+                bool mv2[2];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int p = (seg >> (8 * e)) & 255u;
+                    const int info = pr.pt_info[p];
+                    const int b = info & 15;
+                    T loc[3];
+                    mv2[e] = ((info >> 4) & 3) == BIO_PT_MOVING;
+                    if (mv2[e]) {
+                        mov = (info >> 13) & 7;
+                        T dl[3];
+                        for (int c = 0; c < 3; c++) { loc[c] = K.mv[mov][c]; dl[c] = K.mv[mov][3 + c]; }
+                        matvec3(K.R[b], dl, mdw);
+                    } else {
+                        T l3;
+                        ld4(pr.pt_xyz[p], loc[0], loc[1], loc[2], l3);
+                    }
+                    matvec3(K.R[b], loc, xe[e]);
+                    for (int c = 0; c < 3; c++) xe[e][c] += K.r[b][c];
+                    slot2[e] = (info >> 11) & 3;
+                }
+                const T dx = xe[1][0] - xe[0][0], dy = xe[1][1] - xe[0][1], dz = xe[1][2] - xe[0][2];
+                const T d2 = dx * dx + dy * dy + dz * dz;
+                const T il = Num<T>::rsqrt(d2);
+                L += d2 * il;
+                const T ev[3] = {dx * il, dy * il, dz * il};
+                const T msg = (mv2[0] ? T(1) : T(0)) - (mv2[1] ? T(1) : T(0));
+                mqu += msg * dot3(ev, mdw);
+                if (slot2[0] != slot2[1]) {
+                    T nn[3];
+                    cross3(xe[0], ev, nn);
+#pragma unroll
+                    for (int sl = 0; sl < P2_MAXSLOT; sl++) {
+                        const T sgn = sl == slot2[0] ? T(1) : (sl == slot2[1] ? T(-1) : T(0));
+#pragma unroll
+                        for (int c = 0; c < 3; c++) { Wv[sl][c] += sgn * nn[c]; Wv[sl][3 + c] += sgn * ev[c]; }
+                    }
+                }
+            }
+        } else {
         // one streaming pass over the path points: positions, segment unit vectors and the
         // length; ptf[p] first holds the direction sum (e_out - e_in) and is scaled by the
         // tension once it is known (inactive points keep zero position and force)
-        int pmov = -1, prev = -1;
-        T mdloc[3] = {T(0), T(0), T(0)};
-        T xp[3] = {T(0), T(0), T(0)}, ev[3] = {T(0), T(0), T(0)}, L = T(0);
-        const int pb = m.mus_pt_begin[i], pe = pb + m.mus_pt_count[i];
+        int prev = -1;
+        T xp[3] = {T(0), T(0), T(0)}, ev[3] = {T(0), T(0), T(0)};
         for (int p = pb; p < pe; p++) {
             const int kind = m.pt_kind[p], d = m.pt_dof[p], b = m.pt_body[p];
             T loc[3];
@@ -307,6 +381,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             prev = p;
         }
         if (prev >= 0) for (int c = 0; c < 3; c++) E.x.pt.ptf[prev][c] = -ev[c];
+        }
         const T fiso = m.mus_fiso[i], lopt = m.mus_lopt[i], h = m.mus_height[i], beta = m.mus_beta[i];
         const T amin = m.mus_amin[i], lmin = m.mus_lm_min[i];
         const T lmi = E.lm[i];
@@ -347,13 +422,27 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             E.fact[i] = fiso * afal * fv;
             E.ffib[i] = fiso * (afal * fv + fpe + beta * vn);
         }
-        for (int p = pb; p < pe; p++)
-            for (int c = 0; c < 3; c++) E.x.pt.ptf[p][c] *= tension;
-        // generalized force of the muscle's moving point (at most one per muscle): f . R_b dloc/dq
-        if (pmov >= 0) {
-            T dw[3];
-            matvec3(K.R[m.pt_body[pmov]], mdloc, dw);
-            E.x.pt.ptq[pmov] = dot3(E.x.pt.ptf[pmov], dw);
+        if (compiled) {
+            // wrench sources of this muscle: one per body it touches
+            const int s0 = pr.mus_src0[i], ns = pr.mus_src0[i + 1] - s0;
+#pragma unroll
+            for (int sl = 0; sl < P2_MAXSLOT; sl++) {
+                if (sl < ns) {
+                    T* w = E.x.src6.w[s0 + sl];
+                    st4(w, tension * Wv[sl][0], tension * Wv[sl][1], tension * Wv[sl][2], tension * Wv[sl][3]);
+                    st4(w + 4, tension * Wv[sl][4], tension * Wv[sl][5], T(0), T(0));
+                }
+            }
+            if (mov >= 0) K.mq[mov] = tension * mqu;
+        } else {
+            for (int p = pb; p < pe; p++)
+                for (int c = 0; c < 3; c++) E.x.pt.ptf[p][c] *= tension;
+            // generalized force of the muscle's moving point (at most one per muscle): f . R_b dloc/dq
+            if (pmov >= 0) {
+                T dw[3];
+                matvec3(K.R[m.pt_body[pmov]], mdloc, dw);
+                E.x.pt.ptq[pmov] = dot3(E.x.pt.ptf[pmov], dw);
+            }
         }
     }
     // ---- phase D: lane = contact sphere | coordinate limit ----
@@ -409,7 +498,15 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     if (nm > 0) {
         constexpr int PARTS = G == 32 ? 4 : 1;
         const int gb = lane / PARTS, part = lane % PARTS;
-        if (gb < nb)
+        if (gb < nb && m.prog.gpath_ok) {
+            for (int k = m.prog.inc_begin[gb] + part; k < m.prog.inc_begin[gb + 1]; k += PARTS) {
+                T w0, w1, w2, w3, w4, w5, w6, w7;
+                const T* w = E.x.src6.w[m.prog.inc_src[k]];
+                ld4(w, w0, w1, w2, w3);
+                ld4(w + 4, w4, w5, w6, w7);
+                Wn[0] += w0; Wn[1] += w1; Wn[2] += w2; Wf[0] += w3; Wf[1] += w4; Wf[2] += w5;
+            }
+        } else if (gb < nb)
             for (int k = m.body_pt_begin[gb] + part; k < m.body_pt_begin[gb] + m.body_pt_count[gb]; k += PARTS) {
                 const int p = m.body_pt_list[k];
                 const T f[3] = {E.x.pt.ptf[p][0], E.x.pt.ptf[p][1], E.x.pt.ptf[p][2]};
@@ -497,13 +594,13 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             for (int j = 0; j < 2; j++) {
                 const int l = m.gdof_lim[d][j], p = m.gdof_movpt[d][j];
                 if (l >= 0) { qf += E.limf[l]; ld += E.limD[l]; }
-                if (p >= 0) qf += E.x.pt.ptq[p];
+                if (p >= 0) qf += m.prog.gpath_ok ? K.mq[m.pt_mov[p]] : E.x.pt.ptq[p];
             }
             const int a = m.gdof_act[d];
             if (a >= 0) qf += E.ctrl[a];
         } else {
             for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == d) { qf += E.limf[l]; ld += E.limD[l]; }
-            for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += E.x.pt.ptq[p]; }
+            for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += m.prog.gpath_ok ? K.mq[k] : E.x.pt.ptq[p]; }
             if (m.is_torque) for (int a = 0; a < m.n_act; a++) if (m.act_dof[a] == d) qf += E.ctrl[a];
         }
         K.limDd[d] = ld;

@@ -75,7 +75,7 @@ struct alignas(16) PlanarProg {
     // compiled paths: a segment between two fixed points of one body has a constant length and does no work on
     // the tree, so per variant (state of the muscle's conditional points) the path is a constant length plus
     // its live segments: mc_seg = first point | second point << 8 | 1 << 31
-    int32_t path_ok, mc_nlive, a2_cheap, mc_pad_;   // a2_cheap: phase-A tasks past the first 16 are constants / linear translations     // path_ok: every muscle has this form; mc_nlive: most live segments of any variant
+    int32_t path_ok, mc_nlive, a2_cheap, gpath_ok;  // a2_cheap: phase-A tasks past the first 16 are cheap; gpath_ok: general evaluation uses compiled paths     // path_ok: every muscle has this form; mc_nlive: most live segments of any variant
     int32_t mc_cond[BIO_MAX_MUSCLES][2];       // conditional points of the muscle (-1: none)
     uint32_t mc_seg[BIO_MAX_MUSCLES][P2_MAXVAR][P2_MAXLIVE];
     T mc_len0[BIO_MAX_MUSCLES][P2_MAXVAR];
@@ -468,6 +468,87 @@ void convert_model(const BioModelTables& s, DevModel<T>& d) {
     build_planar_prog(s, d);
 }
 
+// Compiled muscle paths (see PlanarProg::mc_seg); any muscle that does not fit leaves path_ok = 0 and the
+// kernels stream over the path points instead.
+template <typename T>
+void compile_paths(const BioModelTables& s, PlanarProg<T>& pr) {
+    pr.path_ok = 1;
+    pr.mc_nlive = 0;
+    { const char* z = getenv("BIO_PLANAR_STREAM_PATHS"); if (z && z[0] == '1') pr.path_ok = 0; }   // tests: take the fallback
+    for (int i = 0; i < s.n_muscles && pr.path_ok; i++) {
+        const int pb = s.mus_pt_begin[i], pe = pb + s.mus_pt_count[i];
+        int n_cond = 0;
+        pr.mc_cond[i][0] = pr.mc_cond[i][1] = -1;
+        for (int p = pb; p < pe; p++)
+            if (s.pt_kind[p] == BIO_PT_CONDITIONAL) { if (n_cond >= 2) { pr.path_ok = 0; break; } pr.mc_cond[i][n_cond++] = p; }
+        if (pe > 255) pr.path_ok = 0;
+        for (int var = 0; var < P2_MAXVAR && pr.path_ok; var++) {
+            double len0 = 0.0;
+            int n_live = 0, prev = -1;
+            for (int l = 0; l < P2_MAXLIVE; l++) pr.mc_seg[i][var][l] = 0u;
+            for (int p = pb; p < pe; p++) {
+                if (s.pt_kind[p] == BIO_PT_CONDITIONAL) {
+                    const int c = pr.mc_cond[i][0] == p ? 0 : 1;
+                    if (!((var >> c) & 1)) continue;
+                }
+                if (prev >= 0) {
+                    const bool fixed = s.pt_kind[p] != BIO_PT_MOVING && s.pt_kind[prev] != BIO_PT_MOVING;
+                    if (fixed && s.pt_body[p] == s.pt_body[prev]) {
+                        double d2 = 0.0;
+                        for (int c = 0; c < 3; c++) { const double dd = s.pt_loc[p][c] - s.pt_loc[prev][c]; d2 += dd * dd; }
+                        len0 += sqrt(d2);
+                    } else {
+                        if (n_live >= P2_MAXLIVE) { pr.path_ok = 0; break; }
+                        pr.mc_seg[i][var][n_live++] = (uint32_t)prev | ((uint32_t)p << 8) | 0x80000000u;
+                    }
+                }
+                prev = p;
+            }
+            pr.mc_len0[i][var] = (T)len0;
+            if (n_live > pr.mc_nlive) pr.mc_nlive = n_live;
+        }
+    }
+}
+
+// Muscle geometry of the general (spatial) evaluation in the compiled form: point table, one wrench source
+// per (muscle, body it touches) and the sources acting on every body.  gpath_ok = 0: stream over the points.
+template <typename T>
+void build_general_paths(const BioModelTables& s, DevModel<T>& d) {
+    PlanarProg<T>& pr = d.prog;
+    pr.gpath_ok = 0;
+    if (s.n_muscles < 1 || s.n_pathpts > BIO_MAX_PATHPTS) return;
+    int n_src = 0, src_body[P2_MAXSRC];
+    for (int i = 0; i < s.n_muscles; i++) {
+        int slot_body[P2_MAXSLOT], n_slot = 0, n_moving = 0;
+        pr.mus_src0[i] = n_src;
+        for (int p = s.mus_pt_begin[i]; p < s.mus_pt_begin[i] + s.mus_pt_count[i]; p++) {
+            const int b = s.pt_body[p];
+            int slot = -1;
+            for (int k = 0; k < n_slot; k++) if (slot_body[k] == b) slot = k;
+            if (slot < 0) { if (n_slot >= P2_MAXSLOT) return; slot = n_slot; slot_body[n_slot++] = b; }
+            if (s.pt_kind[p] == BIO_PT_MOVING) { n_moving++; if (d.pt_mov[p] < 0) return; }
+            const int dof = s.pt_dof[p] >= 0 ? s.pt_dof[p] : 31;
+            pr.pt_info[p] = b | (s.pt_kind[p] << 4) | (dof << 6) | (slot << 11) | ((d.pt_mov[p] >= 0 ? d.pt_mov[p] : 0) << 13);
+            for (int c = 0; c < 3; c++) pr.pt_xyz[p][c] = (T)s.pt_loc[p][c];
+            pr.pt_xyz[p][3] = T(0);
+        }
+        if (n_moving > 1) return;
+        for (int k = 0; k < n_slot; k++) { if (n_src >= P2_MAXSRC) return; src_body[n_src++] = slot_body[k]; }
+    }
+    pr.mus_src0[s.n_muscles] = n_src;
+    compile_paths(s, pr);
+    if (!pr.path_ok) return;
+    int k = 0;
+    for (int b = 0; b < s.n_bodies; b++) {
+        pr.inc_begin[b] = k;
+        for (int e = 0; e < n_src; e++)
+            if (src_body[e] == b) { if (k >= (int)sizeof(pr.inc_src)) return; pr.inc_src[k++] = (uint8_t)e; }
+    }
+    for (int b = s.n_bodies; b <= BIO_MAX_BODIES; b++) pr.inc_begin[b] = k;
+    pr.n_src = n_src;
+    pr.gpath_ok = 1;
+}
+
 // Planar program of a model (see PlanarProg); prog.ok = 0 when the model does not have the
 // root-plus-chains shape, and the general cooperative evaluation is used instead.
 template <typename T>
@@ -532,7 +613,7 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     }
     if (!pr.chain_ok) return;
     // ---- stage 2 (planar models): the planar program ----
-    if (!d.planar) return;
+    if (!d.planar) { build_general_paths(s, d); return; }
     auto joint_dofs = [&](int b, int* dofs) {             // distinct dofs of the joint, in axis order
         int n = 0;
         for (int a = s.body_axis_begin[b]; a < s.body_axis_begin[b] + s.body_axis_count[b]; a++) {
@@ -639,44 +720,7 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         for (int k = 0; k < n_slot; k++) { if (n_src >= P2_MAXSRC) return; src_body[n_src++] = slot_body[k]; }
     }
     pr.mus_src0[s.n_muscles] = n_src;
-    // compiled paths (see PlanarProg::mc_seg); any muscle that does not fit leaves path_ok = 0 and phase C
-    // streams over the path points instead
-    pr.path_ok = 1;
-    pr.mc_nlive = 0;
-    { const char* z = getenv("BIO_PLANAR_STREAM_PATHS"); if (z && z[0] == '1') pr.path_ok = 0; }   // tests: take the fallback
-    for (int i = 0; i < s.n_muscles && pr.path_ok; i++) {
-        const int pb = s.mus_pt_begin[i], pe = pb + s.mus_pt_count[i];
-        int n_cond = 0;
-        pr.mc_cond[i][0] = pr.mc_cond[i][1] = -1;
-        for (int p = pb; p < pe; p++)
-            if (s.pt_kind[p] == BIO_PT_CONDITIONAL) { if (n_cond >= 2) { pr.path_ok = 0; break; } pr.mc_cond[i][n_cond++] = p; }
-        if (pe > 255) pr.path_ok = 0;
-        for (int var = 0; var < P2_MAXVAR && pr.path_ok; var++) {
-            double len0 = 0.0;
-            int n_live = 0, prev = -1;
-            for (int l = 0; l < P2_MAXLIVE; l++) pr.mc_seg[i][var][l] = 0u;
-            for (int p = pb; p < pe; p++) {
-                if (s.pt_kind[p] == BIO_PT_CONDITIONAL) {
-                    const int c = pr.mc_cond[i][0] == p ? 0 : 1;
-                    if (!((var >> c) & 1)) continue;
-                }
-                if (prev >= 0) {
-                    const bool fixed = s.pt_kind[p] != BIO_PT_MOVING && s.pt_kind[prev] != BIO_PT_MOVING;
-                    if (fixed && s.pt_body[p] == s.pt_body[prev]) {
-                        double d2 = 0.0;
-                        for (int c = 0; c < 3; c++) { const double dd = s.pt_loc[p][c] - s.pt_loc[prev][c]; d2 += dd * dd; }
-                        len0 += sqrt(d2);
-                    } else {
-                        if (n_live >= P2_MAXLIVE) { pr.path_ok = 0; break; }
-                        pr.mc_seg[i][var][n_live++] = (uint32_t)prev | ((uint32_t)p << 8) | 0x80000000u;
-                    }
-                }
-                prev = p;
-            }
-            pr.mc_len0[i][var] = (T)len0;
-            if (n_live > pr.mc_nlive) pr.mc_nlive = n_live;
-        }
-    }
+    compile_paths(s, pr);
     pr.sph_src0 = n_src;
     for (int sp = 0; sp < s.n_spheres; sp++) { if (n_src >= P2_MAXSRC) return; src_body[n_src++] = s.sph_body[sp]; }
     pr.n_src = n_src;
