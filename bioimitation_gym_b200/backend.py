@@ -173,6 +173,37 @@ class VecEnv:
             self.handle, actions.ctypes.data, obs.ctypes.data, reward.ctypes.data, done.ctypes.data,
             terms.ctypes.data if terms is not None else None), "bio_step_host")
 
+    def _host_buffers(self):
+        """Two sets of page-locked buffers, used alternately: the arrays a call returns stay valid until the
+        call after the next one (the reference hands out a fresh array per step)."""
+        if getattr(self, "_hb", None) is None:
+            torch = self.torch
+            pin = lambda *s, dt=None: torch.zeros(s, dtype=dt or self.dtype).pin_memory()
+            N = self.num_envs
+            self._hb = [dict(a=pin(N, self.n_act), o=pin(N, self.obs_dim), r=pin(N), d=pin(N, dt=torch.uint8),
+                             t=pin(N, self.n_terms)) for _ in range(2)]
+            for b in self._hb:
+                b["np"] = {k: v.numpy() for k, v in b.items()}
+            self._hb_turn = 0
+        self._hb_turn ^= 1
+        return self._hb[self._hb_turn]["np"]
+
+    def step_np(self, actions):
+        """numpy in, numpy out (CPU-side trainers): the step kernel reads the actions from and writes obs /
+        reward / done / terms into page-locked host memory in place (bio_step_host)."""
+        b = self._host_buffers()
+        a = np.asarray(actions)
+        if a.shape != (self.num_envs, self.n_act):
+            raise ValueError("actions must have shape (%d, %d)" % (self.num_envs, self.n_act))
+        b["a"][...] = a
+        self.step_host(b["a"], b["o"], b["r"], b["d"], b["t"])
+        return b["o"], b["r"], b["d"].view(np.bool_), {"all_rewards": b["t"]}
+
+    def reset_np(self):
+        b = self._host_buffers()
+        self.reset_host(b["o"])
+        return b["o"]
+
     def reset_host(self, obs: np.ndarray, mask: Optional[np.ndarray] = None):
         _check(self.lib, self.lib.bio_reset_host(
             self.handle, mask.ctypes.data if mask is not None else None, obs.ctypes.data), "bio_reset_host")

@@ -27,12 +27,12 @@ template <typename T, typename C>
 struct WorkGeneral {
     T ax_s[C::NAX], ax_ds[C::NAX], ax_dds[C::NAX];
     T R[BIO_MAX_BODIES][9], r[BIO_MAX_BODIES][3], V[BIO_MAX_BODIES][6], A[BIO_MAX_BODIES][6];
-    T S[C::ND][6];
+    alignas(16) T S[C::ND][8];                     // motion vector of every dof, [6..7] unused (16-byte reads)
     // spatial inertia about O and body force per body: [0] mass, [1..3] m*c, [4..9] I (xx yy zz xy xz yz),
     // [10..15] force (n; f); turned into composite / subtree sums in place
     T BI[BIO_MAX_BODIES][16];
     union {
-        T IS[C::ND][6];                            // I^c_body(i) * S_i (phase G on)
+        alignas(16) T IS[C::ND][8];                // I^c_body(i) * S_i (phase G on), [6..7] unused
         T mv[8][6];                                // moving path points: location [0..2], d/dq [3..5] (phases A..C)
     };
     T H[C::ND * (C::ND + 1) / 2], rhs[C::ND];
@@ -530,8 +530,9 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     }
     if (lane < nb) {
         const int b = lane;
-        for (int s = 0; s < m.n_spheres; s++) {
-            if (m.sph_body[s] != b || E.sphF[s][1] == T(0)) continue;
+        for (int smask = m.prog.body_sph_mask[b]; smask; smask &= smask - 1) {
+            const int s = lowest_bit(smask);
+            if (E.sphF[s][1] == T(0)) continue;
             T n[3];
             cross3(E.sphx[s], E.sphF[s], n);
             for (int c = 0; c < 3; c++) { Wn[c] += n[c]; Wf[c] += E.sphF[s][c]; }
@@ -650,7 +651,27 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         }
     }
 
-    // ---- phase F: composite inertias / subtree forces; task = (body of the level, value) ----
+    // ---- phase F: composite inertias / subtree forces.  Root-plus-chains models on a full warp: lane =
+    // (chain, value) runs the suffix sum down its chain, then 16 lanes add the chain heads to the root;
+    // else task = (body of the level, value) with a barrier per tree level ----
+    if (G == 32 && m.prog.chain_ok && m.prog.n_branches >= 1) {
+        const int cch = lane >> 4, v = lane & 15;
+        if (cch < m.prog.n_branches) {
+            T acc = T(0);
+            for (int k = m.prog.gch_nb[cch] - 1; k >= 0; k--) {
+                const int b = m.prog.gch_body[cch][k];
+                acc += K.BI[b][v];
+                K.BI[b][v] = acc;
+            }
+        }
+        gsync<G>();
+        if (lane < 16) {
+            T acc = K.BI[m.prog.root_body][lane];
+            for (int l = 0; l < m.prog.n_branches; l++) acc += K.BI[m.prog.gch_body[l][0]][lane];
+            K.BI[m.prog.root_body][lane] = acc;
+        }
+        gsync<G>();
+    } else
     for (int lev = m.n_levels - 2; lev >= 0; lev--) {
         const int cnt = (m.level_begin[lev + 1] - m.level_begin[lev]) * 16;
         for (int tsk = lane; tsk < cnt; tsk += G) {
@@ -679,7 +700,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     }
     unsigned act_mask = 0u;      // active contacts of this env (same value on every lane)
     if (h_imp > T(0)) {
-        for (int s = 0; s < m.n_spheres; s++) if (E.sphD[s][1] > T(0)) act_mask |= 1u << s;
+        act_mask = group_ballot<G>(lane < m.n_spheres && E.sphD[lane < m.n_spheres ? lane : 0][1] > T(0));
         // contact Jacobian columns col[s][d] = w_d x p_s + v_d for the dofs on the sphere's chain
         if (act_mask)
             for (int tsk = lane; tsk < m.jc_n; tsk += G) {      // (sphere, dof on its chain)
@@ -693,8 +714,12 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     gsync<G>();
     for (int e = lane; e < m.n_entries; e += G) {
         const int i = m.ent_i[e], j = m.ent_j[e];
+        T sj[8], is[8];
+        ld4(K.S[j], sj[0], sj[1], sj[2], sj[3]); ld4(K.S[j] + 4, sj[4], sj[5], sj[6], sj[7]);
+        ld4(K.IS[i], is[0], is[1], is[2], is[3]); ld4(K.IS[i] + 4, is[4], is[5], is[6], is[7]);
         T v = T(0);
-        for (int c = 0; c < 6; c++) v += K.S[j][c] * K.IS[i][c];
+#pragma unroll
+        for (int c = 0; c < 6; c++) v += sj[c] * is[c];
         if (h_imp > T(0)) {
             unsigned mm = act_mask & m.ent_sph[e];               // active spheres whose chain holds i (and j)
             while (mm) {

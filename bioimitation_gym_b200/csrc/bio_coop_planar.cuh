@@ -45,6 +45,7 @@ __device__ __forceinline__ void coop_solve(const DevModel<T>& m, EnvWork<T, CLS>
         const T bk = K.rhs[k];                   // final z_k: every descendant step is done
 #pragma unroll
         for (int it = 0; it < NIT; it++) {
+            if (it > 0 && pe - pb <= it * G) break;      // (warp-uniform) no pair left for this round
             const int p = pb + lane + it * G;
             if (p < pe) {
                 const uint32_t pk = m.lt_pack[p];

@@ -45,6 +45,8 @@ struct alignas(16) PlanarProg {
     int32_t ok, n_branches, n_atasks, n_src;
     int32_t root_body, root_ndof, sph_src0, scan_ok;   // scan_ok: planar chain walk as warp scans (<= 8 steps per chain)
     int32_t chain_ok, pad_[3];                         // chain lists valid (any model: root + <= 2 chains of <= 16 steps)
+    int32_t gch_nb[P2_MAXBR];                          // bodies of every chain, root side first (any chain_ok model)
+    int32_t gch_body[P2_MAXBR][BIO_MAX_BODIES];
     int32_t root_dof[4];
     int32_t br_nb[P2_MAXBR];
     int32_t br_body[P2_MAXBR][P2_MAXCB];
@@ -555,6 +557,8 @@ template <typename T>
 void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     PlanarProg<T>& pr = d.prog;
     memset(&pr, 0, sizeof(pr));
+    for (int b = 0; b < s.n_bodies && b < BIO_MAX_BODIES; b++)       // contact spheres of every body (any model)
+        for (int sp = 0; sp < s.n_spheres && sp < BIO_MAX_SPHERES; sp++) if (s.sph_body[sp] == b) pr.body_sph_mask[b] |= 1 << sp;
     // ---- stage 1 (any model): root body 0 carrying <= P2_MAXBR unbranched chains; the walk root joint ->
     // leaf of every chain as a list of elementary-axis steps (used by the planar program and by the scan
     // form of the spatial kinematics) ----
@@ -578,6 +582,10 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     }
     pr.root_body = 0;
     pr.chain_ok = 1;
+    for (int l = 0; l < P2_MAXBR; l++) {
+        pr.gch_nb[l] = l < pr.n_branches ? chain_nb[l] : 0;
+        for (int k = 0; k < BIO_MAX_BODIES; k++) pr.gch_body[l][k] = (l < pr.n_branches && k < chain_nb[l]) ? chain_body[l][k] : 0;
+    }
     for (int l = 0; l < (pr.n_branches > 0 ? pr.n_branches : 1); l++) {
         int n = 0;
         auto add_joint = [&](int b, bool root) {
@@ -638,10 +646,6 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         pr.br_nb[l] = chain_nb[l];
     }
     if (s.n_spheres > BIO_MAX_SPHERES) return;
-    for (int b = 0; b < s.n_bodies; b++) {
-        pr.body_sph_mask[b] = 0;
-        for (int sp = 0; sp < s.n_spheres; sp++) if (s.sph_body[sp] == b) pr.body_sph_mask[b] |= 1 << sp;
-    }
     for (int a = 0; a < s.n_axes; a++) {
         const int desc = d.axis_desc[a];
         const T sg = (desc & 2) ? T(-1) : T(1);

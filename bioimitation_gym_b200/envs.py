@@ -88,17 +88,14 @@ class BioImitationEnv:
 
     # ---- reference API -------------------------------------------------
     def reset(self, obs_as_dict: bool = False):
-        obs = self.vec.reset().detach().cpu().numpy()
+        obs = self.vec.reset_np()
         return self._format_obs(obs, obs_as_dict)
 
     def step(self, action, obs_as_dict: bool = False):
-        import torch
-        a = torch.as_tensor(np.asarray(action, dtype=self._np_dtype).reshape(self.num_envs, -1))
-        obs, rew, done, info = self.vec.step(a)
-        obs = obs.detach().cpu().numpy()
-        rew = rew.detach().cpu().numpy()
-        done = done.detach().cpu().numpy().astype(bool)
-        terms = info["all_rewards"].detach().cpu().numpy()
+        # numpy in / numpy out through page-locked buffers the step kernel reads and writes in place
+        a = np.asarray(action, dtype=self._np_dtype).reshape(self.num_envs, -1)
+        obs, rew, done, info = self.vec.step_np(a)
+        terms = info["all_rewards"]
         if self.num_envs == 1:
             return [self._format_obs(obs, obs_as_dict), float(rew[0]), bool(done[0]),
                     {"all_rewards": [float(x) for x in terms[0]]}]

@@ -42,7 +42,7 @@ class BioVectorEnv(_Base):
         self._obs = None
 
     def vector_reset(self) -> List[np.ndarray]:
-        self._obs = self.env.reset().detach().cpu().numpy()
+        self._obs = self.env.reset_np()
         return [o for o in self._obs]
 
     def reset_at(self, index: Optional[int] = None) -> np.ndarray:
@@ -51,13 +51,10 @@ class BioVectorEnv(_Base):
         return self._obs[0 if index is None else int(index)]
 
     def vector_step(self, actions):
-        import torch
-        a = torch.as_tensor(np.asarray(actions, dtype=np.float32))
-        obs, rew, done, info = self.env.step(a)
-        self._obs = obs.detach().cpu().numpy()
-        rew = rew.detach().cpu().numpy()
-        done = done.detach().cpu().numpy().astype(bool)
-        terms = info["all_rewards"].detach().cpu().numpy()
+        # host buffers in, host buffers out: page-locked arrays the step kernel reads / writes in place
+        a = np.asarray(actions, dtype=np.float32 if self.env.dtype == self.env.torch.float32 else np.float64)
+        self._obs, rew, done, info = self.env.step_np(a)
+        terms = info["all_rewards"]
         infos = [{"all_rewards": terms[i].tolist()} for i in range(self.num_envs)]
         return [o for o in self._obs], rew.tolist(), done.tolist(), infos
 

@@ -423,18 +423,21 @@ def test_rllib_vector_env_adapter_interface():
     class Fake:
         num_envs, obs_dim, n_act = 3, 4, 2
         action_low, action_high = np.zeros(2), np.ones(2)
+        dtype = torch.float32
 
         def __init__(self):
             self.t = 0
+            self.torch = torch
 
-        def reset(self):
-            return torch.zeros(3, 4)
+        def reset_np(self):
+            return np.zeros((3, 4), dtype=np.float32)
 
-        def step(self, a):
+        def step_np(self, a):
             self.t += 1
-            assert tuple(a.shape) == (3, 2)
-            done = torch.tensor([0, 1, 0], dtype=torch.uint8)
-            return torch.full((3, 4), float(self.t)), torch.arange(3.0), done, {"all_rewards": torch.ones(3, 5)}
+            assert a.shape == (3, 2) and a.dtype == np.float32
+            done = np.array([0, 1, 0], dtype=bool)
+            return (np.full((3, 4), float(self.t), dtype=np.float32), np.arange(3.0, dtype=np.float32), done,
+                    {"all_rewards": np.ones((3, 5), dtype=np.float32)})
 
         def close(self):
             pass
