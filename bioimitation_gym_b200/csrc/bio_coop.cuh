@@ -913,7 +913,10 @@ __device__ __forceinline__ void coop_flush_obs(EnvWork<T, CLS>* works, T* __rest
 //   640 threads = 20 warps at 96 registers: more items in flight for batches of several items per warp
 //       (measured: 2D 16384 envs +18 %, 131072 envs +7 %; 3D 8192 envs +13 %; 4096 envs -3 %).
 // bio_create picks by the number of item rounds per SM (COOP_SHAPE_COST); fp64 runs 256 threads.
-#define COOP_THREADS_LO(T) (sizeof(T) == 4 ? 512 : 256)
+#ifndef BIO_COOP_LO
+#define BIO_COOP_LO 512
+#endif
+#define COOP_THREADS_LO(T) (sizeof(T) == 4 ? BIO_COOP_LO : 256)
 #define COOP_THREADS_HI(T) (sizeof(T) == 4 ? 640 : 256)
 #define COOP_SHAPE_COST 1.12      // time of one round of items with the HI shape relative to the LO shape
 

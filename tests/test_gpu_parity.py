@@ -342,6 +342,31 @@ def test_host_entry_point_with_page_locked_buffers_matches_device_path():
         e.close()
 
 
+def test_numpy_api_matches_tensor_api():
+    """step_np / reset_np (page-locked double buffers, what the gym classes and the RLlib adapter call) return
+    the same numbers as the tensor API; the arrays of a call stay valid through the next call."""
+    import torch
+    n = 64
+    env, _ = _mk("MuscleWalkingImitation2D-v0", n, "float32")
+    env2, _ = _mk("MuscleWalkingImitation2D-v0", n, "float32")
+    o0 = env.reset().cpu().numpy()
+    assert np.array_equal(o0, env2.reset_np())
+    rng = np.random.default_rng(9)
+    prev = None
+    for _ in range(6):
+        a = rng.uniform(0, 1, (n, 14)).astype(np.float32)
+        o, r, d, info = env.step(torch.as_tensor(a))
+        o2, r2, d2, info2 = env2.step_np(a)
+        assert np.array_equal(o.cpu().numpy(), o2) and np.array_equal(r.cpu().numpy(), r2)
+        assert np.array_equal(d.cpu().numpy().astype(bool), d2)
+        assert np.array_equal(info["all_rewards"].cpu().numpy(), info2["all_rewards"])
+        if prev is not None:
+            assert np.array_equal(prev[0], prev[1])      # the previous call's array was not overwritten
+        prev = (o2, o2.copy())
+    env.close()
+    env2.close()
+
+
 def test_errors_are_reported_not_thrown():
     import torch
     from bioimitation_gym_b200 import backend
