@@ -838,33 +838,9 @@ __device__ __forceinline__ T group_max(T v) {
     return v;
 }
 
-// observation slot o of the env (descriptor table built on the host)
-template <typename T, int CLS>
-__device__ __forceinline__ T obs_value(const DevModel<T>& m, const DevTask<T>& c, const EnvWork<T, CLS>& E, int istep,
-                                       int row_next, const T* pel, int o) {
-    const int desc = m.obs_desc[o], kind = desc >> 16, idx = desc & 0xffff;
-    switch (kind) {
-        case 0: { const T ph = T(istep) / T(c.cycle); return ph - Num<T>::floor(ph); }
-        case 1: return m.coord_dof[idx] >= 0 ? E.q[m.coord_dof[idx]] : m.coord_const[idx];
-        case 2: return m.coord_dof[idx] >= 0 ? E.u[m.coord_dof[idx]] : T(0);
-        case 3: return m.coord_dof[idx] >= 0 ? E.udot[m.coord_dof[idx]] : T(0);
-        case 4: return c.ref_q[(size_t)row_next * c.ref_coords + idx];
-        case 5: return c.ref_u[(size_t)row_next * c.ref_coords + idx];
-        case 6: return E.x.out.obs_pos[idx / 3][idx % 3] - pel[idx % 3];
-        case 7: return E.com_pos[idx] - pel[idx];
-        case 8: return E.x.out.obs_vel[idx / 3][idx % 3];
-        case 9: return E.com_vel[idx];
-        case 10: return E.act[idx];
-        case 11: return E.lm[idx];
-        case 12: return E.lmdot[idx];
-        default: {
-            const T weight = Num<T>::abs(m.total_mass * m.gravity[1]);
-            const int g = idx / 6, j = idx % 6;
-            return E.contact[g][j] / (j < 3 ? weight : weight * c.height);
-        }
-    }
-}
-
+// Observation row of the env from the host-built slot descriptors (build_obs_desc): the source array is
+// picked with selects and read with one indexed load, so the lanes of a group (every one on a different kind of
+// slot) do not serialise over a switch; reference rows come from global memory under a predicate.
 template <typename T, int CLS>
 __device__ void coop_write_obs(const DevModel<T>& m, const DevTask<T>& c, const EnvWork<T, CLS>& E, int lane, int istep,
                                T* orow) {
@@ -873,7 +849,27 @@ __device__ void coop_write_obs(const DevModel<T>& m, const DevTask<T>& c, const 
 #pragma unroll
     for (int k = 0; k < 3; k++) pel[k] = m.pel_dof[k] >= 0 ? E.q[m.pel_dof[k]] : T(0);
     const int row_next = ref_row(c, istep + 1);
-    for (int o = lane; o < c.obs_dim; o += G) orow[o] = obs_value<T, CLS>(m, c, E, istep, row_next, pel, o);
+    const T ph = T(istep) / T(c.cycle);
+    const T phase = ph - Num<T>::floor(ph);
+    const T* pos = &E.x.out.obs_pos[0][0];
+    const T* vel = &E.x.out.obs_vel[0][0];
+    const T* con = &E.contact[0][0];
+    for (int o = lane; o < c.obs_dim; o += G) {
+        const int desc = m.obs_desc[o], kind = desc >> 16, psel = (desc >> 12) & 3, idx = desc & 0xfff;
+        const T cst = m.obs_cst[o];
+        const T* base = kind == 1 ? E.q : kind == 2 ? E.u : kind == 3 ? E.udot : kind == 6 ? pos : kind == 7 ? E.com_pos
+                      : kind == 8 ? vel : kind == 9 ? E.com_vel : kind == 10 ? E.act : kind == 11 ? E.lm
+                      : kind == 12 ? E.lmdot : kind == 13 ? con : E.q;
+        const bool in_work = kind != 0 && kind != 4 && kind != 5 && kind != 14;
+        T v = base[in_work ? idx : 0];
+        v -= psel == 1 ? pel[0] : psel == 2 ? pel[1] : psel == 3 ? pel[2] : T(0);
+        if (kind == 13) v *= cst;
+        if (kind == 4) v = c.ref_q[(size_t)row_next * c.ref_coords + idx];
+        if (kind == 5) v = c.ref_u[(size_t)row_next * c.ref_coords + idx];
+        if (kind == 0) v = phase;
+        if (kind == 14) v = cst;
+        orow[o] = v;
+    }
 }
 
 // Size class 0: the observation rows of the warp's two envs (adjacent in memory) are staged in the planar
@@ -930,7 +926,16 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     constexpr int G = C::G;
     constexpr int EPW = 32 / G;                 // envs per warp
     extern __shared__ __align__(16) unsigned char smem[];
+#ifdef BIO_PHASE_CLOCK
+    long long sk_t[10];
+    int sk_n = 0;
+#define SK_CLK() do { if (sk_n < 10) sk_t[sk_n++] = clock64(); } while (0)
+#else
+#define SK_CLK() do { } while (0)
+#endif
+    SK_CLK();                                   // 0: kernel entry
     const DevModel<T>& m = stage_model(gm, smem);
+    SK_CLK();                                   // 1: model staged
     EnvWork<T, CLS>* works = reinterpret_cast<EnvWork<T, CLS>*>(smem + ((sizeof(DevModel<T>) + 15) / 16) * 16);
     const int slot = threadIdx.x / G, lane = threadIdx.x % G;
     const int warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
@@ -1002,8 +1007,23 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     gsync<G>();
 
     // ---- integrate one control step, evaluate at the new state ----
+    SK_CLK();                                   // 2: state loaded, actions pre-processed
     coop_integrate<T, CLS>(m, c, E, lane, istep, seed, env);
+    SK_CLK();                                   // 3: substeps done
     istep += 1;
+    {   // reference rows read after the evaluation (reward: this row, observation: the next one): into L1 now
+        const size_t r0 = (size_t)ref_row(c, istep), r1 = (size_t)ref_row(c, istep + 1);
+        if (lane < c.ref_coords) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(c.ref_q + r0 * c.ref_coords + lane));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(c.ref_q + r1 * c.ref_coords + lane));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(c.ref_u + r1 * c.ref_coords + lane));
+        }
+        if (lane < 8) {
+            const int sd = lane / 4, j = lane % 4;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(c.ref_body_pos + (r0 * c.ref_bodies + c.rew_refbody[sd][j]) * 3));
+        }
+        if (lane == 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(c.ref_com_pos + r0 * 3));
+    }
     const int ext_pt = c.perturb ? c.perturb_obspt : -1;
     coop_eval_any<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, T(istep) * c.dt), ext_pt, T(0), true);
     gsync<G>();
@@ -1011,9 +1031,11 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     // (now idle) planar work arrays and written by the whole warp at the end, 16 bytes per lane (full 128-byte
     // lines for a caller's page-locked host buffer).  Size class 1: a warp writes its one row directly.
     static_assert(CLS != 0 || sizeof(E.k.p) >= 256 * sizeof(T), "observation stage does not fit the planar work arrays");
+    SK_CLK();                                   // 4: full evaluation done
     T* orow = CLS == 0 ? reinterpret_cast<T*>(&E.k.p) : obs + (size_t)ii * c.obs_dim;
     if (valid || CLS == 0) coop_write_obs<T, CLS>(m, c, E, lane, istep, orow);
 
+    SK_CLK();                                   // 5: observation row staged / written
     // ---- reward (env2D.py:267-358): lane-parallel partial sums ----
     const int row = ref_row(c, istep);
     T qpart = T(0);
@@ -1118,6 +1140,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
             }
         }
     }
+    SK_CLK();                                   // 6: reward, termination, outputs of lane 0
     gsync<G>();   // everyone is done with E.x.out before a reset overwrites it
     // Size class 0: both staged rows go out now (the whole warp writes: 16 bytes per lane)
     if constexpr (CLS == 0) coop_flush_obs<T, CLS>(works, obs, c.obs_dim, item * EPW, n, 3u);
@@ -1156,6 +1179,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
             coop_flush_obs<T, CLS>(works, obs, c.obs_dim, item * EPW, n, rows);
         }
     }
+    SK_CLK();                                   // 7: rows flushed, auto-reset handled
     // ---- write back ----
     if (valid) {
         if (isd) { st.q[(size_t)lane * n + ii] = E.q[lane]; st.u[(size_t)lane * n + ii] = E.u[lane]; }
@@ -1172,6 +1196,13 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
         }
     }
     gsync<G>();   // the warp's work slots are reused by its next item
+    SK_CLK();                                   // 8: state written back
+#ifdef BIO_PHASE_CLOCK
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        printf("step cycles: stage %lld  load+actions %lld  substeps %lld  full eval %lld  obs %lld  reward+done %lld  flush+reset %lld  write back %lld\n",
+               sk_t[1] - sk_t[0], sk_t[2] - sk_t[1], sk_t[3] - sk_t[2], sk_t[4] - sk_t[3], sk_t[5] - sk_t[4], sk_t[6] - sk_t[5],
+               sk_t[7] - sk_t[6], sk_t[8] - sk_t[7]);
+#endif
     }
     if (stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[0], (double)n);
 }

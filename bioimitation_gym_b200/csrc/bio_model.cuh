@@ -176,7 +176,8 @@ struct alignas(16) DevModel {
     int8_t pt_mov[BIO_MAX_PATHPTS];          // index of a moving path point in moving_pt (-1: not moving)
     int32_t ent_i[BIO_MAX_DOF * (BIO_MAX_DOF + 1) / 2];
     int32_t ent_j[BIO_MAX_DOF * (BIO_MAX_DOF + 1) / 2];
-    int32_t obs_desc[256];                   // (kind << 16) | index per observation slot
+    int32_t obs_desc[256];                   // (kind << 16) | pelvis selector << 12 | index per observation slot (build_obs_desc)
+    T obs_cst[256];                          // constant of the slot: locked coordinate value (kind 14), contact scale (kind 13)
     // spline search: 16 uniform buckets per function -> first candidate knot
     T func_bucket_inv[BIO_MAX_FUNCS];
     int8_t func_bucket[BIO_MAX_FUNCS][16];
@@ -761,22 +762,36 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
 // bio_kernels.cuh; reference env2D.py:158-230).
 template <typename T>
 int build_obs_desc(const BioModelTables& s, const BioTaskConfig& t, DevModel<T>& d) {
+    // One descriptor per observation slot, resolved as far as the host can: kind 0 gait phase; 1 / 2 / 3 q / u /
+    // udot of dof idx; 4 / 5 reference q / u of coordinate idx (next row); 6 / 8 position / velocity component idx
+    // of the observed body origins; 7 / 9 centre-of-mass position / velocity; 10 / 11 / 12 activation, fibre
+    // length, fibre velocity of muscle idx; 13 contact wrench component idx times obs_cst (1 / body weight,
+    // 1 / (weight * height) for moments); 14 the constant obs_cst (locked coordinates).  Pelvis selector 1..3:
+    // subtract pelvis_tx / ty / tz (positions are reported relative to the pelvis).
     int o = 0;
-    auto put = [&](int kind, int idx) { if (o < 256) d.obs_desc[o] = (kind << 16) | idx; o++; };
+    auto put = [&](int kind, int idx, int pel = 0, double cst = 0.0) {
+        if (o < 256) { d.obs_desc[o] = (kind << 16) | (pel << 12) | idx; d.obs_cst[o] = (T)cst; }
+        o++;
+    };
+    auto coord = [&](int kind, int i) {
+        if (s.coord_dof[i] >= 0) put(kind, s.coord_dof[i]);
+        else put(14, 0, 0, kind == 1 ? s.coord_const[i] : 0.0);
+    };
     put(0, 0);
-    for (int i = 0; i < s.n_coords; i++) if (!s.coord_pelvis_trans[i]) put(1, i);
-    for (int i = 0; i < s.n_coords; i++) put(2, i);
-    for (int i = 0; i < s.n_coords; i++) put(3, i);
+    for (int i = 0; i < s.n_coords; i++) if (!s.coord_pelvis_trans[i]) coord(1, i);
+    for (int i = 0; i < s.n_coords; i++) coord(2, i);
+    for (int i = 0; i < s.n_coords; i++) coord(3, i);
     if (t.use_target_obs) {
         for (int i = 0; i < s.n_coords; i++) if (s.coord_pelvis_trans[i] != 1) put(4, i);
         for (int i = 0; i < s.n_coords; i++) if (s.coord_pelvis_trans[i] != 1) put(5, i);
     }
-    for (int p = 0; p < t.n_obs_bodies; p++) for (int j = 0; j < 3; j++) put(6, p * 3 + j);
-    for (int j = 0; j < 3; j++) put(7, j);
+    for (int p = 0; p < t.n_obs_bodies; p++) for (int j = 0; j < 3; j++) put(6, p * 3 + j, 1 + j);
+    for (int j = 0; j < 3; j++) put(7, j, 1 + j);
     for (int p = 0; p < t.n_obs_body_vel; p++) for (int j = 0; j < 3; j++) put(8, p * 3 + j);
     for (int j = 0; j < 3; j++) put(9, j);
     for (int i = 0; i < s.n_muscles; i++) { put(10, i); put(11, i); put(12, i); }
-    if (t.use_grf) for (int g = 0; g < 2; g++) for (int j = 0; j < 6; j++) put(13, g * 6 + j);
+    const double weight = fabs(s.total_mass * s.gravity[1]);
+    if (t.use_grf) for (int g = 0; g < 2; g++) for (int j = 0; j < 6; j++) put(13, g * 6 + j, 0, 1.0 / (j < 3 ? weight : weight * t.height));
     return o;
 }
 

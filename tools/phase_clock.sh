@@ -16,5 +16,5 @@ for n in (296, 4096):
     for _ in range(3): env.step(a)
     torch.cuda.synchronize(); print("---- above:", n, "envs (last line = one control step)", flush=True)
     env.close()
-PY' 2>&1 | grep -E "^----|phase cycles" | awk '/^----/{if(last)print last; print; last=""} /phase cycles/{last=$0}'
+PY' 2>&1 | grep -E "^----|phase cycles|step cycles" | awk '/^----/{if(last)print last; print; last=""} /phase cycles/{last=$0} /step cycles/{last2=$0} /^----/{if(last2)print last2; last2=""}'
 python -c "import __graft_entry__ as g; g.build(force=True)"
