@@ -342,6 +342,35 @@ def test_host_entry_point_with_page_locked_buffers_matches_device_path():
         e.close()
 
 
+@pytest.mark.parametrize("env_id,n_act", [("MuscleWalkingImitation2D-v0", 14), ("MuscleWalkingImitation3D-v0", 22),
+                                          ("MuscleLockedKneeImitation3D-v0", 19)])
+def test_compiled_and_streamed_muscle_paths_give_the_same_trajectory(env_id, n_act, monkeypatch):
+    """The kernels evaluate the muscle geometry from compiled paths (constant length + live segments per variant
+    of the conditional points); BIO_PLANAR_STREAM_PATHS=1 at create time makes them stream over the path points
+    instead (the fallback any model may need).  fp64, 30 control steps with auto-reset: same observations."""
+    import torch
+    n = 96
+    monkeypatch.setenv("BIO_PLANAR_STREAM_PATHS", "0")
+    a_env, _ = _mk(env_id, n, "float64")
+    monkeypatch.setenv("BIO_PLANAR_STREAM_PATHS", "1")
+    b_env, _ = _mk(env_id, n, "float64")
+    monkeypatch.setenv("BIO_PLANAR_STREAM_PATHS", "0")
+    oa, ob = a_env.reset().clone(), b_env.reset().clone()
+    assert torch.equal(oa, ob)
+    g = torch.Generator().manual_seed(4)
+    worst = 0.0
+    for _ in range(30):
+        a = torch.rand((n, n_act), generator=g, dtype=torch.float64)
+        oa, ra, da, _ = a_env.step(a)
+        ob, rb, db, _ = b_env.step(a)
+        assert torch.equal(da, db)
+        worst = max(worst, float(((oa - ob).abs() / oa.abs().clamp(min=1.0)).max()), float((ra - rb).abs().max()))
+    print(env_id, "compiled vs streamed paths, worst difference %.2e" % worst)
+    assert worst < 1e-6                      # free-running contact dynamics amplify the 1e-16 rounding differences
+    a_env.close()
+    b_env.close()
+
+
 def test_numpy_api_matches_tensor_api():
     """step_np / reset_np (page-locked double buffers, what the gym classes and the RLlib adapter call) return
     the same numbers as the tensor API; the arrays of a call stay valid through the next call."""
