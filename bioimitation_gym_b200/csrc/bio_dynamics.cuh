@@ -191,14 +191,22 @@ BIO_DEV void curve_eval(const DevModel<T>& m, int c, T x, T& y, T& dy) {
     int i = (int)tc;
     i = i > BIO_CURVE_N - 1 ? BIO_CURVE_N - 1 : i;
     const T s = tc - T(i);
-    const T y0 = m.curve_tab[c][i][0], m0 = m.curve_tab[c][i][1];
-    const T y1 = m.curve_tab[c][i + 1][0], m1 = m.curve_tab[c][i + 1][1];
-    // cubic Hermite in monomial (Horner) form: same polynomial as the basis form
-    const T dl = y1 - y0;
-    const T c2 = T(3) * dl - T(2) * m0 - m1, c3 = m0 + m1 - T(2) * dl;
-    const T dyt = m0 + s * (T(2) * c2 + T(3) * s * c3);
-    y = y0 + s * (m0 + s * (c2 + s * c3)) + dyt * (t - tc);
-    dy = dyt * ih;
+    if constexpr (sizeof(T) == 4) {
+        T c0, c1, c2, c3;                        // monomial form of the interval's cubic (DevModel::curve_q)
+        ld4(m.curve_q[c][i], c0, c1, c2, c3);
+        const T dyt = c1 + s * (T(2) * c2 + T(3) * s * c3);
+        y = c0 + s * (c1 + s * (c2 + s * c3)) + dyt * (t - tc);
+        dy = dyt * ih;
+    } else {
+        const T y0 = m.curve_tab[c][i][0], m0 = m.curve_tab[c][i][1];
+        const T y1 = m.curve_tab[c][i + 1][0], m1 = m.curve_tab[c][i + 1][1];
+        // cubic Hermite in monomial (Horner) form: same polynomial as the basis form
+        const T dl = y1 - y0;
+        const T c2 = T(3) * dl - T(2) * m0 - m1, c3 = m0 + m1 - T(2) * dl;
+        const T dyt = m0 + s * (T(2) * c2 + T(3) * s * c3);
+        y = y0 + s * (m0 + s * (c2 + s * c3)) + dyt * (t - tc);
+        dy = dyt * ih;
+    }
 }
 template <typename T>
 BIO_DEV T curve_value(const DevModel<T>& m, int c, T x) { T y, d; curve_eval(m, c, x, y, d); return y; }

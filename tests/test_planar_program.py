@@ -152,14 +152,17 @@ def test_warm_started_newton_finds_the_same_root(emul_lib, oracle_lib, models):
     assert worst < 1e-8
 
 
-def test_two_ctas_of_the_2d_kernel_fit_one_sm(emul_lib):
-    """Shared-memory budget of the fp32 / 2D instantiation: model block + 16 per-env work buffers per
-    CTA, two CTAs (16 warps) per SM.  228 KB per SM, 1 KB reserved per CTA."""
+def test_both_launch_shapes_fit_the_shared_memory_of_one_sm(emul_lib):
+    """Shared-memory budget of the fp32 instantiations: one CTA per SM holds the model block and one work
+    buffer per env of its 512 (16 warps) or 640 (20 warps) threads; 2D: half a warp per env, 3D: a warp per env.
+    227 KB (232448 B) of dynamic shared memory per CTA on sm_100."""
     out = np.zeros(8, dtype=np.int64)
     emul_lib.emul_sizes(_p(out))
-    model, work = int(out[0]), int(out[1])
-    cta = (model + 15) // 16 * 16 + 16 * work
-    assert cta <= (233472 - 2 * 1024) // 2, "2D fp32 CTA needs %d B of shared memory: only one CTA per SM" % cta
+    model, work2d, work3d = int(out[0]), int(out[1]), int(out[2])
+    base = (model + 15) // 16 * 16
+    for threads in (512, 640):
+        assert base + threads // 16 * work2d <= 232448, "2D fp32, %d threads: %d B" % (threads, base + threads // 16 * work2d)
+        assert base + threads // 32 * work3d <= 232448, "3D fp32, %d threads: %d B" % (threads, base + threads // 32 * work3d)
 
 
 def test_fast_paths_are_enabled_for_the_shipped_models(emul_lib, models):
