@@ -410,14 +410,17 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         xp = x; yp = y; zp = z; prev_slot = slot;
     }
     }
-    const T fiso = m.mus_fiso[i], lopt = m.mus_lopt[i], h = m.mus_height[i], beta = m.mus_beta[i];
-    const T amin = m.mus_amin[i], lmin = m.mus_lm_min[i];
+    // per-muscle constants: three 16-byte reads (PlanarProg::mus_k), reciprocals from the host
+    T fiso, lopt, inv_lopt, h2, beta, amin, lmin, inv_lts, vmax_lopt, inv_tact, inv_tdeact, k11;
+    ld4(pr.mus_k[i], fiso, lopt, inv_lopt, h2);
+    ld4(pr.mus_k[i] + 4, beta, amin, lmin, inv_lts);
+    ld4(pr.mus_k[i] + 8, vmax_lopt, inv_tact, inv_tdeact, k11);
     const T lmi = E.lm[i];
     const T lmc = lmi < lmin ? lmin : lmi;
-    const T lat = Num<T>::sqrt_pos(lmc * lmc - h * h);
+    const T lat = Num<T>::sqrt_pos(lmc * lmc - h2);
     const T cosa = Num<T>::div(lat, lmc);
     T fal, fpe, ft, fv, dfv, dtmp;
-    curve_eval(m, 3, Num<T>::div(L - lat, m.mus_lts[i]), ft, dtmp);
+    curve_eval(m, 3, (L - lat) * inv_lts, ft, dtmp);
     const T tension = fiso * ft;
     {   // wrench sources of this muscle: one per body it touches
         const int s0 = pr.mus_src0[i], ns = pr.mus_src0[i + 1] - s0;
@@ -430,7 +433,7 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         // generalized force of the moving point: f . R_b dloc/dq
         if (mov >= 0) K.mq[mov] = tension * mqu;
     }
-    const T lnorm = Num<T>::div(lmc, lopt);
+    const T lnorm = lmc * inv_lopt;
     curve_eval(m, 0, lnorm, fal, dtmp);
     curve_eval(m, 2, lnorm, fpe, dtmp);
     const T ac = clampv(E.act[i], amin, T(1));
@@ -452,10 +455,11 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     }
     E.vn[i] = vn;
     if (lmi <= lmin && vn < T(0)) vn = T(0);
-    E.lmdot[i] = vn * m.mus_vmax[i] * lopt;
+    E.lmdot[i] = vn * vmax_lopt;
+    // activation ODE: adot = (e - a) / tau, tau = tact (0.5 + 1.5 a) rising, tdeact / (0.5 + 1.5 a) falling
     const T ec = clampv(E.ctrl[i], amin, T(1));
-    const T tau = ec > ac ? m.mus_tact[i] * (T(0.5) + T(1.5) * ac) : Num<T>::div(m.mus_tdeact[i], T(0.5) + T(1.5) * ac);
-    E.adot[i] = Num<T>::div(ec - ac, tau);
+    const T wa = T(0.5) + T(1.5) * ac;
+    E.adot[i] = (ec - ac) * (ec > ac ? inv_tact * Num<T>::rcp(wa) : inv_tdeact * wa);
     if (full) {
         curve_eval(m, 1, vn, fv, dfv);
         E.fact[i] = fiso * afal * fv;
@@ -470,12 +474,15 @@ BIO_DEV void p2_phase_d(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     auto& K = E.k.p;
     if (lane < m.n_spheres) {
         const int s = lane, b = m.sph_body[s];
+        // per-sphere constants: three 16-byte reads (PlanarProg::sph_k)
+        T lx, ly, zc, rad, kk, c15, ud, us2, uv, vt, inv_vt, k11;
+        ld4(pr.sph_k[s], lx, ly, zc, rad);
+        ld4(pr.sph_k[s] + 4, kk, c15, ud, us2);
+        ld4(pr.sph_k[s] + 8, uv, vt, inv_vt, k11);
         T xc, yc, pc, ps, pox, poy;
         ld4(K.pose[b], pc, ps, pox, poy);
-        rot2(pc, ps, m.sph_loc[s][0], m.sph_loc[s][1], xc, yc);
+        rot2(pc, ps, lx, ly, xc, yc);
         xc += pox; yc += poy;
-        const T zc = m.sph_loc[s][2] + m.body_z[b];
-        const T rad = m.sph_radius[s];
         const T depth = rad - (yc + E.O[1]);
         T Fx = T(0), Fy = T(0), D0 = T(0), D1 = T(0);
         const T py = T(-0.5) * depth - E.O[1];
@@ -484,20 +491,18 @@ BIO_DEV void p2_phase_d(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
             ld4(K.V[b], bw, bvx, bvy, b3);
             const T vx = bvx - bw * py, vy = bvy + bw * xc;
             const T vn = -vy;
-            const T kk = m.sph_k[s];
             const T fH = T(4.0 / 3.0) * kk * depth * Num<T>::sqrt_pos(rad * kk * depth);
-            const T f = fH * (T(1) + T(1.5) * m.sph_c[s] * vn);
+            const T f = fH * (T(1) + c15 * vn);
             if (f > T(0)) {
                 Fy = f;
                 const T vs = Num<T>::abs(vx);
-                const T vrel = Num<T>::div(vs, m.sph_vt[s]);
-                const T strib = m.sph_ud[s] + Num<T>::div(T(2) * (m.sph_us[s] - m.sph_ud[s]), T(1) + vrel * vrel);
-                if (vs != T(0)) {
-                    const T ff = f * ((vrel < T(1) ? vrel : T(1)) * strib + m.sph_uv[s] * vs);
-                    Fx = -Num<T>::div(ff * vx, vs);
-                }
-                D0 = f * (Num<T>::rcp(vrel < T(1) ? m.sph_vt[s] : vs) * strib + m.sph_uv[s]);
-                D1 = T(1.5) * m.sph_c[s] * fH;
+                const T vrel = vs * inv_vt;
+                const T strib = ud + Num<T>::div(us2, T(1) + vrel * vrel);
+                // friction opposes the slip: -ff * vx / |vx|
+                const T ff = f * ((vrel < T(1) ? vrel : T(1)) * strib + uv * vs);
+                Fx = vx > T(0) ? -ff : (vx < T(0) ? ff : T(0));
+                D0 = f * ((vrel < T(1) ? inv_vt : Num<T>::rcp(vs)) * strib + uv);
+                D1 = c15 * fH;
             }
         }
         E.sphx[s][0] = xc; E.sphx[s][1] = py; E.sphx[s][2] = zc;
@@ -510,12 +515,15 @@ BIO_DEV void p2_phase_d(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         K.sphI[s][4] = d1;
     } else if (lane - m.n_spheres < m.n_limits) {
         const int l = lane - m.n_spheres, d = m.lim_dof[l];
-        const T w = m.lim_w[l], qq = E.q[d];
-        const T sup = step5(Num<T>::div(qq - m.lim_qup[l], w));
-        const T slo = T(1) - step5(Num<T>::div(qq - (m.lim_qlo[l] - w), w));
-        E.limf[l] = -m.lim_kup[l] * sup * (qq - m.lim_qup[l]) + m.lim_klo[l] * slo * (m.lim_qlo[l] - qq) -
-                    m.lim_damp[l] * (sup + slo) * E.u[d];
-        E.limD[l] = m.lim_damp[l] * (sup + slo);
+        // per-limit constants: two 16-byte reads (PlanarProg::lim_k)
+        T qup, qlo, kup, klo, damp, inv_w, w, k7;
+        ld4(pr.lim_k[l], qup, qlo, kup, klo);
+        ld4(pr.lim_k[l] + 4, damp, inv_w, w, k7);
+        const T qq = E.q[d];
+        const T sup = step5((qq - qup) * inv_w);
+        const T slo = T(1) - step5((qq - (qlo - w)) * inv_w);
+        E.limf[l] = -kup * sup * (qq - qup) + klo * slo * (qlo - qq) - damp * (sup + slo) * E.u[d];
+        E.limD[l] = damp * (sup + slo);
     }
 }
 

@@ -81,6 +81,13 @@ struct alignas(16) PlanarProg {
     int32_t mc_cond[BIO_MAX_MUSCLES][2];       // conditional points of the muscle (-1: none)
     uint32_t mc_seg[BIO_MAX_MUSCLES][P2_MAXVAR][P2_MAXLIVE];
     T mc_len0[BIO_MAX_MUSCLES][P2_MAXVAR];
+    // per-lane constants of phases C and D packed for 16-byte reads, reciprocals taken on the host:
+    //   mus_k[i]: fiso, lopt, 1/lopt, height^2 | beta, amin, lm_min, 1/lts | vmax*lopt, 1/tact, 1/tdeact, 0
+    //   sph_k[s]: loc x, loc y, z in ground axes, radius | k, 1.5 c, ud, 2 (us - ud) | uv, vt, 1/vt, 0
+    //   lim_k[l]: qup, qlo, kup, klo | damping, 1/w, w, 0
+    alignas(16) T mus_k[BIO_MAX_MUSCLES][12];
+    alignas(16) T sph_k[BIO_MAX_SPHERES][12];
+    alignas(16) T lim_k[BIO_MAX_LIMITS][8];
     // generalized-force inputs per dof
     int8_t dof_lim[BIO_MAX_DOF][2], dof_mov[BIO_MAX_DOF][2], dof_act[BIO_MAX_DOF];
     // wrench sources acting on every body
@@ -745,6 +752,22 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     }
     pr.mus_src0[s.n_muscles] = n_src;
     compile_paths(s, pr);
+    for (int i = 0; i < s.n_muscles; i++) {
+        const double k12[12] = {s.mus_fiso[i], s.mus_lopt[i], 1.0 / s.mus_lopt[i], s.mus_height[i] * s.mus_height[i],
+                                s.mus_beta[i], s.mus_amin[i], s.mus_lm_min[i], 1.0 / s.mus_lts[i],
+                                s.mus_vmax[i] * s.mus_lopt[i], 1.0 / s.mus_tact[i], 1.0 / s.mus_tdeact[i], 0.0};
+        for (int c = 0; c < 12; c++) pr.mus_k[i][c] = (T)k12[c];
+    }
+    for (int sp = 0; sp < s.n_spheres; sp++) {
+        const double k12[12] = {s.sph_loc[sp][0], s.sph_loc[sp][1], s.sph_loc[sp][2] + (double)d.body_z[s.sph_body[sp]], s.sph_radius[sp],
+                                s.sph_k[sp], 1.5 * s.sph_c[sp], s.sph_ud[sp], 2.0 * (s.sph_us[sp] - s.sph_ud[sp]),
+                                s.sph_uv[sp], s.sph_vt[sp], 1.0 / s.sph_vt[sp], 0.0};
+        for (int c = 0; c < 12; c++) pr.sph_k[sp][c] = (T)k12[c];
+    }
+    for (int l = 0; l < s.n_limits; l++) {
+        const double k8[8] = {s.lim_qup[l], s.lim_qlo[l], s.lim_kup[l], s.lim_klo[l], s.lim_damp[l], 1.0 / s.lim_w[l], s.lim_w[l], 0.0};
+        for (int c = 0; c < 8; c++) pr.lim_k[l][c] = (T)k8[c];
+    }
     pr.sph_src0 = n_src;
     for (int sp = 0; sp < s.n_spheres; sp++) { if (n_src >= P2_MAXSRC) return; src_body[n_src++] = s.sph_body[sp]; }
     pr.n_src = n_src;
