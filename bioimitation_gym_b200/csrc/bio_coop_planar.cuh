@@ -545,13 +545,13 @@ BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
             ld4(E.x.src.w[pr.inc_src[k]], s0, s1, s2, s3);
             Wn += s0; Wx += s1; Wy += s2;
         }
-        T c, s, ox, oy, cx, cy;
+        T c, s, ox, oy, cx, cy, comx, comy, mb, izz;
         ld4(K.pose[b], c, s, ox, oy);
-        rot2(c, s, m.body_com[b][0], m.body_com[b][1], cx, cy);
+        ld4(pr.body_k[b], comx, comy, mb, izz);
+        rot2(c, s, comx, comy, cx, cy);
         cx += ox; cy += oy;
-        const T mb = m.body_mass[b];
         const T hx = mb * cx, hy = mb * cy;
-        T Iww = m.body_inertia[b][2] + mb * (cx * cx + cy * cy), Iwx = -hy, Iwy = hx, Ixx = mb, Iyy = mb;
+        T Iww = izz + mb * (cx * cx + cy * cy), Iwx = -hy, Iwy = hx, Ixx = mb, Iyy = mb;
         T w, vx, vy, aw, ax, ay, pad3;
         ld4(K.V[b], w, vx, vy, pad3);
         ld4(K.A[b], aw, ax, ay, pad3);
@@ -609,12 +609,14 @@ BIO_DEV void p2_phase_f(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     const PlanarProg<T>& pr = m.prog;
     auto& K = E.k.p;
     if (lane >= pr.n_branches) return;
-    const int l = lane, nb = pr.br_nb[l];
+    const int l = lane;
+    const int4 bb = *reinterpret_cast<const int4*>(pr.br_i8[l]), dd = *reinterpret_cast<const int4*>(pr.br_i8[l] + 4);
+    const int bk[3] = {bb.x, bb.y, bb.z}, dk[3] = {dd.x, dd.y, dd.z};
     T Ia[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, pa[3] = {T(0), T(0), T(0)};
 #pragma unroll
     for (int k = P2_MAXCB - 1; k >= 0; k--) {
-        const int b = k < nb ? pr.br_body[l][k] : -1;
-        const int d = k < nb ? pr.br_dof[l][k] : -1;
+        const int b = bk[k];
+        const int d = dk[k];
         if (b >= 0) {
             T v0, v1, v2, v3, v4, v5, v6, v7;
             ld4(K.bI[b], v0, v1, v2, v3);
@@ -650,10 +652,12 @@ BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     auto& K = E.k.p;
     const int nbr = pr.n_branches > 0 ? pr.n_branches : 1;
     if (lane >= nbr) return;
+    const int4 ri = *reinterpret_cast<const int4*>(pr.root_i4);
+    const int rdof[3] = {ri.x, ri.y, ri.z};
     T a[9];
-    ld4(K.bI[pr.root_body], a[0], a[1], a[2], a[3]);
-    ld4(K.bI[pr.root_body] + 4, a[4], a[5], a[6], a[7]);
-    a[8] = K.bI[pr.root_body][8];
+    ld4(K.bI[ri.w], a[0], a[1], a[2], a[3]);
+    ld4(K.bI[ri.w] + 4, a[4], a[5], a[6], a[7]);
+    a[8] = K.bI[ri.w][8];
 #pragma unroll
     for (int l = 0; l < P2_MAXBR; l++) {
         if (l < pr.n_branches) {
@@ -668,8 +672,8 @@ BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     T Sr[3][3], IS[3][3], H[3][3], rhs[3];
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        const bool has = r < pr.root_ndof;
-        const int d = has ? pr.root_dof[r] : 0;
+        const bool has = rdof[r] >= 0;
+        const int d = has ? rdof[r] : 0;
         T s3;
         ld4(K.S[d], Sr[r][0], Sr[r][1], Sr[r][2], s3);
         if (!has) Sr[r][0] = Sr[r][1] = Sr[r][2] = T(0);
@@ -679,8 +683,8 @@ BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     }
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        const bool has = r < pr.root_ndof;
-        const int d = has ? pr.root_dof[r] : 0;
+        const bool has = rdof[r] >= 0;
+        const int d = has ? rdof[r] : 0;
 #pragma unroll
         for (int c = 0; c <= r; c++) H[r][c] = Sr[c][0] * IS[r][0] + Sr[c][1] * IS[r][1] + Sr[c][2] * IS[r][2];
         H[r][r] += has ? K.Ld[d] : T(1);         // no dof: identity row, zero right-hand side
@@ -699,16 +703,18 @@ BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     ar[0] = rhs[0] * i0 - l10 * ar[1] - l20 * ar[2];
     if (lane == 0) {
 #pragma unroll
-        for (int r = 0; r < 3; r++) if (r < pr.root_ndof) E.udot[pr.root_dof[r]] = ar[r];
+        for (int r = 0; r < 3; r++) if (rdof[r] >= 0) E.udot[rdof[r]] = ar[r];
     }
     if (lane < pr.n_branches) {
         // acceleration of the parent body beyond its bias term
         T a0 = Sr[0][0] * ar[0] + Sr[1][0] * ar[1] + Sr[2][0] * ar[2];
         T a1 = Sr[0][1] * ar[0] + Sr[1][1] * ar[1] + Sr[2][1] * ar[2];
         T a2 = Sr[0][2] * ar[0] + Sr[1][2] * ar[1] + Sr[2][2] * ar[2];
+        const int4 dd = *reinterpret_cast<const int4*>(pr.br_i8[lane] + 4);
+        const int dk[3] = {dd.x, dd.y, dd.z};
 #pragma unroll
         for (int k = 0; k < P2_MAXCB; k++) {
-            const int d = k < pr.br_nb[lane] ? pr.br_dof[lane][k] : -1;
+            const int d = dk[k];
             if (d >= 0) {
                 T W0, W1, W2, ud, S0, S1, S2, s3;
                 ld4(K.brk[lane] + 4 * k, W0, W1, W2, ud);

@@ -85,6 +85,11 @@ struct alignas(16) PlanarProg {
     //   mus_k[i]: fiso, lopt, 1/lopt, height^2 | beta, amin, lm_min, 1/lts | vmax*lopt, 1/tact, 1/tdeact, 0
     //   sph_k[s]: loc x, loc y, z in ground axes, radius | k, 1.5 c, ud, 2 (us - ud) | uv, vt, 1/vt, 0
     //   lim_k[l]: qup, qlo, kup, klo | damping, 1/w, w, 0
+    // chain / root index lists packed for 16-byte reads: br_i8[l] = body of the chain's k-th body (-1: none) x 3, nb |
+    // its dof (-1: none) x 3, 0;  root_i4 = the root's dofs (-1: none) x 3, root body
+    alignas(16) T body_k[BIO_MAX_BODIES][4];   // centre of mass x, y (body frame), mass, inertia about z
+    alignas(16) int32_t br_i8[P2_MAXBR][8];
+    alignas(16) int32_t root_i4[4];
     alignas(16) T mus_k[BIO_MAX_MUSCLES][12];
     alignas(16) T sph_k[BIO_MAX_SPHERES][12];
     alignas(16) T lim_k[BIO_MAX_LIMITS][8];
@@ -752,6 +757,22 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     }
     pr.mus_src0[s.n_muscles] = n_src;
     compile_paths(s, pr);
+    for (int b = 0; b < s.n_bodies; b++) {
+        pr.body_k[b][0] = (T)s.body_com[b][0]; pr.body_k[b][1] = (T)s.body_com[b][1];
+        pr.body_k[b][2] = (T)s.body_mass[b]; pr.body_k[b][3] = (T)s.body_inertia[b][2];
+    }
+    static_assert(P2_MAXCB == 3, "br_i8 packs three bodies per chain");
+    for (int l = 0; l < P2_MAXBR; l++) {
+        for (int k = 0; k < 3; k++) {
+            const bool has = l < pr.n_branches && k < pr.br_nb[l];
+            pr.br_i8[l][k] = has ? pr.br_body[l][k] : -1;
+            pr.br_i8[l][4 + k] = has ? pr.br_dof[l][k] : -1;
+        }
+        pr.br_i8[l][3] = l < pr.n_branches ? pr.br_nb[l] : 0;
+        pr.br_i8[l][7] = 0;
+    }
+    for (int r = 0; r < 3; r++) pr.root_i4[r] = r < pr.root_ndof ? pr.root_dof[r] : -1;
+    pr.root_i4[3] = pr.root_body;
     for (int i = 0; i < s.n_muscles; i++) {
         const double k12[12] = {s.mus_fiso[i], s.mus_lopt[i], 1.0 / s.mus_lopt[i], s.mus_height[i] * s.mus_height[i],
                                 s.mus_beta[i], s.mus_amin[i], s.mus_lm_min[i], 1.0 / s.mus_lts[i],
