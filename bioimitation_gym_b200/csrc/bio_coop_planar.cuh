@@ -539,11 +539,25 @@ BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     if (lane < m.n_bodies) {
         const int b = lane;
         T Wn = T(0), Wx = T(0), Wy = T(0);
+        if (pr.inc8_ok) {
+            // source indices of the body in 8 bytes: the (<= 8) loads below are issued together
+            const uint32_t p0 = pr.inc_pk[b][0], p1 = pr.inc_pk[b][1];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const unsigned e = ((k < 4 ? p0 : p1) >> (8 * (k & 3))) & 255u;
+                if (e != 255u) {
+                    T s0, s1, s2, s3;
+                    ld4(E.x.src.w[e], s0, s1, s2, s3);
+                    Wn += s0; Wx += s1; Wy += s2;
+                }
+            }
+        } else {
 #pragma unroll 4
-        for (int k = pr.inc_begin[b]; k < pr.inc_begin[b + 1]; k++) {
-            T s0, s1, s2, s3;
-            ld4(E.x.src.w[pr.inc_src[k]], s0, s1, s2, s3);
-            Wn += s0; Wx += s1; Wy += s2;
+            for (int k = pr.inc_begin[b]; k < pr.inc_begin[b + 1]; k++) {
+                T s0, s1, s2, s3;
+                ld4(E.x.src.w[pr.inc_src[k]], s0, s1, s2, s3);
+                Wn += s0; Wx += s1; Wy += s2;
+            }
         }
         T c, s, ox, oy, cx, cy, comx, comy, mb, izz;
         ld4(K.pose[b], c, s, ox, oy);
@@ -569,13 +583,26 @@ BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         const T ffx = IAx - w * py - Wx;
         o[8] = IAy + w * px - Wy;
         if (h_imp > T(0)) {
-            int mask = pr.body_sph_mask[b];
-            while (mask) {                       // zero for a sphere out of contact
-                const int sp = lowest_bit(mask);
-                mask &= mask - 1;
-                T a0, a1, a2, a3;
-                ld4(K.sphI[sp], a0, a1, a2, a3);
-                Iww += a0; Iwx += a1; Iwy += a2; Ixx += a3; Iyy += K.sphI[sp][4];
+            if (pr.inc8_ok) {                    // spheres of the body in 4 bytes (zero terms for a sphere out of contact)
+                const uint32_t sp4 = pr.sph_pk[b];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned sp = (sp4 >> (8 * k)) & 255u;
+                    if (sp != 255u) {
+                        T a0, a1, a2, a3;
+                        ld4(K.sphI[sp], a0, a1, a2, a3);
+                        Iww += a0; Iwx += a1; Iwy += a2; Ixx += a3; Iyy += K.sphI[sp][4];
+                    }
+                }
+            } else {
+                int mask = pr.body_sph_mask[b];
+                while (mask) {
+                    const int sp = lowest_bit(mask);
+                    mask &= mask - 1;
+                    T a0, a1, a2, a3;
+                    ld4(K.sphI[sp], a0, a1, a2, a3);
+                    Iww += a0; Iwx += a1; Iwy += a2; Ixx += a3; Iyy += K.sphI[sp][4];
+                }
             }
         }
         st4(o, Iww, Iwx, Iwy, Ixx);

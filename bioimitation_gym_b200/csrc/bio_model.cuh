@@ -88,6 +88,11 @@ struct alignas(16) PlanarProg {
     // chain / root index lists packed for 16-byte reads: br_i8[l] = body of the chain's k-th body (-1: none) x 3, nb |
     // its dof (-1: none) x 3, 0;  root_i4 = the root's dofs (-1: none) x 3, root body
     alignas(16) T body_k[BIO_MAX_BODIES][4];   // centre of mass x, y (body frame), mass, inertia about z
+    // wrench sources (8 bytes: up to 8 source indices, 255 = none) and contact spheres (4 bytes, 255 = none) of every
+    // body, so that phase E issues all its loads at once; inc8_ok = 0: a body has more, walk inc_src / body_sph_mask
+    alignas(8) uint32_t inc_pk[BIO_MAX_BODIES][2];
+    uint32_t sph_pk[BIO_MAX_BODIES];
+    int32_t inc8_ok, inc8_pad_[3];
     alignas(16) int32_t br_i8[P2_MAXBR][8];
     alignas(16) int32_t root_i4[4];
     alignas(16) T mus_k[BIO_MAX_MUSCLES][12];
@@ -818,6 +823,21 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
             if (pr.dof_act[dd] >= 0) return;
             pr.dof_act[dd] = (int8_t)a;
         }
+    pr.inc8_ok = 1;
+    for (int b = 0; b < s.n_bodies; b++) {
+        unsigned char src8[8], sp4[4];
+        memset(src8, 255, sizeof(src8)); memset(sp4, 255, sizeof(sp4));
+        const int cnt = pr.inc_begin[b + 1] - pr.inc_begin[b];
+        if (cnt > 8) pr.inc8_ok = 0;
+        for (int k = 0; k < cnt && k < 8; k++) src8[k] = pr.inc_src[pr.inc_begin[b] + k];
+        int ns = 0;
+        for (int sp = 0; sp < s.n_spheres; sp++)
+            if (s.sph_body[sp] == b) { if (ns < 4) sp4[ns] = (unsigned char)sp; ns++; }
+        if (ns > 4) pr.inc8_ok = 0;
+        pr.inc_pk[b][0] = src8[0] | (src8[1] << 8) | (src8[2] << 16) | ((uint32_t)src8[3] << 24);
+        pr.inc_pk[b][1] = src8[4] | (src8[5] << 8) | (src8[6] << 16) | ((uint32_t)src8[7] << 24);
+        pr.sph_pk[b] = sp4[0] | (sp4[1] << 8) | (sp4[2] << 16) | ((uint32_t)sp4[3] << 24);
+    }
     pr.ok = 1;
 }
 
