@@ -950,11 +950,21 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     const int na = m.n_act, nd = m.n_dof, nm = m.n_muscles, Hh = c.horizon;
     const bool isd = lane < nd, ism = lane < nm, isa = lane < na;
 
-    if (isd) { E.q[lane] = st.q[(size_t)lane * n + ii]; E.u[lane] = st.u[(size_t)lane * n + ii]; }
-    if (ism) { E.act[lane] = st.act[(size_t)lane * n + ii]; E.lm[lane] = st.lm[(size_t)lane * n + ii]; }
+    // every global load of the step's inputs is issued here, before anything waits on one of them: state,
+    // bookkeeping, the action and the action history (one memory round trip; the L2 is cold in the benchmark)
+    const T q_in = isd ? st.q[(size_t)lane * n + ii] : T(0), u_in = isd ? st.u[(size_t)lane * n + ii] : T(0);
+    const T act_in = ism ? st.act[(size_t)lane * n + ii] : T(0), lm_in = ism ? st.lm[(size_t)lane * n + ii] : T(0);
+    const T action_in = isa ? actions[(size_t)ii * na + lane] : T(0);
+    const T last_in = isa ? st.last_action[(size_t)lane * n + ii] : T(0);
+    T hv[BIO_MAX_HORIZON];
+#pragma unroll
+    for (int hh = 0; hh < BIO_MAX_HORIZON; hh++)
+        hv[hh] = (isa && hh < Hh) ? st.history[((size_t)hh * na + lane) * n + ii] : T(0);
     int istep = st.istep[ii];
     int hist_pos = st.hist_pos[ii];
     const bool first = st.first[ii] != 0;
+    if (isd) { E.q[lane] = q_in; E.u[lane] = u_in; }
+    if (ism) { E.act[lane] = act_in; E.lm[lane] = lm_in; }
     if (lane == 0) {   // bookkeeping read after the last evaluation: into L2 now
         asm volatile("prefetch.global.L2 [%0];" ::"l"(st.old_px + ii));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(st.ep_return + ii));
@@ -963,7 +973,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     }
 
     // ---- action pre-processing: lane = actuator ----
-    T action = isa ? actions[(size_t)ii * na + lane] : T(0);
+    T action = action_in;
     const bool lane_nan = action != action;
     const unsigned gmask = group_mask<G>();
     const bool nan = group_ballot<G>(lane_nan) != 0u;
@@ -983,13 +993,12 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     T last_action = T(0), curr = T(0);
     if (first) hist_pos = 0;
     if (isa) {
-        // the loads of the action history (and of the previous mean action) are issued together: one memory
-        // round trip instead of one per entry
-        T hv[BIO_MAX_HORIZON];
+        // the first step of an episode fills the history with its action
+        if (first) {
 #pragma unroll
-        for (int hh = 0; hh < BIO_MAX_HORIZON; hh++)
-            hv[hh] = (hh < Hh && !first) ? st.history[((size_t)hh * na + lane) * n + ii] : action;
-        last_action = first ? action : st.last_action[(size_t)lane * n + ii];
+            for (int hh = 0; hh < BIO_MAX_HORIZON; hh++) hv[hh] = action;
+        }
+        last_action = first ? action : last_in;
         T sum = T(0);
 #pragma unroll
         for (int hh = 0; hh < BIO_MAX_HORIZON; hh++) {
