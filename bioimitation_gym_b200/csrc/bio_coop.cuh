@@ -93,7 +93,10 @@ struct alignas(16) EnvWorkBody : WorkUnions<T, CLS> {
     T sphx[BIO_MAX_SPHERES][3], sphF[BIO_MAX_SPHERES][3], sphD[BIO_MAX_SPHERES][2];
     T limf[BIO_MAX_LIMITS], limD[BIO_MAX_LIMITS];
     T udot[C::ND], adot[C::NM], lmdot[C::NM];
-    T ffib[C::NM], fact[C::NM];
+    // fibre forces of the full evaluation (the last one of a step); during the substeps the same storage holds the
+    // last change of the Newton root and the number of solves of this step (planar program, reset at step start)
+    union { T ffib[C::NM]; T vnd[C::NM]; };
+    union { T fact[C::NM]; T vna[C::NM]; };
     T vn[C::NM];                                           // Newton warm start: last normalised fibre velocity
     T ctrl[C::NM];
     T com_pos[3], com_vel[3];
@@ -1011,7 +1014,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
         E.ctrl[lane] = clampv(c.feed_mean_action ? curr : action, m.act_min[lane], m.act_max[lane]);
     }
     hist_pos = (hist_pos + 1) % Hh;
-    if (ism) E.vn[lane] = T(0);   // every control step starts its Newton solves from 0 (results do not depend on history)
+    if (ism) { E.vn[lane] = T(0); E.vna[lane] = T(0); }   // every control step starts its Newton solves from 0 (results do not depend on history)
     for (int t = lane; t < P2_MAXTASK; t += G) E.knot_hint[t] = 0;   // spline search hints (any start gives the same interval)
     gsync<G>();
 
@@ -1172,7 +1175,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
             }
             if (ism) { E.act[lane] = m.mus_default_act[lane]; E.lm[lane] = c.ref_lm0[(size_t)idx * nm + lane]; }
             if (isa) E.ctrl[lane] = T(0);
-            if (ism) E.vn[lane] = T(0);
+            if (ism) { E.vn[lane] = T(0); E.vna[lane] = T(0); }
             istep = idx;
             first_next = 1;
             ep_return = T(0);

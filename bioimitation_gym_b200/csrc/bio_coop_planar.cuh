@@ -442,7 +442,12 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     // evaluation of this step.  The residual is increasing in vn, convex for vn < 0 and concave for
     // vn > 0, so Newton converges monotonically from 0 and from any point between 0 and the root;
     // an iterate that would cross 0 is put on 0, which makes the iteration globally convergent.
-    T vn = E.vn[i];
+    // ... From the third solve of a control step on the start is extrapolated from the last two roots (the state
+    // moves 0.5 ms per substep): the first correction then is usually below the stop criterion.  A start beyond the
+    // root lands between 0 and the root after one step (tangent of a concave / convex branch), so the
+    // iteration stays globally convergent.
+    const T vlast = E.vn[i], age = E.vna[i];
+    T vn = vlast + (age >= T(2) ? E.vnd[i] : T(0));
     for (int it = 0; it < newton_iters; it++) {
         curve_eval(m, 1, vn, fv, dfv);
         const T err = (afal * fv + fpe + beta * vn) * cosa - ft;
@@ -454,6 +459,8 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         if (!crossed && Num<T>::abs(delta) < Num<T>::newton_tol()) break;
     }
     E.vn[i] = vn;
+    E.vnd[i] = vn - vlast;
+    E.vna[i] = age + T(1);
     if (lmi <= lmin && vn < T(0)) vn = T(0);
     E.lmdot[i] = vn * vmax_lopt;
     // activation ODE: adot = (e - a) / tau, tau = tact (0.5 + 1.5 a) rising, tdeact / (0.5 + 1.5 a) falling
