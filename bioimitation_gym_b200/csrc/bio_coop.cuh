@@ -402,7 +402,9 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         // evaluation of this step.  The residual is increasing in vn, convex for vn < 0 and concave
         // for vn > 0, so Newton converges monotonically from 0 and from any point between 0 and the
         // root; an iterate that would cross 0 is put on 0 (globally convergent).
-        T vn = E.vn[i];
+        // (start: extrapolated from the last two roots of this control step, see p2_phase_c)
+        const T vlast = E.vn[i], age = E.vna[i];
+        T vn = vlast + (age >= T(2) ? E.vnd[i] : T(0));
         for (int it = 0; it < newton_iters; it++) {
             curve_eval(m, 1, vn, fv, dfv);
             const T err = (afal * fv + fpe + beta * vn) * cosa - ft;
@@ -414,6 +416,8 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             if (!crossed && Num<T>::abs(delta) < Num<T>::newton_tol()) break;
         }
         E.vn[i] = vn;
+        E.vnd[i] = vn - vlast;
+        E.vna[i] = age + T(1);
         if (lmi <= lmin && vn < T(0)) vn = T(0);
         E.lmdot[i] = vn * m.mus_vmax[i] * lopt;
         const T ec = clampv(E.ctrl[i], amin, T(1));
