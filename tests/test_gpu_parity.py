@@ -315,7 +315,7 @@ def test_host_entry_point_with_page_locked_buffers_matches_device_path():
     """Page-locked host buffers are read / written by the kernel in place (no staging copies): same results
     as the device path, with a mix of pinned and pageable buffers falling back to the staged copies."""
     import torch
-    n = 300                                    # odd tail: the last warp holds one env
+    n = 301                                    # odd tail: the last warp holds one env
     env, _ = _mk("MuscleWalkingImitation2D-v0", n, "float32")
     env2, _ = _mk("MuscleWalkingImitation2D-v0", n, "float32")
     env3, _ = _mk("MuscleWalkingImitation2D-v0", n, "float32")
