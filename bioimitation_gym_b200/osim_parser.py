@@ -313,7 +313,13 @@ def parse_osim(path: str) -> Dict[str, Any]:
             contact_spheres.append(d)
         elif g.tag == "ContactHalfSpace":
             half_spaces.append(d)
+    # MarkerSet (what calc_markers_info reads, reference opensim_wrapper.py:261-282): name, body, location
+    markers = []
+    ms = model.find("MarkerSet/objects")
+    for mk in (ms.findall("Marker") if ms is not None else []):
+        body = _strip_path(_text(mk, "socket_parent_frame")) if v4 else _text(mk, "body")
+        markers.append(dict(name=mk.get("name"), body=body, loc=_floats(_text(mk, "location", "0 0 0"))))
     raw.update(muscles=muscles, contact_spheres=contact_spheres,
                contact_half_spaces=half_spaces, contact_forces=contact_forces,
-               limit_forces=limit_forces, actuators=actuators)
+               limit_forces=limit_forces, actuators=actuators, markers=markers)
     return raw
