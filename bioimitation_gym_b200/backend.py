@@ -43,7 +43,14 @@ C_API = {
     "bio_get_state": (ctypes.c_int, [ctypes.c_void_p] * 3),
     "bio_set_state": (ctypes.c_int, [ctypes.c_void_p] * 3),
     "bio_eval_debug": (ctypes.c_int, [ctypes.c_void_p] * 4),
+    "bio_set_step_extra": (ctypes.c_int, [ctypes.c_void_p] * 2),
+    "bio_set_host_stream": (ctypes.c_int, [ctypes.c_void_p] * 2),
+    "bio_id_apply": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32] + [ctypes.c_void_p] * 5),
+    "bio_id_multiply_m": (ctypes.c_int, [ctypes.c_void_p] * 4),
+    "bio_id_multiply_minv": (ctypes.c_int, [ctypes.c_void_p] * 4),
+    "bio_id_residual": (ctypes.c_int, [ctypes.c_void_p] * 5),
     "bio_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
+    "bio_kernel_shape": (ctypes.c_int, [ctypes.c_void_p] * 4),
     "bio_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "bio_obs_dim": (ctypes.c_int32, [ctypes.c_void_p]),
     "bio_n_act": (ctypes.c_int32, [ctypes.c_void_p]),
@@ -259,10 +266,58 @@ class VecEnv:
                "bio_eval_debug")
         return out
 
+    def enable_step_extra(self, *names):
+        """Attach extra per-step outputs of the step kernel (BioStepExtra in the header): any of
+        `terminal_obs`, `done_reason` (what a replay buffer needs from an auto-resetting batch) and the
+        dynamics read-outs `udot`, `tendon_force`, `fiber_force`, `fiber_vel`, `contact`, `limit_force` of the
+        end-of-step evaluation.  Returns the dict of env-owned tensors the following steps fill; no names:
+        detach."""
+        torch = self.torch
+        N, nd, nm = self.num_envs, self.n_dof, self.n_muscles
+        mk = lambda *s: torch.zeros(s, dtype=self.dtype, device=self.device)
+        shapes = dict(terminal_obs=(N, self.obs_dim), udot=(N, nd), tendon_force=(N, nm), fiber_force=(N, nm),
+                      fiber_vel=(N, nm), contact=(N, 2, 6), limit_force=(N, self.cm.tables.n_limits))
+        out = {}
+        p = ct.BioStepExtra()
+        for k in names:
+            if k == "done_reason":
+                out[k] = torch.zeros(N, dtype=torch.int32, device=self.device)
+            elif k in shapes:
+                out[k] = mk(*shapes[k])
+            else:
+                raise KeyError("unknown step output %r" % k)
+            if out[k].numel():
+                setattr(p, k, out[k].data_ptr())
+        self.extra = out
+        _check(self.lib, self.lib.bio_set_step_extra(self.handle, ctypes.addressof(p) if names else None),
+               "bio_set_step_extra")
+        return out
+
+    def id_apply(self, op: str, x, controls=None, shift=None):
+        """Inverse-dynamics operator set at the current state (bio_id_apply): op in 'multiply_m',
+        'multiply_minv', 'residual', 'solve_shifted'; x [N, n_dof] -> [N, n_dof]."""
+        torch = self.torch
+        code = ct.MACROS["BIO_ID_" + op.upper()]
+        prep = lambda t: None if t is None else t.to(device=self.device, dtype=self.dtype).contiguous()
+        xx, cc, ss = prep(x), prep(controls), prep(shift)
+        if tuple(xx.shape) != (self.num_envs, self.n_dof):
+            raise ValueError("x must have shape (%d, %d)" % (self.num_envs, self.n_dof))
+        out = torch.empty_like(xx)
+        _check(self.lib, self.lib.bio_id_apply(self.handle, code, _ptr(xx), _ptr(cc), _ptr(ss), _ptr(out),
+                                               self._stream()), "bio_id_apply")
+        return out
+
     def stats(self, reset: bool = False):
         """Device tensor of 16 float64 rollout statistics (see bio_stats in the header)."""
         _check(self.lib, self.lib.bio_stats(self.handle, _ptr(self._stats), int(reset), self._stream()), "bio_stats")
         return self._stats
+
+    def coop_shape(self):
+        """(size class, threads per CTA, resident CTAs per SM) of the step kernel (bio_kernel_shape)."""
+        c, t, k = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        _check(self.lib, self.lib.bio_kernel_shape(self.handle, ctypes.byref(c), ctypes.byref(t), ctypes.byref(k)),
+               "bio_kernel_shape")
+        return c.value, t.value, k.value
 
     @property
     def launch_count(self) -> int:

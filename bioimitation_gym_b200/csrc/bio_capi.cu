@@ -54,6 +54,9 @@ struct HandleBase {
     // page-locked host buffers are read (actions) and written (obs, reward, done, terms) by the kernel in
     // place; BIO_HOST_ZEROCOPY=1: actions only, 0: staged copies for everything
     int host_zero_copy = 2;
+    // stream of the *_host entry points (bio_set_host_stream; default: the legacy stream, which orders
+    // itself against every blocking stream)
+    cudaStream_t host_stream = nullptr;
     virtual ~HandleBase() {}
 };
 
@@ -180,7 +183,10 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
             return cost_hi < cost_lo ? hi : lo;
         };
         // class 0 (half-warp per env) runs the planar program only
-        if (want_coop && prog_ok && prog_src <= P2_MAXSRC && fits(C0::G, C0::ND, C0::NM, C0::NP, C0::NAX)) {
+        // (the cooperative kernels write the observation row from a 256-slot descriptor table)
+        if (task->obs_dim > BIO_COOP_MAX_OBS_DIM) {
+            h->coop_cls = -1;
+        } else if (want_coop && prog_ok && prog_src <= P2_MAXSRC && fits(C0::G, C0::ND, C0::NM, C0::NP, C0::NAX)) {
             h->coop_cls = 0;
             h->coop_threads = pick_threads(C0::G);
             h->coop_smem = base + (h->coop_threads / C0::G) * sizeof(bio::EnvWork<T, 0>);
@@ -365,9 +371,33 @@ int eval_impl(Handle<T>* h, const void* controls, const BioDebugPtrs* o, cudaStr
 }
 
 template <typename T>
+int id_impl(Handle<T>* h, int op, const void* x, const void* controls, const void* shift, void* out, cudaStream_t s) {
+    const int grid = (h->n + h->block - 1) / h->block;
+    bio::launch_id<T>(grid, h->block, h->smem, s, h->d_model, h->task_d, h->st, h->n, h->seed, h->env_offset, op,
+                      (const T*)x, (const T*)controls, (const T*)shift, (T*)out);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int extra_impl(Handle<T>* h, const BioStepExtra* e) {
+    bio::StepExtra<T>& x = h->task_d.ex;
+    memset(&x, 0, sizeof(x));
+    if (!e) return 0;
+    x.terminal_obs = (T*)e->terminal_obs; x.done_reason = e->done_reason; x.udot = (T*)e->udot;
+    x.tendon_force = (T*)e->tendon_force; x.fiber_force = (T*)e->fiber_force; x.fiber_vel = (T*)e->fiber_vel;
+    x.contact = (T*)e->contact; x.limit_force = (T*)e->limit_force;
+    x.any = (e->terminal_obs || e->done_reason || e->udot || e->tendon_force || e->fiber_force || e->fiber_vel ||
+             e->contact || e->limit_force) ? 1 : 0;
+    return 0;
+}
+
+template <typename T>
 int step_host_impl(Handle<T>* h, const void* actions, void* obs, void* reward, uint8_t* done, void* terms) {
     const size_t N = h->n;
     const int na = h->model.n_act, od = h->task.obs_dim, nt = h->task.n_reward_terms;
+    cudaStream_t hs = h->host_stream;
     // actions in page-locked host memory are read by the kernel in place (one 56..88-byte row per env over
     // PCIe instead of a staged copy and its launch); pageable memory goes through the staging buffer
     const void* a_dev = nullptr;
@@ -379,7 +409,7 @@ int step_host_impl(Handle<T>* h, const void* actions, void* obs, void* reward, u
             cudaGetLastError();
     }
     if (!a_dev) {
-        CU(cudaMemcpyAsync(h->h_actions, actions, N * na * sizeof(T), cudaMemcpyHostToDevice, 0));
+        CU(cudaMemcpyAsync(h->h_actions, actions, N * na * sizeof(T), cudaMemcpyHostToDevice, hs));
         a_dev = h->h_actions;
     }
     // page-locked output buffers: the kernel writes them in place over PCIe (measured 245 us per step of 4096
@@ -395,24 +425,24 @@ int step_host_impl(Handle<T>* h, const void* actions, void* obs, void* reward, u
             else { cudaGetLastError(); all = false; }
         }
         if (all) {
-            int rc2 = step_impl<T>(h, a_dev, dv[0], dv[1], (uint8_t*)dv[2], dv[3], 0);
+            int rc2 = step_impl<T>(h, a_dev, dv[0], dv[1], (uint8_t*)dv[2], dv[3], hs);
             if (rc2) return rc2;
-            CU(cudaStreamSynchronize(0));
+            CU(cudaStreamSynchronize(hs));
             return 0;
         }
     }
-    int rc = step_impl<T>(h, a_dev, h->h_obs, h->h_reward, h->h_done, h->h_terms, 0);
+    int rc = step_impl<T>(h, a_dev, h->h_obs, h->h_reward, h->h_done, h->h_terms, hs);
     if (rc) return rc;
     const bool small = reward || done || terms;
     if (small) {
-        CU(cudaEventRecord(h->ev_step, 0));
+        CU(cudaEventRecord(h->ev_step, hs));
         CU(cudaStreamWaitEvent(h->side, h->ev_step, 0));
     }
-    if (obs) CU(cudaMemcpyAsync(obs, h->h_obs, N * od * sizeof(T), cudaMemcpyDeviceToHost, 0));
+    if (obs) CU(cudaMemcpyAsync(obs, h->h_obs, N * od * sizeof(T), cudaMemcpyDeviceToHost, hs));
     if (reward) CU(cudaMemcpyAsync(reward, h->h_reward, N * sizeof(T), cudaMemcpyDeviceToHost, h->side));
     if (done) CU(cudaMemcpyAsync(done, h->h_done, N, cudaMemcpyDeviceToHost, h->side));
     if (terms) CU(cudaMemcpyAsync(terms, h->h_terms, N * nt * sizeof(T), cudaMemcpyDeviceToHost, h->side));
-    CU(cudaStreamSynchronize(0));
+    CU(cudaStreamSynchronize(hs));
     if (small) CU(cudaStreamSynchronize(h->side));
     return 0;
 }
@@ -420,12 +450,21 @@ int step_host_impl(Handle<T>* h, const void* actions, void* obs, void* reward, u
 template <typename T>
 int reset_host_impl(Handle<T>* h, const uint8_t* mask, void* obs) {
     const size_t N = h->n;
-    if (mask) CU(cudaMemcpyAsync(h->h_mask, mask, N, cudaMemcpyHostToDevice, 0));
-    int rc = reset_impl<T>(h, mask ? h->h_mask : nullptr, obs ? h->h_obs : nullptr, 0, 1);
+    cudaStream_t hs = h->host_stream;
+    if (mask) CU(cudaMemcpyAsync(h->h_mask, mask, N, cudaMemcpyHostToDevice, hs));
+    int rc = reset_impl<T>(h, mask ? h->h_mask : nullptr, obs ? h->h_obs : nullptr, hs, 1);
     if (rc) return rc;
-    if (obs) CU(cudaMemcpyAsync(obs, h->h_obs, N * h->task.obs_dim * sizeof(T), cudaMemcpyDeviceToHost, 0));
-    CU(cudaStreamSynchronize(0));
+    if (obs) CU(cudaMemcpyAsync(obs, h->h_obs, N * h->task.obs_dim * sizeof(T), cudaMemcpyDeviceToHost, hs));
+    CU(cudaStreamSynchronize(hs));
     return 0;
+}
+
+// frees everything a handle owns (also the partially built handle of a failed bio_create)
+void release(HandleBase* h) {
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_step) cudaEventDestroy(h->ev_step);
+    delete h;
 }
 
 }  // namespace
@@ -457,14 +496,14 @@ int bio_create(const BioModelTables* model, const BioTaskConfig* task, const Bio
         if (!h) return fail(-4, "out of host memory");
         h->precision = precision;
         rc = create_impl<float>(model, task, ref, n_envs, device, seed, env_offset, h);
-        if (rc) { for (void* p : h->allocs) cudaFree(p); delete h; return rc; }
+        if (rc) { release(h); return rc; }
         *out = (bio_handle)(HandleBase*)h;
     } else if (precision == BIO_PREC_F64) {
         Handle<double>* h = new (std::nothrow) Handle<double>();
         if (!h) return fail(-4, "out of host memory");
         h->precision = precision;
         rc = create_impl<double>(model, task, ref, n_envs, device, seed, env_offset, h);
-        if (rc) { for (void* p : h->allocs) cudaFree(p); delete h; return rc; }
+        if (rc) { release(h); return rc; }
         *out = (bio_handle)(HandleBase*)h;
     } else {
         return fail(-1, "unknown precision");
@@ -477,10 +516,7 @@ int bio_destroy(bio_handle hh) {
     HandleBase* h = (HandleBase*)hh;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (void* p : h->allocs) cudaFree(p);
-    if (h->side) cudaStreamDestroy(h->side);
-    if (h->ev_step) cudaEventDestroy(h->ev_step);
-    delete h;
+    release(h);
     return 0;
 }
 
@@ -535,12 +571,51 @@ int bio_eval_debug(bio_handle hh, const void* controls, const BioDebugPtrs* out,
                     eval_impl<double>(H64(hh), controls, out, (cudaStream_t)stream));
 }
 
+int bio_set_step_extra(bio_handle hh, const BioStepExtra* extra) {
+    ENTER(hh);
+    return DISPATCH(hh, extra_impl<float>(H32(hh), extra), extra_impl<double>(H64(hh), extra));
+}
+
+int bio_set_host_stream(bio_handle hh, void* stream) {
+    ENTER(hh);
+    ((HandleBase*)hh)->host_stream = (cudaStream_t)stream;
+    return 0;
+}
+
+int bio_id_apply(bio_handle hh, int32_t op, const void* x, const void* controls, const void* shift, void* out,
+                 void* stream) {
+    ENTER(hh);
+    if (!x || !out) return fail(-1, "bio_id_apply: null buffer");
+    if (op < BIO_ID_MULTIPLY_M || op > BIO_ID_SOLVE_SHIFTED) return fail(-1, "bio_id_apply: unknown operator");
+    return DISPATCH(hh, id_impl<float>(H32(hh), op, x, controls, shift, out, (cudaStream_t)stream),
+                    id_impl<double>(H64(hh), op, x, controls, shift, out, (cudaStream_t)stream));
+}
+int bio_id_multiply_m(bio_handle hh, const void* a, void* out, void* stream) {
+    return bio_id_apply(hh, BIO_ID_MULTIPLY_M, a, nullptr, nullptr, out, stream);
+}
+int bio_id_multiply_minv(bio_handle hh, const void* tau, void* out, void* stream) {
+    return bio_id_apply(hh, BIO_ID_MULTIPLY_MINV, tau, nullptr, nullptr, out, stream);
+}
+int bio_id_residual(bio_handle hh, const void* qddot, const void* controls, void* out, void* stream) {
+    return bio_id_apply(hh, BIO_ID_RESIDUAL, qddot, controls, nullptr, out, stream);
+}
+
 int bio_stats(bio_handle hh, double* out16, int32_t reset_after, void* stream) {
     ENTER(hh);
     HandleBase* h = (HandleBase*)hh;
     if (!out16) return fail(-1, "null stats buffer");
     CU(cudaMemcpyAsync(out16, h->stats, 16 * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     if (reset_after) CU(cudaMemsetAsync(h->stats, 0, 16 * sizeof(double), (cudaStream_t)stream));
+    return 0;
+}
+
+int bio_kernel_shape(bio_handle hh, int32_t* size_class, int32_t* threads, int32_t* ctas_per_sm) {
+    if (!hh) return fail(-1, "null handle");
+    HandleBase* h = (HandleBase*)hh;
+    const int cls = h->precision == BIO_PREC_F32 ? H32(hh)->coop_cls : H64(hh)->coop_cls;
+    if (size_class) *size_class = cls;
+    if (threads) *threads = cls >= 0 ? h->coop_threads : h->block;
+    if (ctas_per_sm) *ctas_per_sm = cls >= 0 ? h->coop_ctas : 0;
     return 0;
 }
 

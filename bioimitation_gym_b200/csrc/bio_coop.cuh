@@ -97,7 +97,9 @@ struct alignas(16) EnvWorkBody : WorkUnions<T, CLS> {
     // last change of the Newton root and the number of solves of this step (planar program, reset at step start)
     union { T ffib[C::NM]; T vnd[C::NM]; };
     union { T fact[C::NM]; T vna[C::NM]; };
-    T vn[C::NM];                                           // Newton warm start: last normalised fibre velocity
+    // Newton warm start: last normalised fibre velocity.  After a FULL evaluation (the last one of a step: the warm
+    // start is reset before the next solve) the slot holds the tendon force, for BioStepExtra::tendon_force
+    T vn[C::NM];
     T ctrl[C::NM];
     T com_pos[3], com_vel[3];
     int8_t knot_hint[P2_MAXTASK];                          // last spline interval per phase-A task
@@ -428,6 +430,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             curve_eval(m, 1, vn, fv, dfv);
             E.fact[i] = fiso * afal * fv;
             E.ffib[i] = fiso * (afal * fv + fpe + beta * vn);
+            E.vn[i] = tension;                // read-out slot, see EnvWorkBody::vn
         }
         if (compiled) {
             // wrench sources of this muscle: one per body it touches
@@ -1157,9 +1160,35 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
         }
     }
     SK_CLK();                                   // 6: reward, termination, outputs of lane 0
+    if (c.ex.any) {   // optional extra outputs (BioStepExtra) of the end-of-step evaluation, before any reset
+        const StepExtra<T>& x = c.ex;
+        if (valid) {
+            if (x.done_reason && lane == 0) x.done_reason[ii] = reason;
+            if (x.udot && isd) x.udot[(size_t)ii * nd + lane] = E.udot[lane];
+            if (ism) {
+                if (x.tendon_force) x.tendon_force[(size_t)ii * nm + lane] = E.vn[lane];
+                if (x.fiber_force) x.fiber_force[(size_t)ii * nm + lane] = E.ffib[lane];
+                if (x.fiber_vel) x.fiber_vel[(size_t)ii * nm + lane] = E.lmdot[lane];
+            }
+            if (x.contact && lane < 12) x.contact[(size_t)ii * 12 + lane] = E.contact[lane / 6][lane % 6];
+            if (x.limit_force && lane < m.n_limits) x.limit_force[(size_t)ii * m.n_limits + lane] = E.limf[lane];
+        }
+        if (x.terminal_obs) {
+            if constexpr (CLS != 0) {           // a warp owns one env: its row goes out once more
+                if (valid && reason != 0) coop_write_obs<T, CLS>(m, c, E, lane, istep, x.terminal_obs + (size_t)ii * c.obs_dim);
+            }
+        }
+    }
     gsync<G>();   // everyone is done with E.x.out before a reset overwrites it
     // Size class 0: both staged rows go out now (the whole warp writes: 16 bytes per lane)
-    if constexpr (CLS == 0) coop_flush_obs<T, CLS>(works, obs, c.obs_dim, item * EPW, n, 3u);
+    if constexpr (CLS == 0) {
+        coop_flush_obs<T, CLS>(works, obs, c.obs_dim, item * EPW, n, 3u);
+        if (c.ex.terminal_obs) {                // rows of the envs that finished in this step
+            const unsigned fin = __ballot_sync(0xffffffffu, valid && reason != 0);
+            const unsigned rows = ((fin & 0xffffu) ? 1u : 0u) | ((fin >> 16) ? 2u : 0u);
+            if (rows) coop_flush_obs<T, CLS>(works, c.ex.terminal_obs, c.obs_dim, item * EPW, n, rows);
+        }
+    }
     // Auto-reset.  The branch is taken by the whole warp (see group_mask): when only one of its two envs
     // resets, the other one repeats the evaluation of its current state and drops the results.
     const bool do_reset = reason != 0 && c.auto_reset;
@@ -1179,12 +1208,13 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
             }
             if (ism) { E.act[lane] = m.mus_default_act[lane]; E.lm[lane] = c.ref_lm0[(size_t)idx * nm + lane]; }
             if (isa) E.ctrl[lane] = T(0);
-            if (ism) { E.vn[lane] = T(0); E.vna[lane] = T(0); }
             istep = idx;
             first_next = 1;
             ep_return = T(0);
             ep_len = 0;
         }
+        // Newton start of both envs of the warp: 0 (the slots hold the read-outs of the full evaluation)
+        if (ism) { E.vn[lane] = T(0); E.vna[lane] = T(0); }
         gsync<G>();
         coop_eval_any<T, CLS>(m, E, lane, c.newton_iters, perturb_force(c, seed, env, T(istep) * c.dt), ext_pt, T(0), true);
         gsync<G>();

@@ -471,6 +471,7 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         curve_eval(m, 1, vn, fv, dfv);
         E.fact[i] = fiso * afal * fv;
         E.ffib[i] = fiso * (afal * fv + fpe + beta * vn);
+        E.vn[i] = tension;                        // read-out slot, see EnvWorkBody::vn
     }
 }
 

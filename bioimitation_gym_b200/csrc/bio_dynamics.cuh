@@ -361,6 +361,46 @@ struct DebugRow {
 
 #define BIO_MAX_MUSCLE_PTS 8
 
+// Sparse L^T D L of the joint-space inertia H (packed lower triangle, only the tree-coupled entries
+// H[i(i+1)/2 + j], j an ancestor-or-self of i, are stored and touched), in place: D on the diagonal,
+// L_kq,i below it.  Elimination runs from the leaves, so no fill-in appears (Featherstone's L^T D L).
+template <typename T>
+__device__ void ltdl_factor(const DevModel<T>& m, T* H) {
+    for (int kq = m.n_dof - 1; kq >= 0; kq--) {
+        const T dk = H[kq * (kq + 1) / 2 + kq];
+        for (int i = m.dof_parent[kq]; i >= 0; i = m.dof_parent[i]) {
+            const T a = H[kq * (kq + 1) / 2 + i] / dk;
+            for (int j = i; j >= 0; j = m.dof_parent[j]) H[i * (i + 1) / 2 + j] -= a * H[kq * (kq + 1) / 2 + j];
+            H[kq * (kq + 1) / 2 + i] = a;
+        }
+    }
+}
+// x <- (L^T D L)^-1 x with the factor of ltdl_factor
+template <typename T>
+__device__ void ltdl_solve(const DevModel<T>& m, const T* H, T* x) {
+    const int nd = m.n_dof;
+    for (int i = nd - 1; i >= 0; i--)
+        for (int j = m.dof_parent[i]; j >= 0; j = m.dof_parent[j]) x[j] -= H[i * (i + 1) / 2 + j] * x[i];
+    for (int i = 0; i < nd; i++) x[i] /= H[i * (i + 1) / 2 + i];
+    for (int i = 0; i < nd; i++) {
+        T v = x[i];
+        for (int j = m.dof_parent[i]; j >= 0; j = m.dof_parent[j]) v -= H[i * (i + 1) / 2 + j] * x[j];
+        x[i] = v;
+    }
+}
+// y = H x for the packed tree-sparse symmetric H (entries off the tree coupling are zero)
+template <typename T>
+__device__ void tree_sym_matvec(const DevModel<T>& m, const T* H, const T* x, T* y) {
+    const int nd = m.n_dof;
+    for (int i = 0; i < nd; i++) y[i] = H[i * (i + 1) / 2 + i] * x[i];
+    for (int i = 0; i < nd; i++)
+        for (int j = m.dof_parent[i]; j >= 0; j = m.dof_parent[j]) {
+            const T v = H[i * (i + 1) / 2 + j];
+            y[i] += v * x[j];
+            y[j] += v * x[i];
+        }
+}
+
 template <typename T, bool FULL>
 __device__ void eval_dynamics(const DevModel<T>& m, int newton_iters, const T* q, const T* u, const T* act,
                               const T* lm, const T* ctrl, T ext_fx, int ext_pt, T h_imp, EvalOut<T>& o,
@@ -664,23 +704,9 @@ __device__ void eval_dynamics(const DevModel<T>& m, int newton_iters, const T* q
         }
     }
     // ---- sparse L^T D L factorisation along the tree, then solve ----
-    for (int kq = nd - 1; kq >= 0; kq--) {
-        const T dk = H[kq * (kq + 1) / 2 + kq];
-        for (int i = m.dof_parent[kq]; i >= 0; i = m.dof_parent[i]) {
-            const T a = H[kq * (kq + 1) / 2 + i] / dk;
-            for (int j = i; j >= 0; j = m.dof_parent[j]) H[i * (i + 1) / 2 + j] -= a * H[kq * (kq + 1) / 2 + j];
-            H[kq * (kq + 1) / 2 + i] = a;
-        }
-    }
-    for (int i = nd - 1; i >= 0; i--)
-        for (int j = m.dof_parent[i]; j >= 0; j = m.dof_parent[j]) rhs[j] -= H[i * (i + 1) / 2 + j] * rhs[i];
-    for (int i = 0; i < nd; i++) rhs[i] /= H[i * (i + 1) / 2 + i];
-    for (int i = 0; i < nd; i++) {
-        T v = rhs[i];
-        for (int j = m.dof_parent[i]; j >= 0; j = m.dof_parent[j]) v -= H[i * (i + 1) / 2 + j] * rhs[j];
-        rhs[i] = v;
-        o.udot[i] = v;
-    }
+    ltdl_factor(m, H);
+    ltdl_solve(m, H, rhs);
+    for (int i = 0; i < nd; i++) o.udot[i] = rhs[i];
     // ---- read-outs for obs / reward / done ----
     if (FULL) {
         for (int p = 0; p < m.n_obspts; p++) {

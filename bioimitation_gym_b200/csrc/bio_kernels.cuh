@@ -364,6 +364,24 @@ __global__ void bio_step_kernel(const DevModel<T>* __restrict__ gm, const DevTas
     else if (c.term_feet_cross && ev.obs_pos[c.feet_obspt[0]][2] - ev.obs_pos[c.feet_obspt[1]][2] < T(0)) reason = BIO_DONE_FEET_CROSS;
     reward[i] = rew;
     done[i] = reason != 0;
+    if (c.ex.any) {      // optional extra outputs (BioStepExtra), before a reset overwrites the state
+        const StepExtra<T>& x = c.ex;
+        if (x.done_reason) x.done_reason[i] = reason;
+        if (x.terminal_obs && reason) for (int o = 0; o < c.obs_dim; o++) x.terminal_obs[(size_t)i * c.obs_dim + o] = orow[o];
+        if (x.udot) for (int d = 0; d < m.n_dof; d++) x.udot[(size_t)i * m.n_dof + d] = ev.udot[d];
+        if (x.fiber_force) for (int k = 0; k < nm; k++) x.fiber_force[(size_t)i * nm + k] = ev.fiber_force[k];
+        if (x.fiber_vel) for (int k = 0; k < nm; k++) x.fiber_vel[(size_t)i * nm + k] = ev.lmdot[k];
+        if (x.contact) for (int k = 0; k < 12; k++) x.contact[(size_t)i * 12 + k] = ev.contact[k / 6][k % 6];
+        if (x.tendon_force || x.limit_force) {   // not kept by the evaluation: one more pass with the debug sinks
+            DebugRow<T> row;
+            row.path_len = row.path_vel = row.mass_matrix = row.bias = nullptr;
+            row.tendon_force = x.tendon_force ? x.tendon_force + (size_t)i * nm : nullptr;
+            row.limit_force = x.limit_force ? x.limit_force + (size_t)i * m.n_limits : nullptr;
+            EvalOut<T> e2;
+            eval_dynamics<T, true>(m, c.newton_iters, s.q, s.u, s.act, s.lm, ctrl, perturb_force(c, seed, env, T(istep) * c.dt),
+                                   c.perturb ? c.perturb_obspt : -1, T(0), e2, &row);
+        }
+    }
     T ep_return = st.ep_return[i] + rew;
     int ep_len = st.ep_len[i] + 1;
     long long episode = st.episode[i];
@@ -486,6 +504,48 @@ __global__ void bio_eval_kernel(const DevModel<T>* __restrict__ gm, const DevTas
     if (out.fiber_vel) for (int k = 0; k < nm; k++) out.fiber_vel[(size_t)i * nm + k] = ev.lmdot[k];
     if (out.act_dot) for (int k = 0; k < nm; k++) out.act_dot[(size_t)i * nm + k] = ev.adot[k];
     if (out.contact) for (int k = 0; k < 12; k++) out.contact[(size_t)i * 12 + k] = ev.contact[k / 6][k % 6];
+}
+
+// Inverse-dynamics operator set (bio_id_apply; inverse_dynamics.cpp:65-197) at the current state of every env:
+// one dynamics evaluation gives the joint-space inertia and the bias, the operators then run on the packed
+// tree-sparse matrix with the factorisation of the step path (ltdl_factor / ltdl_solve).
+template <typename T>
+__global__ void bio_id_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, const EnvState<T> st, int n,
+                              unsigned long long seed, long long env_offset, int op, const T* __restrict__ x,
+                              const T* __restrict__ controls, const T* __restrict__ shift, T* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const DevModel<T>& m = stage_model(gm, smem);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int nd = m.n_dof;
+    Local<T> s;
+    load_state(m, st, i, n, s);
+    T ctrl[BIO_MAX_ACT];
+    for (int j = 0; j < m.n_act; j++) ctrl[j] = controls ? controls[(size_t)i * m.n_act + j] : T(0);
+    T Md[BIO_MAX_DOF * BIO_MAX_DOF], bias[BIO_MAX_DOF];
+    DebugRow<T> row;
+    row.tendon_force = row.path_len = row.path_vel = row.limit_force = nullptr;
+    row.mass_matrix = Md;
+    row.bias = bias;
+    EvalOut<T> ev;
+    const T fx = perturb_force(c, seed, (unsigned long long)(env_offset + i), T(st.istep[i]) * c.dt);
+    eval_dynamics<T, false>(m, c.newton_iters, s.q, s.u, s.act, s.lm, ctrl, fx, c.perturb ? c.perturb_obspt : -1, T(0), ev,
+                            &row);
+    T H[BIO_MAX_DOF * (BIO_MAX_DOF + 1) / 2], v[BIO_MAX_DOF], y[BIO_MAX_DOF];
+    for (int a = 0; a < nd; a++)
+        for (int b = a; b >= 0; b = m.dof_parent[b]) H[a * (a + 1) / 2 + b] = Md[a * nd + b];
+    for (int a = 0; a < nd; a++) v[a] = x[(size_t)i * nd + a];
+    if (op == BIO_ID_MULTIPLY_M || op == BIO_ID_RESIDUAL) {
+        tree_sym_matvec(m, H, v, y);
+        if (op == BIO_ID_RESIDUAL) for (int a = 0; a < nd; a++) y[a] += bias[a];
+    } else {
+        if (op == BIO_ID_SOLVE_SHIFTED && shift)
+            for (int a = 0; a < nd; a++) H[a * (a + 1) / 2 + a] += shift[(size_t)i * nd + a];
+        ltdl_factor(m, H);
+        ltdl_solve(m, H, v);
+        for (int a = 0; a < nd; a++) y[a] = v[a];
+    }
+    for (int a = 0; a < nd; a++) out[(size_t)i * nd + a] = y[a];
 }
 
 // [N][k] row-major <-> SoA [k][N]

@@ -27,6 +27,10 @@ void launch_eval(int grid, int block, size_t smem, cudaStream_t s, const DevMode
                  const EnvState<T>& st, int n, unsigned long long seed, long long env_offset, const T* controls,
                  const DebugOut<T>& d);
 template <typename T>
+void launch_id(int grid, int block, size_t smem, cudaStream_t s, const DevModel<T>* gm, const DevTask<T>& c,
+               const EnvState<T>& st, int n, unsigned long long seed, long long env_offset, int op, const T* x,
+               const T* controls, const T* shift, T* out);
+template <typename T>
 void launch_transpose(unsigned grid, int block, cudaStream_t s, const T* src, T* dst, int n, int k, int to_soa);
 
 // cooperative kernel, launch shape `threads` (COOP_THREADS_LO / COOP_THREADS_HI)

@@ -193,8 +193,9 @@ struct alignas(16) DevModel {
     int8_t pt_mov[BIO_MAX_PATHPTS];          // index of a moving path point in moving_pt (-1: not moving)
     int32_t ent_i[BIO_MAX_DOF * (BIO_MAX_DOF + 1) / 2];
     int32_t ent_j[BIO_MAX_DOF * (BIO_MAX_DOF + 1) / 2];
-    int32_t obs_desc[256];                   // (kind << 16) | pelvis selector << 12 | index per observation slot (build_obs_desc)
-    T obs_cst[256];                          // constant of the slot: locked coordinate value (kind 14), contact scale (kind 13)
+#define BIO_COOP_MAX_OBS_DIM 256            /* larger observation rows take the thread-per-env kernel */
+    int32_t obs_desc[BIO_COOP_MAX_OBS_DIM];                   // (kind << 16) | pelvis selector << 12 | index per observation slot (build_obs_desc)
+    T obs_cst[BIO_COOP_MAX_OBS_DIM];                          // constant of the slot: locked coordinate value (kind 14), contact scale (kind 13)
     // spline search: 16 uniform buckets per function -> first candidate knot
     T func_bucket_inv[BIO_MAX_FUNCS];
     int8_t func_bucket[BIO_MAX_FUNCS][16];
@@ -235,6 +236,14 @@ struct alignas(16) DevModel {
     PlanarProg<T> prog;
 };
 
+// optional extra outputs of the step kernels (BioStepExtra), typed; `any` = some member is set
+template <typename T>
+struct StepExtra {
+    T* terminal_obs; int32_t* done_reason; T* udot; T* tendon_force; T* fiber_force; T* fiber_vel; T* contact;
+    T* limit_force;
+    int32_t any, pad;
+};
+
 template <typename T>
 struct DevTask {
     int32_t n_substeps, integrator, newton_iters, horizon, feed_mean_action, use_pd, n_pd;
@@ -256,6 +265,7 @@ struct DevTask {
     const T* ref_body_pos;
     const T* ref_com_pos;
     const T* ref_lm0;     // [rows][n_muscles] static fibre equilibrium per reference row
+    StepExtra<T> ex;      // all null unless bio_set_step_extra attached buffers
 };
 
 // SoA per-env state, [k][n_envs]
@@ -853,7 +863,7 @@ int build_obs_desc(const BioModelTables& s, const BioTaskConfig& t, DevModel<T>&
     // subtract pelvis_tx / ty / tz (positions are reported relative to the pelvis).
     int o = 0;
     auto put = [&](int kind, int idx, int pel = 0, double cst = 0.0) {
-        if (o < 256) { d.obs_desc[o] = (kind << 16) | (pel << 12) | idx; d.obs_cst[o] = (T)cst; }
+        if (o < BIO_COOP_MAX_OBS_DIM) { d.obs_desc[o] = (kind << 16) | (pel << 12) | idx; d.obs_cst[o] = (T)cst; }
         o++;
     };
     auto coord = [&](int kind, int i) {

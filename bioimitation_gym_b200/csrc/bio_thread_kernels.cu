@@ -14,6 +14,7 @@ cudaError_t thread_set_smem<BIO_T>(int smem) {
     if ((e = cudaFuncSetAttribute(bio_step_kernel<BIO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
     if ((e = cudaFuncSetAttribute(bio_reset_kernel<BIO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
     if ((e = cudaFuncSetAttribute(bio_eval_kernel<BIO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(bio_id_kernel<BIO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
     return cudaFuncSetAttribute(bio_lm0_kernel<BIO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
@@ -44,6 +45,13 @@ void launch_eval<BIO_T>(int grid, int block, size_t smem, cudaStream_t s, const 
                         const DevTask<BIO_T>& c, const EnvState<BIO_T>& st, int n, unsigned long long seed,
                         long long env_offset, const BIO_T* controls, const DebugOut<BIO_T>& d) {
     bio_eval_kernel<BIO_T><<<grid, block, smem, s>>>(gm, c, st, n, seed, env_offset, controls, d);
+}
+
+template <>
+void launch_id<BIO_T>(int grid, int block, size_t smem, cudaStream_t s, const DevModel<BIO_T>* gm, const DevTask<BIO_T>& c,
+                      const EnvState<BIO_T>& st, int n, unsigned long long seed, long long env_offset, int op,
+                      const BIO_T* x, const BIO_T* controls, const BIO_T* shift, BIO_T* out) {
+    bio_id_kernel<BIO_T><<<grid, block, smem, s>>>(gm, c, st, n, seed, env_offset, op, x, controls, shift, out);
 }
 
 template <>

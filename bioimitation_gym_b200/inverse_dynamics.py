@@ -5,10 +5,12 @@ B200 equivalent of the reference's only native component, the boost.python class
 and of the controllers built on it in tests/example_position_control.py:113-198.
 
 The reference wraps one OpenSim model per process and takes Python lists; here N independent
-states are evaluated per call: the joint-space mass matrix and the bias forces come from the
-dynamics evaluation kernel through the C ABI (`bio_eval_debug`, include/bio_b200.h), the small
-batched matrix products on top are torch ops on the same device.  Method names, argument order
-(`t` first) and sign conventions follow the reference:
+states are evaluated per call, and every operator runs INSIDE the native library
+(`bio_id_apply` / `bio_id_multiply_m` / `bio_id_multiply_minv` / `bio_id_residual`,
+include/bio_b200.h): joint-space inertia from the composite-inertia pass and the sparse L^T D L
+factorisation along the kinematic tree that the step kernel's own solve uses -- no cuBLAS /
+cuSOLVER, torch only allocates the tensors.  Method names, argument order (`t` first) and sign
+conventions follow the reference:
 
     M(q) qddot + c(q, qdot) = g(q) + tau_applied        (inverse_dynamics.cpp:122,139)
     calculateTotalForces   f  with  M qddot + f = tau    (:96-121)
@@ -89,9 +91,8 @@ class InverseDynamics:
     def calculateResidualForces(self, t, q, qDot, qDDot):
         """tau_residual = M qddot + f_internal - f_applied (inverse_dynamics.cpp:65-94)."""
         qq, uu, aa = self._in(q), self._in(qDot), self._in(qDDot)
-        ev = self._eval(self.full, qq, uu)
-        M = self._eval(self.bare, qq, self.torch.zeros_like(qq))["mass_matrix"]
-        return self._out(self.torch.bmm(M, aa[:, :, None])[:, :, 0] + ev["bias"], q)
+        self.full.set_state(dict(q=qq, u=uu))
+        return self._out(self.full.id_apply("residual", aa), q)
 
     def calculateTotalForces(self, t, q, qDot):
         """f with M qddot + f = tau: Coriolis - gravity - contact - limits (inverse_dynamics.cpp:96-121)."""
@@ -109,37 +110,42 @@ class InverseDynamics:
         b0 = self._eval(self.bare, qq, self.torch.zeros_like(qq))["bias"]
         return self._out(b1 - b0, q)
 
+    def _at(self, q):
+        qq = self._in(q)
+        self.bare.set_state(dict(q=qq, u=self.torch.zeros_like(qq)))
+        return qq
+
     def multiplyByM(self, t, q, a):
         """M(q) a (inverse_dynamics.cpp:158-174)."""
-        M = self.mass_matrix(q)
-        return self._out(self.torch.bmm(M, self._in(a)[:, :, None])[:, :, 0], q)
+        self._at(q)
+        return self._out(self.bare.id_apply("multiply_m", self._in(a)), q)
 
     def multiplyByMInv(self, t, q, tau):
         """M(q)^-1 tau (inverse_dynamics.cpp:176-192)."""
-        M = self.mass_matrix(q)
-        L = self.torch.linalg.cholesky(M)
-        return self._out(self.torch.cholesky_solve(self._in(tau)[:, :, None], L)[:, :, 0], q)
+        self._at(q)
+        return self._out(self.bare.id_apply("multiply_minv", self._in(tau)), q)
 
     # ------------------------------------------------------------------ controllers
     def computed_torque(self, t, q, qDot, qDDot_des, tau_pd):
         """tau = M tau_pd + ID(q, qdot, qddot_des)  (example_position_control.py:113-141)."""
         qq = self._in(q)
-        M = self.mass_matrix(qq)
         res = self.calculateResidualForces(t, qq, self._in(qDot), self._in(qDDot_des))
-        return self._out(self.torch.bmm(M, self._in(tau_pd)[:, :, None])[:, :, 0] + res, q)
+        return self._out(self.multiplyByM(t, qq, self._in(tau_pd)) + res, q)
 
     def stable_pd(self, t, q, qDot, tau_pd, Kd, step_size):
         """Stable PD (example_position_control.py:143-190): qddot = (M + Kd h)^-1 (tau_pd - ID(q, qdot, 0)),
-        tau = tau_pd - Kd h qddot."""
+        tau = tau_pd - Kd h qddot, with the reference's diagonal gain (`np.diagflat([Kd * step_size] * n)`,
+        :181): Kd is a scalar, [n_dof] or [N, n_dof]."""
         torch = self.torch
         qq, uu, tp = self._in(q), self._in(qDot), self._in(tau_pd)
-        M = self.mass_matrix(qq)
         res = self.calculateResidualForces(t, qq, uu, torch.zeros_like(qq))
-        kd = torch.as_tensor(Kd, dtype=M.dtype, device=M.device)
-        Kd_m = torch.diag_embed(kd.expand(self.num_envs, self.n_dof)) if kd.dim() <= 1 else kd.expand_as(M)
-        Mbar = M + Kd_m * float(step_size)
-        qdd = torch.linalg.solve(Mbar, (tp - res)[:, :, None])[:, :, 0]
-        return self._out(tp - torch.bmm(Kd_m * float(step_size), qdd[:, :, None])[:, :, 0], q)
+        kd = torch.as_tensor(Kd, dtype=qq.dtype, device=qq.device)
+        if kd.dim() > 2 or (kd.dim() == 2 and tuple(kd.shape) != (self.num_envs, self.n_dof)):
+            raise ValueError("Kd must be a scalar, [n_dof] or [N, n_dof] (diagonal gain)")
+        shift = (kd * float(step_size)).expand(self.num_envs, self.n_dof).contiguous()
+        self._at(qq)
+        qdd = self.bare.id_apply("solve_shifted", tp - res, shift=shift)
+        return self._out(tp - shift * qdd, q)
 
     def close(self):
         self.full.close()

@@ -247,6 +247,111 @@ def synth_gait_2d(cm: CompiledModel, curves_deg: Dict[str, Sequence[float]],
     return build_reference(cm, time, q, names, dt=dt, lowpass_hz=-1.0)
 
 
+def _locked_columns(cm: CompiledModel, q: np.ndarray) -> None:
+    """Locked coordinates keep their compiled value in the tables (as the reference's q_d frames do)."""
+    for j, n in enumerate(cm.coord_names):
+        if n not in cm.dof_names:
+            q[:, j] = cm.tables.coord_const[j]
+
+
+def _solve_pelvis_height(cm: CompiledModel, q: np.ndarray, rows, penetration: float) -> None:
+    """pelvis_ty per row such that the lowest contact sphere sinks `penetration` into the ground."""
+    names = cm.coord_names
+    jy = names.index("pelvis_ty")
+    dof_cols = [names.index(n) for n in cm.dof_names]
+    for i in rows:
+        q[i, jy] = 1.0
+        q[i, jy] = 1.0 - sphere_bottoms(cm, q[i, dof_cols]).min() - penetration
+
+
+def synth_gait(cm: CompiledModel, curves_deg: Dict[str, Sequence[float]], cycle_steps: int, n_rows: int,
+               speed: float, dt: float = 0.01, penetration: float = 0.008) -> Dict[str, np.ndarray]:
+    """`synth_gait_2d` for any of the gait models, by coordinate name: the sagittal coordinates
+    follow the healthy mean curves, every other free coordinate (pelvis list / rotation / tz, hip
+    adduction of the 3D models) stays at zero, locked coordinates at their compiled value.  Used for
+    the 3D running task, whose reference directory (`running_reference_data`, reference
+    ``muscle_running_imitation_env3D.py:47-53``, cycle 70 ``:177``) is not shipped."""
+    names = cm.coord_names
+    phase = (np.arange(n_rows) / float(cycle_steps)) % 1.0
+
+    def curve(name, ph):
+        y = np.asarray(curves_deg[name], dtype=np.float64)
+        y = np.concatenate([y[:-1], y[:1]])
+        return np.deg2rad(np.interp(ph % 1.0, np.linspace(0.0, 1.0, y.size), y))
+
+    q = np.zeros((n_rows, len(names)))
+    for j, n in enumerate(names):
+        left = 0.5 if n.endswith("_l") else 0.0
+        if n == "pelvis_tilt":
+            q[:, j] = curve("pelvis_tilt", phase)
+        elif n == "pelvis_tx":
+            q[:, j] = speed * dt * np.arange(n_rows)
+        elif n.startswith("hip_flexion"):
+            q[:, j] = curve("hip_flexion", phase + left)
+        elif n.startswith("knee_angle"):
+            q[:, j] = -curve("knee_angle", phase + left)
+        elif n.startswith("ankle_angle"):
+            q[:, j] = curve("ankle_angle", phase + left)
+    q = lowpass_zero_phase(q, 1.0 / dt, 6.0)
+    _locked_columns(cm, q)
+    _solve_pelvis_height(cm, q, range(n_rows), penetration)
+    jy = names.index("pelvis_ty")
+    q[:, jy] = lowpass_zero_phase(q[:, jy:jy + 1], 1.0 / dt, 6.0)[:, 0]
+    return build_reference(cm, dt * np.arange(n_rows), q, names, dt=dt, lowpass_hz=-1.0)
+
+
+def synth_jump(cm: CompiledModel, n_rows: int = 102, dt: float = 0.01, takeoff_speed: float = 2.2,
+               penetration: float = 0.008) -> Dict[str, np.ndarray]:
+    """Synthetic counter-movement jump up to the apex.  The jumping envs read
+    `highjump_reference_data` / `jumping_reference_data` (reference
+    ``muscle_jumping_imitation_env2D.py:47-53``, ``muscle_jumping_imitation_env3D.py:47-53``), which are
+    not shipped; they run the table forwards and then mirrored (``:290-294``: index = 2 cycle - istep,
+    cycle = N / 2 = rows - 2), so the table holds the way up only: quiet stance, crouch (hip 75 deg,
+    knee -95 deg, ankle 25 deg dorsiflexion, trunk 25 deg forward), extension to take-off with the
+    ankle plantarflexed, ballistic flight of the pelvis to the apex.  Both legs move together; the feet
+    stay on the ground (lowest contact sphere `penetration` deep) until take-off, pelvis_ty follows
+    y0 + v t - g t^2 / 2 afterwards with v = `takeoff_speed`."""
+    names = cm.coord_names
+    g = abs(float(cm.tables.gravity[1]))
+    t_fly = takeoff_speed / g                                  # take-off -> apex
+    n_fly = int(round(t_fly / dt))
+    n_ground = n_rows - n_fly
+    if n_ground < 40:
+        raise ValueError("synth_jump: too few rows for stance + crouch + extension")
+    n_stand = n_ground // 5
+    n_ext = n_ground // 5
+    n_crouch = n_ground - n_stand - n_ext
+
+    def smooth(a, b, n):                                       # C2 blend a -> b over n samples
+        x = np.linspace(0.0, 1.0, n, endpoint=False)
+        return a + (b - a) * (10 * x ** 3 - 15 * x ** 4 + 6 * x ** 5)
+
+    def profile(stand, crouch, takeoff, flight):
+        return np.concatenate([np.full(n_stand, stand), smooth(stand, crouch, n_crouch),
+                               smooth(crouch, takeoff, n_ext), smooth(takeoff, flight, n_fly)])
+
+    deg = np.pi / 180.0
+    q = np.zeros((n_rows, len(names)))
+    for j, n in enumerate(names):
+        if n == "pelvis_tilt":
+            q[:, j] = profile(0.0, -25 * deg, 0.0, 0.0)
+        elif n.startswith("hip_flexion"):
+            q[:, j] = profile(0.0, 75 * deg, -5 * deg, 10 * deg)
+        elif n.startswith("knee_angle"):
+            q[:, j] = profile(-2 * deg, -95 * deg, -3 * deg, -20 * deg)
+        elif n.startswith("ankle_angle"):
+            q[:, j] = profile(0.0, 25 * deg, -30 * deg, -15 * deg)
+    q = lowpass_zero_phase(q, 1.0 / dt, 6.0)
+    _locked_columns(cm, q)
+    _solve_pelvis_height(cm, q, range(n_ground + 1), penetration)
+    jy = names.index("pelvis_ty")
+    tf = dt * np.arange(1, n_fly + 1)
+    # flight: continue from the last grounded frame at the take-off speed
+    q[n_ground:, jy] = q[n_ground - 1, jy] + takeoff_speed * tf[:n_rows - n_ground] - 0.5 * g * tf[:n_rows - n_ground] ** 2
+    q[:, jy] = lowpass_zero_phase(q[:, jy:jy + 1], 1.0 / dt, 6.0)[:, 0]
+    return build_reference(cm, dt * np.arange(n_rows), q, names, dt=dt, lowpass_hz=-1.0)
+
+
 def load_ik_motion(path: str):
     """IK .mot -> (time, q[T, ncol] in rad/m, labels without 'time')."""
     labels, data, in_deg = read_storage(path)

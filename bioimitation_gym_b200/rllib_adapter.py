@@ -12,6 +12,14 @@ Episode ends: the step kernel resets finished envs itself (reference-state initi
 muscle_walking_imitation_env2D.py:133-156), so the observation of a finished env returned by
 `vector_step` is already the first observation of its next episode and `reset_at(i)` only hands
 that row out again; nothing is launched per env.
+
+Every array handed to RLlib is a COPY: `VecEnv.step_np` returns views of two alternating page-locked
+buffers that the GPU overwrites in place two calls later, while RLlib's sample collectors keep
+observation references for a whole rollout fragment.
+
+Supported interface: the pre-gymnasium `VectorEnv` of ray <= 2.2 (4-tuple `vector_step`, `reset_at(index)`),
+i.e. the ray 1.8 the reference pins (scripts/requirements.txt); `vector_step_v26` returns the
+terminated / truncated split newer ray versions expect (truncated = the episode hit its step limit).
 """
 from __future__ import annotations
 
@@ -42,21 +50,34 @@ class BioVectorEnv(_Base):
         self._obs = None
 
     def vector_reset(self) -> List[np.ndarray]:
-        self._obs = self.env.reset_np()
-        return [o for o in self._obs]
+        self._obs = self.env.reset_np().copy()
+        return [o.copy() for o in self._obs]
 
     def reset_at(self, index: Optional[int] = None) -> np.ndarray:
         if self._obs is None:
             self.vector_reset()
-        return self._obs[0 if index is None else int(index)]
+        return self._obs[0 if index is None else int(index)].copy()
 
     def vector_step(self, actions):
         # host buffers in, host buffers out: page-locked arrays the step kernel reads / writes in place
         a = np.asarray(actions, dtype=np.float32 if self.env.dtype == self.env.torch.float32 else np.float64)
-        self._obs, rew, done, info = self.env.step_np(a)
+        obs, rew, done, info = self.env.step_np(a)
+        self._obs = obs.copy()
         terms = info["all_rewards"]
         infos = [{"all_rewards": terms[i].tolist()} for i in range(self.num_envs)]
-        return [o for o in self._obs], rew.tolist(), done.tolist(), infos
+        return [o.copy() for o in self._obs], rew.tolist(), done.tolist(), infos
+
+    def vector_step_v26(self, actions):
+        """(obs, rewards, terminateds, truncateds, infos): `truncated` = the env ended on its step limit
+        (BIO_DONE_HORIZON), from the step kernel's per-env done reason."""
+        from . import ctables as ct
+        if getattr(self, "_reason", None) is None:
+            self._reason = self.env.enable_step_extra("done_reason")["done_reason"]
+        obs, rew, done, infos = self.vector_step(actions)
+        reason = self._reason.cpu().numpy()
+        trunc = (reason == ct.MACROS["BIO_DONE_HORIZON"])
+        term = np.asarray(done, dtype=bool) & ~trunc
+        return obs, rew, term.tolist(), trunc.tolist(), infos
 
     def get_sub_environments(self):
         return []          # the envs live on the device; there are no per-env Python objects

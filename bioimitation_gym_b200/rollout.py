@@ -61,13 +61,44 @@ class DeviceReplayBuffer:
         self.size = min(self.size + n, self.capacity)
 
     def insert_step(self, observation, action, reward, done, next_observation, time_limit_done=None):
-        """Batch insert from one VecEnv.step: mask = 0 where the episode really ended
-        (sample_baselines_training.py:72-75: a time-limit end keeps mask 1)."""
+        """Batch insert of one step of N envs: mask = 0 where the episode really ended
+        (sample_baselines_training.py:72-75: a time-limit end keeps mask 1).  `observation` and
+        `next_observation` must be different storage: `VecEnv.step` returns the SAME env-owned tensor every
+        call, and after an auto-reset it holds the first observation of the next episode, not the terminal one
+        -- use `attach` + `step_and_insert` for a VecEnv."""
+        if hasattr(observation, "data_ptr") and hasattr(next_observation, "data_ptr") and \
+                observation.data_ptr() == next_observation.data_ptr():
+            raise ValueError("observation and next_observation alias one tensor (VecEnv.step returns its own "
+                             "buffer): clone the observation before stepping, or use attach/step_and_insert")
         done_f = done.to(self.rewards.dtype)
         mask = 1.0 - done_f
         if time_limit_done is not None:
             mask = self.torch.where(time_limit_done.bool(), self.torch.ones_like(mask), mask)
         self.insert(observation, action, reward, mask, done_f, next_observation)
+
+    # ---- feeding from a VecEnv (the learner loop of sample_baselines_training.py:59-87, batched) ----
+    def attach(self, env, observation=None):
+        """Start collecting from `env`: asks the step kernel for the terminal observation and the done reason
+        of finished envs (BioStepExtra) and keeps a private copy of the current observation (pass the tensor
+        `env.reset()` returned, default: the env's observation buffer)."""
+        from . import ctables as ct
+        self._env = env
+        self._extra = env.enable_step_extra("terminal_obs", "done_reason")
+        self._horizon_bit = ct.MACROS["BIO_DONE_HORIZON"]
+        self._prev = (env.obs if observation is None else observation).detach().clone()
+
+    def step_and_insert(self, actions):
+        """env.step(actions) and insert the N transitions: next_observation of a finished env is its TERMINAL
+        observation (the step kernel has already put the first observation of the next episode into the
+        returned batch), mask stays 1 when the episode only hit its step limit.  Returns what env.step does."""
+        torch = self.torch
+        env = self._env
+        obs, rew, done, info = env.step(actions)
+        fin = done.bool()
+        nxt = torch.where(fin[:, None], self._extra["terminal_obs"], obs)
+        self.insert_step(self._prev, actions, rew, done, nxt, self._extra["done_reason"] == self._horizon_bit)
+        self._prev.copy_(obs)
+        return obs, rew, done, info
 
     def sample(self, batch_size: int, generator=None) -> Batch:
         if self.size == 0:

@@ -34,6 +34,13 @@ FIXTURES = [
     ("torque_walking_2d.npz", "TorqueWalkingImitation2D-v0", 150),
     ("muscle_walking_3d.npz", "MuscleWalkingImitation3D-v0", 150),
     ("muscle_locked_knee_3d.npz", "MuscleLockedKneeImitation3D-v0", 100),
+    ("muscle_palsy_3d.npz", "MusclePalsyImitation3D-v0", 100),
+    ("torque_walking_3d.npz", "TorqueWalkingImitation3D-v0", 100),
+    ("muscle_running_2d.npz", "MuscleRunningImitation2D-v0", 100),
+    ("muscle_locked_knee_2d.npz", "MuscleLockedKneeImitation2D-v0", 100),
+    ("muscle_jumping_2d.npz", "MuscleJumpingImitation2D-v0", 220),     # past the mirror point of the reference index
+    ("muscle_jumping_3d.npz", "MuscleJumpingImitation3D-v0", 100),
+    ("torque_running_3d.npz", "TorqueRunningImitation3D-v0", 100),
 ]
 STATE_KEYS = ("q", "u", "act", "lm", "last_action", "history", "old_px", "istep", "first", "hist_pos", "episode")
 
@@ -84,7 +91,10 @@ def generate(env_id, steps, seed=0):
 
 
 def main():
+    only = set(sys.argv[1:])              # file names to (re)generate; default: all
     for fname, env_id, steps in FIXTURES:
+        if only and fname not in only:
+            continue
         res = generate(env_id, steps)
         path = os.path.join(HERE, fname)
         np.savez_compressed(path, **res)

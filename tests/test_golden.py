@@ -8,7 +8,8 @@ import pytest
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FILES = ["config1_muscle_walking_2d.npz", "torque_walking_2d.npz", "muscle_walking_3d.npz",
-         "muscle_locked_knee_3d.npz"]
+         "muscle_locked_knee_3d.npz", "muscle_palsy_3d.npz", "torque_walking_3d.npz", "muscle_running_2d.npz",
+         "muscle_locked_knee_2d.npz", "muscle_jumping_2d.npz", "muscle_jumping_3d.npz", "torque_running_3d.npz"]
 
 
 def _env(env_id, seed):

@@ -66,11 +66,56 @@ def test_operators_against_oracle_and_forward_dynamics(model):
     udot_full = idm.full.eval_debug(torch.as_tensor(tau_act))["udot"].clone()
     res = idm.calculateResidualForces(0.0, q, u, udot_full).cpu().numpy()
     assert np.max(np.abs(res - tau) / np.maximum(np.abs(tau), 1.0)) < 1e-7
-    # M^-1 M a = a
+    # the in-library operators (bio_id_multiply_m / _minv: composite inertias + the step path's sparse L^T D L)
+    # against dense algebra on the oracle-checked mass matrix, and M^-1 M a = a
     a = rng.normal(0, 1, (n, nd))
+    Ma = idm.multiplyByM(0.0, q, a).cpu().numpy()
+    assert np.max(np.abs(Ma - np.einsum("nij,nj->ni", M, a))) < 1e-9 * np.max(np.abs(Ma))
+    Mia = idm.multiplyByMInv(0.0, q, a).cpu().numpy()
+    want = np.stack([np.linalg.solve(M[i], a[i]) for i in range(n)])
+    assert np.max(np.abs(Mia - want) / np.maximum(np.abs(want), 1.0)) < 1e-8
     back = idm.multiplyByMInv(0.0, q, idm.multiplyByM(0.0, q, a)).cpu().numpy()
     assert np.max(np.abs(back - a)) < 1e-8
+    # residual = M qddot + total forces; stable PD against its closed form (example_position_control.py:143-190)
+    res2 = idm.calculateResidualForces(0.0, q, u, a).cpu().numpy()
+    assert np.max(np.abs(res2 - (np.einsum("nij,nj->ni", M, a) + f)) / np.maximum(np.abs(res2), 1.0)) < 1e-8
+    tau_pd = rng.normal(0, 20, (n, nd))
+    kd, h = 35.0, 0.01
+    got = idm.stable_pd(0.0, q, u, tau_pd, kd, h).cpu().numpy()
+    res0 = idm.calculateResidualForces(0.0, q, u, np.zeros_like(q)).cpu().numpy()
+    want = np.stack([tau_pd[i] - kd * h * np.linalg.solve(M[i] + kd * h * np.eye(nd), tau_pd[i] - res0[i]) for i in range(n)])
+    assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0)) < 1e-8
+    launches = idm.bare.launch_count
+    idm.multiplyByMInv(0.0, q, a)
+    assert idm.bare.launch_count - launches <= 3           # state transposes + one operator kernel, no library solver
     idm.close()
+
+
+def test_operators_in_fp32_and_through_the_raw_abi():
+    """The operator kernels in the production precision, called through the named C entry points."""
+    import ctypes
+    import torch
+    from bioimitation_gym_b200.inverse_dynamics import InverseDynamics
+    n = 32
+    idm = InverseDynamics("3D", num_envs=n, dtype="float32")
+    idd = InverseDynamics("3D", num_envs=n, dtype="float64")
+    q, u, rng = _states(idm, n)
+    a = rng.normal(0, 1, (n, idm.n_dof))
+    m32 = idm.multiplyByM(0.0, q, a).double().cpu().numpy()
+    m64 = idd.multiplyByM(0.0, q, a).cpu().numpy()
+    assert np.max(np.abs(m32 - m64)) < 2e-5 * np.max(np.abs(m64))
+    i32 = idm.multiplyByMInv(0.0, q, m64).double().cpu().numpy()
+    assert np.max(np.abs(i32 - a)) < 5e-3                  # cond(M) ~ 1e4: foot vs trunk inertia
+    env = idd.bare
+    x = torch.as_tensor(a, dtype=torch.float64, device=env.device).contiguous()
+    out = torch.empty_like(x)
+    s = ctypes.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)
+    assert env.lib.bio_id_multiply_m(env.handle, x.data_ptr(), out.data_ptr(), s) == 0
+    assert np.allclose(out.cpu().numpy(), m64, rtol=1e-12, atol=1e-12)
+    assert env.lib.bio_id_apply(env.handle, 99, x.data_ptr(), None, None, out.data_ptr(), s) != 0
+    assert b"unknown operator" in env.lib.bio_last_error()
+    idm.close()
+    idd.close()
 
 
 def test_controllers_and_list_interface():

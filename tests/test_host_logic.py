@@ -172,9 +172,37 @@ def test_task_constants_follow_the_reference_classes():
     assert tq.effort_torque == 1 and tq.n_reward_terms == 4
 
 
-def test_missing_reference_motion_is_reported():
+def test_missing_reference_motion_is_reported(monkeypatch):
+    from bioimitation_gym_b200 import assets
+    monkeypatch.setattr(assets, "DATA_DIR", "/nonexistent")
     with pytest.raises(FileNotFoundError):
-        registry.build_env_tables("MuscleJumpingImitation3D-v0", {})
+        registry.build_env_tables("MuscleJumpingImitation3D-v0", {}, model=assets.load_model("3d_muscle"))
+
+
+def test_every_env_id_has_tables_and_the_jump_reference_mirrors(models):
+    """All 17 registered IDs construct (reference bioimitation/__init__.py:23-133); the jumping tasks
+    run their table forwards then mirrored (muscle_jumping_imitation_env2D.py:73-76,290-294: N = 2 (rows - 2),
+    cycle = N / 2, effort progress along pelvis_ty :341)."""
+    for env_id in tasks.ENV_SPECS:
+        spec, cm, ref, task = registry.build_env_tables(env_id, {})
+        assert ref["q"].shape[1] == cm.tables.n_coords and task.reset_max_index <= ref["q"].shape[0] - 2
+    spec, cm, ref, task = registry.build_env_tables("MuscleJumpingImitation2D-v0", {})
+    rows = ref["q"].shape[0]
+    assert task.n_steps == 2 * (rows - 2) and task.cycle == rows - 2 and task.ref_mirror == 1 and task.effort_use_dy == 1
+    ty = cm.coord_names.index("pelvis_ty")
+    # the table is the way UP: the pelvis ends at its apex, above the standing height, feet off the ground
+    assert ref["q"][-1, ty] > ref["q"][0, ty] + 0.15 and abs(ref["u"][-1, ty]) < 0.35
+    dof_cols = [cm.coord_names.index(n) for n in cm.dof_names]
+    assert refmotion.sphere_bottoms(cm, ref["q"][-1, dof_cols]).min() > 0.1
+    assert abs(refmotion.sphere_bottoms(cm, ref["q"][0, dof_cols]).min() + 0.008) < 2e-3
+    spec, cm3, ref3, task3 = registry.build_env_tables("MuscleRunningImitation3D-v0", {})
+    assert task3.cycle == 70 and ref3["q"].shape == (282, 17)
+    # locked coordinates keep their compiled value, the right foot stays on the right
+    for j, n in enumerate(cm3.coord_names):
+        if n not in cm3.dof_names:
+            assert np.allclose(ref3["q"][:, j], cm3.tables.coord_const[j])
+    bn = list(ref3["body_names"])
+    assert (ref3["body_pos"][:, bn.index("calcn_r"), 2] > ref3["body_pos"][:, bn.index("calcn_l"), 2]).all()
 
 
 # ----------------------------------------------------------------- oracle env semantics
@@ -448,4 +476,40 @@ def test_rllib_vector_env_adapter_interface():
     o, r, d, info = v.vector_step([[0.1, 0.2]] * 3)
     assert len(o) == 3 and r == [0.0, 1.0, 2.0] and d == [False, True, False] and len(info[1]["all_rewards"]) == 5
     assert np.array_equal(v.reset_at(1), o[1])          # the finished env already holds its next episode's first obs
+    # every array handed out is a copy: later steps (the GPU overwrites its page-locked buffers) do not change it
+    keep = o[0].copy()
+    v.vector_step([[0.1, 0.2]] * 3)
+    v.vector_step([[0.1, 0.2]] * 3)
+    assert np.array_equal(o[0], keep) and not np.shares_memory(o[0], v._obs)
     assert v.action_space.shape == (2,) and v.observation_space.shape == (4,) and v.get_sub_environments() == []
+
+
+def test_bioimitation_shim_serves_the_reference_import_path(monkeypatch):
+    """`import gym, bioimitation; gym.make(id, config=cfg)` (reference tests/test_env.py:15-26): the shim
+    registers the 17 IDs under the reference's module paths.  gym is not installed here, so a minimal
+    stand-in registry plays its part (register / make resolving `module:Class` entry points)."""
+    import importlib
+    import sys
+    import types
+    reg = {}
+    gym = types.ModuleType("gym")
+    gym_envs = types.ModuleType("gym.envs")
+    gym_reg = types.ModuleType("gym.envs.registration")
+    gym_reg.register = lambda id, entry_point, **kw: reg.__setitem__(id, entry_point)
+    gym.envs, gym_envs.registration = gym_envs, gym_reg
+    for name, mod in (("gym", gym), ("gym.envs", gym_envs), ("gym.envs.registration", gym_reg)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    for name in [k for k in sys.modules if k == "bioimitation" or k.startswith("bioimitation.")]:
+        monkeypatch.delitem(sys.modules, name)
+    bio = importlib.import_module("bioimitation")
+    assert bio.REGISTERED["gym"] and len(reg) == 17
+    assert reg["MuscleWalkingImitation2D-v0"] == \
+        "bioimitation.imitation_envs.envs.muscle.planar.muscle_walking_imitation_env2D:MuscleWalkingImitationEnv2D"
+    assert reg["TorqueLockedKneeImitation3D-v0"] == \
+        "bioimitation.imitation_envs.envs.torque.spatial.torque_locked_knee_imitation_env3D:TorqueLockedKneeImitationEnv3D"
+    for env_id, ep in reg.items():                      # every entry point resolves the way gym resolves it
+        mod, cls = ep.split(":")
+        assert getattr(importlib.import_module(mod), cls).ENV_ID == env_id
+    # the reference's own module paths exist for each registered class (reference bioimitation/__init__.py:11-20,75-86)
+    from bioimitation.imitation_envs.envs.muscle.spatial.muscle_palsy_imitation_env3D import MusclePalsyImitationEnv3D
+    assert MusclePalsyImitationEnv3D.ENV_ID == "MusclePalsyImitation3D-v0"

@@ -95,6 +95,11 @@ def main():
     cm2 = models["2d_muscle"]
     save_ref("2d_walking", refmotion.synth_gait_2d(cm2, curves, cycle_steps=132, n_rows=400, speed=1.0))
     save_ref("2d_running", refmotion.synth_gait_2d(cm2, curves, cycle_steps=70, n_rows=282, speed=1.9))
+    # tasks whose reference directories the reference does not ship (highjump / jumping / 3D running)
+    save_ref("2d_jumping", refmotion.synth_jump(cm2, n_rows=102))
+    cm3 = models["3d_muscle"]
+    save_ref("3d_running", refmotion.synth_gait(cm3, curves, cycle_steps=70, n_rows=282, speed=1.6))
+    save_ref("3d_jumping", refmotion.synth_jump(cm3, n_rows=102, takeoff_speed=2.0))
 
 
 if __name__ == "__main__":
