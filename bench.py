@@ -13,7 +13,16 @@ after the timed region).
 
 The reference arm cannot run OpenSim (not installable offline): it
 times the CPU restatement of the same algorithm (oracle/, kind "port") on all
-host cores, on a bounded sample of the same workload.
+host cores -- the benchmark build of the oracle (-O3 -march=native, FMA
+contraction, OpenMP over envs, compiled on the host that runs it), the SAME
+batch as the CUDA arm (4096 envs), INNER control steps per timed "step".
+
+Before anything is timed the CUDA arm rolls the batch 150 control steps
+(untimed, independent of --warmup), so that the timed window holds the
+auto-resets of a steady-state rollout (`rollout.episodes` counts the episodes
+that ended inside the timed + end-to-end loops).  With --gpus N >= 2 the line
+also carries `config5`: BASELINE.json's 1 048 576-env sweep (Palsy3D and
+LockedKnee3D at 1 048 576 / N envs per GPU).
 """
 from __future__ import annotations
 
@@ -122,34 +131,181 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.sm), "source": self.source}
 
 
-def cpu_arm(env_id, n_envs, steps, warmup, budget_s, threads, integrator=None):
+PREROLL = 150          # untimed control steps before warm-up (steady-state mix of episode ages)
+REF_INNER = 4          # control steps of the whole batch per timed "step" of the reference arm
+
+
+def _fast_oracle():
+    """The benchmark build of the oracle for this host; returns the oracle module bound to it."""
+    from oracle import oracle as orc
+    try:
+        os.environ["BIO_ORACLE_LIB"] = orc.build_fast()
+        orc._lib = None
+        kind = "-O3 -march=native -ffp-contract=fast, OpenMP"
+    except Exception as e:                 # no compiler on this host: the parity build that travelled with the repo
+        os.environ.pop("BIO_ORACLE_LIB", None)
+        orc._lib = None
+        orc.build()
+        kind = "parity build -O2 (fast build failed: %s)" % type(e).__name__
+    return orc, kind
+
+
+def cpu_arm(env_id, n_envs, steps, warmup, budget_s, threads, integrator=None, inner=1):
     """Oracle (CPU port) throughput on `threads` host threads; integrator=None: the stated fixed-step
     scheme of the CUDA path, 'adaptive_rkm': error-controlled Runge-Kutta-Merson at accuracy 1e-3, the
-    stand-in for the reference's default opensim.Manager integrator (restated algorithm, not OpenSim)."""
+    stand-in for the reference's default opensim.Manager integrator (restated algorithm, not OpenSim).
+    One "step" = `inner` control steps of all n_envs envs."""
     from bioimitation_gym_b200 import registry
-    from oracle import oracle as orc
-    orc.build()
+    orc, build = _fast_oracle()
     spec, cm, ref, task = registry.build_env_tables(env_id, dict(integrator=integrator) if integrator else {})
     rt = orc.RefTables(ref["q"], ref["u"], ref["body_pos"], ref["com_pos"])
     env = orc.OracleVecEnv(cm.tables, task, rt, n_envs, seed=0, threads=threads)
     env.reset()
     rng = np.random.default_rng(0)
     lo, hi = (-1.0, 1.0) if spec.torque else (0.0, 1.0)
-    for _ in range(warmup):
-        env.step(rng.uniform(lo, hi, (n_envs, cm.tables.n_act)))
+    acts = [rng.uniform(lo, hi, (n_envs, cm.tables.n_act)) for _ in range(4)]
+    for k in range(warmup * inner):
+        env.step(acts[k % 4])
     t0 = time.perf_counter()
     done_steps = 0
-    for _ in range(steps):
-        env.step(rng.uniform(lo, hi, (n_envs, cm.tables.n_act)))
+    for k in range(steps):
+        for j in range(inner):
+            env.step(acts[(k * inner + j) % 4])
         done_steps += 1
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return dict(value=n_envs * done_steps / dt, unit="env-steps/s", cores=threads, kind="port",
-                sample="%d envs x %d control steps of %s on %d threads (oracle/bio_oracle.c, fp64, %s)"
-                       % (n_envs, done_steps, env_id, threads,
+    return dict(value=n_envs * inner * done_steps / dt, unit="env-steps/s", cores=threads, kind="port",
+                sample="%d envs x %d control steps of %s on %d threads in %.1f s (oracle/bio_oracle.c, fp64, %s, %s)"
+                       % (n_envs, done_steps * inner, env_id, threads, dt, build,
                           "adaptive Runge-Kutta-Merson, accuracy 1e-3" if integrator else "same fixed-step scheme")), \
-        dt / max(done_steps, 1)
+        dt / max(done_steps * inner, 1)
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """CPU affinity of this rank = the cores of its GPU's NUMA node (sysfs), before any pinned allocation, so
+    that the page-locked buffers the step kernel writes over PCIe are node-local.  Returns what was done."""
+    info = {"numa_node": None, "cpus": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
+            "bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = int(vis.split(",")[local_rank]) if vis else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        base = "/sys/bus/pci/devices/" + bus
+        info["numa_node"] = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        want = cpus & allowed
+        if want and want != allowed:
+            os.sched_setaffinity(0, want)
+            info["bound"] = True
+        info["cpus"] = len(os.sched_getaffinity(0))
+    except Exception as e:                  # no NVML / sysfs: leave the affinity alone
+        info["error"] = type(e).__name__
+    return info
+
+
+def timed_loop(env, pool, steps, flush, barrier):
+    """`steps` control steps, each bracketed by CUDA events on the launching stream; returns total ms."""
+    import torch
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    barrier()
+    for k in range(steps):
+        if flush is not None:
+            flush.fill_(k & 0xFF)          # evict L2 between timed iterations (untimed)
+        starts[k].record()
+        env.step(pool[k % len(pool)])
+        stops[k].record()
+    barrier()
+    return float(sum(s.elapsed_time(e) for s, e in zip(starts, stops)))
+
+
+def e2e_loop(env, pool, steps, barrier):
+    """Host-buffer entry point (pinned host memory in, pinned host memory out, synchronous): wall seconds."""
+    import torch
+    N, na, D = env.num_envs, env.n_act, env.obs_dim
+    pin = lambda *s, dt=None: torch.empty(s, dtype=dt or env.dtype).pin_memory()
+    a_pin = [pin(N, na) for _ in range(4)]
+    for i, ap_ in enumerate(a_pin):
+        ap_.copy_(pool[i].cpu())
+    o_pin, r_pin, d_pin, t_pin = pin(N, D), pin(N), pin(N, dt=torch.uint8), pin(N, env.n_terms)
+    a_np = [t_.numpy() for t_ in a_pin]
+    o_np, r_np, d_np, t_np = o_pin.numpy(), r_pin.numpy(), d_pin.numpy(), t_pin.numpy()
+    for k in range(3):
+        env.step_host(a_np[k % 4], o_np, r_np, d_np, t_np)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        env.step_host(a_np[k % 4], o_np, r_np, d_np, t_np)
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0
+
+
+def run_config(env_id, n_per_gpu, steps, warmup, rank, world, local_rank, args, preroll, e2e_steps, barrier, flush):
+    """One workload: create, pre-roll, warm up, timed loop, end-to-end loop, statistics.  Returns a dict
+    (identical on every rank for the all-reduced fields)."""
+    import torch
+    import torch.distributed as dist
+    from bioimitation_gym_b200 import backend
+    dev = torch.device("cuda", local_rank)
+    cfg = dict(num_envs=n_per_gpu, device=local_rank, dtype=args.dtype, seed=1234, env_offset=rank * n_per_gpu)
+    if args.substeps:
+        cfg["substeps"] = args.substeps
+    if args.integrator:
+        cfg["integrator"] = args.integrator
+    env = backend.VecEnv(env_id, cfg)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    lo, hi = (-1.0, 1.0) if env.spec.torque else (0.0, 1.0)
+    pool = [torch.rand((n_per_gpu, env.n_act), generator=g, device=dev, dtype=env.dtype) * (hi - lo) + lo
+            for _ in range(16 if n_per_gpu <= 65536 else 4)]
+    env.reset()
+    for k in range(preroll + warmup):
+        env.step(pool[k % len(pool)])
+    barrier()
+    env.stats(reset=True)                      # count the episodes of the timed + end-to-end loops only
+    launches0 = env.launch_count
+    total_ms = timed_loop(env, pool, steps, flush, barrier)
+    launches = env.launch_count - launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    e2e_s = e2e_loop(env, pool, e2e_steps, barrier)
+    t = torch.tensor([e2e_s, -e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_max, e2e_min = float(t[0].item()), -float(t[1].item())
+    stats = env.stats().clone()
+    if world > 1:                              # the only collective: rollout statistics, outside the step path
+        gathered = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(gathered, stats)
+        stats = torch.stack(gathered).sum(0)
+    stats = stats.cpu().numpy()
+    esz = 4 if env.dtype == torch.float32 else 8
+    out = dict(env=env, value=n_per_gpu * world * steps / (total_ms * 1e-3), ms_per_step=total_ms / steps,
+               launches=int(launches), lo=lo, hi=hi,
+               e2e={"value": n_per_gpu * world * e2e_steps / e2e_max, "unit": "env-steps/s",
+                    "h2d_bytes_per_step": n_per_gpu * env.n_act * esz,
+                    "d2h_bytes_per_step": n_per_gpu * (env.obs_dim + 1 + env.n_terms) * esz + n_per_gpu,
+                    "steps": e2e_steps,
+                    "per_rank_ms_per_step": {"min": e2e_min / e2e_steps * 1e3, "max": e2e_max / e2e_steps * 1e3}},
+               rollout={"env_steps": float(stats[0]), "episodes": float(stats[1]),
+                        "mean_return": float(stats[2] / max(stats[1], 1)),
+                        "mean_length": float(stats[3] / max(stats[1], 1)),
+                        "done_height": float(stats[4]), "done_limit": float(stats[5]),
+                        "done_accel": float(stats[6]), "done_horizon": float(stats[7]),
+                        "done_feet": float(stats[8]), "done_nonfinite": float(stats[9]),
+                        "preroll_steps": preroll})
+    return out
 
 
 def main():
@@ -165,6 +321,8 @@ def main():
     ap.add_argument("--integrator", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the 1M-env sweep lines at --gpus >= 2")
+    ap.add_argument("--preroll", type=int, default=PREROLL)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -175,16 +333,17 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        n = cores * 16
-        cb, spstep = cpu_arm(args.env_id, n, args.steps, max(1, min(args.warmup, 2)), 120.0, cores)
+        warm = max(3, args.warmup)
+        cb, spstep = cpu_arm(args.env_id, args.envs_per_gpu, args.steps, min(warm, 3), 240.0, cores, inner=REF_INNER)
         from bioimitation_gym_b200 import registry, tasks
         spec, cm, ref, task = registry.build_env_tables(args.env_id, {})
         line = {"impl": "reference", "metric": "env_steps_per_sec", "value": cb["value"], "unit": "env-steps/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": spstep * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "%s, %d envs/GPU (reference arm: bounded sample of %d envs on host CPU)"
-                                       % (args.env_id, args.envs_per_gpu, n),
+                "config": {"workload": "%s, %d envs/GPU (reference arm: the same batch of %d envs on the host CPU, "
+                                       "one timed step = %d control steps of the batch)"
+                                       % (args.env_id, args.envs_per_gpu, args.envs_per_gpu, REF_INNER),
                            "integrator": tasks.DEFAULT_INTEGRATOR, "substeps": task.n_substeps,
                            "note": "OpenSim 4.1 is not installable offline; this is the CPU restatement "
                                    "(oracle port) of the same algorithm, not OpenSim"},
@@ -195,9 +354,10 @@ def main():
         print(json.dumps(line))
         return
 
+    affinity = bind_to_gpu_numa_node(local_rank)   # before CUDA / pinned allocations
     import torch
     import torch.distributed as dist
-    from bioimitation_gym_b200 import backend, tasks
+    from bioimitation_gym_b200 import tasks
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -217,18 +377,7 @@ def main():
             os.close(saved)
     dev = torch.device("cuda", local_rank)
     N = args.envs_per_gpu
-    cfg = dict(num_envs=N, device=local_rank, dtype=args.dtype, seed=1234, env_offset=rank * N)
-    if args.substeps:
-        cfg["substeps"] = args.substeps
-    if args.integrator:
-        cfg["integrator"] = args.integrator
-    env = backend.VecEnv(args.env_id, cfg)
-    na, D = env.n_act, env.obs_dim
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    lo, hi = (-1.0, 1.0) if env.spec.torque else (0.0, 1.0)
-    pool = [torch.rand((N, na), generator=g, device=dev, dtype=env.dtype) * (hi - lo) + lo for _ in range(16)]
     flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    env.reset()
 
     def barrier():
         if world > 1:
@@ -240,71 +389,34 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for k in range(args.warmup):
-        env.step(pool[k % len(pool)])
-    barrier()
-    launches0 = env.launch_count
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
-    for k in range(args.steps):
-        if flush is not None:
-            flush.fill_(k & 0xFF)          # evict L2 between timed iterations (untimed)
-        starts[k].record()
-        env.step(pool[k % len(pool)])
-        stops[k].record()
-    barrier()
-    launches = env.launch_count - launches0
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
-    total_ms = float(sum(step_ms))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = N * world * args.steps / (total_ms * 1e-3)
-
-    # ---- end-to-end through the host-buffer entry point (pinned host memory) ----
-    np_dt = np.float32 if env.dtype == torch.float32 else np.float64
-    pin = lambda *s, dt=None: torch.empty(s, dtype=dt or env.dtype).pin_memory()
-    a_pin = [pin(N, na) for _ in range(4)]
-    for i, ap_ in enumerate(a_pin):
-        ap_.copy_(pool[i].cpu())
-    o_pin, r_pin, d_pin, t_pin = pin(N, D), pin(N), pin(N, dt=torch.uint8), pin(N, env.n_terms)
-    e2e_steps = max(10, min(args.steps, 100))
-    # page-locked buffers: bio_step_host lets the step kernel read the actions from and write the results into
-    # them in place (PCIe traffic inside the timed region: h2d / d2h bytes below), and returns after a stream
-    # synchronisation, i.e. when the host can read the results
-    a_np = [t_.numpy() for t_ in a_pin]
-    o_np, r_np, d_np, t_np = o_pin.numpy(), r_pin.numpy(), d_pin.numpy(), t_pin.numpy()
-    for k in range(3):
-        env.step_host(a_np[k % 4], o_np, r_np, d_np, t_np)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        env.step_host(a_np[k % 4], o_np, r_np, d_np, t_np)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = N * world * e2e_steps / float(t.item())
-    esz = 4 if env.dtype == torch.float32 else 8
-    h2d = N * na * esz
-    d2h = N * (D + 1 + env.n_terms) * esz + N
-
-    # ---- rollout statistics: the only collective (outside the step path) ----
-    stats = env.stats().clone()
-    if world > 1:
-        gathered = [torch.zeros_like(stats) for _ in range(world)]
-        dist.all_gather(gathered, stats)
-        stats = torch.stack(gathered).sum(0)
-    stats = stats.cpu().numpy()
-
+    res = run_config(args.env_id, N, args.steps, args.warmup, rank, world, local_rank, args, args.preroll,
+                     max(10, min(args.steps, 100)), barrier, flush)
+    env = res["env"]
+    shape = dict(zip(("size_class", "threads", "ctas_per_sm"), env.coop_shape()))
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
+    if res["rollout"]["episodes"] <= 0 and args.preroll >= PREROLL and env.task.auto_reset:
+        raise SystemExit("no episode ended inside the timed region: the window does not hold auto-resets")
+
+    # ---- BASELINE.json config 5 at N >= 2: 1 048 576 envs over the N GPUs (kept short: 3 + 10 steps) ----
+    config5 = None
+    if world > 1 and not args.no_config5 and args.env_id == ENV_ID:
+        config5 = {}
+        env.close()
+        for env5 in ("MusclePalsyImitation3D-v0", "MuscleLockedKneeImitation3D-v0"):
+            n5 = 1048576 // world
+            r5 = run_config(env5, n5, 10, 3, rank, world, local_rank, args, 0, 5, barrier, None)
+            f5, _ = _flops_per_env_step(r5["env"].task, env5)
+            r5["env"].close()
+            config5[env5] = {"envs_total": n5 * world, "envs_per_gpu": n5, "value": r5["value"],
+                             "ms_per_step": r5["ms_per_step"], "e2e": r5["e2e"], "steps": 10, "warmup": 3,
+                             "l2": "inputs larger than L2 (no flush)", "episodes": r5["rollout"]["episodes"],
+                             "flops_per_env_step": f5}
+
+    if rank == 0:
         flops, fdetail = _flops_per_env_step(env.task, args.env_id)
-        ms_launch = total_ms / args.steps
+        ms_launch = res["ms_per_step"]
         roofline = None
         peaks = {}
         try:
@@ -317,9 +429,9 @@ def main():
             fp32_peak = v if v > 0 else None
         except Exception:
             pass
+        peak = fp32_peak or 148 * 128 * 2 * 1.965e9 / 1e12
         if flops is not None:
             achieved = flops * N / (ms_launch * 1e-3) / 1e12
-            peak = fp32_peak or 148 * 128 * 2 * 1.965e9 / 1e12
             roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                         "frac": achieved / peak,
                         "peak_source": "measured on this GPU by bio_measure_fp32_peak (FFMA chain, FMA = 2 flops)" if fp32_peak
@@ -330,39 +442,44 @@ def main():
                     "bytes_per_launch"]
             except Exception:
                 pass
+        if config5:
+            for v5 in config5.values():
+                if v5["flops_per_env_step"]:
+                    v5["frac_of_fp32_peak_per_gpu"] = v5["flops_per_env_step"] * v5["value"] / world / 1e12 / peak
+        esz = 4 if env.dtype == torch.float32 else 8
+        na, D = env.n_act, env.obs_dim
         state_bytes = (2 * env.n_dof + 2 * env.n_muscles) * esz
         alg_bytes = (na * esz + 2 * state_bytes + 2 * env.task.horizon * na * esz + D * esz + (2 + env.n_terms) * esz)
         hbm = {"bound": "hbm", "achieved": alg_bytes * N / (ms_launch * 1e-3) / 1e9,
                "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s", "bytes_per_env_step": alg_bytes,
                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
         hbm["frac"] = hbm["achieved"] / hbm["peak"]
-        line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
+        line = {"metric": "env_steps_per_sec", "value": res["value"], "unit": "env-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_launch, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if env.dtype == torch.float32 else "f64", "data": "synthetic",
-                "config": {"workload": "%s, %d envs/GPU, actions U[%g,%g] resident in HBM" % (args.env_id, N, lo, hi),
+                "config": {"workload": "%s, %d envs/GPU, actions U[%g,%g] resident in HBM"
+                                       % (args.env_id, N, res["lo"], res["hi"]),
                            "integrator": [k for k, v in tasks.INTEGRATORS.items() if v == env.task.integrator][0],
                            "substeps": env.task.n_substeps, "h_seconds": env.task.dt / env.task.n_substeps,
+                           "preroll": "%d untimed control steps before warm-up (steady-state episode mix)" % args.preroll,
                            "l2": "flushed between timed iterations (256 MiB write, untimed)" if flush is not None
-                           else "not flushed", "sharding": "env index, no collective in the step path"},
-                "roofline": roofline, "roofline_hbm": hbm,
-                "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-                "gpu_launches": int(launches), "clocks": sampler.summary(),
-                "rollout": {"env_steps": float(stats[0]), "episodes": float(stats[1]),
-                            "mean_return": float(stats[2] / max(stats[1], 1)),
-                            "mean_length": float(stats[3] / max(stats[1], 1)),
-                            "done_height": float(stats[4]), "done_limit": float(stats[5]),
-                            "done_accel": float(stats[6]), "done_horizon": float(stats[7]),
-                            "done_feet": float(stats[8]), "done_nonfinite": float(stats[9])}}
+                           else "not flushed", "sharding": "env index, no collective in the step path",
+                           "kernel_shape": shape},
+                "roofline": roofline, "roofline_hbm": hbm, "e2e": res["e2e"],
+                "gpu_launches": res["launches"], "clocks": sampler.summary(), "rollout": res["rollout"],
+                "affinity": affinity}
+        if config5:
+            line["config5"] = config5
         if world == 1 and not args.no_cpu_baseline:
-            cb, _ = cpu_arm(args.env_id, cores * 16, 10 ** 9, 1, 15.0, cores)
+            cb, _ = cpu_arm(args.env_id, N, 10 ** 9, 1, 15.0, cores)
             # the reference's own integrator setting (adaptive, accuracy 1e-3), restated: context for the ratio
-            ad, _ = cpu_arm(args.env_id, cores * 8, 10 ** 9, 1, 8.0, cores, integrator="adaptive_rkm")
+            ad, _ = cpu_arm(args.env_id, min(N, cores * 32), 10 ** 9, 1, 8.0, cores, integrator="adaptive_rkm")
             cb["adaptive_scheme"] = {"value": ad["value"], "unit": ad["unit"], "sample": ad["sample"]}
             line["cpu_baseline"] = cb
         print(json.dumps(line))
-    env.close()
+    if not config5:
+        env.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -6,14 +6,21 @@
  * __graft_entry__.smoke() as the checker and by bench.py's cpu_baseline /
  * --impl reference legs.
  *
- * PARITY UNPINNED: the arithmetic of this path lives in opensim==4.1
- * (reference setup.py:7; mitkof6/opensim-core@bindings_timestepper,
- * reference scripts/build_opensim-core:32) and its bundled Simbody, neither
- * of which is under /root/reference nor installable offline, and the
- * reference ships no golden vectors.  The physics below restates the
- * published models (Millard 2013 muscle, Simbody Hunt-Crossley contact,
- * OpenSim CoordinateLimitForce, SIMM splines, rigid-body dynamics); it is
- * pinned only by the first-principles tests in tests/test_oracle_physics.py.
+ * PARITY UNPINNED for the dynamics as a whole: the arithmetic of this path
+ * lives in opensim==4.1 (reference setup.py:7;
+ * mitkof6/opensim-core@bindings_timestepper, reference
+ * scripts/build_opensim-core:32) and its bundled Simbody, neither of which is
+ * under /root/reference nor installable offline, and the reference ships no
+ * golden vectors.  The physics below restates the published models (Millard
+ * 2013 muscle, Simbody Hunt-Crossley contact, OpenSim CoordinateLimitForce,
+ * SIMM splines, rigid-body dynamics); it is pinned by the first-principles
+ * tests in tests/test_oracle_physics.py and, for forward kinematics, mass
+ * distribution, rigid-body inverse dynamics, moment arms and the active
+ * force-length-velocity curves, by the OpenSim-produced artefacts the
+ * reference holds (tests/test_reference_artefacts.py: ScaleTool static pose to
+ * 5e-7 m, IK solution, force plates, StaticOptimization).  Contact, limit
+ * forces, tendon compliance, activation dynamics and the integrator have no
+ * OpenSim-produced number anywhere and stay unpinned.
  * Everything that IS reference source (observation layout, reward,
  * termination, reset, action pre-processing) follows the cited lines.
  *
@@ -1022,6 +1029,34 @@ void orc_batch_step(const BioModelTables* m, const BioTaskConfig* c, const BioRe
             orc_reset_env(m, c, ref, &envs[i], seed, (uint64_t)(env_offset + i), obs + (size_t)i * od);
         }
     }
+}
+
+/* The same over all envs on `threads` OpenMP threads (the CPU arms of bench.py; built with -fopenmp in the
+   "fast" build only, plain loop otherwise). */
+void orc_batch_step_mt(const BioModelTables* m, const BioTaskConfig* c, const BioRefTables* ref, OrcEnv* envs,
+                       int n, uint64_t seed, int64_t env_offset, const double* actions, double* obs,
+                       double* reward, uint8_t* done, double* terms, int* reasons, int threads) {
+    int od = orc_obs_dim(m, c);
+    const int chunk = 8;
+    const int nchunks = (n + chunk - 1) / chunk;
+    (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+#endif
+    for (int k = 0; k < nchunks; k++) {
+        const int i0 = k * chunk, cnt = (i0 + chunk <= n) ? chunk : n - i0;
+        orc_batch_step(m, c, ref, envs + i0, cnt, seed, env_offset + i0, actions + (size_t)i0 * m->n_act,
+                       obs + (size_t)i0 * od, reward + i0, done + i0,
+                       terms ? terms + (size_t)i0 * c->n_reward_terms : NULL, reasons ? reasons + i0 : NULL);
+    }
+}
+
+int orc_openmp(void) {
+#ifdef _OPENMP
+    return 1;
+#else
+    return 0;
+#endif
 }
 
 void orc_batch_reset(const BioModelTables* m, const BioTaskConfig* c, const BioRefTables* ref, OrcEnv* envs,

@@ -56,6 +56,22 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def build_fast() -> str:
+    """The benchmark build (-O3 -march=native, FMA contraction, OpenMP) for the host this runs on; compiled here
+    when missing.  Never used by parity tests (its results differ from the parity build in the last bits)."""
+    import hashlib
+    try:
+        flags = [ln for ln in open("/proc/cpuinfo") if ln.startswith(("flags", "model name"))][:2]
+    except OSError:
+        flags = []
+    tag = hashlib.sha1("".join(flags).encode()).hexdigest()[:10]
+    path = os.path.join(_HERE, "_build", "libbio_oracle_fast_%s.so" % tag)
+    src = os.path.join(_HERE, "bio_oracle.c")
+    if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(src), os.path.getmtime(ct.HEADER)):
+        subprocess.check_call(["make", "-C", _HERE, "fast", "TAG=" + tag], stdout=subprocess.DEVNULL)
+    return path
+
+
 _lib = None
 
 
@@ -64,8 +80,9 @@ def lib():
     if _lib is None:
         if not os.path.exists(_LIB_PATH):
             build()
-        # BIO_ORACLE_LIB: the op-counting build (oracle/count_flops.py)
+        # BIO_ORACLE_LIB: the op-counting build (oracle/count_flops.py) or the benchmark build (build_fast)
         L = ctypes.CDLL(os.environ.get("BIO_ORACLE_LIB", _LIB_PATH))
+        L.orc_openmp.restype = ctypes.c_int
         for f in ("orc_sizeof_env", "orc_sizeof_eval", "orc_sizeof_model_tables",
                   "orc_sizeof_task_config", "orc_splitmix64", "orc_rand"):
             getattr(L, f).restype = ctypes.c_uint64
@@ -226,7 +243,13 @@ class OracleVecEnv:
                                   ctypes.c_int64(self.env_offset + i0), _p(actions[i0:i1]),
                                   _p(obs[i0:i1]), _p(rew[i0:i1]), _p(done[i0:i1]),
                                   _p(terms[i0:i1]), _p(reasons[i0:i1]))
-        if self._pool:
+        if self.threads > 1 and self.L.orc_openmp():
+            # benchmark build: one call, OpenMP over chunks of envs inside the library
+            self.L.orc_batch_step_mt(ctypes.byref(self.tables), ctypes.byref(self.task), ctypes.byref(self.ref.struct),
+                                     ctypes.c_void_p(base), self.n, ctypes.c_uint64(self.seed),
+                                     ctypes.c_int64(self.env_offset), _p(actions), _p(obs), _p(rew), _p(done), _p(terms),
+                                     _p(reasons), int(self.threads))
+        elif self._pool:
             list(self._pool.map(run, self._slices()))
         else:
             run((0, self.n))
