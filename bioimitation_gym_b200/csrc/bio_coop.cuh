@@ -393,11 +393,11 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         const T lmc = lmi < lmin ? lmin : lmi;
         const T lat = Num<T>::sqrt_pos(lmc * lmc - h * h);
         const T cosa = Num<T>::div(lat, lmc);
-        T fal, fpe, ft, fv, dfv, dtmp;
+        T fal, fpe, ft, fv, dfv, dfal, dfpe, dft;
         const T lnorm = Num<T>::div(lmc, lopt);
-        curve_eval(m, 0, lnorm, fal, dtmp);
-        curve_eval(m, 2, lnorm, fpe, dtmp);
-        curve_eval(m, 3, Num<T>::div(L - lat, m.mus_lts[i]), ft, dtmp);
+        curve_eval(m, 0, lnorm, fal, dfal);
+        curve_eval(m, 2, lnorm, fpe, dfpe);
+        curve_eval(m, 3, Num<T>::div(L - lat, m.mus_lts[i]), ft, dft);
         const T ac = clampv(E.act[i], amin, T(1));
         const T afal = ac * fal;
         // Newton on the damped-equilibrium residual, warm-started from the root of the previous
@@ -407,10 +407,12 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         // (start: extrapolated from the last two roots of this control step, see p2_phase_c)
         const T vlast = E.vn[i], age = E.vna[i];
         T vn = vlast + (age >= T(2) ? E.vnd[i] : T(0));
+        T fsum = T(0), derr = T(1);
         for (int it = 0; it < newton_iters; it++) {
             curve_eval(m, 1, vn, fv, dfv);
-            const T err = (afal * fv + fpe + beta * vn) * cosa - ft;
-            const T derr = (afal * dfv + beta) * cosa;
+            fsum = afal * fv + fpe + beta * vn;
+            const T err = fsum * cosa - ft;
+            derr = (afal * dfv + beta) * cosa;
             const T delta = -Num<T>::div(err, derr);
             const T vnew = vn + delta;
             const bool crossed = vnew * vn < T(0);
@@ -421,7 +423,13 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         E.vnd[i] = vn - vlast;
         E.vna[i] = age + T(1);
         if (lmi <= lmin && vn < T(0)) vn = T(0);
-        E.lmdot[i] = vn * m.mus_vmax[i] * lopt;
+        // linearly implicit fibre-length update (fibre_gain): lmdot carries the factor 1 / (1 - h lambda) in the
+        // substep evaluations (h_imp > 0); the full evaluation (h_imp = 0) reports the fibre velocity itself
+        T gain = T(1);
+        if (h_imp > T(0))
+            gain = fibre_gain(h_imp, m.mus_vmax[i] * lopt, derr, ac * dfal * fv + dfpe, Num<T>::rcp(lopt), cosa, fsum, lmc, lat,
+                              h * h, dft, Num<T>::rcp(m.mus_lts[i]));
+        E.lmdot[i] = vn * m.mus_vmax[i] * lopt * gain;
         const T ec = clampv(E.ctrl[i], amin, T(1));
         const T tau = ec > ac ? m.mus_tact[i] * (T(0.5) + T(1.5) * ac) : Num<T>::div(m.mus_tdeact[i], T(0.5) + T(1.5) * ac);
         E.adot[i] = Num<T>::div(ec - ac, tau);

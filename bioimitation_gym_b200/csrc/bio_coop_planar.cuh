@@ -291,7 +291,7 @@ __device__ __forceinline__ void p2_phase_b_scan(const DevModel<T>& m, EnvWork<T,
 // ---- phase C: lane = muscle ----
 template <typename T, int CLS>
 BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane, const int newton_iters,
-                        const bool full) {
+                        const T h_imp, const bool full) {
     const PlanarProg<T>& pr = m.prog;
     auto& K = E.k.p;
     if (lane >= m.n_muscles) return;
@@ -419,8 +419,8 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     const T lmc = lmi < lmin ? lmin : lmi;
     const T lat = Num<T>::sqrt_pos(lmc * lmc - h2);
     const T cosa = Num<T>::div(lat, lmc);
-    T fal, fpe, ft, fv, dfv, dtmp;
-    curve_eval(m, 3, (L - lat) * inv_lts, ft, dtmp);
+    T fal, fpe, ft, fv, dfv, dfal, dfpe, dft;
+    curve_eval(m, 3, (L - lat) * inv_lts, ft, dft);
     const T tension = fiso * ft;
     {   // wrench sources of this muscle: one per body it touches
         const int s0 = pr.mus_src0[i], ns = pr.mus_src0[i + 1] - s0;
@@ -434,8 +434,8 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         if (mov >= 0) K.mq[mov] = tension * mqu;
     }
     const T lnorm = lmc * inv_lopt;
-    curve_eval(m, 0, lnorm, fal, dtmp);
-    curve_eval(m, 2, lnorm, fpe, dtmp);
+    curve_eval(m, 0, lnorm, fal, dfal);
+    curve_eval(m, 2, lnorm, fpe, dfpe);
     const T ac = clampv(E.act[i], amin, T(1));
     const T afal = ac * fal;
     // Newton on the damped-equilibrium residual, warm-started from the root of the previous
@@ -448,10 +448,12 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     // iteration stays globally convergent.
     const T vlast = E.vn[i], age = E.vna[i];
     T vn = vlast + (age >= T(2) ? E.vnd[i] : T(0));
+    T fsum = T(0), derr = T(1);
     for (int it = 0; it < newton_iters; it++) {
         curve_eval(m, 1, vn, fv, dfv);
-        const T err = (afal * fv + fpe + beta * vn) * cosa - ft;
-        const T derr = (afal * dfv + beta) * cosa;
+        fsum = afal * fv + fpe + beta * vn;
+        const T err = fsum * cosa - ft;
+        derr = (afal * dfv + beta) * cosa;
         const T delta = -Num<T>::div(err, derr);
         const T vnew = vn + delta;
         const bool crossed = vnew * vn < T(0);
@@ -462,7 +464,11 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     E.vnd[i] = vn - vlast;
     E.vna[i] = age + T(1);
     if (lmi <= lmin && vn < T(0)) vn = T(0);
-    E.lmdot[i] = vn * vmax_lopt;
+    // linearly implicit fibre-length update (fibre_gain): lmdot carries the factor 1 / (1 - h lambda) in the substep
+    // evaluations (h_imp > 0); the full evaluation (h_imp = 0) reports the fibre velocity itself
+    T gain = T(1);
+    if (h_imp > T(0)) gain = fibre_gain(h_imp, vmax_lopt, derr, ac * dfal * fv + dfpe, inv_lopt, cosa, fsum, lmc, lat, h2, dft, inv_lts);
+    E.lmdot[i] = vn * vmax_lopt * gain;
     // activation ODE: adot = (e - a) / tau, tau = tact (0.5 + 1.5 a) rising, tdeact / (0.5 + 1.5 a) falling
     const T ec = clampv(E.ctrl[i], amin, T(1));
     const T wa = T(0.5) + T(1.5) * ac;
@@ -847,7 +853,7 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
     else p2_phase_b<T, CLS>(m, E, lane);
     gsync<G>();
     P2_CLK(1);
-    p2_phase_c<T, CLS>(m, E, lane, newton_iters, full);
+    p2_phase_c<T, CLS>(m, E, lane, newton_iters, h_imp, full);
     P2_CLK(2);
     p2_phase_d<T, CLS>(m, E, lane, h_imp);
     gsync<G>();

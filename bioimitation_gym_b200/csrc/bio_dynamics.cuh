@@ -211,6 +211,21 @@ BIO_DEV void curve_eval(const DevModel<T>& m, int c, T x, T& y, T& dy) {
 template <typename T>
 BIO_DEV T curve_value(const DevModel<T>& m, int c, T x) { T y, d; curve_eval(m, c, x, y, d); return y; }
 
+// Linearly implicit fibre-length update of the stated scheme (h_imp > 0, substep evaluations only): the integrator
+// advances lm by h lmdot / (1 - h lambda), lambda = d(lmdot)/d(lm) = -vmax lopt g_lm / g_vn of the damped equilibrium
+// g(vn, lm) = 0 at the last Newton iterate (same recipe as muscle_dynamics of the oracle, see there):
+//   g_lm = (a fal' fv + fpe') cos(alpha) / lopt + fsum sin^2(alpha) / (lm cos(alpha)) + ft' / (lts cos(alpha)) >= 0
+// Returns 1 / (1 - h lambda), the factor on lmdot.  With lat = lm cos(alpha) (fibre length along the tendon) and
+// h2 = (lm sin(alpha))^2 (constant fibre height squared): sin^2 / (lm cos) = h2 / (lm^2 lat), 1 / cos = lm / lat.
+template <typename T>
+BIO_DEV T fibre_gain(const T h_imp, const T vmax_lopt, const T g_vn, const T dact_pe, const T inv_lopt, const T cosa,
+                     const T fsum, const T lmc, const T lat, const T h2, const T dft, const T inv_lts) {
+    const T ilat = Num<T>::rcp(lat), ilm = cosa * ilat;             // 1 / lat, 1 / lm
+    T glm = dact_pe * inv_lopt * cosa + (fsum * h2 * ilm * ilm + dft * inv_lts * lmc) * ilat;
+    glm = glm < T(0) ? T(0) : glm;
+    return Num<T>::div(g_vn, g_vn + h_imp * vmax_lopt * glm);
+}
+
 template <typename T>
 struct Kin {
     T O[3];
@@ -469,23 +484,27 @@ __device__ void eval_dynamics(const DevModel<T>& m, int newton_iters, const T* q
         const T lmc = lmi < lmin ? lmin : lmi;
         const T lat = Num<T>::sqrt(lmc * lmc - h * h);
         const T cosa = lat / lmc;
-        T fal, fpe, ft, fv, dfv, dtmp;
-        curve_eval(m, 0, lmc / lopt, fal, dtmp);
-        curve_eval(m, 2, lmc / lopt, fpe, dtmp);
-        curve_eval(m, 3, (L - lat) / m.mus_lts[i], ft, dtmp);
+        T fal, fpe, ft, fv, dfv, dfal, dfpe, dft;
+        curve_eval(m, 0, lmc / lopt, fal, dfal);
+        curve_eval(m, 2, lmc / lopt, fpe, dfpe);
+        curve_eval(m, 3, (L - lat) / m.mus_lts[i], ft, dft);
         const T ac = clampv(act[i], amin, T(1));
         const T afal = ac * fal;
-        T vn = T(0);
+        T vn = T(0), gain = T(1);
         for (int it = 0; it < newton_iters; it++) {
             curve_eval(m, 1, vn, fv, dfv);
-            const T err = (afal * fv + fpe + beta * vn) * cosa - ft;
+            const T fsum = afal * fv + fpe + beta * vn;
+            const T err = fsum * cosa - ft;
             const T derr = (afal * dfv + beta) * cosa;
             const T delta = -err / derr;
+            if (h_imp > T(0))
+                gain = fibre_gain(h_imp, m.mus_vmax[i] * lopt, derr, ac * dfal * fv + dfpe, T(1) / lopt, cosa, fsum, lmc, lat,
+                                  h * h, dft, T(1) / m.mus_lts[i]);
             vn += delta;
             if (Num<T>::abs(delta) < Num<T>::newton_tol()) break;
         }
         if (lmi <= lmin && vn < T(0)) vn = T(0);
-        o.lmdot[i] = vn * m.mus_vmax[i] * lopt;
+        o.lmdot[i] = vn * m.mus_vmax[i] * lopt * gain;
         const T ec = clampv(ctrl[i], amin, T(1));
         const T tau = ec > ac ? m.mus_tact[i] * (T(0.5) + T(1.5) * ac) : m.mus_tdeact[i] / (T(0.5) + T(1.5) * ac);
         o.adot[i] = (ec - ac) / tau;

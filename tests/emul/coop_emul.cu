@@ -28,7 +28,7 @@ int run(const BioModelTables* s, int newton_iters, const double* q, const double
     for (int i = 0; i < s->n_act; i++) E->ctrl[i] = (T)ctrl[i];
     for (int l = 0; l < G; l++) p2_phase_a<T, 0>(*m, *E, l);
     for (int l = 0; l < G; l++) p2_phase_b<T, 0>(*m, *E, l);
-    for (int l = 0; l < G; l++) { p2_phase_c<T, 0>(*m, *E, l, newton_iters, true); p2_phase_d<T, 0>(*m, *E, l, (T)h_imp); }
+    for (int l = 0; l < G; l++) { p2_phase_c<T, 0>(*m, *E, l, newton_iters, (T)h_imp, true); p2_phase_d<T, 0>(*m, *E, l, (T)h_imp); }
     for (int l = 0; l < G; l++) p2_phase_e<T, 0>(*m, *E, l, (T)h_imp, (T)ext_fx, ext_pt);
     for (int l = 0; l < G; l++) p2_phase_f<T, 0>(*m, *E, l);
     for (int l = 0; l < G; l++) p2_phase_g<T, 0>(*m, *E, l);
