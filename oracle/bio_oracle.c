@@ -258,33 +258,36 @@ static void muscle_dynamics(const BioModelTables* m, int i, double L, double a, 
     orc_curve_eval(m, 2, lmc / lopt, &fpe, &dfpe);
     orc_curve_eval(m, 3, lt / lts, &ft, &dft);
     double ac = clampd(a, amin, 1.0);
-    double vn = 0.0, gain = 1.0;
+    double vn = 0.0, gain = 1.0, fsum = 0.0, derr = 1.0;
+    fv = 1.0; dfv = 0.0;
     for (int it = 0; it < newton_iters; it++) {
         orc_curve_eval(m, 1, vn, &fv, &dfv);
-        double fsum = ac * fal * fv + fpe + beta * vn;
+        fsum = ac * fal * fv + fpe + beta * vn;
         double err = fsum * cosa - ft;
-        double derr = (ac * fal * dfv + beta) * cosa;
+        derr = (ac * fal * dfv + beta) * cosa;
         double delta = -err / derr;
-        /* Linearly implicit fibre-length update of the stated scheme (h_imp > 0): the fibre
-           velocity of the damped equilibrium g(vn, lm) = 0 falls steeply with the fibre length where the passive
-           element and the tendon are stretched, lambda = d(lmdot)/d(lm) = -vmax lopt g_lm / g_vn (measured down to
-           -4.2e3 1/s for the glutei of the 3D models, h lambda = -2.1 at h = 0.5 ms: beyond explicit Euler).  The
-           integrator advances lm by h lmdot / (1 - h lambda); g_lm and g_vn are taken at the last Newton iterate:
+        vn += delta;
+        if (fabs(delta) < 1e-12) break;
+    }
+    if (h_imp > 0) {
+        /* Linearly implicit fibre-length update of the stated scheme: the fibre velocity of
+           the damped equilibrium g(vn, lm) = 0 falls steeply with the fibre length where the passive element and
+           the tendon are stretched, lambda = d(lmdot)/d(lm) = -vmax lopt g_lm / g_vn (measured down to -4.2e3 1/s
+           for the glutei of the 3D models, h lambda = -2.1 at h = 0.5 ms: beyond explicit Euler).  The integrator
+           advances lm by h lmdot / (1 - h lambda); g_lm and g_vn (= derr) are taken at the last Newton iterate:
              g_lm = (a fal' fv + fpe') cos(alpha) / lopt + (a fal fv + fpe + beta vn) sin^2(alpha) / (lm cos(alpha))
                     + ft' / (lts cos(alpha)),   clamped at >= 0 (descending limb of the active curve) */
         double glm = (ac * dfal * fv + dfpe) / lopt * cosa + fsum * (1.0 - cosa * cosa) / (lmc * cosa)
                      + dft / (lts * cosa);
         if (glm < 0) glm = 0;
-        gain = 1.0 / (1.0 + h_imp * m->mus_vmax[i] * lopt * glm / derr);
-        vn += delta;
-        if (fabs(delta) < 1e-12) break;
+        gain = derr / (derr + h_imp * m->mus_vmax[i] * lopt * glm);
     }
     if (lm <= m->mus_lm_min[i] && vn < 0) vn = 0.0;   /* clamped fibre cannot shorten */
     orc_curve_eval(m, 1, vn, &fv, &dfv);
     o->Fact = fiso * ac * fal * fv;
     o->Ffib = fiso * (ac * fal * fv + fpe + beta * vn);
     o->T = fiso * ft;
-    o->lmdot = vn * m->mus_vmax[i] * lopt * (h_imp > 0 ? gain : 1.0);
+    o->lmdot = vn * m->mus_vmax[i] * lopt * gain;
     double ec = clampd(e, amin, 1.0);
     double tau = ec > ac ? m->mus_tact[i] * (0.5 + 1.5 * ac) : m->mus_tdeact[i] / (0.5 + 1.5 * ac);
     o->adot = (ec - ac) / tau;

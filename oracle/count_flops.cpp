@@ -42,6 +42,8 @@ static inline cd exp(const cd& a) { g_ops[4]++; return cd(::exp(a.v)); }
 static inline cd fabs(const cd& a) { g_ops[5]++; return cd(::fabs(a.v)); }
 static inline cd floor(const cd& a) { g_ops[5]++; return cd(::floor(a.v)); }
 static inline cd ceil(const cd& a) { g_ops[5]++; return cd(::ceil(a.v)); }
+static inline cd pow(const cd& a, const cd& b) { g_ops[4]++; return cd(::pow(a.v, b.v)); }
+static inline cd pow(const cd& a, double b) { g_ops[4]++; return cd(::pow(a.v, b)); }
 static inline cd fmod(const cd& a, const cd& b) { g_ops[2]++; return cd(::fmod(a.v, b.v)); }
 #undef isnan
 #undef isfinite

@@ -27,7 +27,8 @@ sys.path = [p for p in sys.path if os.path.abspath(p or ".") != HERE]
 sys.path.insert(0, ROOT)
 LIB = os.path.join(HERE, "_build", "libbio_oracle_count.so")
 
-ENVS = ["MuscleWalkingImitation2D-v0", "TorqueWalkingImitation2D-v0", "MuscleWalkingImitation3D-v0",
+ENVS = ["MuscleWalkingImitation2D-v0", "TorqueWalkingImitation2D-v0", "MuscleRunningImitation2D-v0",
+        "MuscleJumpingImitation2D-v0", "MuscleLockedKneeImitation2D-v0", "MuscleWalkingImitation3D-v0",
         "MusclePalsyImitation3D-v0", "MuscleLockedKneeImitation3D-v0", "TorqueWalkingImitation3D-v0"]
 
 
