@@ -126,7 +126,7 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
     if (const char* e = getenv("BIO_BLOCK")) { int b = atoi(e); if (b >= 32 && b <= 256 && b % 32 == 0) h->block = b; }
     int rc;
     if ((rc = set_kernel_attrs(h))) return rc;
-    bool prog_ok = false;
+    bool prog_ok = false, gpath_ok = false;
     int prog_src = 0;
     // model block
     {
@@ -141,6 +141,7 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
         cudaError_t e = cudaMemcpy(h->d_model, hm, sizeof(bio::DevModel<T>), cudaMemcpyHostToDevice);
         prog_ok = hm->prog.ok != 0;
         prog_src = hm->prog.n_src;
+        gpath_ok = hm->prog.gpath_ok != 0;
         delete hm;
         CU(e);
     }
@@ -172,14 +173,20 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
                    model->n_obspts <= COOP_MAXOBS && model->n_coords <= 2 * G && task->n_pd <= G;
         };
         const size_t base = ((sizeof(bio::DevModel<T>) + 15) / 16) * 16;
-        // launch shape by the number of item rounds per SM (see COOP_THREADS_LO / _HI in bio_coop.cuh)
-        auto pick_threads = [&](int G) {
-            const int lo = COOP_THREADS_LO(T), hi = COOP_THREADS_HI(T);
-            if (const char* e = getenv("BIO_COOP_THREADS")) { const int v = atoi(e); if (v == lo || v == hi) return v; }
+        // launch shape by the number of item rounds per SM (see COOP_THREADS_LO / _HI in bio_coop.cuh);
+        // BIO_COOP_THREADS = lo | hi | <thread count of one of the two shapes> forces one (tests, experiments)
+        auto pick_threads = [&](int G, int cls) {
+            const int lo = COOP_THREADS_LO(T), hi = cls == 1 ? COOP_THREADS_HI(T, 1) : COOP_THREADS_HI(T, 0);
+            if (const char* e = getenv("BIO_COOP_THREADS")) {
+                if (!strcmp(e, "lo")) return lo;
+                if (!strcmp(e, "hi")) return hi;
+                const int v = atoi(e);
+                if (v == lo || v == hi) return v;
+            }
             const long items = (n + (32 / G) - 1) / (32 / G);
             const long ipsm = (items + h->n_sms - 1) / h->n_sms;
             const double cost_lo = (double)((ipsm + lo / 32 - 1) / (lo / 32));
-            const double cost_hi = (double)((ipsm + hi / 32 - 1) / (hi / 32)) * COOP_SHAPE_COST;
+            const double cost_hi = (double)((ipsm + hi / 32 - 1) / (hi / 32)) * COOP_SHAPE_COST(cls);
             return cost_hi < cost_lo ? hi : lo;
         };
         // class 0 (half-warp per env) runs the planar program only
@@ -188,13 +195,15 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
             h->coop_cls = -1;
         } else if (want_coop && prog_ok && prog_src <= P2_MAXSRC && fits(C0::G, C0::ND, C0::NM, C0::NP, C0::NAX)) {
             h->coop_cls = 0;
-            h->coop_threads = pick_threads(C0::G);
+            h->coop_threads = pick_threads(C0::G, 0);
             h->coop_smem = base + (h->coop_threads / C0::G) * sizeof(bio::EnvWork<T, 0>);
             CU((bio::coop_set_smem<T, 0>(h->coop_threads, (int)h->coop_smem)));
             h->coop_ctas = bio::coop_ctas_per_sm<T, 0>(h->coop_threads, (int)h->coop_smem);
-        } else if (want_coop && fits(C1::G, C1::ND, C1::NM, C1::NP, C1::NAX)) {
+        } else if (want_coop && fits(C1::G, C1::ND, C1::NM, C1::NP, C1::NAX) &&
+                   (prog_ok ? prog_src <= P2_MAXSRC : (model->n_muscles == 0 || (gpath_ok && prog_src <= COOP_MAXSRC6)))) {
+            // class 1 (warp per env): planar program, or the general evaluation with compiled muscle paths
             h->coop_cls = 1;
-            h->coop_threads = pick_threads(C1::G);
+            h->coop_threads = pick_threads(C1::G, 1);
             h->coop_smem = base + (h->coop_threads / C1::G) * sizeof(bio::EnvWork<T, 1>);
             CU((bio::coop_set_smem<T, 1>(h->coop_threads, (int)h->coop_smem)));
             h->coop_ctas = bio::coop_ctas_per_sm<T, 1>(h->coop_threads, (int)h->coop_smem);

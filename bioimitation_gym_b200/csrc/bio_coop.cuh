@@ -22,23 +22,27 @@ template <> struct CoopCls<1> { enum { G = 32, ND = 16, NM = 24, NP = 80, NAX = 
 
 #define COOP_MAXOBS 12
 
-// working arrays of the general (spatial) evaluation, coop_eval
+// working arrays of the general (spatial) evaluation, coop_eval.  Arrays whose lifetimes do not overlap share
+// storage (a warp of the 3D kernels owns 6.1 KB, so that 28 warps fit one SM next to the model block).
 template <typename T, typename C>
 struct WorkGeneral {
-    T ax_s[C::NAX], ax_ds[C::NAX], ax_dds[C::NAX];
     T R[BIO_MAX_BODIES][9], r[BIO_MAX_BODIES][3], V[BIO_MAX_BODIES][6], A[BIO_MAX_BODIES][6];
     alignas(16) T S[C::ND][8];                     // motion vector of every dof, [6..7] unused (16-byte reads)
     // spatial inertia about O and body force per body: [0] mass, [1..3] m*c, [4..9] I (xx yy zz xy xz yz),
     // [10..15] force (n; f); turned into composite / subtree sums in place
     T BI[BIO_MAX_BODIES][16];
     union {
-        alignas(16) T IS[C::ND][8];                // I^c_body(i) * S_i (phase G on), [6..7] unused
-        T mv[8][6];                                // moving path points: location [0..2], d/dq [3..5] (phases A..C)
+        T mv[8][6];                                // phases A..C: moving path points, location [0..2], d/dq [3..5]
+        alignas(16) T IS[C::ND][8];                // phase G: I^c_body(i) * S_i, [6..7] unused
+        T Lw[C::ND * (C::ND + 1) / 2];             // phase H: factor L of L^T D L (apart from H: no write-after-read barrier)
     };
-    T H[C::ND * (C::ND + 1) / 2], rhs[C::ND];
-    T Lw[C::ND * (C::ND + 1) / 2];                 // factor L of L^T D L (kept apart from H: no write-after-read barrier)
+    union {
+        struct { T ax_s[C::NAX], ax_ds[C::NAX], ax_dds[C::NAX]; };   // phases A, B: joint functions and derivatives
+        T H[C::ND * (C::ND + 1) / 2];                                // phases G, H: joint-space inertia
+    };
+    T rhs[C::ND];
     T Q[C::ND], limDd[C::ND];
-    T mq[8];                                       // generalized force of the moving path points (compiled paths)
+    T mq[8];                                       // generalized force of the moving path points
 };
 
 // working arrays of the planar program, coop_eval_planar
@@ -62,8 +66,9 @@ template <typename T, typename C>
 struct WorkReadout { T obs_pos[COOP_MAXOBS][3], obs_vel[COOP_MAXOBS][3], comp[BIO_MAX_BODIES][6]; };   // full evaluation
 template <typename T>
 struct WorkSources { alignas(16) T w[P2_MAXSRC][4]; };                                                 // planar program
+#define COOP_MAXSRC6 48      // wrench sources of a 3D model (one per body a muscle touches; the reference's models: 46)
 template <typename T>
-struct WorkSources6 { alignas(16) T w[P2_MAXSRC][8]; };      // general evaluation, compiled paths: moment about O [0..2], force [3..5]
+struct WorkSources6 { alignas(16) T w[COOP_MAXSRC6][8]; };   // general evaluation: moment about O [0..2], force [3..5]
 
 // Size class 0 (half-warp per env) runs the planar program only, so its buffer holds no arrays of the
 // general evaluation; class 1 (warp per env) keeps both.
@@ -77,11 +82,10 @@ template <typename T> struct WorkUnions<T, 1> {
     typedef CoopCls<1> C;
     union { WorkGeneral<T, C> g; WorkPlanar<T, C> p; } k;
     union {
-        struct { T ptx[C::NP][3], ptf[C::NP][3], ptq[C::NP]; } pt;   // phases C..E
         struct { T col[BIO_MAX_SPHERES][C::ND][3]; } jac;             // phase G (implicit damping)
         WorkReadout<T, C> out;
         WorkSources<T> src;
-        WorkSources6<T> src6;
+        WorkSources6<T> src6;                                        // phases C..E
     } x;
 };
 
@@ -278,114 +282,71 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     if (lane < nm) {
         const int i = lane;
         const PlanarProg<T>& pr = m.prog;
-        const bool compiled = pr.gpath_ok != 0;
         T L = T(0);
-        int pmov = -1;
-        T mdloc[3] = {T(0), T(0), T(0)};
-        const int pb = m.mus_pt_begin[i], pe = pb + m.mus_pt_count[i];
-        // compiled paths (PlanarProg::mc_seg): constant length of the variant selected by the conditional points
-        // plus its live segments; a live segment that crosses bodies leaves +-(x cross e, e) on the two bodies
+        // compiled paths (PlanarProg::mc_seg; bio_create gives a 3D model without them to the thread-per-env kernel):
+        // constant length of the variant selected by the conditional points plus its live segments; a live segment
+        // that crosses bodies leaves +-(x cross e, e) on the two bodies
         T Wv[P2_MAXSLOT][6];
         T mqu = T(0);
         int mov = -1;
-        if (compiled) {
 #pragma unroll
-            for (int sl = 0; sl < P2_MAXSLOT; sl++)
+        for (int sl = 0; sl < P2_MAXSLOT; sl++)
 #pragma unroll
-                for (int c = 0; c < 6; c++) Wv[sl][c] = T(0);
-            int var = 0;
+            for (int c = 0; c < 6; c++) Wv[sl][c] = T(0);
+        int var = 0;
 #pragma unroll
-            for (int cc = 0; cc < 2; cc++) {
-                const int p = pr.mc_cond[i][cc];
-                if (p >= 0) {
-                    const T v = E.q[(pr.pt_info[p] >> 6) & 31];
-                    if (v >= m.pt_range[p][0] - T(1e-5) && v <= m.pt_range[p][1] + T(1e-5)) var |= 1 << cc;
-                }
+        for (int cc = 0; cc < 2; cc++) {
+            const int p = pr.mc_cond[i][cc];
+            if (p >= 0) {
+                const T v = E.q[(pr.pt_info[p] >> 6) & 31];
+                if (v >= m.pt_range[p][0] - T(1e-5) && v <= m.pt_range[p][1] + T(1e-5)) var |= 1 << cc;
             }
-            L = pr.mc_len0[i][var];
-            T mdw[3] = {T(0), T(0), T(0)};           // moving point: R_b d(location)/dq
-            for (int j = 0; j < pr.mc_nlive; j++) {
-                const uint32_t seg = pr.mc_seg[i][var][j];
-                if (!(seg >> 31)) continue;
-                T xe[2][3];
-                int slot2[2];
-                bool mv2[2];
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int p = (seg >> (8 * e)) & 255u;
-                    const int info = pr.pt_info[p];
-                    const int b = info & 15;
-                    T loc[3];
-                    mv2[e] = ((info >> 4) & 3) == BIO_PT_MOVING;
-                    if (mv2[e]) {
-                        mov = (info >> 13) & 7;
-                        T dl[3];
-                        for (int c = 0; c < 3; c++) { loc[c] = K.mv[mov][c]; dl[c] = K.mv[mov][3 + c]; }
-                        matvec3(K.R[b], dl, mdw);
-                    } else {
-                        T l3;
-                        ld4(pr.pt_xyz[p], loc[0], loc[1], loc[2], l3);
-                    }
-                    matvec3(K.R[b], loc, xe[e]);
-                    for (int c = 0; c < 3; c++) xe[e][c] += K.r[b][c];
-                    slot2[e] = (info >> 11) & 3;
-                }
-                const T dx = xe[1][0] - xe[0][0], dy = xe[1][1] - xe[0][1], dz = xe[1][2] - xe[0][2];
-                const T d2 = dx * dx + dy * dy + dz * dz;
-                const T il = Num<T>::rsqrt(d2);
-                L += d2 * il;
-                const T ev[3] = {dx * il, dy * il, dz * il};
-                const T msg = (mv2[0] ? T(1) : T(0)) - (mv2[1] ? T(1) : T(0));
-                mqu += msg * dot3(ev, mdw);
-                if (slot2[0] != slot2[1]) {
-                    T nn[3];
-                    cross3(xe[0], ev, nn);
-#pragma unroll
-                    for (int sl = 0; sl < P2_MAXSLOT; sl++) {
-                        const T sgn = sl == slot2[0] ? T(1) : (sl == slot2[1] ? T(-1) : T(0));
-#pragma unroll
-                        for (int c = 0; c < 3; c++) { Wv[sl][c] += sgn * nn[c]; Wv[sl][3 + c] += sgn * ev[c]; }
-                    }
-                }
-            }
-        } else {
-        // one streaming pass over the path points: positions, segment unit vectors and the
-        // length; ptf[p] first holds the direction sum (e_out - e_in) and is scaled by the
-        // tension once it is known (inactive points keep zero position and force)
-        int prev = -1;
-        T xp[3] = {T(0), T(0), T(0)}, ev[3] = {T(0), T(0), T(0)};
-        for (int p = pb; p < pe; p++) {
-            const int kind = m.pt_kind[p], d = m.pt_dof[p], b = m.pt_body[p];
-            T loc[3];
-            if (kind == BIO_PT_CONDITIONAL) {
-                const T v = E.q[d];
-                if (!(v >= m.pt_range[p][0] - T(1e-5) && v <= m.pt_range[p][1] + T(1e-5))) {
-                    for (int c = 0; c < 3; c++) { E.x.pt.ptf[p][c] = T(0); E.x.pt.ptx[p][c] = T(0); }
-                    continue;
-                }
-            }
-            if (kind == BIO_PT_MOVING) {
-                const int mk = m.pt_mov[p];
-                for (int c = 0; c < 3; c++) { loc[c] = K.mv[mk][c]; mdloc[c] = K.mv[mk][3 + c]; }
-                pmov = p;
-            } else {
-                for (int c = 0; c < 3; c++) loc[c] = m.pt_loc[p][c];
-            }
-            T x[3];
-            matvec3(K.R[b], loc, x);
-            for (int c = 0; c < 3; c++) { x[c] += K.r[b][c]; E.x.pt.ptx[p][c] = x[c]; }
-            if (prev >= 0) {
-                const T dx = x[0] - xp[0], dy = x[1] - xp[1], dz = x[2] - xp[2];
-                const T d2 = dx * dx + dy * dy + dz * dz;
-                const T il = Num<T>::rsqrt(d2);
-                L += d2 * il;
-                const T nv[3] = {dx * il, dy * il, dz * il};
-                for (int c = 0; c < 3; c++) { E.x.pt.ptf[prev][c] = nv[c] - ev[c]; ev[c] = nv[c]; }
-            }
-            for (int c = 0; c < 3; c++) xp[c] = x[c];
-            prev = p;
         }
-        if (prev >= 0) for (int c = 0; c < 3; c++) E.x.pt.ptf[prev][c] = -ev[c];
+        L = pr.mc_len0[i][var];
+        T mdw[3] = {T(0), T(0), T(0)};           // moving point: R_b d(location)/dq
+        for (int j = 0; j < pr.mc_nlive; j++) {
+            const uint32_t seg = pr.mc_seg[i][var][j];
+            if (!(seg >> 31)) continue;
+            T xe[2][3];
+            int slot2[2];
+            bool mv2[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int p = (seg >> (8 * e)) & 255u;
+                const int info = pr.pt_info[p];
+                const int b = info & 15;
+                T loc[3];
+                mv2[e] = ((info >> 4) & 3) == BIO_PT_MOVING;
+                if (mv2[e]) {
+                    mov = (info >> 13) & 7;
+                    T dl[3];
+                    for (int c = 0; c < 3; c++) { loc[c] = K.mv[mov][c]; dl[c] = K.mv[mov][3 + c]; }
+                    matvec3(K.R[b], dl, mdw);
+                } else {
+                    T l3;
+                    ld4(pr.pt_xyz[p], loc[0], loc[1], loc[2], l3);
+                }
+                matvec3(K.R[b], loc, xe[e]);
+                for (int c = 0; c < 3; c++) xe[e][c] += K.r[b][c];
+                slot2[e] = (info >> 11) & 3;
+            }
+            const T dx = xe[1][0] - xe[0][0], dy = xe[1][1] - xe[0][1], dz = xe[1][2] - xe[0][2];
+            const T d2 = dx * dx + dy * dy + dz * dz;
+            const T il = Num<T>::rsqrt(d2);
+            L += d2 * il;
+            const T ev[3] = {dx * il, dy * il, dz * il};
+            const T msg = (mv2[0] ? T(1) : T(0)) - (mv2[1] ? T(1) : T(0));
+            mqu += msg * dot3(ev, mdw);
+            if (slot2[0] != slot2[1]) {
+                T nn[3];
+                cross3(xe[0], ev, nn);
+#pragma unroll
+                for (int sl = 0; sl < P2_MAXSLOT; sl++) {
+                    const T sgn = sl == slot2[0] ? T(1) : (sl == slot2[1] ? T(-1) : T(0));
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { Wv[sl][c] += sgn * nn[c]; Wv[sl][3 + c] += sgn * ev[c]; }
+                }
+            }
         }
         const T fiso = m.mus_fiso[i], lopt = m.mus_lopt[i], h = m.mus_height[i], beta = m.mus_beta[i];
         const T amin = m.mus_amin[i], lmin = m.mus_lm_min[i];
@@ -440,8 +401,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             E.ffib[i] = fiso * (afal * fv + fpe + beta * vn);
             E.vn[i] = tension;                // read-out slot, see EnvWorkBody::vn
         }
-        if (compiled) {
-            // wrench sources of this muscle: one per body it touches
+        {   // wrench sources of this muscle: one per body it touches
             const int s0 = pr.mus_src0[i], ns = pr.mus_src0[i + 1] - s0;
 #pragma unroll
             for (int sl = 0; sl < P2_MAXSLOT; sl++) {
@@ -452,15 +412,6 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
                 }
             }
             if (mov >= 0) K.mq[mov] = tension * mqu;
-        } else {
-            for (int p = pb; p < pe; p++)
-                for (int c = 0; c < 3; c++) E.x.pt.ptf[p][c] *= tension;
-            // generalized force of the muscle's moving point (at most one per muscle): f . R_b dloc/dq
-            if (pmov >= 0) {
-                T dw[3];
-                matvec3(K.R[m.pt_body[pmov]], mdloc, dw);
-                E.x.pt.ptq[pmov] = dot3(E.x.pt.ptf[pmov], dw);
-            }
         }
     }
     // ---- phase D: lane = contact sphere | coordinate limit ----
@@ -516,7 +467,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     if (nm > 0) {
         constexpr int PARTS = G == 32 ? 4 : 1;
         const int gb = lane / PARTS, part = lane % PARTS;
-        if (gb < nb && m.prog.gpath_ok) {
+        if (gb < nb) {
             for (int k = m.prog.inc_begin[gb] + part; k < m.prog.inc_begin[gb + 1]; k += PARTS) {
                 T w0, w1, w2, w3, w4, w5, w6, w7;
                 const T* w = E.x.src6.w[m.prog.inc_src[k]];
@@ -524,14 +475,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
                 ld4(w + 4, w4, w5, w6, w7);
                 Wn[0] += w0; Wn[1] += w1; Wn[2] += w2; Wf[0] += w3; Wf[1] += w4; Wf[2] += w5;
             }
-        } else if (gb < nb)
-            for (int k = m.body_pt_begin[gb] + part; k < m.body_pt_begin[gb] + m.body_pt_count[gb]; k += PARTS) {
-                const int p = m.body_pt_list[k];
-                const T f[3] = {E.x.pt.ptf[p][0], E.x.pt.ptf[p][1], E.x.pt.ptf[p][2]};
-                T n[3];                                                   // inactive points: zero force and position
-                cross3(E.x.pt.ptx[p], f, n);
-                for (int c = 0; c < 3; c++) { Wn[c] += n[c]; Wf[c] += f[c]; }
-            }
+        }
         if (PARTS > 1) {
             const unsigned mask = group_mask<G>();
 #pragma unroll
@@ -613,13 +557,13 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             for (int j = 0; j < 2; j++) {
                 const int l = m.gdof_lim[d][j], p = m.gdof_movpt[d][j];
                 if (l >= 0) { qf += E.limf[l]; ld += E.limD[l]; }
-                if (p >= 0) qf += m.prog.gpath_ok ? K.mq[m.pt_mov[p]] : E.x.pt.ptq[p];
+                if (p >= 0) qf += K.mq[m.pt_mov[p]];
             }
             const int a = m.gdof_act[d];
             if (a >= 0) qf += E.ctrl[a];
         } else {
             for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == d) { qf += E.limf[l]; ld += E.limD[l]; }
-            for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += m.prog.gpath_ok ? K.mq[k] : E.x.pt.ptq[p]; }
+            for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += K.mq[k]; }
             if (m.is_torque) for (int a = 0; a < m.n_act; a++) if (m.act_dof[a] == d) qf += E.ctrl[a];
         }
         K.limDd[d] = ld;
@@ -921,18 +865,25 @@ __device__ __forceinline__ void coop_flush_obs(EnvWork<T, CLS>* works, T* __rest
 // Persistent launch: one CTA per SM, the model block is staged once per SM, and every warp walks the work
 // items (one item = the 32/G envs of a warp) item = blockIdx + gridDim * (warp + warps_per_cta * k), so
 // that the items are dealt round-robin over the SMs first.  Two launch shapes per fp32 instantiation:
-//   512 threads = 16 warps at 128 registers: least latency per item.  4096 envs on 148 SMs: warps 0..13
+//   LO  512 threads = 16 warps at 128 registers: least latency per item.  4096 2D envs on 148 SMs: warps 0..13
 //       of every SM are busy, i.e. 4,4,3,3 warps on the four schedulers (two CTAs of 8 warps left 4,4,4,2
 //       and staged the model twice; measured 5 % slower).
-//   640 threads = 20 warps at 96 registers: more items in flight for batches of several items per warp
-//       (measured: 2D 16384 envs +18 %, 131072 envs +7 %; 3D 8192 envs +13 %; 4096 envs -3 %).
+//   HI  more items in flight for batches of several items per warp:
+//       2D (size class 0): 640 threads = 20 warps at 96 registers (measured: 16384 envs +18 %, 131072 envs +7 %,
+//       4096 envs -3 %); 3D (size class 1): 896 threads = 28 warps at 72 registers -- the 3D work buffer is 6.1 KB
+//       per warp, so 28 of them fit next to the model block; 8192 envs are 55.4 items per SM: two rounds of 28
+//       warps instead of three rounds of 20.
 // bio_create picks by the number of item rounds per SM (COOP_SHAPE_COST); fp64 runs 256 threads.
 #ifndef BIO_COOP_LO
 #define BIO_COOP_LO 512
 #endif
+#ifndef BIO_COOP_HI3D
+#define BIO_COOP_HI3D 896
+#endif
 #define COOP_THREADS_LO(T) (sizeof(T) == 4 ? BIO_COOP_LO : 256)
-#define COOP_THREADS_HI(T) (sizeof(T) == 4 ? 640 : 256)
-#define COOP_SHAPE_COST 1.12      // time of one round of items with the HI shape relative to the LO shape
+#define COOP_THREADS_HI(T, CLS) (sizeof(T) == 4 ? ((CLS) == 1 ? BIO_COOP_HI3D : 640) : 256)
+// time of one round of items with the HI shape relative to the LO shape
+#define COOP_SHAPE_COST(CLS) ((CLS) == 1 ? 1.45 : 1.12)
 
 template <typename T, int CLS, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)

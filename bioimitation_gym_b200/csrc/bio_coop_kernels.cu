@@ -10,7 +10,7 @@
 namespace bio {
 
 namespace {
-constexpr int LO = COOP_THREADS_LO(BIO_T), HI = COOP_THREADS_HI(BIO_T);
+constexpr int LO = COOP_THREADS_LO(BIO_T), HI = COOP_THREADS_HI(BIO_T, BIO_CLS);
 }
 
 template <>

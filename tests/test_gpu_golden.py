@@ -64,7 +64,7 @@ def test_free_running_trajectory_fp64(fname):
 GOLDEN_FP32_TOL = dict(obs=1.4e-2, rew=6e-6, q=5e-6, tendon=2e-4, contact=2e-4, udot=1.4e-2)
 
 
-@pytest.mark.parametrize("dtype,threads", [("float64", 0), ("float32", 512), ("float32", 640)])
+@pytest.mark.parametrize("dtype,threads", [("float64", ""), ("float32", "lo"), ("float32", "hi")])
 @pytest.mark.parametrize("fname", FILES)
 def test_one_step_from_every_golden_state(fname, dtype, threads, monkeypatch):
     """Env i of the batch is loaded with the golden pre-step state of step i; one launch
@@ -75,11 +75,11 @@ def test_one_step_from_every_golden_state(fname, dtype, threads, monkeypatch):
     g = np.load(os.path.join(GOLDEN, fname))
     n = g["action"].shape[0]
     if threads:
-        monkeypatch.setenv("BIO_COOP_THREADS", str(threads))
+        monkeypatch.setenv("BIO_COOP_THREADS", threads)
     env = backend.VecEnv(str(g["env_id"]), dict(num_envs=n, dtype=dtype, seed=int(g["seed"])))
     if threads:
         monkeypatch.delenv("BIO_COOP_THREADS")
-        assert env.coop_shape()[1] == threads
+        assert env.coop_shape()[1] == {"lo": 512, "hi": 896 if env.spec.spatial else 640}[threads]
     ex = env.enable_step_extra("udot", "tendon_force", "contact")
     env.set_state({k: g[k] for k in STATE_KEYS})
     obs, rew, done, info = env.step(torch.as_tensor(g["action"], dtype=env.dtype, device=env.device))

@@ -225,19 +225,20 @@ def test_step_parity_fp64_100_steps(env_id):
     env.close()
 
 
-@pytest.mark.parametrize("threads", [512, 640])
+@pytest.mark.parametrize("threads", ["lo", "hi"])
 @pytest.mark.parametrize("env_id", ENV_IDS_FP32)
 def test_step_parity_fp32_resynchronised(env_id, threads, monkeypatch):
-    """fp32 production build in BOTH launch shapes bio_create picks from (512 threads / 128 registers and
-    640 threads / 96 registers, BIO_COOP_THREADS), one control step from identical states (the fp64
+    """fp32 production build in BOTH launch shapes bio_create picks from (lo: 512 threads / 128 registers; hi: 640
+    threads / 96 registers for the 2D models, 896 threads / 72 registers for the 3D models; BIO_COOP_THREADS), one control step from identical states (the fp64
     oracle state is copied to the GPU before every step).  Stated per-step tolerances = twice the worst
     value measured over these env IDs and shapes (printed): see FP32_TOL.  Checked twice: plainly on the envs whose
     step is well conditioned, and for every env against 20 x its own conditioning floor."""
     import torch
     n = 64
-    monkeypatch.setenv("BIO_COOP_THREADS", str(threads))
+    monkeypatch.setenv("BIO_COOP_THREADS", threads)
     env, cpu = _mk(env_id, n, "float32")
     monkeypatch.delenv("BIO_COOP_THREADS")
+    assert env.coop_shape()[1] == {"lo": 512, "hi": 896 if env.spec.spatial else 640}[threads]
     rng = np.random.default_rng(21)
     env.reset()
     cpu.reset()
@@ -320,7 +321,7 @@ def _tol_class(env):
 @pytest.mark.parametrize("env_id,n,threads", [("MuscleWalkingImitation2D-v0", 4096, 512),
                                                ("MuscleRunningImitation2D-v0", 16384, 640),
                                                ("TorqueWalkingImitation2D-v0", 16384, 640),
-                                               ("MuscleWalkingImitation3D-v0", 8192, 640)])
+                                               ("MuscleWalkingImitation3D-v0", 8192, 896)])
 def test_step_parity_at_the_baseline_batch_sizes_fp32(env_id, n, threads):
     """BASELINE.json batch sizes with the launch shape bio_create picks for them: 12 control steps of the
     whole batch on the GPU; a strided subset of 256 envs is re-synchronised into the fp64 oracle before every

@@ -154,14 +154,15 @@ def test_warm_started_newton_finds_the_same_root(emul_lib, oracle_lib, models):
 
 def test_both_launch_shapes_fit_the_shared_memory_of_one_sm(emul_lib):
     """Shared-memory budget of the fp32 instantiations: one CTA per SM holds the model block and one work
-    buffer per env of its 512 (16 warps) or 640 (20 warps) threads; 2D: half a warp per env, 3D: a warp per env.
-    227 KB (232448 B) of dynamic shared memory per CTA on sm_100."""
+    buffer per env of its threads; 2D: half a warp per env, 512 (16 warps) or 640 (20 warps) threads; 3D: a warp
+    per env, 512 or 896 (28 warps) threads.  227 KB (232448 B) of dynamic shared memory per CTA on sm_100."""
     out = np.zeros(8, dtype=np.int64)
     emul_lib.emul_sizes(_p(out))
     model, work2d, work3d = int(out[0]), int(out[1]), int(out[2])
     base = (model + 15) // 16 * 16
     for threads in (512, 640):
         assert base + threads // 16 * work2d <= 232448, "2D fp32, %d threads: %d B" % (threads, base + threads // 16 * work2d)
+    for threads in (512, 896):
         assert base + threads // 32 * work3d <= 232448, "3D fp32, %d threads: %d B" % (threads, base + threads // 32 * work3d)
 
 
