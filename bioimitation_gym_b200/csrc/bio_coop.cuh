@@ -28,19 +28,26 @@ template <typename T, typename C>
 struct WorkGeneral {
     T R[BIO_MAX_BODIES][9], r[BIO_MAX_BODIES][3], V[BIO_MAX_BODIES][6], A[BIO_MAX_BODIES][6];
     alignas(16) T S[C::ND][8];                     // motion vector of every dof, [6..7] unused (16-byte reads)
-    // spatial inertia about O and body force per body: [0] mass, [1..3] m*c, [4..9] I (xx yy zz xy xz yz),
-    // [10..15] force (n; f); turned into composite / subtree sums in place
-    T BI[BIO_MAX_BODIES][16];
     union {
-        T mv[8][6];                                // phases A..C: moving path points, location [0..2], d/dq [3..5]
-        alignas(16) T IS[C::ND][8];                // phase G: I^c_body(i) * S_i, [6..7] unused
-        T Lw[C::ND * (C::ND + 1) / 2];             // phase H: factor L of L^T D L (apart from H: no write-after-read barrier)
+        struct {
+            // joint-space path (coop_solve): spatial inertia about O and body force per body: [0] mass, [1..3] m*c,
+            // [4..9] I (xx yy zz xy xz yz), [10..15] force (n; f); turned into composite / subtree sums in place
+            T BI[BIO_MAX_BODIES][16];
+            union {
+                T mv[8][6];                            // phases A..C: moving path points, location [0..2], d/dq [3..5]
+                alignas(16) T IS[C::ND][8];            // phase G: I^c_body(i) * S_i, [6..7] unused
+                T Lw[C::ND * (C::ND + 1) / 2];         // phase H: factor L of L^T D L (apart from H: no write-after-read barrier)
+            };
+            union {
+                struct { T ax_s[C::NAX], ax_ds[C::NAX], ax_dds[C::NAX]; };   // phases A, B: joint functions and derivatives
+                T H[C::ND * (C::ND + 1) / 2];                                // phases G, H: joint-space inertia
+            };
+            T rhs[C::ND];
+        };
+        // articulated-body path (p3_aba): the 6 x 6 spatial inertia of every body about O by columns, force as the
+        // seventh column: [c * 6 + r]; written in phase E, when mv and the joint functions are dead
+        alignas(16) T BIc[BIO_MAX_BODIES][42];
     };
-    union {
-        struct { T ax_s[C::NAX], ax_ds[C::NAX], ax_dds[C::NAX]; };   // phases A, B: joint functions and derivatives
-        T H[C::ND * (C::ND + 1) / 2];                                // phases G, H: joint-space inertia
-    };
-    T rhs[C::ND];
     T Q[C::ND], limDd[C::ND];
     T mq[8];                                       // generalized force of the moving path points
 };
@@ -86,6 +93,9 @@ template <typename T> struct WorkUnions<T, 1> {
         WorkReadout<T, C> out;
         WorkSources<T> src;
         WorkSources6<T> src6;                                        // phases C..E
+        // articulated-body pass, behind the read-outs of a full evaluation: per dof U / D [0..5] and -u / D [6] for the
+        // way back; exchange of U between the lanes of a chain (double-buffered by step parity)
+        struct { T pad_[128]; alignas(16) T W[C::ND][8]; alignas(16) T Ux[2][2][8]; } aba;
     } x;
 };
 
@@ -164,6 +174,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     constexpr int G = C::G;
     const int nb = m.n_bodies, nd = m.n_dof, nm = m.n_muscles;
     auto& K = E.k.g;
+    const bool aba = G == 32 && m.prog.aba_ok;   // root-plus-chains model: articulated-body pass instead of phases F..H
 
     // ---- phase A: joint functions of the coordinates, and the location functions of moving path
     // points (task n_axes + 3 k + c: component c of moving point k); the spline interval of the
@@ -542,6 +553,20 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         for (int j = 0; j < 3; j++) { IA[j] += t1[j]; IA[3 + j] = mb * A[3 + j] - t2[j]; }
         T c1[3], c2[3], c3[3];
         cross3(V, IV, c1); cross3(V + 3, IV + 3, c2); cross3(V, IV + 3, c3);
+        if (aba) {
+            // columns of [[I, h x], [-(h x), m 1]] and the body force as the seventh (p3_aba)
+            T* o = K.BIc[b];
+            const T z = T(0);
+            st2(o, I6[0], I6[3]); st2(o + 2, I6[4], z); st2(o + 4, -hh[2], hh[1]);
+            st2(o + 6, I6[3], I6[1]); st2(o + 8, I6[5], hh[2]); st2(o + 10, z, -hh[0]);
+            st2(o + 12, I6[4], I6[5]); st2(o + 14, I6[2], -hh[1]); st2(o + 16, hh[0], z);
+            st2(o + 18, z, hh[2]); st2(o + 20, -hh[1], mb); st2(o + 22, z, z);
+            st2(o + 24, -hh[2], z); st2(o + 26, hh[0], z); st2(o + 28, mb, z);
+            st2(o + 30, hh[1], -hh[0]); st2(o + 32, z, z); st2(o + 34, z, mb);
+            st2(o + 36, IA[0] + c1[0] + c2[0] - Wn[0], IA[1] + c1[1] + c2[1] - Wn[1]);
+            st2(o + 38, IA[2] + c1[2] + c2[2] - Wn[2], IA[3] + c3[0] - Wf[0]);
+            st2(o + 40, IA[4] + c3[1] - Wf[1], IA[5] + c3[2] - Wf[2]);
+        } else {
         K.BI[b][0] = mb;
         for (int j = 0; j < 3; j++) {
             K.BI[b][1 + j] = hh[j];
@@ -549,6 +574,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             K.BI[b][13 + j] = IA[3 + j] + c3[j] - Wf[j];
         }
         for (int j = 0; j < 6; j++) K.BI[b][4 + j] = I6[j];
+        }
     } else if (lane - nb < nd) {
         const int d = lane - nb;
         T qf = T(0), ld = T(0);
@@ -566,7 +592,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += K.mq[k]; }
             if (m.is_torque) for (int a = 0; a < m.n_act; a++) if (m.act_dof[a] == d) qf += E.ctrl[a];
         }
-        K.limDd[d] = ld;
+        K.limDd[d] = h_imp * ld;
         K.Q[d] = qf;
     }
     gsync<G>();
@@ -611,6 +637,11 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             for (int l = 0; l < m.n_limits; l++) { const T a = Num<T>::abs(E.limf[l]); mx = a > mx ? a : mx; }
             E.max_limit = mx;
         }
+    }
+
+    // ---- root-plus-chains models on a full warp: articulated-body pass (bio_coop_spatial.cuh) ----
+    if constexpr (G == 32) {
+        if (aba) { p3_aba<T, CLS>(m, E, lane, h_imp); return; }
     }
 
     // ---- phase F: composite inertias / subtree forces.  Root-plus-chains models on a full warp: lane =
@@ -691,7 +722,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
                 const T* cj = E.x.jac.col[s][j];
                 v += h_imp * (E.sphD[s][0] * (ci[0] * cj[0] + ci[2] * cj[2]) + E.sphD[s][1] * ci[1] * cj[1]);
             }
-            if (i == j) v += h_imp * K.limDd[i];
+            if (i == j) v += K.limDd[i];
         }
         K.H[i * (i + 1) / 2 + j] = v;
     }

@@ -175,4 +175,118 @@ __device__ __forceinline__ void p3_phase_b_scan(const DevModel<T>& m, EnvWork<T,
     }
 }
 
+// ---------------------------------------------------------------------------
+// Articulated-body pass of the spatial evaluation (replaces the composite inertias, the joint-space
+// matrix and its sparse L^T D L for root-plus-chains models; PlanarProg::aba_*).
+//
+// Every spatial quantity is expressed in ground axes about the common point O, so handing an inertia or a
+// force to the parent body is a plain sum.  A half-warp owns a chain; lane c < 6 of it keeps column c of
+// the chain's articulated inertia I^A (symmetric 6 x 6) in registers, lane 6 the force p^A as a seventh
+// column.  Per dof d, from the leaf (motion vector S, generalized force Q, h * limit damping Ld):
+//   U = I^A S          lane c: U_c = S . column_c  (lane 6: S . p^A)       -- no reduction across lanes
+//   D = S . U + Ld     every lane, from the U exchanged through shared memory
+//   column_c -= U (U_c - [c = 6] Q) / D            i.e.  I^a = I^A - U U^T / D,  p^a = p^A + U (Q - S . p^A) / D
+// and the coefficients (U / D, -(Q - S . p^A) / D) stay in shared memory for the way back.  A body joins
+// the chain by adding its columns (phase E wrote them: BIc); the implicit contact damping h J^T D J of a foot's
+// active spheres is added to the foot's columns on the fly (J = [-(p x), 1]: column c is (p x g, g) with
+// g = diag(D0, D1, D0) (e_c x p) for c < 3, diag(D0, D1, D0) e_(c-3) else).  Both half-warps then take the
+// root body plus the two chain heads and eliminate the root's dofs (redundantly), and every lane walks
+// the accelerations back down: qdd = u / D - (U / D) . a,  a += S qdd.
+// The same block elimination from the leaves as coop_solve and the oracle's Cholesky, in another order of
+// operations; one __syncwarp per dof, no shuffles.
+// ---------------------------------------------------------------------------
+template <typename T, int CLS>
+__device__ __forceinline__ void p3_aba(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane, const T h_imp) {
+    const PlanarProg<T>& pr = m.prog;
+    auto& K = E.k.g;
+    auto& X = E.x.aba;
+    const int grp = lane >> 4;
+    const int cc = (lane & 15) < 6 ? (lane & 15) : 6;    // lanes 6..15 of a half-warp all carry the force column
+    const bool fcol = cc == 6;
+    // active contacts of this env (same value on every lane)
+    unsigned act = 0u;
+    if (h_imp > T(0)) act = __ballot_sync(0xffffffffu, lane < m.n_spheres && E.sphD[lane < m.n_spheres ? lane : 0][1] > T(0));
+    // unit motion of column cc: angular part ua (c < 3), linear part ub (3 <= c < 6)
+    const T ua0 = cc == 0 ? T(1) : T(0), ua1 = cc == 1 ? T(1) : T(0), ua2 = cc == 2 ? T(1) : T(0);
+    const T ub0 = cc == 3 ? T(1) : T(0), ub1 = cc == 4 ? T(1) : T(0), ub2 = cc == 5 ? T(1) : T(0);
+    T col[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+    auto add_body = [&](const int b) {
+        const T* src = &K.BIc[b][cc * 6];
+        T v0, v1, v2, v3, v4, v5;
+        ld2(src, v0, v1); ld2(src + 2, v2, v3); ld2(src + 4, v4, v5);
+        col[0] += v0; col[1] += v1; col[2] += v2; col[3] += v3; col[4] += v4; col[5] += v5;
+        unsigned mm = act & (unsigned)pr.body_sph_mask[b];
+        while (mm) {
+            const int s = __ffs(mm) - 1;
+            mm &= mm - 1u;
+            const T px = E.sphx[s][0], py = E.sphx[s][1], pz = E.sphx[s][2];
+            const T d0 = h_imp * E.sphD[s][0], d1 = h_imp * E.sphD[s][1];
+            // velocity of the contact point for the unit motion, times the damping
+            const T gx = d0 * (ua1 * pz - ua2 * py + ub0);
+            const T gy = d1 * (ua2 * px - ua0 * pz + ub1);
+            const T gz = d0 * (ua0 * py - ua1 * px + ub2);
+            col[0] += py * gz - pz * gy; col[1] += pz * gx - px * gz; col[2] += px * gy - py * gx;
+            col[3] += gx; col[4] += gy; col[5] += gz;
+        }
+    };
+    int par = 0;
+    auto eliminate = [&](const int d, const bool on) {
+        T s0, s1, s2, s3, s4, s5, s6, s7;
+        ld4(K.S[d], s0, s1, s2, s3); ld4(K.S[d] + 4, s4, s5, s6, s7);
+        const T Uc = s0 * col[0] + s1 * col[1] + s2 * col[2] + s3 * col[3] + s4 * col[4] + s5 * col[5];
+        X.Ux[par][grp][cc] = Uc;
+        __syncwarp();
+        T u0, u1, u2, u3, u4, u5, u6, u7;
+        ld4(X.Ux[par][grp], u0, u1, u2, u3); ld4(X.Ux[par][grp] + 4, u4, u5, u6, u7);
+        par ^= 1;
+        const T D = s0 * u0 + s1 * u1 + s2 * u2 + s3 * u3 + s4 * u4 + s5 * u5 + K.limDd[d];
+        T coef = (Uc - (fcol ? K.Q[d] : T(0))) * Num<T>::rcp(D);
+        if (on) X.W[d][cc] = coef; else coef = T(0);
+        col[0] -= u0 * coef; col[1] -= u1 * coef; col[2] -= u2 * coef;
+        col[3] -= u3 * coef; col[4] -= u4 * coef; col[5] -= u5 * coef;
+    };
+    // chains, leaf -> root (a chain with fewer dofs idles through the last steps)
+    const int nst = pr.aba_nsteps;
+    for (int s = 0; s < nst; s++) {
+        const int code = pr.aba_step[grp][s];
+        const bool on = code != 255;
+        if (on && (code >> 4)) add_body((code >> 4) - 1);
+        eliminate(on ? (code & 15) : 0, on);
+    }
+    // chain heads to shared memory (in place of the first body of the chain), then the root
+    if (grp < pr.n_branches) {
+        T* dst = &K.BIc[pr.gch_body[grp][0]][cc * 6];
+        st2(dst, col[0], col[1]); st2(dst + 2, col[2], col[3]); st2(dst + 4, col[4], col[5]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 6; r++) col[r] = T(0);
+    add_body(pr.root_body);
+    for (int l = 0; l < pr.n_branches; l++) {
+        const T* src = &K.BIc[pr.gch_body[l][0]][cc * 6];
+        T v0, v1, v2, v3, v4, v5;
+        ld2(src, v0, v1); ld2(src + 2, v2, v3); ld2(src + 4, v4, v5);
+        col[0] += v0; col[1] += v1; col[2] += v2; col[3] += v3; col[4] += v4; col[5] += v5;
+    }
+    const int nroot = pr.aba_nroot;
+    for (int k = 0; k < nroot; k++) eliminate(pr.aba_root[k], true);
+    __syncwarp();
+    // way back: every lane carries the spatial acceleration beyond the bias term
+    T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0), a4 = T(0), a5 = T(0);
+    auto back = [&](const int d, const bool store) {
+        T w0, w1, w2, w3, w4, w5, w6, w7, s0, s1, s2, s3, s4, s5, s6, s7;
+        ld4(X.W[d], w0, w1, w2, w3); ld4(X.W[d] + 4, w4, w5, w6, w7);
+        ld4(K.S[d], s0, s1, s2, s3); ld4(K.S[d] + 4, s4, s5, s6, s7);
+        const T qdd = -w6 - (w0 * a0 + w1 * a1 + w2 * a2 + w3 * a3 + w4 * a4 + w5 * a5);
+        if (store) E.udot[d] = qdd;
+        a0 += s0 * qdd; a1 += s1 * qdd; a2 += s2 * qdd; a3 += s3 * qdd; a4 += s4 * qdd; a5 += s5 * qdd;
+    };
+    for (int k = nroot - 1; k >= 0; k--) back(pr.aba_root[k], lane == 0);
+    for (int s = nst - 1; s >= 0; s--) {
+        const int code = pr.aba_step[grp][s];
+        if (code != 255) back(code & 15, (lane & 15) == 0);
+    }
+    __syncwarp();
+}
+
 }  // namespace bio

@@ -30,6 +30,7 @@ namespace bio {
 #define P2_MAXMOV 4       // moving path points
 #define P2_MAXTASK (BIO_MAX_AXES + 3 * P2_MAXMOV)
 #define P2_MAXVAR 4       // variants of a muscle path: on/off states of its (<= 2) conditional points
+#define P2_MAXABA 12      // dofs of one chain (articulated-body schedule)
 #define P2_MAXLIVE 2      // live segments of a variant (they cross bodies or touch a moving point)
 #define P2_F_FIRST (1 << 17)     // first axis of its body
 #define P2_F_LAST (1 << 18)      // last axis of its body: publish the body frame
@@ -103,6 +104,12 @@ struct alignas(16) PlanarProg {
     // wrench sources acting on every body
     int32_t inc_begin[BIO_MAX_BODIES + 1];
     uint8_t inc_src[3 * BIO_MAX_MUSCLES + BIO_MAX_SPHERES + 8];
+    // articulated-body schedule of the spatial (3D) evaluation (p3_aba, bio_coop_spatial.cuh): per chain the dofs
+    // in elimination order, leaf first: dof | (body whose inertia joins before this dof + 1) << 4, 255 = no step;
+    // then the root's dofs, last first
+    int32_t aba_ok, aba_nsteps, aba_nroot, aba_pad_;
+    uint8_t aba_step[P2_MAXBR][P2_MAXABA];
+    uint8_t aba_root[8];
 };
 
 template <typename T>
@@ -667,6 +674,32 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         }
     }
     if (!pr.chain_ok) return;
+    // ---- articulated-body schedule of the spatial evaluation: every chain from its leaf, then the root ----
+    if (!d.planar) {
+        bool ok = true;
+        int nmax = 0, nroot = 0;
+        memset(pr.aba_step, 255, sizeof(pr.aba_step));
+        for (int l = 0; l < pr.n_branches; l++) {
+            int n = 0;
+            for (int k = chain_nb[l] - 1; k >= 0; k--) {
+                const int b = chain_body[l][k];
+                bool first = true;
+                for (int dd = s.n_dof - 1; dd >= 0; dd--) {
+                    if (s.dof_body[dd] != b) continue;
+                    if (n >= P2_MAXABA || dd > 15) { ok = false; break; }
+                    pr.aba_step[l][n++] = (uint8_t)(dd | ((first ? b + 1 : 0) << 4));
+                    first = false;
+                }
+                if (first) ok = false;                    // a body without a dof of its own does not occur after weld merging
+            }
+            if (n > nmax) nmax = n;
+        }
+        for (int dd = s.n_dof - 1; dd >= 0; dd--)
+            if (s.dof_body[dd] == 0) { if (nroot < 8) pr.aba_root[nroot] = (uint8_t)dd; nroot++; }
+        if (nroot > 8) ok = false;
+        { const char* z = getenv("BIO_NO_ABA"); if (z && z[0] == '1') ok = false; }   // tests: joint-space L^T D L instead
+        pr.aba_nsteps = nmax; pr.aba_nroot = nroot > 8 ? 8 : nroot; pr.aba_ok = ok ? 1 : 0;
+    }
     // ---- stage 2 (planar models): the planar program ----
     if (!d.planar) { build_general_paths(s, d); return; }
     auto joint_dofs = [&](int b, int* dofs) {             // distinct dofs of the joint, in axis order
