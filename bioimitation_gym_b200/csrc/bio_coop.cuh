@@ -592,8 +592,8 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += K.mq[k]; }
             if (m.is_torque) for (int a = 0; a < m.n_act; a++) if (m.act_dof[a] == d) qf += E.ctrl[a];
         }
-        K.limDd[d] = h_imp * ld;
-        K.Q[d] = qf;
+        if (aba) { K.S[d][6] = qf; K.S[d][7] = h_imp * ld; }   // next to the motion vector: one read per elimination step
+        else { K.limDd[d] = h_imp * ld; K.Q[d] = qf; }
     }
     gsync<G>();
 

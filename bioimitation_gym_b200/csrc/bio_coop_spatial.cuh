@@ -229,18 +229,20 @@ __device__ __forceinline__ void p3_aba(const DevModel<T>& m, EnvWork<T, CLS>& E,
             col[3] += gx; col[4] += gy; col[5] += gz;
         }
     };
-    int par = 0;
+    T* ux = X.Ux[0][grp];                                // exchange buffers, swapped every step
+    T* uy = X.Ux[1][grp];
     auto eliminate = [&](const int d, const bool on) {
         T s0, s1, s2, s3, s4, s5, s6, s7;
         ld4(K.S[d], s0, s1, s2, s3); ld4(K.S[d] + 4, s4, s5, s6, s7);
         const T Uc = s0 * col[0] + s1 * col[1] + s2 * col[2] + s3 * col[3] + s4 * col[4] + s5 * col[5];
-        X.Ux[par][grp][cc] = Uc;
+        ux[cc] = Uc;
         __syncwarp();
         T u0, u1, u2, u3, u4, u5, u6, u7;
-        ld4(X.Ux[par][grp], u0, u1, u2, u3); ld4(X.Ux[par][grp] + 4, u4, u5, u6, u7);
-        par ^= 1;
-        const T D = s0 * u0 + s1 * u1 + s2 * u2 + s3 * u3 + s4 * u4 + s5 * u5 + K.limDd[d];
-        T coef = (Uc - (fcol ? K.Q[d] : T(0))) * Num<T>::rcp(D);
+        ld4(ux, u0, u1, u2, u3); ld4(ux + 4, u4, u5, u6, u7);
+        { T* t = ux; ux = uy; uy = t; }
+        // S[d][6] = generalized force Q, S[d][7] = h * limit damping of the dof (phase E)
+        const T D = s0 * u0 + s1 * u1 + s2 * u2 + s3 * u3 + s4 * u4 + s5 * u5 + s7;
+        T coef = (Uc - (fcol ? s6 : T(0))) * Num<T>::rcp(D);
         if (on) X.W[d][cc] = coef; else coef = T(0);
         col[0] -= u0 * coef; col[1] -= u1 * coef; col[2] -= u2 * coef;
         col[3] -= u3 * coef; col[4] -= u4 * coef; col[5] -= u5 * coef;
