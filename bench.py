@@ -182,11 +182,16 @@ def cpu_arm(env_id, n_envs, steps, warmup, budget_s, threads, integrator=None, i
         dt / max(done_steps * inner, 1)
 
 
-def bind_to_gpu_numa_node(local_rank):
+def bind_to_gpu_numa_node(local_rank, world=1):
     """CPU affinity of this rank = the cores of its GPU's NUMA node (sysfs), before any pinned allocation, so
-    that the page-locked buffers the step kernel writes over PCIe are node-local.  Returns what was done."""
+    that the page-locked buffers the step kernel writes over PCIe are node-local.  Where the host hides the
+    topology (a VM with one virtual node: numa_node = -1 for every device) the affinity is left alone unless
+    BIO_BENCH_BIND_SLICES=1 gives each rank its own contiguous slice of the allowed cores (measured: no gain).
+    BIO_BENCH_NO_BIND=1 leaves the affinity alone.  Returns what was done."""
     info = {"numa_node": None, "cpus": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
             "bound": False}
+    if os.environ.get("BIO_BENCH_NO_BIND") == "1":
+        return info
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -210,6 +215,16 @@ def bind_to_gpu_numa_node(local_rank):
         info["cpus"] = len(os.sched_getaffinity(0))
     except Exception as e:                  # no NVML / sysfs: leave the affinity alone
         info["error"] = type(e).__name__
+    # measured on an 8 x B200 box (32 vCPUs, one virtual node; gpurun_out/e2e_probe_8_*.json): slices 152.4 M end-to-end
+    # env-steps/s, no binding 155.9 M -- so the slices are opt-in
+    if not info["bound"] and world > 1 and os.environ.get("BIO_BENCH_BIND_SLICES") == "1" and hasattr(os, "sched_getaffinity"):
+        allowed = sorted(os.sched_getaffinity(0))
+        per = len(allowed) // world
+        if per >= 2:
+            os.sched_setaffinity(0, set(allowed[local_rank * per:(local_rank + 1) * per]))
+            info["bound"] = True
+            info["slice"] = "%d cores from the %d-th of %d slices" % (per, local_rank, world)
+            info["cpus"] = per
     return info
 
 
@@ -354,7 +369,7 @@ def main():
         print(json.dumps(line))
         return
 
-    affinity = bind_to_gpu_numa_node(local_rank)   # before CUDA / pinned allocations
+    affinity = bind_to_gpu_numa_node(local_rank, world)   # before CUDA / pinned allocations
     import torch
     import torch.distributed as dist
     from bioimitation_gym_b200 import tasks

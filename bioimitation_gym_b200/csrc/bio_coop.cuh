@@ -60,17 +60,29 @@ struct WorkPlanar {
     alignas(16) T pose[BIO_MAX_BODIES][4];         // cos, sin, x, y (about O, ground axes)
     alignas(16) T V[BIO_MAX_BODIES][4], A[BIO_MAX_BODIES][4];  // (w, vx, vy), bias acceleration likewise
     alignas(16) T S[C::ND][4];                     // motion vector of every dof
-    alignas(16) T bI[BIO_MAX_BODIES][12];          // spatial inertia about O [0..5] and force [6..8] per body
+    // spatial inertia about O (symmetric 3 x 3 in ww wx wy xx xy yy order = I0..I5) and force per body, by columns
+    // padded to four: (I0 I1 I2 -) (I1 I3 I4 -) (I2 I4 I5 -) (p0 p1 p2 -)
+    alignas(16) T bI[BIO_MAX_BODIES][16];
     T Qf[C::ND], Ld[C::ND];                        // generalized force and h * limit damping per dof
     alignas(16) T mv[P2_MAXMOV][8];                // moving points: location [0..2], d/dq [4..6]
     alignas(16) T sphI[BIO_MAX_SPHERES][8];        // h * contact damping of a sphere as an inertia about O: ww wx wy xx yy
     T mq[P2_MAXMOV];                               // their generalized force
-    alignas(16) T brx[P2_MAXBR][12];               // chain -> root: articulated inertia [0..5] and force [6..8] of its first body
-    alignas(16) T brk[P2_MAXBR][12];               // per chain dof: U / D [0..2], u / D [3], kept for the way back
+};
+// articulated-body pass of the planar program, behind the read-outs of a full evaluation (the wrench sources are dead
+// by then): cooperative pass (p2_aba_coop) W = per dof U / D [0..2], -u / D [3]; one-lane-per-chain pass
+// (p2_phase_f / _g, host emulation): brx = chain -> root articulated inertia [0..5] and force [6..8] of its first
+// body, brk = per chain dof U / D [0..2], u / D [3]
+template <typename T, typename C>
+struct WorkPlanarAba {
+    T pad_[128];
+    alignas(16) T W[C::ND][4];
+    alignas(16) T brx[P2_MAXBR][12];
+    alignas(16) T brk[P2_MAXBR][12];
 };
 
 template <typename T, typename C>
 struct WorkReadout { T obs_pos[COOP_MAXOBS][3], obs_vel[COOP_MAXOBS][3], comp[BIO_MAX_BODIES][6]; };   // full evaluation
+static_assert(sizeof(WorkReadout<double, CoopCls<1>>) <= 128 * sizeof(double), "read-outs overlap the articulated-body arrays");
 template <typename T>
 struct WorkSources { alignas(16) T w[P2_MAXSRC][4]; };                                                 // planar program
 #define COOP_MAXSRC6 48      // wrench sources of a 3D model (one per body a muscle touches; the reference's models: 46)
@@ -83,7 +95,7 @@ template <typename T, int CLS> struct WorkUnions;
 template <typename T> struct WorkUnions<T, 0> {
     typedef CoopCls<0> C;
     struct { WorkPlanar<T, C> p; } k;
-    union { WorkReadout<T, C> out; WorkSources<T> src; } x;
+    union { WorkReadout<T, C> out; WorkSources<T> src; WorkPlanarAba<T, C> pa; } x;
 };
 template <typename T> struct WorkUnions<T, 1> {
     typedef CoopCls<1> C;
@@ -96,6 +108,7 @@ template <typename T> struct WorkUnions<T, 1> {
         // articulated-body pass, behind the read-outs of a full evaluation: per dof U / D [0..5] and -u / D [6] for the
         // way back; exchange of U between the lanes of a chain (double-buffered by step parity)
         struct { T pad_[128]; alignas(16) T W[C::ND][8]; alignas(16) T Ux[2][2][8]; } aba;
+        WorkPlanarAba<T, C> pa;
     } x;
 };
 

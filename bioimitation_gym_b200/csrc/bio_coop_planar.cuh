@@ -595,7 +595,7 @@ BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         T* o = K.bI[b];
         const T fn = IAn + (vx * py - vy * px) - Wn;   // V x* (I V): n = v x p, f = w z x p
         const T ffx = IAx - w * py - Wx;
-        o[8] = IAy + w * px - Wy;
+        const T ffy = IAy + w * px - Wy;
         if (h_imp > T(0)) {
             if (pr.inc8_ok) {                    // spheres of the body in 4 bytes (zero terms for a sphere out of contact)
                 const uint32_t sp4 = pr.sph_pk[b];
@@ -619,8 +619,10 @@ BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
                 }
             }
         }
-        st4(o, Iww, Iwx, Iwy, Ixx);
-        st4(o + 4, T(0), Iyy, fn, ffx);
+        st4(o, Iww, Iwx, Iwy, T(0));
+        st4(o + 4, Iwx, Ixx, T(0), T(0));
+        st4(o + 8, Iwy, T(0), Iyy, T(0));
+        st4(o + 12, fn, ffx, ffy, T(0));
     } else if (lane - m.n_bodies < m.n_dof) {
         const int d = lane - m.n_bodies;
         T qf = T(0), ld = T(0);
@@ -634,6 +636,7 @@ BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         const int a = pr.dof_act[d];
         if (a >= 0) qf += E.ctrl[a];
         K.Qf[d] = qf;
+        K.S[d][3] = qf;                           // next to the motion vector (p2_aba_coop: one read per step)
         K.Ld[d] = h_imp * ld;
     }
 }
@@ -659,11 +662,13 @@ BIO_DEV void p2_phase_f(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         const int b = bk[k];
         const int d = dk[k];
         if (b >= 0) {
-            T v0, v1, v2, v3, v4, v5, v6, v7;
-            ld4(K.bI[b], v0, v1, v2, v3);
-            ld4(K.bI[b] + 4, v4, v5, v6, v7);
+            T v0, v1, v2, v3, v4, v5, v6, v7, v8, pd;
+            ld4(K.bI[b], v0, v1, v2, pd);
+            ld4(K.bI[b] + 4, pd, v3, v4, pd);
+            ld4(K.bI[b] + 8, pd, pd, v5, pd);
+            ld4(K.bI[b] + 12, v6, v7, v8, pd);
             Ia[0] += v0; Ia[1] += v1; Ia[2] += v2; Ia[3] += v3; Ia[4] += v4; Ia[5] += v5;
-            pa[0] += v6; pa[1] += v7; pa[2] += K.bI[b][8];
+            pa[0] += v6; pa[1] += v7; pa[2] += v8;
         }
         if (d >= 0) {
             T S0, S1, S2, s3;
@@ -677,12 +682,12 @@ BIO_DEV void p2_phase_f(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
             Ia[0] -= U0 * W0; Ia[1] -= U0 * W1; Ia[2] -= U0 * W2;
             Ia[3] -= U1 * W1; Ia[4] -= U1 * W2; Ia[5] -= U2 * W2;
             pa[0] += U0 * ud; pa[1] += U1 * ud; pa[2] += U2 * ud;
-            st4(K.brk[l] + 4 * k, W0, W1, W2, ud);
+            st4(E.x.pa.brk[l] + 4 * k, W0, W1, W2, ud);
         }
     }
-    st4(K.brx[l], Ia[0], Ia[1], Ia[2], Ia[3]);
-    st4(K.brx[l] + 4, Ia[4], Ia[5], pa[0], pa[1]);
-    K.brx[l][8] = pa[2];
+    st4(E.x.pa.brx[l], Ia[0], Ia[1], Ia[2], Ia[3]);
+    st4(E.x.pa.brx[l] + 4, Ia[4], Ia[5], pa[0], pa[1]);
+    E.x.pa.brx[l][8] = pa[2];
 }
 
 // ---- phase G: root solve on the articulated inertia (every chain lane repeats it), then the chain's way
@@ -695,19 +700,20 @@ BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     if (lane >= nbr) return;
     const int4 ri = *reinterpret_cast<const int4*>(pr.root_i4);
     const int rdof[3] = {ri.x, ri.y, ri.z};
-    T a[9];
-    ld4(K.bI[ri.w], a[0], a[1], a[2], a[3]);
-    ld4(K.bI[ri.w] + 4, a[4], a[5], a[6], a[7]);
-    a[8] = K.bI[ri.w][8];
+    T a[9], pd;
+    ld4(K.bI[ri.w], a[0], a[1], a[2], pd);
+    ld4(K.bI[ri.w] + 4, pd, a[3], a[4], pd);
+    ld4(K.bI[ri.w] + 8, pd, pd, a[5], pd);
+    ld4(K.bI[ri.w] + 12, a[6], a[7], a[8], pd);
 #pragma unroll
     for (int l = 0; l < P2_MAXBR; l++) {
         if (l < pr.n_branches) {
             T v[8];
-            ld4(K.brx[l], v[0], v[1], v[2], v[3]);
-            ld4(K.brx[l] + 4, v[4], v[5], v[6], v[7]);
+            ld4(E.x.pa.brx[l], v[0], v[1], v[2], v[3]);
+            ld4(E.x.pa.brx[l] + 4, v[4], v[5], v[6], v[7]);
 #pragma unroll
             for (int e = 0; e < 8; e++) a[e] += v[e];
-            a[8] += K.brx[l][8];
+            a[8] += E.x.pa.brx[l][8];
         }
     }
     T Sr[3][3], IS[3][3], H[3][3], rhs[3];
@@ -758,13 +764,85 @@ BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
             const int d = dk[k];
             if (d >= 0) {
                 T W0, W1, W2, ud, S0, S1, S2, s3;
-                ld4(K.brk[lane] + 4 * k, W0, W1, W2, ud);
+                ld4(E.x.pa.brk[lane] + 4 * k, W0, W1, W2, ud);
                 ld4(K.S[d], S0, S1, S2, s3);
                 const T qdd = ud - (W0 * a0 + W1 * a1 + W2 * a2);
                 E.udot[d] = qdd;
                 a0 += S0 * qdd; a1 += S1 * qdd; a2 += S2 * qdd;
             }
         }
+    }
+}
+
+// ---- phases F and G as one cooperative pass (device; p2_phase_f / _g are the same elimination with one lane per
+// chain, kept for the host emulation and BIO_PLANAR_SERIAL_ABA=1).  Four lanes own a chain: lane c < 3 keeps column c
+// of the chain's articulated inertia (symmetric 3 x 3) in registers, lane 3 the force as a fourth column.  Per dof,
+// from the leaf:  U_c = S . column_c (lane 3: S . p^A);  the four U go round by shuffles;  D = S . U + Ld;
+// column_c -= U (U_c - [c = 3] Q) / D  (I^a = I^A - U U^T / D,  p^a = p^A + U (Q - S . p^A) / D);  the coefficients
+// (U / D, -(Q - S . p^A) / D) stay in shared memory for the way back.  The two chains swap their heads by a shuffle,
+// every group adds the root body and eliminates the root's dofs, and every lane walks the accelerations back down. ----
+template <typename T, int CLS>
+__device__ __forceinline__ void p2_aba_coop(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
+    constexpr int G = CoopCls<CLS>::G;
+    const PlanarProg<T>& pr = m.prog;
+    auto& K = E.k.p;
+    auto& X = E.x.pa;
+    const unsigned mask = group_mask<G>();
+    const int l = lane >> 2, c = lane & 3;
+    const bool live = l < pr.n_branches;
+    const int lc = live ? l : 0;
+    const int4 bb = *reinterpret_cast<const int4*>(pr.br_i8[lc]), dd = *reinterpret_cast<const int4*>(pr.br_i8[lc] + 4);
+    const int bk[3] = {bb.x, bb.y, bb.z}, dk[3] = {dd.x, dd.y, dd.z};
+    const int4 ri = *reinterpret_cast<const int4*>(pr.root_i4);
+    const int rdof[3] = {ri.x, ri.y, ri.z};
+    T c0 = T(0), c1 = T(0), c2 = T(0);
+    auto add_body = [&](const int b) {
+        T v0, v1, v2, v3;
+        ld4(K.bI[b] + 4 * c, v0, v1, v2, v3);
+        c0 += v0; c1 += v1; c2 += v2;
+    };
+    auto eliminate = [&](const int d, const bool on) {
+        T S0, S1, S2, Q;
+        ld4(K.S[d], S0, S1, S2, Q);
+        const T Ld = K.Ld[d];
+        const T Uc = S0 * c0 + S1 * c1 + S2 * c2;
+        const T U0 = __shfl_sync(mask, Uc, 0, 4), U1 = __shfl_sync(mask, Uc, 1, 4), U2 = __shfl_sync(mask, Uc, 2, 4);
+        const T D = S0 * U0 + S1 * U1 + S2 * U2 + Ld;
+        T coef = (Uc - (c == 3 ? Q : T(0))) * Num<T>::rcp(D);
+        if (on) X.W[d][c] = coef; else coef = T(0);
+        c0 -= U0 * coef; c1 -= U1 * coef; c2 -= U2 * coef;
+    };
+#pragma unroll
+    for (int k = P2_MAXCB - 1; k >= 0; k--) {
+        const int b = bk[k], d = dk[k];
+        if (live && b >= 0) add_body(b);
+        eliminate(d >= 0 ? d : 0, live && d >= 0);
+    }
+    if (!live) { c0 = T(0); c1 = T(0); c2 = T(0); }
+    // chain heads: the two chain groups (lanes 0..3, 4..7) swap theirs, then everybody holds the root's columns
+    {
+        const T o0 = __shfl_xor_sync(mask, c0, 4, 8), o1 = __shfl_xor_sync(mask, c1, 4, 8), o2 = __shfl_xor_sync(mask, c2, 4, 8);
+        c0 += o0; c1 += o1; c2 += o2;
+        add_body(ri.w);
+    }
+#pragma unroll
+    for (int r = 2; r >= 0; r--) eliminate(rdof[r] >= 0 ? rdof[r] : 0, l == 0 && rdof[r] >= 0);
+    __syncwarp();
+    // way back: qdd = u / D - (U / D) . a(parent), a(body) = a(parent) + S qdd
+    T a0 = T(0), a1 = T(0), a2 = T(0);
+    auto back = [&](const int d, const bool store) {
+        T W0, W1, W2, W3, S0, S1, S2, s3;
+        ld4(X.W[d], W0, W1, W2, W3);
+        ld4(K.S[d], S0, S1, S2, s3);
+        const T qdd = -W3 - (W0 * a0 + W1 * a1 + W2 * a2);
+        if (store) E.udot[d] = qdd;
+        a0 += S0 * qdd; a1 += S1 * qdd; a2 += S2 * qdd;
+    };
+#pragma unroll
+    for (int r = 0; r < 3; r++) if (rdof[r] >= 0) back(rdof[r], lane == 0);
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < P2_MAXCB; k++) if (dk[k] >= 0) back(dk[k], c == 0);
     }
 }
 
@@ -861,10 +939,18 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
     p2_phase_e<T, CLS>(m, E, lane, h_imp, ext_fx, ext_pt);
     gsync<G>();
     P2_CLK(4);
-    p2_phase_f<T, CLS>(m, E, lane);
-    gsync<G>();
-    P2_CLK(5);
-    p2_phase_g<T, CLS>(m, E, lane);
+#ifdef __CUDA_ARCH__
+    if (m.prog.coop_aba) {
+        p2_aba_coop<T, CLS>(m, E, lane);
+        P2_CLK(5);
+    } else
+#endif
+    {
+        p2_phase_f<T, CLS>(m, E, lane);
+        gsync<G>();
+        P2_CLK(5);
+        p2_phase_g<T, CLS>(m, E, lane);
+    }
     if (full) {
         p2_readout_1<T, CLS>(m, E, lane);
         gsync<G>();

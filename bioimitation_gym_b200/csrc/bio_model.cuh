@@ -107,7 +107,7 @@ struct alignas(16) PlanarProg {
     // articulated-body schedule of the spatial (3D) evaluation (p3_aba, bio_coop_spatial.cuh): per chain the dofs
     // in elimination order, leaf first: dof | (body whose inertia joins before this dof + 1) << 4, 255 = no step;
     // then the root's dofs, last first
-    int32_t aba_ok, aba_nsteps, aba_nroot, aba_pad_;
+    int32_t aba_ok, aba_nsteps, aba_nroot, coop_aba;   // coop_aba: planar program runs phases F, G as p2_aba_coop
     uint8_t aba_step[P2_MAXBR][P2_MAXABA];
     uint8_t aba_root[8];
 };
@@ -882,6 +882,8 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         pr.sph_pk[b] = sp4[0] | (sp4[1] << 8) | (sp4[2] << 16) | ((uint32_t)sp4[3] << 24);
     }
     pr.ok = 1;
+    pr.coop_aba = 1;
+    { const char* z = getenv("BIO_PLANAR_SERIAL_ABA"); if (z && z[0] == '1') pr.coop_aba = 0; }   // tests: one lane per chain
 }
 
 // Observation layout as a descriptor per slot (same order as write_obs in
