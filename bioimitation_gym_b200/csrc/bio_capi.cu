@@ -229,6 +229,7 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
     }
     // env state
     const size_t N = (size_t)n;
+    h->st.aos = h->coop_cls >= 0 ? 1 : 0;   // env-major records for the cooperative kernels (EnvState)
     if ((rc = dev_alloc(h, &h->st.q, N * nd))) return rc;
     if ((rc = dev_alloc(h, &h->st.u, N * nd))) return rc;
     if ((rc = dev_alloc(h, &h->st.act, N * nm))) return rc;
@@ -341,6 +342,11 @@ int state_impl(Handle<T>* h, const BioStatePtrs* p, cudaStream_t s, bool set) {
                     {p->old_px, h->st.old_px, 1}};
     for (auto& it : items) {
         if (!it.user || it.k == 0) continue;
+        if (h->st.aos || it.k == 1) {            // env-major state: the caller's [N][k] rows are the storage layout
+            if (set) CU(cudaMemcpyAsync(it.soa, it.user, sizeof(T) * h->n * it.k, cudaMemcpyDeviceToDevice, s));
+            else CU(cudaMemcpyAsync(it.user, it.soa, sizeof(T) * h->n * it.k, cudaMemcpyDeviceToDevice, s));
+            continue;
+        }
         if (set) rc = transpose<T>(h, (const T*)it.user, it.soa, it.k, 1, s);
         else rc = transpose<T>(h, it.soa, (T*)it.user, it.k, 0, s);
         if (rc) return rc;

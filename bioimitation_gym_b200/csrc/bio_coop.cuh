@@ -965,14 +965,14 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
 
     // every global load of the step's inputs is issued here, before anything waits on one of them: state,
     // bookkeeping, the action and the action history (one memory round trip; the L2 is cold in the benchmark)
-    const T q_in = isd ? st.q[(size_t)lane * n + ii] : T(0), u_in = isd ? st.u[(size_t)lane * n + ii] : T(0);
-    const T act_in = ism ? st.act[(size_t)lane * n + ii] : T(0), lm_in = ism ? st.lm[(size_t)lane * n + ii] : T(0);
+    const T q_in = isd ? st.q[sx(st.aos, lane, ii, nd, n)] : T(0), u_in = isd ? st.u[sx(st.aos, lane, ii, nd, n)] : T(0);
+    const T act_in = ism ? st.act[sx(st.aos, lane, ii, nm, n)] : T(0), lm_in = ism ? st.lm[sx(st.aos, lane, ii, nm, n)] : T(0);
     const T action_in = isa ? actions[(size_t)ii * na + lane] : T(0);
-    const T last_in = isa ? st.last_action[(size_t)lane * n + ii] : T(0);
+    const T last_in = isa ? st.last_action[sx(st.aos, lane, ii, na, n)] : T(0);
     T hv[BIO_MAX_HORIZON];
 #pragma unroll
     for (int hh = 0; hh < BIO_MAX_HORIZON; hh++)
-        hv[hh] = (isa && hh < Hh) ? st.history[((size_t)hh * na + lane) * n + ii] : T(0);
+        hv[hh] = (isa && hh < Hh) ? st.history[sx(st.aos, hh * na + lane, ii, Hh * na, n)] : T(0);
     int istep = st.istep[ii];
     int hist_pos = st.hist_pos[ii];
     const bool first = st.first[ii] != 0;
@@ -1017,7 +1017,7 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
         for (int hh = 0; hh < BIO_MAX_HORIZON; hh++) {
             if (hh < Hh) {
                 sum += hh == hist_pos ? action : hv[hh];
-                if (valid && (first || hh == hist_pos)) st.history[((size_t)hh * na + lane) * n + ii] = action;
+                if (valid && (first || hh == hist_pos)) st.history[sx(st.aos, hh * na + lane, ii, Hh * na, n)] = action;
             }
         }
         curr = sum / T(Hh);
@@ -1231,9 +1231,9 @@ bio_coop_step_kernel(const DevModel<T>* __restrict__ gm, const DevTask<T> c, con
     SK_CLK();                                   // 7: rows flushed, auto-reset handled
     // ---- write back ----
     if (valid) {
-        if (isd) { st.q[(size_t)lane * n + ii] = E.q[lane]; st.u[(size_t)lane * n + ii] = E.u[lane]; }
-        if (ism) { st.act[(size_t)lane * n + ii] = E.act[lane]; st.lm[(size_t)lane * n + ii] = E.lm[lane]; }
-        if (isa) st.last_action[(size_t)lane * n + ii] = first_next ? T(0) : curr;
+        if (isd) { st.q[sx(st.aos, lane, ii, nd, n)] = E.q[lane]; st.u[sx(st.aos, lane, ii, nd, n)] = E.u[lane]; }
+        if (ism) { st.act[sx(st.aos, lane, ii, nm, n)] = E.act[lane]; st.lm[sx(st.aos, lane, ii, nm, n)] = E.lm[lane]; }
+        if (isa) st.last_action[sx(st.aos, lane, ii, na, n)] = first_next ? T(0) : curr;
         if (lane == 0) {
             st.old_px[ii] = progress_coord;
             st.istep[ii] = istep;

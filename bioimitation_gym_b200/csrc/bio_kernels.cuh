@@ -204,13 +204,13 @@ __device__ int reset_state(const DevModel<T>& m, const DevTask<T>& c, Local<T>& 
 
 template <typename T>
 __device__ void load_state(const DevModel<T>& m, const EnvState<T>& st, int i, int n, Local<T>& s) {
-    for (int d = 0; d < m.n_dof; d++) { s.q[d] = st.q[(size_t)d * n + i]; s.u[d] = st.u[(size_t)d * n + i]; }
-    for (int k = 0; k < m.n_muscles; k++) { s.act[k] = st.act[(size_t)k * n + i]; s.lm[k] = st.lm[(size_t)k * n + i]; }
+    for (int d = 0; d < m.n_dof; d++) { s.q[d] = st.q[sx(st.aos, d, i, m.n_dof, n)]; s.u[d] = st.u[sx(st.aos, d, i, m.n_dof, n)]; }
+    for (int k = 0; k < m.n_muscles; k++) { s.act[k] = st.act[sx(st.aos, k, i, m.n_muscles, n)]; s.lm[k] = st.lm[sx(st.aos, k, i, m.n_muscles, n)]; }
 }
 template <typename T>
 __device__ void store_state(const DevModel<T>& m, const EnvState<T>& st, int i, int n, const Local<T>& s) {
-    for (int d = 0; d < m.n_dof; d++) { st.q[(size_t)d * n + i] = s.q[d]; st.u[(size_t)d * n + i] = s.u[d]; }
-    for (int k = 0; k < m.n_muscles; k++) { st.act[(size_t)k * n + i] = s.act[k]; st.lm[(size_t)k * n + i] = s.lm[k]; }
+    for (int d = 0; d < m.n_dof; d++) { st.q[sx(st.aos, d, i, m.n_dof, n)] = s.q[d]; st.u[sx(st.aos, d, i, m.n_dof, n)] = s.u[d]; }
+    for (int k = 0; k < m.n_muscles; k++) { st.act[sx(st.aos, k, i, m.n_muscles, n)] = s.act[k]; st.lm[sx(st.aos, k, i, m.n_muscles, n)] = s.lm[k]; }
 }
 
 template <typename T>
@@ -257,17 +257,17 @@ __global__ void bio_step_kernel(const DevModel<T>* __restrict__ gm, const DevTas
     if (first) {
         for (int j = 0; j < na; j++) {
             last_action[j] = action[j];
-            for (int hh = 0; hh < H; hh++) st.history[((size_t)hh * na + j) * n + i] = action[j];
+            for (int hh = 0; hh < H; hh++) st.history[sx(st.aos, hh * na + j, i, H * na, n)] = action[j];
         }
         hist_pos = 0;
     } else {
-        for (int j = 0; j < na; j++) last_action[j] = st.last_action[(size_t)j * n + i];
+        for (int j = 0; j < na; j++) last_action[j] = st.last_action[sx(st.aos, j, i, na, n)];
     }
-    for (int j = 0; j < na; j++) st.history[((size_t)hist_pos * na + j) * n + i] = action[j];
+    for (int j = 0; j < na; j++) st.history[sx(st.aos, hist_pos * na + j, i, H * na, n)] = action[j];
     hist_pos = (hist_pos + 1) % H;
     for (int j = 0; j < na; j++) {
         T sum = T(0);
-        for (int hh = 0; hh < H; hh++) sum += st.history[((size_t)hh * na + j) * n + i];
+        for (int hh = 0; hh < H; hh++) sum += st.history[sx(st.aos, hh * na + j, i, H * na, n)];
         curr[j] = sum / T(H);
         ctrl[j] = clampv(c.feed_mean_action ? curr[j] : action[j], m.act_min[j], m.act_max[j]);
     }
@@ -408,7 +408,7 @@ __global__ void bio_step_kernel(const DevModel<T>* __restrict__ gm, const DevTas
     }
     // ---- write back ----
     store_state(m, st, i, n, s);
-    for (int j = 0; j < na; j++) st.last_action[(size_t)j * n + i] = first_next ? T(0) : curr[j];
+    for (int j = 0; j < na; j++) st.last_action[sx(st.aos, j, i, na, n)] = first_next ? T(0) : curr[j];
     st.old_px[i] = progress_coord;
     st.istep[i] = istep;
     st.first[i] = first_next;
@@ -442,7 +442,7 @@ __global__ void bio_reset_kernel(const DevModel<T>* __restrict__ gm, const DevTa
     st.ep_return[i] = T(0);
     st.ep_len[i] = 0;
     st.episode[i] = episode;
-    for (int j = 0; j < m.n_act; j++) st.last_action[(size_t)j * n + i] = T(0);
+    for (int j = 0; j < m.n_act; j++) st.last_action[sx(st.aos, j, i, m.n_act, n)] = T(0);
     if (obs) {
         T ctrl[BIO_MAX_ACT];
         for (int j = 0; j < m.n_act; j++) ctrl[j] = T(0);

@@ -275,9 +275,14 @@ struct DevTask {
     StepExtra<T> ex;      // all null unless bio_set_step_extra attached buffers
 };
 
-// SoA per-env state, [k][n_envs]
+// Per-env state.  Every array holds K variables per env (q, u: n_dof; act, lm: n_muscles; last_action: n_act;
+// history: horizon * n_act) in one of two layouts, picked at create time by the kernel that steps the handle:
+//   aos = 1  [n_envs][K]  cooperative kernels: the lanes of an env's group read / write consecutive words
+//   aos = 0  [K][n_envs]  thread-per-env kernels: the lanes of a warp (consecutive envs) read consecutive words
+// sx() is the element index of variable v of env i.
 template <typename T>
 struct EnvState {
+    int32_t aos, pad_;
     T* q;
     T* u;
     T* act;
@@ -292,6 +297,10 @@ struct EnvState {
     int32_t* ep_len;
     long long* episode;
 };
+
+__host__ __device__ __forceinline__ size_t sx(const int aos, const int v, const int i, const int K, const int n) {
+    return aos ? (size_t)i * K + v : (size_t)v * n + i;
+}
 
 #define BIO_CP(field)                                                                  \
     do {                                                                               \
