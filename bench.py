@@ -265,6 +265,41 @@ def e2e_loop(env, pool, steps, barrier):
     return time.perf_counter() - t0
 
 
+def e2e_pipelined_loop(env_id, cfg, pool, steps, preroll, barrier, n_groups=4):
+    """The same end-to-end step through the send / recv entry points (backend.EnvGroups): the batch as
+    `n_groups` groups on disjoint SMs, each group's next step sent as soon as its results are in host memory, so
+    that one group's PCIe tail overlaps the others' substeps.  Every control step of every group reads its
+    actions from and writes its observation rows to page-locked host memory, as in e2e_loop.  Wall seconds for
+    `steps` control steps of the whole batch."""
+    import torch
+    from bioimitation_gym_b200 import backend
+    groups = backend.EnvGroups(env_id, cfg, groups=n_groups)
+    ng = groups.n_group
+    acts = [[pool[i][g * ng:(g + 1) * ng].cpu().numpy().copy() for g in range(n_groups)] for i in range(4)]
+    groups.reset()
+    for g in range(n_groups):
+        groups.send(g, acts[0][g])
+    for k in range(1, preroll + 3):           # the same steady-state episode mix as the synchronous loops
+        for g in range(n_groups):
+            groups.recv(g)
+            groups.send(g, acts[k % 4][g])
+    for g in range(n_groups):
+        groups.recv(g)
+    barrier()
+    t0 = time.perf_counter()
+    for g in range(n_groups):
+        groups.send(g, acts[0][g])
+    for k in range(1, steps):
+        for g in range(n_groups):
+            groups.recv(g)
+            groups.send(g, acts[k % 4][g])
+    for g in range(n_groups):
+        groups.recv(g)
+    dt = time.perf_counter() - t0
+    groups.close()
+    return dt
+
+
 def run_config(env_id, n_per_gpu, steps, warmup, rank, world, local_rank, args, preroll, e2e_steps, barrier, flush):
     """One workload: create, pre-roll, warm up, timed loop, end-to-end loop, statistics.  Returns a dict
     (identical on every rank for the all-reduced fields)."""
@@ -299,6 +334,17 @@ def run_config(env_id, n_per_gpu, steps, warmup, rank, world, local_rank, args, 
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_max, e2e_min = float(t[0].item()), -float(t[1].item())
+    pipe = None
+    if args.pipelined_groups > 1 and n_per_gpu % args.pipelined_groups == 0 and n_per_gpu <= 65536:
+        pipe_s = e2e_pipelined_loop(env_id, cfg, pool, e2e_steps, preroll, barrier, args.pipelined_groups)
+        t = torch.tensor([pipe_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pipe = {"value": n_per_gpu * world * e2e_steps / float(t.item()), "unit": "env-steps/s",
+                "groups": args.pipelined_groups, "steps": e2e_steps,
+                "api": "backend.EnvGroups send / recv (bio_step_host_begin / _end): %d groups of %d envs per GPU on "
+                       "disjoint SMs, same host buffers and bytes per step as e2e.value"
+                       % (args.pipelined_groups, n_per_gpu // args.pipelined_groups)}
     stats = env.stats().clone()
     if world > 1:                              # the only collective: rollout statistics, outside the step path
         gathered = [torch.zeros_like(stats) for _ in range(world)]
@@ -312,7 +358,8 @@ def run_config(env_id, n_per_gpu, steps, warmup, rank, world, local_rank, args, 
                     "h2d_bytes_per_step": n_per_gpu * env.n_act * esz,
                     "d2h_bytes_per_step": n_per_gpu * (env.obs_dim + 1 + env.n_terms) * esz + n_per_gpu,
                     "steps": e2e_steps,
-                    "per_rank_ms_per_step": {"min": e2e_min / e2e_steps * 1e3, "max": e2e_max / e2e_steps * 1e3}},
+                    "per_rank_ms_per_step": {"min": e2e_min / e2e_steps * 1e3, "max": e2e_max / e2e_steps * 1e3},
+                    **({"pipelined": pipe} if pipe else {})},
                rollout={"env_steps": float(stats[0]), "episodes": float(stats[1]),
                         "mean_return": float(stats[2] / max(stats[1], 1)),
                         "mean_length": float(stats[3] / max(stats[1], 1)),
@@ -338,6 +385,8 @@ def main():
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="skip the 1M-env sweep lines at --gpus >= 2")
     ap.add_argument("--preroll", type=int, default=PREROLL)
+    ap.add_argument("--pipelined-groups", type=int, default=4,
+                    help="env groups of the send / recv end-to-end measurement (e2e.pipelined); <= 1: skip")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -40,6 +40,9 @@ C_API = {
     "bio_step": (ctypes.c_int, [ctypes.c_void_p] * 7),
     "bio_step_host": (ctypes.c_int, [ctypes.c_void_p] * 6),
     "bio_reset_host": (ctypes.c_int, [ctypes.c_void_p] * 3),
+    "bio_step_host_begin": (ctypes.c_int, [ctypes.c_void_p] * 6),
+    "bio_step_host_end": (ctypes.c_int, [ctypes.c_void_p]),
+    "bio_set_grid": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "bio_get_state": (ctypes.c_int, [ctypes.c_void_p] * 3),
     "bio_set_state": (ctypes.c_int, [ctypes.c_void_p] * 3),
     "bio_eval_debug": (ctypes.c_int, [ctypes.c_void_p] * 4),
@@ -179,6 +182,20 @@ class VecEnv:
         _check(self.lib, self.lib.bio_step_host(
             self.handle, actions.ctypes.data, obs.ctypes.data, reward.ctypes.data, done.ctypes.data,
             terms.ctypes.data if terms is not None else None), "bio_step_host")
+
+    def step_host_begin(self, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, done: np.ndarray,
+                        terms: np.ndarray):
+        """First half of step_host: launch and return (page-locked buffers only); step_host_end waits."""
+        _check(self.lib, self.lib.bio_step_host_begin(
+            self.handle, actions.ctypes.data, obs.ctypes.data, reward.ctypes.data, done.ctypes.data,
+            terms.ctypes.data), "bio_step_host_begin")
+
+    def step_host_end(self):
+        _check(self.lib, self.lib.bio_step_host_end(self.handle), "bio_step_host_end")
+
+    def set_grid(self, ctas: int):
+        """Persistent grid of the step kernel (bio_set_grid): `ctas` SMs instead of the whole device."""
+        _check(self.lib, self.lib.bio_set_grid(self.handle, int(ctas)), "bio_set_grid")
 
     def _host_buffers(self):
         """Two sets of page-locked buffers, used alternately: the arrays a call returns stay valid until the
@@ -333,3 +350,82 @@ class VecEnv:
             self.close()
         except Exception:
             pass
+
+
+class EnvGroups:
+    """The batch as G groups stepped in a pipeline (the send / recv pattern of asynchronous vector envs): group g
+    holds envs [g N/G, (g+1) N/G) of the same seeded batch (the reset RNG is keyed by the global env index, so
+    the union equals one VecEnv of N envs) and steps on its own N_SM / G SMs, so that while one group's
+    observation rows drain over PCIe and its caller picks the next actions, the other groups keep computing.
+
+        groups = EnvGroups("MuscleWalkingImitation2D-v0", dict(num_envs=4096), groups=4)
+        obs = groups.reset()                       # list of G arrays [N/G, D] (page-locked host memory)
+        for g in range(groups.G): groups.send(g, policy(obs[g]))
+        while training:
+            for g in range(groups.G):
+                o, r, d, info = groups.recv(g)     # waits for group g only
+                groups.send(g, policy(o))
+    """
+
+    def __init__(self, env_id: str, config: Optional[Mapping[str, Any]] = None, groups: int = 4):
+        import torch
+        cfg = dict(tasks.merged_config(config))
+        n = int(cfg["num_envs"])
+        if groups < 1 or n % groups:
+            raise ValueError("num_envs must be a multiple of the number of groups")
+        self.G, self.n_group = groups, n // groups
+        self.envs = []
+        off0 = int(cfg["env_offset"])
+        for g in range(groups):
+            c = dict(cfg)
+            c["num_envs"] = self.n_group
+            c["env_offset"] = off0 + g * self.n_group
+            self.envs.append(VecEnv(env_id, c))
+        e0 = self.envs[0]
+        sms = torch.cuda.get_device_properties(e0.device).multi_processor_count
+        if groups > 1:
+            for e in self.envs:
+                e.set_grid(max(1, sms // groups))
+        pin = lambda *s, dt=None: torch.zeros(s, dtype=dt or e0.dtype).pin_memory()
+        self._pinned = [dict(a=pin(self.n_group, e0.n_act), o=pin(self.n_group, e0.obs_dim), r=pin(self.n_group),
+                             d=pin(self.n_group, dt=torch.uint8), t=pin(self.n_group, e0.n_terms)) for _ in range(groups)]
+        self.buf = [{k: v.numpy() for k, v in b.items()} for b in self._pinned]
+        self._in_flight = [False] * groups
+        self.n_act, self.obs_dim, self.num_envs = e0.n_act, e0.obs_dim, n
+
+    def reset(self):
+        for g, e in enumerate(self.envs):
+            if self._in_flight[g]:
+                e.step_host_end()
+                self._in_flight[g] = False
+            e.reset_host(self.buf[g]["o"])
+        self.envs[0].torch.cuda.synchronize(self.envs[0].device)
+        return [b["o"] for b in self.buf]
+
+    def send(self, g: int, actions):
+        """Start the next control step of group g with `actions` [N/G, A] (copied into the group's page-locked
+        action buffer; pass the buffer itself, groups.buf[g]['a'], to skip the copy)."""
+        if self._in_flight[g]:
+            raise BioError("group %d is already stepping: recv() it first" % g)
+        b = self.buf[g]
+        if actions is not b["a"]:
+            b["a"][...] = actions
+        self.envs[g].step_host_begin(b["a"], b["o"], b["r"], b["d"], b["t"])
+        self._in_flight[g] = True
+
+    def recv(self, g: int):
+        """Wait for group g's step: (obs, reward, done, info) views of its page-locked buffers, valid until the
+        group's next send()."""
+        if not self._in_flight[g]:
+            raise BioError("group %d has no step in flight" % g)
+        self.envs[g].step_host_end()
+        self._in_flight[g] = False
+        b = self.buf[g]
+        return b["o"], b["r"], b["d"].view(np.bool_), {"all_rewards": b["t"]}
+
+    def close(self):
+        for g, e in enumerate(self.envs):
+            if self._in_flight[g]:
+                e.step_host_end()
+            e.close()
+        self.envs = []

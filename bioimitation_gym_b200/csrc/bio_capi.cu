@@ -462,6 +462,20 @@ int step_host_impl(Handle<T>* h, const void* actions, void* obs, void* reward, u
     return 0;
 }
 
+// bio_step_host_begin: the zero-copy launch of step_host_impl without the wait
+template <typename T>
+int step_host_begin_impl(Handle<T>* h, const void* actions, void* obs, void* reward, uint8_t* done, void* terms) {
+    void* dv[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    const void* hv[5] = {actions, obs, reward, (const void*)done, terms};
+    for (int k = 0; k < 5; k++) {
+        cudaPointerAttributes at;
+        if (hv[k] && cudaPointerGetAttributes(&at, hv[k]) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            dv[k] = at.devicePointer;
+        else { cudaGetLastError(); return fail(-1, "bio_step_host_begin: every buffer must be page-locked host memory"); }
+    }
+    return step_impl<T>(h, dv[0], dv[1], dv[2], (uint8_t*)dv[3], dv[4], h->host_stream ? h->host_stream : h->side);
+}
+
 template <typename T>
 int reset_host_impl(Handle<T>* h, const uint8_t* mask, void* obs) {
     const size_t N = h->n;
@@ -558,6 +572,25 @@ int bio_step_host(bio_handle hh, const void* actions, void* obs, void* reward, u
     if (!actions) return fail(-1, "bio_step_host: null actions");
     return DISPATCH(hh, step_host_impl<float>(H32(hh), actions, obs, reward, done, reward_terms),
                     step_host_impl<double>(H64(hh), actions, obs, reward, done, reward_terms));
+}
+
+int bio_step_host_begin(bio_handle hh, const void* actions, void* obs, void* reward, uint8_t* done, void* reward_terms) {
+    ENTER(hh);
+    return DISPATCH(hh, step_host_begin_impl<float>(H32(hh), actions, obs, reward, done, reward_terms),
+                    step_host_begin_impl<double>(H64(hh), actions, obs, reward, done, reward_terms));
+}
+
+int bio_step_host_end(bio_handle hh) {
+    ENTER(hh);
+    HandleBase* b = (HandleBase*)hh;
+    CU(cudaStreamSynchronize(b->host_stream ? b->host_stream : b->side));
+    return 0;
+}
+
+int bio_set_grid(bio_handle hh, int32_t ctas) {
+    ENTER(hh);
+    ((HandleBase*)hh)->coop_grid = ctas > 0 ? ctas : 0;
+    return 0;
 }
 
 int bio_reset_host(bio_handle hh, const uint8_t* mask, void* obs) {

@@ -61,8 +61,9 @@ struct WorkPlanar {
     alignas(16) T V[BIO_MAX_BODIES][4], A[BIO_MAX_BODIES][4];  // (w, vx, vy), bias acceleration likewise
     alignas(16) T S[C::ND][4];                     // motion vector of every dof
     // spatial inertia about O (symmetric 3 x 3 in ww wx wy xx xy yy order = I0..I5) and force per body, by columns
-    // padded to four: (I0 I1 I2 -) (I1 I3 I4 -) (I2 I4 I5 -) (p0 p1 p2 -)
-    alignas(16) T bI[BIO_MAX_BODIES][16];
+    // padded to four: (I0 I1 I2 -) (I1 I3 I4 -) (I2 I4 I5 -) (p0 p1 p2 -); rows of 20 words, so that the body lanes
+    // of phase E store to distinct banks (16-word rows: 4-way conflicts, 24 excess wavefronts per evaluation)
+    alignas(16) T bI[BIO_MAX_BODIES][20];
     T Qf[C::ND], Ld[C::ND];                        // generalized force and h * limit damping per dof
     alignas(16) T mv[P2_MAXMOV][8];                // moving points: location [0..2], d/dq [4..6]
     alignas(16) T sphI[BIO_MAX_SPHERES][8];        // h * contact damping of a sphere as an inertia about O: ww wx wy xx yy
@@ -136,12 +137,16 @@ struct alignas(16) EnvWorkBody : WorkUnions<T, CLS> {
 
 // Two envs share a warp in class 0 and touch the same fields at the same time: the buffer size is
 // an odd multiple of 64 bytes, so that the second env's copy starts 16 banks away from the first's.
-template <typename T, int CLS>
-struct alignas(16) EnvWork : EnvWorkBody<T, CLS> {
+template <size_t PAD> struct PadBytes { unsigned char bank_pad[PAD]; };
+template <> struct PadBytes<0> {};
+template <typename T, int CLS> struct EnvWorkSize {
     static constexpr size_t raw = sizeof(EnvWorkBody<T, CLS>);
     static constexpr size_t want = CLS == 0 ? (((raw + 63) / 64) | 1) * 64 : ((raw + 15) / 16) * 16 + 16;
-    unsigned char bank_pad[want - raw > 0 ? want - raw : 128];
 };
+template <typename T, int CLS>
+struct alignas(16) EnvWork : EnvWorkBody<T, CLS>, PadBytes<EnvWorkSize<T, CLS>::want - EnvWorkSize<T, CLS>::raw> {};
+static_assert(sizeof(EnvWork<float, 0>) == EnvWorkSize<float, 0>::want && sizeof(EnvWork<float, 1>) == EnvWorkSize<float, 1>::want,
+              "work buffer padding");
 
 // Two envs sharing a warp (G = 16) run in lockstep: every branch that contains a barrier, shuffle or ballot is
 // taken by the whole warp (an auto-reset of one env makes the other repeat its evaluation, see the step

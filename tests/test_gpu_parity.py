@@ -680,6 +680,45 @@ def test_persistent_launch_walks_every_env(env_id, n_act):
         e.close()
 
 
+def test_env_groups_send_recv_equal_the_single_batch():
+    """backend.EnvGroups (bio_step_host_begin / _end, bio_set_grid): four groups stepped in a pipeline on disjoint
+    SMs give bit for bit the rows of one VecEnv of the same seeded batch, over 150 steps with auto-resets."""
+    import torch
+    from bioimitation_gym_b200 import backend
+    env_id, n, G = "MuscleWalkingImitation2D-v0", 1024, 4
+    full = backend.VecEnv(env_id, dict(num_envs=n, seed=5))
+    groups = backend.EnvGroups(env_id, dict(num_envs=n, seed=5), groups=G)
+    ng = n // G
+    of = full.reset().cpu().numpy()
+    og = groups.reset()
+    for g in range(G):
+        assert np.array_equal(of[g * ng:(g + 1) * ng], og[g])
+    rng = np.random.default_rng(4)
+    acts = rng.uniform(0, 1, (150, n, 14)).astype(np.float32)
+    for g in range(G):
+        groups.send(g, acts[0][g * ng:(g + 1) * ng])
+    n_done = 0
+    for k in range(150):
+        o, r, d, info = full.step(torch.as_tensor(acts[k]))
+        o, r, d, t = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy(), info["all_rewards"].cpu().numpy()
+        n_done += int(d.sum())
+        for g in range(G):
+            sl = slice(g * ng, (g + 1) * ng)
+            o1, r1, d1, i1 = groups.recv(g)
+            assert np.array_equal(o[sl], o1) and np.array_equal(r[sl], r1) and np.array_equal(d[sl] != 0, d1)
+            assert np.array_equal(t[sl], i1["all_rewards"])
+            if k + 1 < 150:
+                groups.send(g, acts[k + 1][sl])
+    assert n_done > 0                           # auto-reset was exercised
+    with pytest.raises(backend.BioError):
+        groups.recv(0)                          # nothing in flight
+    pageable = np.zeros((ng, 14), dtype=np.float32)
+    with pytest.raises(backend.BioError):
+        groups.envs[0].step_host_begin(pageable, groups.buf[0]["o"], groups.buf[0]["r"], groups.buf[0]["d"], groups.buf[0]["t"])
+    groups.close()
+    full.close()
+
+
 def test_host_buffer_entry_point_matches_device_path():
     import torch
     env, _ = _mk("MuscleWalkingImitation2D-v0", 256, "float32")
