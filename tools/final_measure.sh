@@ -13,6 +13,7 @@ run() { python bench.py --no-cpu-baseline --env-id "$1" --envs-per-gpu "$2" --st
 run TorqueWalkingImitation2D-v0 16384 200
 run MuscleRunningImitation2D-v0 16384 200
 run MuscleLockedKneeImitation2D-v0 16384 200
+run MuscleJumpingImitation2D-v0 16384 200
 run MuscleWalkingImitation2D-v0 16384 200
 run MuscleWalkingImitation2D-v0 131072 50
 run MuscleWalkingImitation3D-v0 8192 100
