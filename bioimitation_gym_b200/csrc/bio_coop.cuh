@@ -111,6 +111,10 @@ template <typename T> struct WorkUnions<T, 1> {
         struct { T pad_[128]; alignas(16) T W[C::ND][8]; alignas(16) T Ux[2][2][8]; } aba;
         WorkPlanarAba<T, C> pa;
     } x;
+    // arguments of the running evaluation (coop_eval re-reads them where it uses them, see there):
+    // flags = Newton iterations | (perturbed observation point + 1) << 8 | full evaluation << 16
+    // (flags bits 24..31: substep counter of the stated integrator's loop; t0: time at the start of the control step)
+    struct { T fx, himp; int32_t flags; T t0; } ev;
 };
 
 template <typename T, int CLS>
@@ -160,6 +164,9 @@ template <int G> __device__ __forceinline__ unsigned group_ballot(bool pred) {
     return G == 32 ? b : (b >> ((threadIdx.x & 31) / G * G)) & ((1u << (G & 31)) - 1u);
 }
 
+// re-read of a shared-memory word at the point of use (never kept in a register across phases)
+template <typename U> __device__ __forceinline__ U ldv(const U& x) { return *reinterpret_cast<const volatile U*>(&x); }
+
 // column K of a row-major 3x3 (times a sign), and R <- R * Rot(e_K, angle) as a mix of the two other columns
 template <typename T, int K>
 __device__ __forceinline__ void axis_col(const T* R, T sg, T* aw) {
@@ -186,13 +193,26 @@ namespace bio {
 // read-outs for obs / reward / done.  All G lanes of the env must call this.
 // ---------------------------------------------------------------------------
 template <typename T, int CLS>
-__device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane, const int newton_iters,
-                          const T ext_fx, const int ext_pt, const T h_imp, const bool full) {
+__device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
     typedef CoopCls<CLS> C;
     constexpr int G = C::G;
-    const int nb = m.n_bodies, nd = m.n_dof, nm = m.n_muscles;
     auto& K = E.k.g;
-    const bool aba = G == 32 && m.prog.aba_ok;   // root-plus-chains model: articulated-body pass instead of phases F..H
+    // The scalars that live through the whole evaluation -- its arguments (E.ev, written by coop_eval_any), the
+    // model's counts, the path switch -- stay in shared memory and are re-read where they are used.  Kept in
+    // registers they are what the compiler spills at 72 registers per thread, and with 232 KB of the SM's 256 KB
+    // configured as shared memory a spill reload is an L2 round trip (ncu: ~15 reload sites per evaluation, 14 % of
+    // the stall samples of the 896-thread shape).  Every phase takes its own copies (one read per phase, not one per
+    // use inside its loops).  No call to a libdevice slow path inside: the function is a leaf and keeps its return
+    // address in a register.
+#define EV_NB ldv(m.n_bodies)
+#define EV_ND ldv(m.n_dof)
+#define EV_NM ldv(m.n_muscles)
+#define EV_ABA (G == 32 && ldv(m.prog.aba_ok) != 0)   /* root-plus-chains model: articulated-body pass instead of phases F..H */
+#define EV_FULL (((ldv(E.ev.flags) >> 16) & 1) != 0)
+#define EV_H_IMP ldv(E.ev.himp)
+#define EV_EXT_FX ldv(E.ev.fx)
+#define EV_EXT_PT (((ldv(E.ev.flags) >> 8) & 255) - 1)
+#define EV_NEWTON_ITERS (ldv(E.ev.flags) & 255)
 
     // ---- phase A: joint functions of the coordinates, and the location functions of moving path
     // points (task n_axes + 3 k + c: component c of moving point k); the spline interval of the
@@ -308,9 +328,12 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     }
 
     // ---- phase C: lane = muscle ----
-    if (lane < nm) {
+    if (lane < EV_NM) {
         const int i = lane;
         const PlanarProg<T>& pr = m.prog;
+        const T h_imp = EV_H_IMP;
+        const int evf = ldv(E.ev.flags), newton_iters = evf & 255;
+        const bool full = ((evf >> 16) & 1) != 0;
         T L = T(0);
         // compiled paths (PlanarProg::mc_seg; bio_create gives a 3D model without them to the thread-per-env kernel):
         // constant length of the variant selected by the conditional points plus its live segments; a live segment
@@ -463,7 +486,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             const T f = fH * (T(1) + T(1.5) * m.sph_c[s] * vn);
             if (f > T(0)) {
                 F[1] = f;
-                const T vs = Num<T>::sqrt(v[0] * v[0] + v[2] * v[2]);
+                const T vs = Num<T>::sqrt_fast(v[0] * v[0] + v[2] * v[2]);
                 const T vrel = Num<T>::div(vs, m.sph_vt[s]);
                 const T strib = m.sph_ud[s] + Num<T>::div(T(2) * (m.sph_us[s] - m.sph_ud[s]), T(1) + vrel * vrel);
                 if (vs != T(0)) {
@@ -493,10 +516,10 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     // wrench of the path points on every body: on a full warp four lanes share the point list of a
     // body (the pelvis carries a third of all points), quad butterfly, then the body lane fetches the sum
     T Wn[3] = {T(0), T(0), T(0)}, Wf[3] = {T(0), T(0), T(0)};
-    if (nm > 0) {
+    if (EV_NM > 0) {
         constexpr int PARTS = G == 32 ? 4 : 1;
         const int gb = lane / PARTS, part = lane % PARTS;
-        if (gb < nb) {
+        if (gb < EV_NB) {
             for (int k = m.prog.inc_begin[gb] + part; k < m.prog.inc_begin[gb + 1]; k += PARTS) {
                 T w0, w1, w2, w3, w4, w5, w6, w7;
                 const T* w = E.x.src6.w[m.prog.inc_src[k]];
@@ -519,7 +542,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             }
         }
     }
-    if (lane < nb) {
+    if (lane < EV_NB) {
         const int b = lane;
         for (int smask = m.prog.body_sph_mask[b]; smask; smask &= smask - 1) {
             const int s = lowest_bit(smask);
@@ -528,9 +551,10 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             cross3(E.sphx[s], E.sphF[s], n);
             for (int c = 0; c < 3; c++) { Wn[c] += n[c]; Wf[c] += E.sphF[s][c]; }
         }
+        const int ext_pt = EV_EXT_PT;
         if (ext_pt >= 0 && m.obs_body[ext_pt] == b) {
             T x[3], n[3];
-            const T fx[3] = {ext_fx, T(0), T(0)};
+            const T fx[3] = {EV_EXT_FX, T(0), T(0)};
             matvec3(K.R[b], m.obs_loc[ext_pt], x);
             for (int c = 0; c < 3; c++) x[c] += K.r[b][c];
             cross3(x, fx, n);
@@ -571,7 +595,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         for (int j = 0; j < 3; j++) { IA[j] += t1[j]; IA[3 + j] = mb * A[3 + j] - t2[j]; }
         T c1[3], c2[3], c3[3];
         cross3(V, IV, c1); cross3(V + 3, IV + 3, c2); cross3(V, IV + 3, c3);
-        if (aba) {
+        if (EV_ABA) {
             // columns of [[I, h x], [-(h x), m 1]] and the body force as the seventh (p3_aba)
             T* o = K.BIc[b];
             const T z = T(0);
@@ -593,8 +617,9 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         }
         for (int j = 0; j < 6; j++) K.BI[b][4 + j] = I6[j];
         }
-    } else if (lane - nb < nd) {
-        const int d = lane - nb;
+    } else if (lane - EV_NB < EV_ND) {
+        const int d = lane - EV_NB;
+        const T h_imp = EV_H_IMP;
         T qf = T(0), ld = T(0);
         if (m.gdof_ok) {                         // host lists: the (<= 2) limits / moving points and the actuator of the dof
 #pragma unroll
@@ -610,13 +635,14 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += K.mq[k]; }
             if (m.is_torque) for (int a = 0; a < m.n_act; a++) if (m.act_dof[a] == d) qf += E.ctrl[a];
         }
-        if (aba) { K.S[d][6] = qf; K.S[d][7] = h_imp * ld; }   // next to the motion vector: one read per elimination step
+        if (EV_ABA) { K.S[d][6] = qf; K.S[d][7] = h_imp * ld; }   // next to the motion vector: one read per elimination step
         else { K.limDd[d] = h_imp * ld; K.Q[d] = qf; }
     }
     gsync<G>();
 
     // ---- full evaluation read-outs (pt region is dead now) ----
-    if (full) {
+    if (EV_FULL) {
+        const int nb = EV_NB;
         if (lane < nb) {
             const int b = lane;
             T cpos[3], vc[3];
@@ -636,7 +662,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         if (lane < 3) {
             T ms = T(0), ps = T(0);
             for (int b = 0; b < nb; b++) { ms += E.x.out.comp[b][lane]; ps += E.x.out.comp[b][3 + lane]; }
-            const T im = T(1) / m.total_mass;
+            const T im = Num<T>::rcp(m.total_mass);
             E.com_pos[lane] = ms * im + E.O[lane];
             E.com_vel[lane] = ps * im;
         } else if (lane < 5) {
@@ -659,7 +685,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
 
     // ---- root-plus-chains models on a full warp: articulated-body pass (bio_coop_spatial.cuh) ----
     if constexpr (G == 32) {
-        if (aba) { p3_aba<T, CLS>(m, E, lane, h_imp); return; }
+        if (EV_ABA) { p3_aba<T, CLS>(m, E, lane, EV_H_IMP); return; }
     }
 
     // ---- phase F: composite inertias / subtree forces.  Root-plus-chains models on a full warp: lane =
@@ -695,6 +721,8 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     }
 
     // ---- phase G: I^c S per dof, contact Jacobian columns, then one lane per coupled (i,j) entry ----
+    const int nd = EV_ND;
+    const T h_imp = EV_H_IMP;
     if (lane < nd) {
         const int i = lane, b = m.dof_body[i];
         const T* S = K.S[i];
@@ -749,19 +777,46 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     // ---- phase H: sparse L^T D L along the tree + solve (bio_coop_planar.cuh) ----
     coop_solve<T, CLS>(m, E, lane);
 }
+#undef EV_NB
+#undef EV_ND
+#undef EV_NM
+#undef EV_ABA
+#undef EV_FULL
+#undef EV_H_IMP
+#undef EV_EXT_FX
+#undef EV_EXT_PT
+#undef EV_NEWTON_ITERS
 
 // planar (2D) models take the planar program; size class 0 holds nothing else (bio_create puts a model
 // there only when the host could build the program)
 template <typename T, int CLS>
 __device__ __forceinline__ void coop_eval_any(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane,
                                               const int newton_iters, const T ext_fx, const int ext_pt, const T h_imp,
-                                              const bool full) {
+                                              const bool full, const int sub_next = 0) {
     if constexpr (CLS == 0) {
         coop_eval_planar<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
     } else {
+        // every lane stores the same words, so no barrier is needed before a lane reads them back
+        E.ev.fx = ext_fx; E.ev.himp = h_imp;
+        E.ev.flags = (newton_iters & 255) | ((ext_pt + 1) << 8) | ((full ? 1 : 0) << 16) | (sub_next << 24);
         if (m.prog.ok) coop_eval_planar<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
-        else coop_eval<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
+        else coop_eval<T, CLS>(m, E, lane);
     }
+}
+
+// The warp's work buffer and the model block from the thread index alone (read through a volatile asm, so that the
+// compiler does not merge them with the pointers the step kernel holds): what the substep loop of the 3D kernels
+// uses in place of values that would otherwise be spilled around the call of the evaluation and reloaded from L2.
+template <typename T, int CLS>
+__device__ __forceinline__ EnvWork<T, CLS>& coop_fresh_work(unsigned& tid) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    return reinterpret_cast<EnvWork<T, CLS>*>(smem + ((sizeof(DevModel<T>) + 15) / 16) * 16)[tid / CoopCls<CLS>::G];
+}
+template <typename T>
+__device__ __forceinline__ const DevModel<T>& coop_fresh_model() {
+    extern __shared__ __align__(16) unsigned char smem[];
+    return *reinterpret_cast<const DevModel<T>*>(smem);
 }
 
 // state <-> work buffer helpers (lane d < nd owns a dof, lane k < nm owns a muscle)
@@ -778,7 +833,40 @@ __device__ void coop_integrate(const DevModel<T>& m, const DevTask<T>& c, EnvWor
                                unsigned long long seed, unsigned long long env) {
     constexpr int G = CoopCls<CLS>::G;
     const int nd = m.n_dof, nm = m.n_muscles;
-    const T h = c.dt / T(c.n_substeps);
+    if constexpr (CLS == 1 && sizeof(T) == 4) {
+        if (c.integrator == BIO_INT_SEMI_IMPLICIT_EULER || c.integrator == BIO_INT_IMPLICIT_DAMPING) {
+            // Substep loop of the stated scheme for the 3D kernels (72 registers per thread at 896 threads): nothing
+            // of the loop lives in a register across the call of the evaluation -- the counter and the start time
+            // sit in E.ev, the pointers are re-derived from the thread index, the rest comes from the constant bank
+            // -- so nothing is spilled and reloaded per substep (a reload is an L2 round trip here, see coop_eval).
+            E.ev.t0 = T(istep) * c.dt;
+            E.ev.flags = 0;
+            for (;;) {
+                unsigned tid;
+                EnvWork<T, CLS>& W = coop_fresh_work<T, CLS>(tid);
+                const int sub = (int)((unsigned)ldv(W.ev.flags) >> 24);
+                if (sub >= c.n_substeps) break;
+                const T fx = c.perturb ? perturb_force(c, seed, env, ldv(W.ev.t0) + T(sub) * c.h_sub) : T(0);
+                coop_eval_any<T, CLS>(coop_fresh_model<T>(), W, (int)(tid % G), c.newton_iters, fx,
+                                      c.perturb ? c.perturb_obspt : -1,
+                                      c.integrator == BIO_INT_IMPLICIT_DAMPING ? c.h_sub : T(0), false, sub + 1);
+                unsigned tid2;
+                EnvWork<T, CLS>& V = coop_fresh_work<T, CLS>(tid2);
+                const DevModel<T>& mm = coop_fresh_model<T>();
+                const int ln = (int)(tid2 % G);
+                const T hs = c.h_sub;
+                if (ln < ldv(mm.n_dof)) { const T un = V.u[ln] + hs * V.udot[ln]; V.u[ln] = un; V.q[ln] += hs * un; }
+                if (ln < ldv(mm.n_muscles)) {          // explicit Euler with the clamps of coop_clamp
+                    const T lmn = V.lm[ln] + hs * V.lmdot[ln], lmin = mm.mus_lm_min[ln];
+                    V.act[ln] = clampv(V.act[ln] + hs * V.adot[ln], mm.mus_amin[ln], T(1));
+                    V.lm[ln] = lmn < lmin ? lmin : lmn;
+                }
+                gsync<G>();
+            }
+            return;
+        }
+    }
+    const T h = c.h_sub;
     const T t0 = T(istep) * c.dt;
     const int ext_pt = c.perturb ? c.perturb_obspt : -1;
     const bool isd = lane < nd, ism = lane < nm;

@@ -51,10 +51,13 @@ template <> struct Num<float> {
     static BIO_DEV float div(float a, float b) { return __fdividef(a, b); }
     static BIO_DEV float rcp(float b) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return r; }
     static BIO_DEV float sqrt_pos(float x) { return x * rsqrtf(x); }
+    // square root of a number that may be zero, special-function unit only (no slow-path call: keeps the caller a leaf)
+    static BIO_DEV float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #else
     static BIO_DEV float div(float a, float b) { return a / b; }
     static BIO_DEV float rcp(float b) { return 1.0f / b; }
     static BIO_DEV float sqrt_pos(float x) { return sqrtf(x); }
+    static BIO_DEV float sqrt_fast(float x) { return sqrtf(x); }
 #endif
     static BIO_DEV float abs(float x) { return fabsf(x); }
     static BIO_DEV float floor(float x) { return floorf(x); }
@@ -73,6 +76,7 @@ template <> struct Num<double> {
     static BIO_DEV double div(double a, double b) { return a / b; }
     static BIO_DEV double rcp(double b) { return 1.0 / b; }
     static BIO_DEV double sqrt_pos(double x) { return ::sqrt(x); }
+    static BIO_DEV double sqrt_fast(double x) { return ::sqrt(x); }
     static BIO_DEV double abs(double x) { return ::fabs(x); }
     static BIO_DEV double floor(double x) { return ::floor(x); }
     static BIO_DEV double exp(double x) { return ::exp(x); }

@@ -263,6 +263,7 @@ struct DevTask {
     int32_t pd_x_coord[BIO_MAX_ACT], pd_v_coord[BIO_MAX_ACT];
     T pd_kp[BIO_MAX_ACT], pd_kv[BIO_MAX_ACT];
     T dt, term_height, term_limit_force, term_acc;
+    T h_sub, h_pad_;   // dt / n_substeps, divided on the host in T arithmetic (the quotient the kernels used to form)
     T w_imitate, w_effort, w_action, action_r_scale, max_actuation, height;
     T perturb_thresh, perturb_force;
     // reference tables (device)
@@ -949,7 +950,7 @@ void convert_task(const BioTaskConfig& s, DevTask<T>& d) {
     d.perturb = s.perturb; d.perturb_obspt = s.perturb_obspt;
     d.perturb_negative_only = s.perturb_negative_only;
     BIO_CPI(pd_x_coord); BIO_CPI(pd_v_coord); BIO_CP(pd_kp); BIO_CP(pd_kv);
-    d.dt = (T)s.dt; d.term_height = (T)s.term_height; d.term_limit_force = (T)s.term_limit_force;
+    d.dt = (T)s.dt; d.h_sub = d.dt / (T)d.n_substeps; d.h_pad_ = T(0); d.term_height = (T)s.term_height; d.term_limit_force = (T)s.term_limit_force;
     d.term_acc = (T)s.term_acc; d.w_imitate = (T)s.w_imitate; d.w_effort = (T)s.w_effort;
     d.w_action = (T)s.w_action; d.action_r_scale = (T)s.action_r_scale;
     d.max_actuation = (T)s.max_actuation; d.height = (T)s.height;
