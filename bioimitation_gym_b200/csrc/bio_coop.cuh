@@ -512,7 +512,13 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     }
     gsync<G>();
 
-    // ---- phase E: lane = body (wrench gather, inertia, body force) | dof (generalized forces) ----
+    // ---- phase E.  Root-plus-chains models on a full warp (articulated-body path): three lanes per body
+    // (p3_phase_e, bio_coop_spatial.cuh).  Else: lane = body (wrench gather, inertia, body force) | dof ----
+    bool e_done = false;
+    if constexpr (G == 32) {
+        if (EV_ABA) { p3_phase_e<T, CLS>(m, E, lane); e_done = true; }
+    }
+    if (!e_done) {
     // wrench of the path points on every body: on a full warp four lanes share the point list of a
     // body (the pelvis carries a third of all points), quad butterfly, then the body lane fetches the sum
     T Wn[3] = {T(0), T(0), T(0)}, Wf[3] = {T(0), T(0), T(0)};
@@ -595,20 +601,6 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         for (int j = 0; j < 3; j++) { IA[j] += t1[j]; IA[3 + j] = mb * A[3 + j] - t2[j]; }
         T c1[3], c2[3], c3[3];
         cross3(V, IV, c1); cross3(V + 3, IV + 3, c2); cross3(V, IV + 3, c3);
-        if (EV_ABA) {
-            // columns of [[I, h x], [-(h x), m 1]] and the body force as the seventh (p3_aba)
-            T* o = K.BIc[b];
-            const T z = T(0);
-            st2(o, I6[0], I6[3]); st2(o + 2, I6[4], z); st2(o + 4, -hh[2], hh[1]);
-            st2(o + 6, I6[3], I6[1]); st2(o + 8, I6[5], hh[2]); st2(o + 10, z, -hh[0]);
-            st2(o + 12, I6[4], I6[5]); st2(o + 14, I6[2], -hh[1]); st2(o + 16, hh[0], z);
-            st2(o + 18, z, hh[2]); st2(o + 20, -hh[1], mb); st2(o + 22, z, z);
-            st2(o + 24, -hh[2], z); st2(o + 26, hh[0], z); st2(o + 28, mb, z);
-            st2(o + 30, hh[1], -hh[0]); st2(o + 32, z, z); st2(o + 34, z, mb);
-            st2(o + 36, IA[0] + c1[0] + c2[0] - Wn[0], IA[1] + c1[1] + c2[1] - Wn[1]);
-            st2(o + 38, IA[2] + c1[2] + c2[2] - Wn[2], IA[3] + c3[0] - Wf[0]);
-            st2(o + 40, IA[4] + c3[1] - Wf[1], IA[5] + c3[2] - Wf[2]);
-        } else {
         K.BI[b][0] = mb;
         for (int j = 0; j < 3; j++) {
             K.BI[b][1 + j] = hh[j];
@@ -616,7 +608,6 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             K.BI[b][13 + j] = IA[3 + j] + c3[j] - Wf[j];
         }
         for (int j = 0; j < 6; j++) K.BI[b][4 + j] = I6[j];
-        }
     } else if (lane - EV_NB < EV_ND) {
         const int d = lane - EV_NB;
         const T h_imp = EV_H_IMP;
@@ -635,8 +626,8 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             for (int k = 0; k < m.n_moving; k++) { const int p = m.moving_pt[k]; if (m.pt_dof[p] == d) qf += K.mq[k]; }
             if (m.is_torque) for (int a = 0; a < m.n_act; a++) if (m.act_dof[a] == d) qf += E.ctrl[a];
         }
-        if (EV_ABA) { K.S[d][6] = qf; K.S[d][7] = h_imp * ld; }   // next to the motion vector: one read per elimination step
-        else { K.limDd[d] = h_imp * ld; K.Q[d] = qf; }
+        K.limDd[d] = h_imp * ld; K.Q[d] = qf;
+    }
     }
     gsync<G>();
 

@@ -176,6 +176,121 @@ __device__ __forceinline__ void p3_phase_b_scan(const DevModel<T>& m, EnvWork<T,
 }
 
 // ---------------------------------------------------------------------------
+// Phase E of the articulated-body path: body inertias and forces with THREE lanes per body (lane = 4 * body + part;
+// the wrench gather uses all four).  The muscle wrench sources of the body are dealt over its four lanes, its
+// (<= 4) contact spheres one per lane, the perturbation force goes to lane 3; a quad butterfly leaves the total
+// wrench in every lane.  Lane `part` < 3 then owns row `part` of the body's inertia about O (R I_b R^T + the
+// parallel-axis term), the matching component of I V and I A (the three lanes exchange I V by shuffles for the
+// V x* I V term), and writes columns `part` and 3 + `part` of the 6 x 6 spatial inertia and components
+// `part`, 3 + `part` of the body force (BIc, read by p3_aba).  Components are picked with the unit vector e_p of
+// the lane: (h x v)_p = (e_p x h) . v, and e_p x h is also the lower half of column p.  lane = dof afterwards:
+// generalized force and limit damping next to the motion vector.  (7 busy lanes -> 21; ncu: phase E was 11 % of the
+// instructions at 13 threads per instruction.)
+// ---------------------------------------------------------------------------
+template <typename T, int CLS>
+__device__ __forceinline__ void p3_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
+    const PlanarProg<T>& pr = m.prog;
+    auto& K = E.k.g;
+    const unsigned mask = 0xffffffffu;
+    const int b = lane >> 2, part = lane & 3;        // b < BIO_MAX_BODIES: every lane reads valid rows
+    const bool live = b < ldv(m.n_bodies);
+    T Wn0 = T(0), Wn1 = T(0), Wn2 = T(0), Wf0 = T(0), Wf1 = T(0), Wf2 = T(0);
+    if (live) {
+        if (ldv(m.n_muscles) > 0) {
+            for (int k = pr.inc_begin[b] + part; k < pr.inc_begin[b + 1]; k += 4) {
+                T w0, w1, w2, w3, w4, w5, w6, w7;
+                const T* w = E.x.src6.w[pr.inc_src[k]];
+                ld4(w, w0, w1, w2, w3);
+                ld4(w + 4, w4, w5, w6, w7);
+                Wn0 += w0; Wn1 += w1; Wn2 += w2; Wf0 += w3; Wf1 += w4; Wf2 += w5;
+            }
+        }
+        const unsigned sp = (pr.sph_pk[b] >> (8 * part)) & 255u;
+        if (sp != 255u && E.sphF[sp][1] != T(0)) {
+            T n[3];
+            cross3(E.sphx[sp], E.sphF[sp], n);
+            Wn0 += n[0]; Wn1 += n[1]; Wn2 += n[2];
+            Wf0 += E.sphF[sp][0]; Wf1 += E.sphF[sp][1]; Wf2 += E.sphF[sp][2];
+        }
+        const int ext_pt = ((ldv(E.ev.flags) >> 8) & 255) - 1;
+        if (part == 3 && ext_pt >= 0 && m.obs_body[ext_pt] == b) {
+            T x[3], n[3];
+            const T fx[3] = {ldv(E.ev.fx), T(0), T(0)};
+            matvec3(K.R[b], m.obs_loc[ext_pt], x);
+            for (int c = 0; c < 3; c++) x[c] += K.r[b][c];
+            cross3(x, fx, n);
+            Wn0 += n[0]; Wn1 += n[1]; Wn2 += n[2]; Wf0 += fx[0];
+        }
+    }
+    Wn0 += __shfl_xor_sync(mask, Wn0, 1); Wn1 += __shfl_xor_sync(mask, Wn1, 1); Wn2 += __shfl_xor_sync(mask, Wn2, 1);
+    Wf0 += __shfl_xor_sync(mask, Wf0, 1); Wf1 += __shfl_xor_sync(mask, Wf1, 1); Wf2 += __shfl_xor_sync(mask, Wf2, 1);
+    Wn0 += __shfl_xor_sync(mask, Wn0, 2); Wn1 += __shfl_xor_sync(mask, Wn1, 2); Wn2 += __shfl_xor_sync(mask, Wn2, 2);
+    Wf0 += __shfl_xor_sync(mask, Wf0, 2); Wf1 += __shfl_xor_sync(mask, Wf1, 2); Wf2 += __shfl_xor_sync(mask, Wf2, 2);
+    {
+        const int p = part < 3 ? part : 0;
+        const T ux = p == 0 ? T(1) : T(0), uy = p == 1 ? T(1) : T(0), uz = p == 2 ? T(1) : T(0);
+        const T* R = K.R[b];
+        const T R0 = R[0], R1 = R[1], R2 = R[2], R3 = R[3], R4 = R[4], R5 = R[5], R6 = R[6], R7 = R[7], R8 = R[8];
+        const T r0 = R[3 * p], r1 = R[3 * p + 1], r2 = R[3 * p + 2];
+        const T cm0 = m.body_com[b][0], cm1 = m.body_com[b][1], cm2 = m.body_com[b][2];
+        const T cx = R0 * cm0 + R1 * cm1 + R2 * cm2 + K.r[b][0];
+        const T cy = R3 * cm0 + R4 * cm1 + R5 * cm2 + K.r[b][1];
+        const T cz = R6 * cm0 + R7 * cm1 + R8 * cm2 + K.r[b][2];
+        const T cp = r0 * cm0 + r1 * cm1 + r2 * cm2 + K.r[b][p];
+        const T mb = m.body_mass[b], mcc = mb * (cx * cx + cy * cy + cz * cz), mcp = mb * cp;
+        const T* i6 = m.body_inertia[b];
+        const T i0 = i6[0], i1 = i6[1], i2 = i6[2], i3 = i6[3], i4 = i6[4], i5 = i6[5];
+        const T t0 = r0 * i0 + r1 * i3 + r2 * i4, t1 = r0 * i3 + r1 * i1 + r2 * i5, t2 = r0 * i4 + r1 * i5 + r2 * i2;
+        // row p of the inertia about O
+        const T Ig0 = t0 * R0 + t1 * R1 + t2 * R2 - mcp * cx + ux * mcc;
+        const T Ig1 = t0 * R3 + t1 * R4 + t2 * R5 - mcp * cy + uy * mcc;
+        const T Ig2 = t0 * R6 + t1 * R7 + t2 * R8 - mcp * cz + uz * mcc;
+        const T hx = mb * cx, hy = mb * cy, hz = mb * cz;
+        const T g0 = uy * hz - uz * hy, g1 = uz * hx - ux * hz, g2 = ux * hy - uy * hx;      // e_p x h
+        const T V0 = K.V[b][0], V1 = K.V[b][1], V2 = K.V[b][2], V3 = K.V[b][3], V4 = K.V[b][4], V5 = K.V[b][5];
+        const T A0 = K.A[b][0], A1 = K.A[b][1], A2 = K.A[b][2], A3 = K.A[b][3], A4 = K.A[b][4], A5 = K.A[b][5];
+        // component p of I V and I A: angular Ig . w + (h x v)_p, linear m v_p - (h x w)_p
+        const T IVn = Ig0 * V0 + Ig1 * V1 + Ig2 * V2 + (g0 * V3 + g1 * V4 + g2 * V5);
+        const T IVf = mb * (ux * V3 + uy * V4 + uz * V5) - (g0 * V0 + g1 * V1 + g2 * V2);
+        const T IAn = Ig0 * A0 + Ig1 * A1 + Ig2 * A2 + (g0 * A3 + g1 * A4 + g2 * A5);
+        const T IAf = mb * (ux * A3 + uy * A4 + uz * A5) - (g0 * A0 + g1 * A1 + g2 * A2);
+        // all of I V from the three lanes of the body; component p of w x (I V)_n + v x (I V)_f and of w x (I V)_f
+        const T n0 = __shfl_sync(mask, IVn, 0, 4), n1 = __shfl_sync(mask, IVn, 1, 4), n2 = __shfl_sync(mask, IVn, 2, 4);
+        const T f0 = __shfl_sync(mask, IVf, 0, 4), f1 = __shfl_sync(mask, IVf, 1, 4), f2 = __shfl_sync(mask, IVf, 2, 4);
+        const T a0 = uy * V2 - uz * V1, a1 = uz * V0 - ux * V2, a2 = ux * V1 - uy * V0;      // e_p x w
+        const T b0 = uy * V5 - uz * V4, b1 = uz * V3 - ux * V5, b2 = ux * V4 - uy * V3;      // e_p x v
+        const T fn = IAn + (a0 * n0 + a1 * n1 + a2 * n2) + (b0 * f0 + b1 * f1 + b2 * f2) - (ux * Wn0 + uy * Wn1 + uz * Wn2);
+        const T ff = IAf + (a0 * f0 + a1 * f1 + a2 * f2) - (ux * Wf0 + uy * Wf1 + uz * Wf2);
+        if (live && part < 3) {
+            T* o = K.BIc[b] + 6 * p;
+            st2(o, Ig0, Ig1); st2(o + 2, Ig2, g0); st2(o + 4, g1, g2);
+            st2(o + 18, -g0, -g1); st2(o + 20, -g2, mb * ux); st2(o + 22, mb * uy, mb * uz);
+            K.BIc[b][36 + p] = fn; K.BIc[b][39 + p] = ff;
+        }
+    }
+    // lane = dof: generalized force of its (<= 2) limits / moving points and its actuator, h * limit damping
+    if (lane < ldv(m.n_dof)) {
+        const int d = lane;
+        T qf = T(0), ld = T(0);
+        if (m.gdof_ok) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int l = m.gdof_lim[d][j], pt = m.gdof_movpt[d][j];
+                if (l >= 0) { qf += E.limf[l]; ld += E.limD[l]; }
+                if (pt >= 0) qf += K.mq[m.pt_mov[pt]];
+            }
+            const int a = m.gdof_act[d];
+            if (a >= 0) qf += E.ctrl[a];
+        } else {
+            for (int l = 0; l < m.n_limits; l++) if (m.lim_dof[l] == d) { qf += E.limf[l]; ld += E.limD[l]; }
+            for (int k = 0; k < m.n_moving; k++) { const int pt = m.moving_pt[k]; if (m.pt_dof[pt] == d) qf += K.mq[k]; }
+            if (m.is_torque) for (int a = 0; a < m.n_act; a++) if (m.act_dof[a] == d) qf += E.ctrl[a];
+        }
+        K.S[d][6] = qf; K.S[d][7] = ldv(E.ev.himp) * ld;   // next to the motion vector: one read per elimination step
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Articulated-body pass of the spatial evaluation (replaces the composite inertias, the joint-space
 // matrix and its sparse L^T D L for root-plus-chains models; PlanarProg::aba_*).
 //

@@ -687,6 +687,14 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     // ---- articulated-body schedule of the spatial evaluation: every chain from its leaf, then the root ----
     if (!d.planar) {
         bool ok = true;
+        for (int b = 0; b < s.n_bodies; b++) {           // contact spheres of every body in 4 bytes (p3_phase_e)
+            unsigned char sp4[4] = {255, 255, 255, 255};
+            int ns = 0;
+            for (int sp = 0; sp < s.n_spheres; sp++)
+                if (s.sph_body[sp] == b) { if (ns < 4) sp4[ns] = (unsigned char)sp; ns++; }
+            if (ns > 4) ok = false;
+            pr.sph_pk[b] = sp4[0] | (sp4[1] << 8) | (sp4[2] << 16) | ((uint32_t)sp4[3] << 24);
+        }
         int nmax = 0, nroot = 0;
         memset(pr.aba_step, 255, sizeof(pr.aba_step));
         for (int l = 0; l < pr.n_branches; l++) {
