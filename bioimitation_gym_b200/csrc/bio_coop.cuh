@@ -217,6 +217,11 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     // ---- phase A: joint functions of the coordinates, and the location functions of moving path
     // points (task n_axes + 3 k + c: component c of moving point k); the spline interval of the
     // previous evaluation is the search hint ----
+    bool a_done = false;
+    if constexpr (G == 32) {
+        if (ldv(m.prog.atask_ok) != 0) { p3_phase_a<T, CLS>(m, E, lane); a_done = true; }
+    }
+    if (!a_done)
     for (int a = lane; a < m.n_axes + 3 * m.n_moving; a += G) {
         T s, ds, dds;
         if (a < m.n_axes) {

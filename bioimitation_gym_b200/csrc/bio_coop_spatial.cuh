@@ -176,6 +176,55 @@ __device__ __forceinline__ void p3_phase_b_scan(const DevModel<T>& m, EnvWork<T,
 }
 
 // ---------------------------------------------------------------------------
+// Phase A of the spatial evaluation from the packed task descriptors (PlanarProg::at_i4 / at_f4, the tables of
+// p2_phase_a): lane = joint-axis function | location function of a moving path point, one 2 x 16-byte descriptor
+// per task (kind, destination, dof, knot range, coefficients) instead of seven dependent index loads, the spline
+// interval of the previous evaluation as the search hint.  Outputs: value and two derivatives of every axis
+// function (the half-angle quaternions are formed in the scan), location and d/dq of the moving points.
+// ---------------------------------------------------------------------------
+template <typename T, int CLS>
+__device__ __forceinline__ void p3_phase_a(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
+    const PlanarProg<T>& pr = m.prog;
+    auto& K = E.k.g;
+    for (int t = lane; t < pr.n_atasks; t += 32) {
+        const int4 ti = *reinterpret_cast<const int4*>(pr.at_i4[t]);
+        T c0, c1, add, f3;
+        ld4(pr.at_f4[t], c0, c1, add, f3);
+        const int kind = ti.x & 3, dst = ti.x >> 8, d = ti.y;
+        const T x = d >= 0 ? E.q[d] : T(0);
+        T s, ds, dds = T(0);
+        if (kind == BIO_FUNC_SPLINE) {
+            // SimmSpline: cubic piece of the interval [knot i, knot i + 1), straight lines beyond the end knots
+            const int kb = ti.z, n = ti.w;
+            int i = E.knot_hint[t];
+            i = i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
+            while (i > 0 && x < m.knot_x[kb + i]) i--;
+            while (i + 1 < n - 1 && x >= m.knot_x[kb + i + 1]) i++;
+            E.knot_hint[t] = (int8_t)i;
+            const bool below = x <= c0, above = x >= c1;
+            i = above ? n - 1 : (below ? 0 : i);
+            T k0, k1, k2, k3;
+            ld4(m.knot_c[kb + i], k0, k1, k2, k3);
+            if (below || above) { k2 = T(0); k3 = T(0); }
+            const T dx = x - m.knot_x[kb + i];
+            s = k0 + dx * (k1 + dx * (k2 + dx * k3));
+            ds = k1 + dx * (T(2) * k2 + T(3) * dx * k3);
+            dds = T(2) * k2 + T(6) * dx * k3;
+        } else {
+            const bool lin = kind == BIO_FUNC_LINEAR;
+            s = lin ? c0 * x + c1 : c0;
+            ds = lin ? c0 : T(0);
+        }
+        if (dst < 64) {
+            K.ax_s[dst] = s; K.ax_ds[dst] = ds; K.ax_dds[dst] = dds;
+        } else {
+            const int k = (dst - 64) / 3, c = (dst - 64) % 3;
+            K.mv[k][c] = s; K.mv[k][3 + c] = ds;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Phase E of the articulated-body path: body inertias and forces with THREE lanes per body (lane = 4 * body + part;
 // the wrench gather uses all four).  The muscle wrench sources of the body are dealt over its four lanes, its
 // (<= 4) contact spheres one per lane, the perturbation force goes to lane 3; a quad butterfly leaves the total

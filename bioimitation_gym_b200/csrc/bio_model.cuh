@@ -93,7 +93,7 @@ struct alignas(16) PlanarProg {
     // body, so that phase E issues all its loads at once; inc8_ok = 0: a body has more, walk inc_src / body_sph_mask
     alignas(8) uint32_t inc_pk[BIO_MAX_BODIES][2];
     uint32_t sph_pk[BIO_MAX_BODIES];
-    int32_t inc8_ok, inc8_pad_[3];
+    int32_t inc8_ok, atask_ok, inc8_pad_[2];       // atask_ok: spatial evaluation runs phase A from the packed tasks
     alignas(16) int32_t br_i8[P2_MAXBR][8];
     alignas(16) int32_t root_i4[4];
     alignas(16) T mus_k[BIO_MAX_MUSCLES][12];
@@ -684,6 +684,55 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         }
     }
     if (!pr.chain_ok) return;
+    // phase A tasks (planar program: p2_phase_a; spatial evaluation: p3_phase_a)
+    int n_mov = 0, mov_of_pt[BIO_MAX_PATHPTS];
+    auto build_atasks = [&](const bool planar_z) -> bool {
+        n_mov = 0;
+        for (int a = 0; a < s.n_axes; a++) { pr.at_func[a] = s.axis_func[a]; pr.at_dof[a] = s.axis_dof[a]; pr.at_add[a] = T(0); pr.at_dst[a] = a; }
+        for (int p = 0; p < s.n_pathpts; p++) {
+            mov_of_pt[p] = -1;
+            if (s.pt_kind[p] != BIO_PT_MOVING) continue;
+            if (n_mov >= P2_MAXMOV) return false;
+            for (int c = 0; c < 3; c++) {
+                const int t = s.n_axes + 3 * n_mov + c;
+                pr.at_func[t] = s.pt_func[p][c];
+                pr.at_dof[t] = s.pt_dof[p];
+                pr.at_add[t] = (planar_z && c == 2) ? d.body_z[s.pt_body[p]] : T(0);
+                pr.at_dst[t] = 64 + 3 * n_mov + c;
+            }
+            pr.mov_dof[n_mov] = s.pt_dof[p];
+            mov_of_pt[p] = n_mov++;
+        }
+        pr.n_atasks = s.n_axes + 3 * n_mov;
+        {   // stable insertion sort by cost: splines, then rotations (sin / cos), then the rest
+            auto rank = [&](int t) {
+                if (d.func_kind[pr.at_func[t]] == BIO_FUNC_SPLINE) return 0;
+                if (pr.at_dst[t] < 64 && (d.axis_desc[pr.at_dst[t]] & 1)) return 1;
+                return d.func_kind[pr.at_func[t]] == BIO_FUNC_LINEAR ? 2 : 3;
+            };
+            for (int i = 1; i < pr.n_atasks; i++)
+                for (int j = i; j > 0 && rank(j) < rank(j - 1); j--) {
+                    std::swap(pr.at_func[j], pr.at_func[j - 1]); std::swap(pr.at_dof[j], pr.at_dof[j - 1]);
+                    std::swap(pr.at_add[j], pr.at_add[j - 1]); std::swap(pr.at_dst[j], pr.at_dst[j - 1]);
+                }
+            pr.a2_cheap = 1;
+            for (int t = 16; t < pr.n_atasks; t++) if (rank(t) < 2) pr.a2_cheap = 0;
+            for (int t = 0; t < pr.n_atasks; t++) {
+                const int f = pr.at_func[t], kind = d.func_kind[f], dst = pr.at_dst[t];
+                const int desc = dst < 64 ? d.axis_desc[dst] : 0;
+                const int kb = s.func_knot_begin[f], n = s.func_knot_count[f];
+                pr.at_i4[t][0] = kind | ((desc & 1) << 2) | (((desc >> 1) & 1) << 3) | (dst << 8);
+                pr.at_i4[t][1] = pr.at_dof[t];
+                pr.at_i4[t][2] = kind == BIO_FUNC_SPLINE ? kb : 0;
+                pr.at_i4[t][3] = kind == BIO_FUNC_SPLINE ? n : 0;
+                pr.at_f4[t][0] = kind == BIO_FUNC_SPLINE ? (T)s.knot_x[kb] : d.func_c[f][0];
+                pr.at_f4[t][1] = kind == BIO_FUNC_SPLINE ? (T)s.knot_x[kb + n - 1] : d.func_c[f][1];
+                pr.at_f4[t][2] = pr.at_add[t];
+                pr.at_f4[t][3] = T(0);
+            }
+        }
+        return true;
+    };
     // ---- articulated-body schedule of the spatial evaluation: every chain from its leaf, then the root ----
     if (!d.planar) {
         bool ok = true;
@@ -717,6 +766,7 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         if (nroot > 8) ok = false;
         { const char* z = getenv("BIO_NO_ABA"); if (z && z[0] == '1') ok = false; }   // tests: joint-space L^T D L instead
         pr.aba_nsteps = nmax; pr.aba_nroot = nroot > 8 ? 8 : nroot; pr.aba_ok = ok ? 1 : 0;
+        pr.atask_ok = (build_atasks(false) && n_mov == d.n_moving) ? 1 : 0;   // packed phase-A tasks (p3_phase_a)
     }
     // ---- stage 2 (planar models): the planar program ----
     if (!d.planar) { build_general_paths(s, d); return; }
@@ -754,51 +804,7 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     }
     pr.scan_ok = pr.n_branches >= 1;
     for (int l = 0; l < pr.n_branches; l++) if (pr.ch_n[l] > 8) pr.scan_ok = 0;
-    // phase A tasks
-    int n_mov = 0, mov_of_pt[BIO_MAX_PATHPTS];
-    for (int a = 0; a < s.n_axes; a++) { pr.at_func[a] = s.axis_func[a]; pr.at_dof[a] = s.axis_dof[a]; pr.at_add[a] = T(0); pr.at_dst[a] = a; }
-    for (int p = 0; p < s.n_pathpts; p++) {
-        mov_of_pt[p] = -1;
-        if (s.pt_kind[p] != BIO_PT_MOVING) continue;
-        if (n_mov >= P2_MAXMOV) return;
-        for (int c = 0; c < 3; c++) {
-            const int t = s.n_axes + 3 * n_mov + c;
-            pr.at_func[t] = s.pt_func[p][c];
-            pr.at_dof[t] = s.pt_dof[p];
-            pr.at_add[t] = c == 2 ? d.body_z[s.pt_body[p]] : T(0);
-            pr.at_dst[t] = 64 + 3 * n_mov + c;
-        }
-        pr.mov_dof[n_mov] = s.pt_dof[p];
-        mov_of_pt[p] = n_mov++;
-    }
-    pr.n_atasks = s.n_axes + 3 * n_mov;
-    {   // stable insertion sort by cost: splines, then rotations (sin / cos), then the rest
-        auto rank = [&](int t) {
-            if (d.func_kind[pr.at_func[t]] == BIO_FUNC_SPLINE) return 0;
-            if (pr.at_dst[t] < 64 && (d.axis_desc[pr.at_dst[t]] & 1)) return 1;
-            return d.func_kind[pr.at_func[t]] == BIO_FUNC_LINEAR ? 2 : 3;
-        };
-        for (int i = 1; i < pr.n_atasks; i++)
-            for (int j = i; j > 0 && rank(j) < rank(j - 1); j--) {
-                std::swap(pr.at_func[j], pr.at_func[j - 1]); std::swap(pr.at_dof[j], pr.at_dof[j - 1]);
-                std::swap(pr.at_add[j], pr.at_add[j - 1]); std::swap(pr.at_dst[j], pr.at_dst[j - 1]);
-            }
-        pr.a2_cheap = 1;
-        for (int t = 16; t < pr.n_atasks; t++) if (rank(t) < 2) pr.a2_cheap = 0;
-        for (int t = 0; t < pr.n_atasks; t++) {
-            const int f = pr.at_func[t], kind = d.func_kind[f], dst = pr.at_dst[t];
-            const int desc = dst < 64 ? d.axis_desc[dst] : 0;
-            const int kb = s.func_knot_begin[f], n = s.func_knot_count[f];
-            pr.at_i4[t][0] = kind | ((desc & 1) << 2) | (((desc >> 1) & 1) << 3) | (dst << 8);
-            pr.at_i4[t][1] = pr.at_dof[t];
-            pr.at_i4[t][2] = kind == BIO_FUNC_SPLINE ? kb : 0;
-            pr.at_i4[t][3] = kind == BIO_FUNC_SPLINE ? n : 0;
-            pr.at_f4[t][0] = kind == BIO_FUNC_SPLINE ? (T)s.knot_x[kb] : d.func_c[f][0];
-            pr.at_f4[t][1] = kind == BIO_FUNC_SPLINE ? (T)s.knot_x[kb + n - 1] : d.func_c[f][1];
-            pr.at_f4[t][2] = pr.at_add[t];
-            pr.at_f4[t][3] = T(0);
-        }
-    }
+    if (!build_atasks(true)) return;
     // path points, muscle slots and wrench sources
     int n_src = 0;
     int src_body[P2_MAXSRC];
