@@ -300,6 +300,13 @@ def e2e_pipelined_loop(env_id, cfg, pool, steps, preroll, barrier, n_groups=4):
     return dt
 
 
+def e2e_steps_for(n_per_gpu, steps):
+    """Control steps of the end-to-end loops: at least ~40 ms of wall time (a 4 ms window of 20 small steps lets
+    one scheduling hiccup on one of eight ranks move the max-over-ranks figure by 10 %), at most 1000."""
+    per_step_ms = max(0.2, n_per_gpu / 4096.0 * 0.2)
+    return int(max(min(steps, 1000), min(1000, round(40.0 / per_step_ms)), 10))
+
+
 def run_config(env_id, n_per_gpu, steps, warmup, rank, world, local_rank, args, preroll, e2e_steps, barrier, flush):
     """One workload: create, pre-roll, warm up, timed loop, end-to-end loop, statistics.  Returns a dict
     (identical on every rank for the all-reduced fields)."""
@@ -454,7 +461,7 @@ def main():
     if rank == 0:
         sampler.start()
     res = run_config(args.env_id, N, args.steps, args.warmup, rank, world, local_rank, args, args.preroll,
-                     max(10, min(args.steps, 100)), barrier, flush)
+                     e2e_steps_for(N, args.steps), barrier, flush)
     env = res["env"]
     shape = dict(zip(("size_class", "threads", "ctas_per_sm"), env.coop_shape()))
     if rank == 0:
