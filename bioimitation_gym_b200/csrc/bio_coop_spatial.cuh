@@ -435,10 +435,83 @@ __device__ __forceinline__ void p3_aba(const DevModel<T>& m, EnvWork<T, CLS>& E,
         col[0] += v0; col[1] += v1; col[2] += v2; col[3] += v3; col[4] += v4; col[5] += v5;
     }
     const int nroot = pr.aba_nroot;
-    for (int k = 0; k < nroot; k++) eliminate(pr.aba_root[k], true);
-    __syncwarp();
     // way back: every lane carries the spatial acceleration beyond the bias term
     T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0), a4 = T(0), a5 = T(0);
+    if (pr.aba_freeroot) {
+        // Free root joint (three translations along the ground axes, then three rotations about axes through O; no
+        // limit or moving point on its dofs, actuators on the rotations only: PlanarProg::aba_fr): its motion vectors
+        // span all of R^6, so the
+        // root's spatial acceleration solves  I^A a = -p^A  directly -- with I^A = [[A, B], [B^T, M]] two symmetric
+        // 3 x 3 inverses (the mass block M and the Schur complement A - B M^-1 B^T) instead of six elimination and six
+        // way-back steps with their barriers -- and the coordinates follow as  qdd_trans = a_v,  qdd_rot = R^-1 a_w
+        // with R = the rotation axes.  Every lane needs all of I^A and p^A: the columns go through shared memory once
+        // (in place of the root body's own columns, which every lane has consumed).
+        __syncwarp();
+        T* g = K.BIc[pr.root_body];
+        st2(g + cc * 6, col[0], col[1]); st2(g + cc * 6 + 2, col[2], col[3]); st2(g + cc * 6 + 4, col[4], col[5]);
+        __syncwarp();
+        T A00, A10, A20, A01, A11, A21, A02, A12, A22;              // A[i][j] = column j, row i
+        ld2(g, A00, A10); A20 = g[2];
+        ld2(g + 6, A01, A11); A21 = g[8];
+        ld2(g + 12, A02, A12); A22 = g[14];
+        T B00, B10, B20, M00, M10, M20, B01, B11, B21, M01, M11, M21, B02, B12, B22, M02, M12, M22;
+        ld2(g + 18, B00, B10); ld2(g + 20, B20, M00); ld2(g + 22, M10, M20);      // column 3: B[:,0], M[:,0]
+        ld2(g + 24, B01, B11); ld2(g + 26, B21, M01); ld2(g + 28, M11, M21);      // column 4
+        ld2(g + 30, B02, B12); ld2(g + 32, B22, M02); ld2(g + 34, M12, M22);      // column 5
+        T n0, n1, n2, f0, f1, f2;
+        ld2(g + 36, n0, n1); ld2(g + 38, n2, f0); ld2(g + 40, f1, f2);
+        // Minv = M^-1 (symmetric, cofactors)
+        T c00 = M11 * M22 - M12 * M12, c01 = M02 * M12 - M01 * M22, c02 = M01 * M12 - M02 * M11;
+        T c11 = M00 * M22 - M02 * M02, c12 = M01 * M02 - M00 * M12, c22 = M00 * M11 - M01 * M01;
+        T idet = Num<T>::rcp(M00 * c00 + M01 * c01 + M02 * c02);
+        const T m00 = c00 * idet, m01 = c01 * idet, m02 = c02 * idet, m11 = c11 * idet, m12 = c12 * idet, m22 = c22 * idet;
+        // X = B Minv
+        const T X00 = B00 * m00 + B01 * m01 + B02 * m02, X01 = B00 * m01 + B01 * m11 + B02 * m12, X02 = B00 * m02 + B01 * m12 + B02 * m22;
+        const T X10 = B10 * m00 + B11 * m01 + B12 * m02, X11 = B10 * m01 + B11 * m11 + B12 * m12, X12 = B10 * m02 + B11 * m12 + B12 * m22;
+        const T X20 = B20 * m00 + B21 * m01 + B22 * m02, X21 = B20 * m01 + B21 * m11 + B22 * m12, X22 = B20 * m02 + B21 * m12 + B22 * m22;
+        // Schur complement S = A - X B^T (symmetric) and right-hand side  -(n - X f)
+        const T S00 = A00 - (X00 * B00 + X01 * B01 + X02 * B02), S01 = A01 - (X00 * B10 + X01 * B11 + X02 * B12);
+        const T S02 = A02 - (X00 * B20 + X01 * B21 + X02 * B22), S11 = A11 - (X10 * B10 + X11 * B11 + X12 * B12);
+        const T S12 = A12 - (X10 * B20 + X11 * B21 + X12 * B22), S22 = A22 - (X20 * B20 + X21 * B21 + X22 * B22);
+        // rotation axes e0 e1 e2 (columns of R), the rows of R^-1 as cross products / det, and the generalized
+        // torques Q of the rotations (actuators of the torque models; phase E left them next to the motion vectors):
+        // R^T (A a_w + B a_v + n) = Q, so the angular right-hand side is  R^-T Q - n
+        const int4 fr = *reinterpret_cast<const int4*>(pr.aba_fr);       // dofs: tx | ty << 8 | tz << 16, r0 | r1 << 8 | r2 << 16
+        const int dr0 = fr.y & 255, dr1 = (fr.y >> 8) & 255, dr2 = (fr.y >> 16) & 255;
+        T e00, e10, e20, e01, e11, e21, e02, e12, e22, pad;
+        ld4(K.S[dr0], e00, e10, e20, pad); ld4(K.S[dr1], e01, e11, e21, pad); ld4(K.S[dr2], e02, e12, e22, pad);
+        const T Q0 = K.S[dr0][6], Q1 = K.S[dr1][6], Q2 = K.S[dr2][6];
+        const T x0 = e11 * e22 - e21 * e12, x1 = e21 * e02 - e01 * e22, x2 = e01 * e12 - e11 * e02;      // e1 x e2
+        const T y0 = e12 * e20 - e22 * e10, y1 = e22 * e00 - e02 * e20, y2 = e02 * e10 - e12 * e00;      // e2 x e0
+        const T z0 = e10 * e21 - e20 * e11, z1 = e20 * e01 - e00 * e21, z2 = e00 * e11 - e10 * e01;      // e0 x e1
+        const T id3 = Num<T>::rcp(e00 * x0 + e10 * x1 + e20 * x2);
+        const T q0 = (Q0 * x0 + Q1 * y0 + Q2 * z0) * id3, q1 = (Q0 * x1 + Q1 * y1 + Q2 * z1) * id3;
+        const T q2 = (Q0 * x2 + Q1 * y2 + Q2 * z2) * id3;
+        const T r0 = q0 - (n0 - (X00 * f0 + X01 * f1 + X02 * f2)), r1 = q1 - (n1 - (X10 * f0 + X11 * f1 + X12 * f2));
+        const T r2 = q2 - (n2 - (X20 * f0 + X21 * f1 + X22 * f2));
+        c00 = S11 * S22 - S12 * S12; c01 = S02 * S12 - S01 * S22; c02 = S01 * S12 - S02 * S11;
+        c11 = S00 * S22 - S02 * S02; c12 = S01 * S02 - S00 * S12; c22 = S00 * S11 - S01 * S01;
+        idet = Num<T>::rcp(S00 * c00 + S01 * c01 + S02 * c02);
+        a0 = (c00 * r0 + c01 * r1 + c02 * r2) * idet;
+        a1 = (c01 * r0 + c11 * r1 + c12 * r2) * idet;
+        a2 = (c02 * r0 + c12 * r1 + c22 * r2) * idet;
+        // a_v = -Minv (f + B^T a_w)
+        const T t0 = f0 + (B00 * a0 + B10 * a1 + B20 * a2), t1 = f1 + (B01 * a0 + B11 * a1 + B21 * a2);
+        const T t2 = f2 + (B02 * a0 + B12 * a1 + B22 * a2);
+        a3 = -(m00 * t0 + m01 * t1 + m02 * t2);
+        a4 = -(m01 * t0 + m11 * t1 + m12 * t2);
+        a5 = -(m02 * t0 + m12 * t1 + m22 * t2);
+        // coordinates: translations read a_v off, rotations solve [e0 e1 e2] qdd = a_w
+        if (lane == 0) {
+            E.udot[fr.x & 255] = a3; E.udot[(fr.x >> 8) & 255] = a4; E.udot[(fr.x >> 16) & 255] = a5;
+            E.udot[dr0] = (x0 * a0 + x1 * a1 + x2 * a2) * id3;
+            E.udot[dr1] = (y0 * a0 + y1 * a1 + y2 * a2) * id3;
+            E.udot[dr2] = (z0 * a0 + z1 * a1 + z2 * a2) * id3;
+        }
+    } else {
+        for (int k = 0; k < nroot; k++) eliminate(pr.aba_root[k], true);
+    }
+    __syncwarp();
     auto back = [&](const int d, const bool store) {
         T w0, w1, w2, w3, w4, w5, w6, w7, s0, s1, s2, s3, s4, s5, s6, s7;
         ld4(X.W[d], w0, w1, w2, w3); ld4(X.W[d] + 4, w4, w5, w6, w7);
@@ -447,7 +520,7 @@ __device__ __forceinline__ void p3_aba(const DevModel<T>& m, EnvWork<T, CLS>& E,
         if (store) E.udot[d] = qdd;
         a0 += s0 * qdd; a1 += s1 * qdd; a2 += s2 * qdd; a3 += s3 * qdd; a4 += s4 * qdd; a5 += s5 * qdd;
     };
-    for (int k = nroot - 1; k >= 0; k--) back(pr.aba_root[k], lane == 0);
+    if (!pr.aba_freeroot) for (int k = nroot - 1; k >= 0; k--) back(pr.aba_root[k], lane == 0);
     for (int s = nst - 1; s >= 0; s--) {
         const int code = pr.aba_step[grp][s];
         if (code != 255) back(code & 15, (lane & 15) == 0);

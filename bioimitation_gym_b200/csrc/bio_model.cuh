@@ -110,6 +110,11 @@ struct alignas(16) PlanarProg {
     int32_t aba_ok, aba_nsteps, aba_nroot, coop_aba;   // coop_aba: planar program runs phases F, G as p2_aba_coop
     uint8_t aba_step[P2_MAXBR][P2_MAXABA];
     uint8_t aba_root[8];
+    // free root joint (p3_aba): dofs of the translations along x, y, z (one byte each) | dofs of the three rotations
+    // in axis order; aba_freeroot = the root is such a joint with no limit / moving point on its dofs (actuators on
+    // the rotations are fine)
+    alignas(16) int32_t aba_fr[4];
+    int32_t aba_freeroot, aba_fr_pad_[3];
 };
 
 template <typename T>
@@ -767,6 +772,44 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         { const char* z = getenv("BIO_NO_ABA"); if (z && z[0] == '1') ok = false; }   // tests: joint-space L^T D L instead
         pr.aba_nsteps = nmax; pr.aba_nroot = nroot > 8 ? 8 : nroot; pr.aba_ok = ok ? 1 : 0;
         pr.atask_ok = (build_atasks(false) && n_mov == d.n_moving) ? 1 : 0;   // packed phase-A tasks (p3_phase_a)
+        {   // free root joint: translations along +x, +y, +z of the ground (unit rate) before three rotations (unit rate)
+            bool fr = ok && s.body_axis_count[0] == 6 && nroot == 6 && d.gdof_ok;
+            int dt[3] = {-1, -1, -1}, drot[3] = {-1, -1, -1};
+            const int ab = s.body_axis_begin[0];
+            auto unit_rate = [&](int a) {
+                const int f = s.axis_func[a];
+                return s.func_kind[f] == BIO_FUNC_LINEAR && s.func_c[f][0] == 1.0 && s.func_c[f][1] == 0.0;
+            };
+            for (int j = 0; j < 3 && fr; j++) {
+                const int a = ab + j, dd = s.axis_dof[a];
+                if (s.axis_kind[a] != BIO_AXIS_TRANS || dd < 0 || !unit_rate(a)) { fr = false; break; }
+                int comp = -1;
+                for (int k = 0; k < 3; k++)
+                    if (s.axis_vec[a][k] == 1.0 && s.axis_vec[a][(k + 1) % 3] == 0.0 && s.axis_vec[a][(k + 2) % 3] == 0.0) comp = k;
+                if (comp < 0 || dt[comp] >= 0) { fr = false; break; }
+                dt[comp] = dd;
+            }
+            for (int j = 0; j < 3 && fr; j++) {
+                const int a = ab + 3 + j, dd = s.axis_dof[a];
+                if (s.axis_kind[a] != BIO_AXIS_ROT || dd < 0 || !unit_rate(a)) { fr = false; break; }
+                drot[j] = dd;
+            }
+            for (int j = 0; j < 3 && fr; j++) {
+                for (int k = 0; k < 3; k++) if (dt[j] == drot[k] || (k != j && (drot[j] == drot[k] || dt[j] == dt[k]))) fr = false;
+                for (int dd : {dt[j], drot[j]}) {
+                    if (dd < 0 || dd > 15) { fr = false; continue; }
+                    if (d.gdof_lim[dd][0] >= 0 || d.gdof_lim[dd][1] >= 0 || d.gdof_movpt[dd][0] >= 0 || d.gdof_movpt[dd][1] >= 0)
+                        fr = false;
+                }
+                if (dt[j] >= 0 && dt[j] <= 15 && d.gdof_act[dt[j]] >= 0) fr = false;   // actuators: rotations only
+            }
+            { const char* z = getenv("BIO_NO_FREEROOT"); if (z && z[0] == '1') fr = false; }   // tests: dof-by-dof root
+            pr.aba_freeroot = fr ? 1 : 0;
+            if (fr) {
+                pr.aba_fr[0] = dt[0] | (dt[1] << 8) | (dt[2] << 16);
+                pr.aba_fr[1] = drot[0] | (drot[1] << 8) | (drot[2] << 16);
+            }
+        }
     }
     // ---- stage 2 (planar models): the planar program ----
     if (!d.planar) { build_general_paths(s, d); return; }
