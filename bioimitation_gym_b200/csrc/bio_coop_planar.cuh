@@ -825,11 +825,30 @@ __device__ __forceinline__ void p2_aba_coop(const DevModel<T>& m, EnvWork<T, CLS
         c0 += o0; c1 += o1; c2 += o2;
         add_body(ri.w);
     }
-#pragma unroll
-    for (int r = 2; r >= 0; r--) eliminate(rdof[r] >= 0 ? rdof[r] : 0, l == 0 && rdof[r] >= 0);
-    __syncwarp();
     // way back: qdd = u / D - (U / D) . a(parent), a(body) = a(parent) + S qdd
     T a0 = T(0), a1 = T(0), a2 = T(0);
+    if (pr.root_ident) {
+        // Free planar root (translations along +x, +y of the ground, then a rotation about +z through O; no limit or
+        // moving point on its dofs: PlanarProg::root_id4): its motion vectors are the unit vectors of (w, x, y), so the
+        // root's acceleration solves  I^A a = Q - p^A  directly (one symmetric 3 x 3 inverse instead of three
+        // elimination and three way-back steps) and the coordinates ARE its components.
+        const int4 rid = *reinterpret_cast<const int4*>(pr.root_id4);
+        const T I00 = __shfl_sync(mask, c0, 0, 4), I01 = __shfl_sync(mask, c1, 0, 4), I02 = __shfl_sync(mask, c2, 0, 4);
+        const T I11 = __shfl_sync(mask, c1, 1, 4), I12 = __shfl_sync(mask, c2, 1, 4), I22 = __shfl_sync(mask, c2, 2, 4);
+        const T p0 = __shfl_sync(mask, c0, 3, 4), p1 = __shfl_sync(mask, c1, 3, 4), p2 = __shfl_sync(mask, c2, 3, 4);
+        const T r0 = K.S[rid.x][3] - p0, r1 = K.S[rid.y][3] - p1, r2 = K.S[rid.z][3] - p2;
+        const T k00 = I11 * I22 - I12 * I12, k01 = I02 * I12 - I01 * I22, k02 = I01 * I12 - I02 * I11;
+        const T k11 = I00 * I22 - I02 * I02, k12 = I01 * I02 - I00 * I12, k22 = I00 * I11 - I01 * I01;
+        const T idet = Num<T>::rcp(I00 * k00 + I01 * k01 + I02 * k02);
+        a0 = (k00 * r0 + k01 * r1 + k02 * r2) * idet;
+        a1 = (k01 * r0 + k11 * r1 + k12 * r2) * idet;
+        a2 = (k02 * r0 + k12 * r1 + k22 * r2) * idet;
+        if (lane == 0) { E.udot[rid.x] = a0; E.udot[rid.y] = a1; E.udot[rid.z] = a2; }
+    } else {
+#pragma unroll
+        for (int r = 2; r >= 0; r--) eliminate(rdof[r] >= 0 ? rdof[r] : 0, l == 0 && rdof[r] >= 0);
+    }
+    __syncwarp();
     auto back = [&](const int d, const bool store) {
         T W0, W1, W2, W3, S0, S1, S2, s3;
         ld4(X.W[d], W0, W1, W2, W3);
@@ -838,8 +857,10 @@ __device__ __forceinline__ void p2_aba_coop(const DevModel<T>& m, EnvWork<T, CLS
         if (store) E.udot[d] = qdd;
         a0 += S0 * qdd; a1 += S1 * qdd; a2 += S2 * qdd;
     };
+    if (!pr.root_ident) {
 #pragma unroll
-    for (int r = 0; r < 3; r++) if (rdof[r] >= 0) back(rdof[r], lane == 0);
+        for (int r = 0; r < 3; r++) if (rdof[r] >= 0) back(rdof[r], lane == 0);
+    }
     if (live) {
 #pragma unroll
         for (int k = 0; k < P2_MAXCB; k++) if (dk[k] >= 0) back(dk[k], c == 0);

@@ -114,7 +114,10 @@ struct alignas(16) PlanarProg {
     // in axis order; aba_freeroot = the root is such a joint with no limit / moving point on its dofs (actuators on
     // the rotations are fine)
     alignas(16) int32_t aba_fr[4];
-    int32_t aba_freeroot, aba_fr_pad_[3];
+    int32_t aba_freeroot, root_ident, aba_fr_pad_[2];
+    // free planar root (p2_aba_coop): dofs of the rotation about +z and of the translations along +x, +y; root_ident =
+    // the root is such a joint (unit rates, no limit / moving point on its dofs)
+    alignas(16) int32_t root_id4[4];
 };
 
 template <typename T>
@@ -947,6 +950,36 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         pr.inc_pk[b][0] = src8[0] | (src8[1] << 8) | (src8[2] << 16) | ((uint32_t)src8[3] << 24);
         pr.inc_pk[b][1] = src8[4] | (src8[5] << 8) | (src8[6] << 16) | ((uint32_t)src8[7] << 24);
         pr.sph_pk[b] = sp4[0] | (sp4[1] << 8) | (sp4[2] << 16) | ((uint32_t)sp4[3] << 24);
+    }
+    {   // free planar root: +x and +y translations of the ground (unit rate), then a rotation about +z (unit rate)
+        bool fr = s.body_axis_count[0] == 3 && pr.root_ndof == 3;
+        int dw = -1, dx = -1, dy = -1;
+        const int ab = s.body_axis_begin[0];
+        auto unit_rate = [&](int a) {
+            const int f = s.axis_func[a];
+            return s.func_kind[f] == BIO_FUNC_LINEAR && s.func_c[f][0] == 1.0 && s.func_c[f][1] == 0.0;
+        };
+        for (int j = 0; j < 3 && fr; j++) {
+            const int a = ab + j, dd = s.axis_dof[a];
+            const double vx = s.axis_vec[a][0], vy = s.axis_vec[a][1], vz = s.axis_vec[a][2];
+            if (dd < 0 || !unit_rate(a)) { fr = false; break; }
+            if (j < 2) {
+                if (s.axis_kind[a] != BIO_AXIS_TRANS) { fr = false; break; }
+                if (vx == 1.0 && vy == 0.0 && vz == 0.0 && dx < 0) dx = dd;
+                else if (vx == 0.0 && vy == 1.0 && vz == 0.0 && dy < 0) dy = dd;
+                else fr = false;
+            } else {
+                if (s.axis_kind[a] != BIO_AXIS_ROT || !(vx == 0.0 && vy == 0.0 && vz == 1.0)) fr = false;
+                dw = dd;
+            }
+        }
+        if (fr && (dw == dx || dw == dy || dx == dy || dw < 0 || dx < 0 || dy < 0)) fr = false;
+        if (fr)
+            for (int dd : {dw, dx, dy})
+                if (pr.dof_lim[dd][0] >= 0 || pr.dof_lim[dd][1] >= 0 || pr.dof_mov[dd][0] >= 0 || pr.dof_mov[dd][1] >= 0) fr = false;
+        { const char* z = getenv("BIO_NO_FREEROOT"); if (z && z[0] == '1') fr = false; }   // tests: dof-by-dof root
+        pr.root_ident = fr ? 1 : 0;
+        pr.root_id4[0] = fr ? dw : 0; pr.root_id4[1] = fr ? dx : 0; pr.root_id4[2] = fr ? dy : 0; pr.root_id4[3] = 0;
     }
     pr.ok = 1;
     pr.coop_aba = 1;

@@ -167,10 +167,11 @@ def test_joint_space_solve_of_the_spatial_evaluation(env_id, dtype, monkeypatch)
     env.close()
 
 
-@pytest.mark.parametrize("env_id", ["MuscleWalkingImitation3D-v0", "TorqueWalkingImitation3D-v0"])
+@pytest.mark.parametrize("env_id", ["MuscleWalkingImitation3D-v0", "TorqueWalkingImitation3D-v0",
+                                    "MuscleWalkingImitation2D-v0", "TorqueWalkingImitation2D-v0"])
 def test_dof_by_dof_root_of_the_articulated_body_pass_fp64(env_id, monkeypatch):
-    """BIO_NO_FREEROOT=1: the articulated-body pass eliminating the root's six dofs one at a time (roots that are not a
-    free joint) instead of the direct 6 x 6 solve the shipped 3D models take: against the oracle, 20 free-running
+    """BIO_NO_FREEROOT=1: the articulated-body passes eliminating the root's dofs one at a time (roots that are not a
+    free joint) instead of the direct 6 x 6 / 3 x 3 solve the shipped models take: against the oracle, 20 free-running
     control steps (TorqueWalking3D actuates the pelvis rotations: the generalized-torque term of the direct solve is
     covered by the default path of the other tests)."""
     import torch
