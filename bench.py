@@ -296,8 +296,19 @@ def e2e_pipelined_loop(env_id, cfg, pool, steps, preroll, barrier, n_groups=4):
     for g in range(n_groups):
         groups.recv(g)
     dt = time.perf_counter() - t0
+    # the same loop inside the library (bio_groups_run): no host-language code between a group's steps, the four
+    # action buffers of every group replayed in place from page-locked memory
+    ring = [[torch.as_tensor(acts[i][g]).pin_memory() for i in range(4)] for g in range(n_groups)]
+    groups.run(3, action_ring=ring)
+    for e in groups.envs:
+        e.stats(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    groups.run(steps, action_ring=ring)
+    dt_native = time.perf_counter() - t0
+    episodes = float(sum(float(e.stats()[1].item()) for e in groups.envs))
     groups.close()
-    return dt
+    return dt, dt_native, episodes
 
 
 def e2e_steps_for(n_per_gpu, steps):
@@ -341,17 +352,26 @@ def run_config(env_id, n_per_gpu, steps, warmup, rank, world, local_rank, args, 
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_max, e2e_min = float(t[0].item()), -float(t[1].item())
-    pipe = None
+    pipe = native = None
     if args.pipelined_groups > 1 and n_per_gpu % args.pipelined_groups == 0 and n_per_gpu <= 65536:
-        pipe_s = e2e_pipelined_loop(env_id, cfg, pool, e2e_steps, preroll, barrier, args.pipelined_groups)
-        t = torch.tensor([pipe_s], dtype=torch.float64, device=dev)
+        pipe_s, native_s, native_eps = e2e_pipelined_loop(env_id, cfg, pool, e2e_steps, preroll, barrier,
+                                                          args.pipelined_groups)
+        t = torch.tensor([pipe_s, native_s, -native_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        pipe = {"value": n_per_gpu * world * e2e_steps / float(t.item()), "unit": "env-steps/s",
+        ng = n_per_gpu // args.pipelined_groups
+        pipe = {"value": n_per_gpu * world * e2e_steps / float(t[0].item()), "unit": "env-steps/s",
                 "groups": args.pipelined_groups, "steps": e2e_steps,
-                "api": "backend.EnvGroups send / recv (bio_step_host_begin / _end): %d groups of %d envs per GPU on "
-                       "disjoint SMs, same host buffers and bytes per step as e2e.value"
-                       % (args.pipelined_groups, n_per_gpu // args.pipelined_groups)}
+                "api": "backend.EnvGroups send / recv from a Python loop (bio_step_host_begin / _end): %d groups of %d "
+                       "envs per GPU on disjoint SMs, same host buffers and bytes per step" % (args.pipelined_groups, ng)}
+        native = {"value": n_per_gpu * world * e2e_steps / float(t[1].item()),
+                  "per_rank_ms_per_step": {"min": -float(t[2].item()) / e2e_steps * 1e3,
+                                           "max": float(t[1].item()) / e2e_steps * 1e3},
+                  "episodes_rank0": native_eps,
+                  "api": "bio_groups_run (backend.EnvGroups.run): native send / recv loop over %d groups of %d envs per "
+                         "GPU on disjoint SMs; every control step of every group reads its actions from and writes "
+                         "its observation / reward / done / terms rows to page-locked host memory (the kernel, in "
+                         "place), next step launched when the rows have landed" % (args.pipelined_groups, ng)}
     stats = env.stats().clone()
     if world > 1:                              # the only collective: rollout statistics, outside the step path
         gathered = [torch.zeros_like(stats) for _ in range(world)]
@@ -359,13 +379,24 @@ def run_config(env_id, n_per_gpu, steps, warmup, rank, world, local_rank, args, 
         stats = torch.stack(gathered).sum(0)
     stats = stats.cpu().numpy()
     esz = 4 if env.dtype == torch.float32 else 8
+    # issue-bound kernels (3D) gain nothing from groups: e2e.value is the better of the two public calls, the other
+    # one is kept beside it
+    sync_better = bool(native) and native["value"] < n_per_gpu * world * e2e_steps / e2e_max
+    sync_e2e = {"value": n_per_gpu * world * e2e_steps / e2e_max, "unit": "env-steps/s",
+                "per_rank_ms_per_step": {"min": e2e_min / e2e_steps * 1e3, "max": e2e_max / e2e_steps * 1e3},
+                "api": "bio_step_host (VecEnv.step_host): the whole batch in one synchronous call, page-locked host "
+                       "buffers read and written by the kernel in place"}
+    best = sync_e2e if (native is None or sync_better) else native
     out = dict(env=env, value=n_per_gpu * world * steps / (total_ms * 1e-3), ms_per_step=total_ms / steps,
                launches=int(launches), lo=lo, hi=hi,
-               e2e={"value": n_per_gpu * world * e2e_steps / e2e_max, "unit": "env-steps/s",
+               e2e={"value": best["value"], "unit": "env-steps/s",
                     "h2d_bytes_per_step": n_per_gpu * env.n_act * esz,
                     "d2h_bytes_per_step": n_per_gpu * (env.obs_dim + 1 + env.n_terms) * esz + n_per_gpu,
                     "steps": e2e_steps,
-                    "per_rank_ms_per_step": {"min": e2e_min / e2e_steps * 1e3, "max": e2e_max / e2e_steps * 1e3},
+                    "api": best["api"],
+                    "per_rank_ms_per_step": best["per_rank_ms_per_step"],
+                    "synchronous": sync_e2e,
+                    **({"native_groups": native} if native else {}),
                     **({"pipelined": pipe} if pipe else {})},
                rollout={"env_steps": float(stats[0]), "episodes": float(stats[1]),
                         "mean_return": float(stats[2] / max(stats[1], 1)),

@@ -43,6 +43,8 @@ C_API = {
     "bio_step_host_begin": (ctypes.c_int, [ctypes.c_void_p] * 6),
     "bio_step_host_end": (ctypes.c_int, [ctypes.c_void_p]),
     "bio_set_grid": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    "bio_groups_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64,
+                                      ctypes.c_void_p, ctypes.c_void_p]),
     "bio_get_state": (ctypes.c_int, [ctypes.c_void_p] * 3),
     "bio_set_state": (ctypes.c_int, [ctypes.c_void_p] * 3),
     "bio_eval_debug": (ctypes.c_int, [ctypes.c_void_p] * 4),
@@ -59,6 +61,9 @@ C_API = {
     "bio_n_act": (ctypes.c_int32, [ctypes.c_void_p]),
     "bio_measure_fp32_peak": (ctypes.c_double, [ctypes.c_int32]),
 }
+
+
+POLICY_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64)
 
 
 def load_library(path: Optional[str] = None):
@@ -422,6 +427,39 @@ class EnvGroups:
         self._in_flight[g] = False
         b = self.buf[g]
         return b["o"], b["r"], b["d"].view(np.bool_), {"all_rewards": b["t"]}
+
+    def run(self, steps: int, policy=None, action_ring=None):
+        """`steps` control steps of every group through the native sampler loop (bio_groups_run): a group's next step
+        is launched the moment its previous one has landed in its page-locked buffers, with no Python between the
+        launches.  `policy(g, k)`, if given, is called before step k of group g to fill self.buf[g]['a'] from
+        self.buf[g]['o']; else `action_ring` = list over groups of lists of page-locked torch tensors [N/G, A] used
+        round-robin (a replayed action sequence); else every step re-uses self.buf[g]['a'].  Results of the last step
+        are in self.buf[g]; bit-identical to the same steps through send / recv."""
+        for g in range(self.G):
+            if self._in_flight[g]:
+                raise BioError("group %d is stepping: recv() it first" % g)
+        e0 = self.envs[0]
+        handles = (ctypes.c_void_p * self.G)(*[e.handle.value for e in self.envs])
+        bufs = (ct.BioGroupBuffers * self.G)()
+        keep = []
+        for g in range(self.G):
+            b = self.buf[g]
+            bufs[g].actions, bufs[g].obs, bufs[g].reward = b["a"].ctypes.data, b["o"].ctypes.data, b["r"].ctypes.data
+            bufs[g].done, bufs[g].reward_terms = b["d"].ctypes.data, b["t"].ctypes.data
+            if policy is None and action_ring is not None:
+                ring = action_ring[g]
+                for t in ring:
+                    if not t.is_pinned() or tuple(t.shape) != (self.n_group, self.n_act) or not t.is_contiguous():
+                        raise ValueError("action_ring entries must be page-locked contiguous [N/G, A] tensors")
+                arr = (ctypes.c_void_p * len(ring))(*[t.data_ptr() for t in ring])
+                keep.append(arr)
+                bufs[g].action_ring = ctypes.addressof(arr)
+                bufs[g].ring_len = len(ring)
+        cb = POLICY_FN(lambda user, g, k: policy(int(g), int(k))) if policy is not None else None
+        _check(e0.lib, e0.lib.bio_groups_run(ctypes.cast(handles, ctypes.c_void_p), self.G,
+                                             ctypes.cast(bufs, ctypes.c_void_p), int(steps),
+                                             ctypes.cast(cb, ctypes.c_void_p) if cb is not None else None, None),
+               "bio_groups_run")
 
     def close(self):
         for g, e in enumerate(self.envs):

@@ -747,6 +747,52 @@ def test_env_groups_send_recv_equal_the_single_batch():
     full.close()
 
 
+def test_native_group_loop_equals_the_single_batch():
+    """EnvGroups.run (bio_groups_run, the native send / recv loop): 40 steps with a replayed action ring, then 40
+    steps with a policy callback, give bit for bit the rows of one VecEnv of the same seeded batch."""
+    import torch
+    from bioimitation_gym_b200 import backend
+    env_id, n, G, K = "MuscleWalkingImitation2D-v0", 1024, 4, 40
+    full = backend.VecEnv(env_id, dict(num_envs=n, seed=9))
+    groups = backend.EnvGroups(env_id, dict(num_envs=n, seed=9), groups=G)
+    ng = n // G
+    full.reset()
+    groups.reset()
+    rng = np.random.default_rng(7)
+    acts = rng.uniform(0, 1, (2 * K, n, 14)).astype(np.float32)
+    ring = [[torch.as_tensor(acts[k][g * ng:(g + 1) * ng].copy()).pin_memory() for k in range(K)] for g in range(G)]
+    groups.run(K, action_ring=ring)
+    n_done = 0
+    for k in range(K):
+        o, r, d, info = full.step(torch.as_tensor(acts[k]))
+        n_done += int(d.sum())
+    o, r, d, t = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy(), info["all_rewards"].cpu().numpy()
+    for g in range(G):
+        sl, b = slice(g * ng, (g + 1) * ng), groups.buf[g]
+        assert np.array_equal(o[sl], b["o"]) and np.array_equal(r[sl], b["r"]) and np.array_equal(d[sl], b["d"])
+        assert np.array_equal(t[sl], b["t"])
+    calls = []
+
+    def policy(g, k):
+        calls.append((g, k))
+        groups.buf[g]["a"][...] = acts[K + k][g * ng:(g + 1) * ng]
+
+    groups.run(K, policy=policy)
+    for k in range(K):
+        o, r, d, info = full.step(torch.as_tensor(acts[K + k]))
+        n_done += int(d.sum())
+    o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+    for g in range(G):
+        sl, b = slice(g * ng, (g + 1) * ng), groups.buf[g]
+        assert np.array_equal(o[sl], b["o"]) and np.array_equal(r[sl], b["r"]) and np.array_equal(d[sl], b["d"])
+    assert sorted(calls) == [(g, k) for g in range(G) for k in range(K)]
+    assert n_done > 0                           # auto-reset was exercised
+    with pytest.raises(ValueError):
+        groups.run(1, action_ring=[[torch.zeros(ng, 14)] for _ in range(G)])      # pageable ring
+    groups.close()
+    full.close()
+
+
 def test_host_buffer_entry_point_matches_device_path():
     import torch
     env, _ = _mk("MuscleWalkingImitation2D-v0", 256, "float32")

@@ -13,5 +13,5 @@ done
 python - <<'PY'
 import json
 for ln in open('gpurun_out/bench_quick.jsonl'):
-    d=json.loads(ln); print(d['config']['workload'][:48], '%.2fM' % (d['value']/1e6), 'ms %.4f' % d['ms_per_step'], 'e2e %.2fM' % (d['e2e']['value']/1e6), 'frac %.3f' % d['roofline']['frac'], 'episodes', d['rollout']['episodes'])
+    d=json.loads(ln); print(d['config']['workload'][:48], '%.2fM' % (d['value']/1e6), 'ms %.4f' % d['ms_per_step'], 'e2e %.2fM (sync %.2fM)' % (d['e2e']['value']/1e6, d['e2e']['synchronous']['value']/1e6), 'frac %.3f' % d['roofline']['frac'], 'episodes', d['rollout']['episodes'])
 PY
