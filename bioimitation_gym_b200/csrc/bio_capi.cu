@@ -111,6 +111,45 @@ int set_kernel_attrs(Handle<T>* h) {
     return 0;
 }
 
+// Launch shape of the cooperative kernel by the number of item rounds per SM (see COOP_THREADS_LO / _HI in
+// bio_coop.cuh), over the SMs the handle launches on (bio_set_grid: a group of a quarter of the batch on a quarter
+// of the SMs has the item count per SM of the whole batch, not a quarter of it); BIO_COOP_THREADS = lo | hi |
+// <thread count of one of the two shapes> forces one (tests, experiments).  Sets coop_threads / coop_smem / coop_ctas.
+template <typename T>
+int pick_coop_shape(Handle<T>* h) {
+    if (h->coop_cls < 0) return 0;
+    const int cls = h->coop_cls;
+    const int G = cls == 0 ? (int)bio::CoopCls<0>::G : (int)bio::CoopCls<1>::G;
+    const int lo = COOP_THREADS_LO(T), hi = cls == 1 ? COOP_THREADS_HI(T, 1) : COOP_THREADS_HI(T, 0);
+    int threads = 0;
+    if (const char* e = getenv("BIO_COOP_THREADS")) {
+        if (!strcmp(e, "lo")) threads = lo;
+        else if (!strcmp(e, "hi")) threads = hi;
+        else { const int v = atoi(e); if (v == lo || v == hi) threads = v; }
+    }
+    if (!threads) {
+        const long sms = h->coop_grid > 0 ? h->coop_grid : h->n_sms;
+        const long items = (h->n + (32 / G) - 1) / (32 / G);
+        const long ipsm = (items + sms - 1) / sms;
+        const double cost_lo = (double)((ipsm + lo / 32 - 1) / (lo / 32));
+        const double cost_hi = (double)((ipsm + hi / 32 - 1) / (hi / 32)) * (cls == 1 ? COOP_SHAPE_COST(1) : COOP_SHAPE_COST(0));
+        threads = cost_hi < cost_lo ? hi : lo;
+    }
+    const size_t base = ((sizeof(bio::DevModel<T>) + 15) / 16) * 16;
+    h->coop_threads = threads;
+    if (cls == 0) {
+        h->coop_smem = base + (threads / G) * sizeof(bio::EnvWork<T, 0>);
+        CU((bio::coop_set_smem<T, 0>(threads, (int)h->coop_smem)));
+        h->coop_ctas = bio::coop_ctas_per_sm<T, 0>(threads, (int)h->coop_smem);
+    } else {
+        h->coop_smem = base + (threads / G) * sizeof(bio::EnvWork<T, 1>);
+        CU((bio::coop_set_smem<T, 1>(threads, (int)h->coop_smem)));
+        h->coop_ctas = bio::coop_ctas_per_sm<T, 1>(threads, (int)h->coop_smem);
+    }
+    if (h->coop_ctas < 1) return fail(-2, "the cooperative step kernel does not fit an SM");
+    return 0;
+}
+
 template <typename T>
 int create_impl(const BioModelTables* model, const BioTaskConfig* task, const BioRefTables* ref, int n, int device,
                 unsigned long long seed, long long env_offset, Handle<T>* h) {
@@ -173,41 +212,18 @@ int create_impl(const BioModelTables* model, const BioTaskConfig* task, const Bi
                    model->n_bodies + model->n_obspts <= G && model->n_spheres + model->n_limits <= G &&
                    model->n_obspts <= COOP_MAXOBS && model->n_coords <= 2 * G && task->n_pd <= G;
         };
-        const size_t base = ((sizeof(bio::DevModel<T>) + 15) / 16) * 16;
-        // launch shape by the number of item rounds per SM (see COOP_THREADS_LO / _HI in bio_coop.cuh);
-        // BIO_COOP_THREADS = lo | hi | <thread count of one of the two shapes> forces one (tests, experiments)
-        auto pick_threads = [&](int G, int cls) {
-            const int lo = COOP_THREADS_LO(T), hi = cls == 1 ? COOP_THREADS_HI(T, 1) : COOP_THREADS_HI(T, 0);
-            if (const char* e = getenv("BIO_COOP_THREADS")) {
-                if (!strcmp(e, "lo")) return lo;
-                if (!strcmp(e, "hi")) return hi;
-                const int v = atoi(e);
-                if (v == lo || v == hi) return v;
-            }
-            const long items = (n + (32 / G) - 1) / (32 / G);
-            const long ipsm = (items + h->n_sms - 1) / h->n_sms;
-            const double cost_lo = (double)((ipsm + lo / 32 - 1) / (lo / 32));
-            const double cost_hi = (double)((ipsm + hi / 32 - 1) / (hi / 32)) * COOP_SHAPE_COST(cls);
-            return cost_hi < cost_lo ? hi : lo;
-        };
         // class 0 (half-warp per env) runs the planar program only
         // (the cooperative kernels write the observation row from a 256-slot descriptor table)
         if (task->obs_dim > BIO_COOP_MAX_OBS_DIM) {
             h->coop_cls = -1;
         } else if (want_coop && prog_ok && prog_src <= P2_MAXSRC && fits(C0::G, C0::ND, C0::NM, C0::NP, C0::NAX)) {
             h->coop_cls = 0;
-            h->coop_threads = pick_threads(C0::G, 0);
-            h->coop_smem = base + (h->coop_threads / C0::G) * sizeof(bio::EnvWork<T, 0>);
-            CU((bio::coop_set_smem<T, 0>(h->coop_threads, (int)h->coop_smem)));
-            h->coop_ctas = bio::coop_ctas_per_sm<T, 0>(h->coop_threads, (int)h->coop_smem);
+            if ((rc = pick_coop_shape<T>(h))) return rc;
         } else if (want_coop && fits(C1::G, C1::ND, C1::NM, C1::NP, C1::NAX) &&
                    (prog_ok ? prog_src <= P2_MAXSRC : (model->n_muscles == 0 || (gpath_ok && prog_src <= COOP_MAXSRC6)))) {
             // class 1 (warp per env): planar program, or the general evaluation with compiled muscle paths
             h->coop_cls = 1;
-            h->coop_threads = pick_threads(C1::G, 1);
-            h->coop_smem = base + (h->coop_threads / C1::G) * sizeof(bio::EnvWork<T, 1>);
-            CU((bio::coop_set_smem<T, 1>(h->coop_threads, (int)h->coop_smem)));
-            h->coop_ctas = bio::coop_ctas_per_sm<T, 1>(h->coop_threads, (int)h->coop_smem);
+            if ((rc = pick_coop_shape<T>(h))) return rc;
         }
         if (h->coop_cls >= 0 && h->coop_ctas < 1) return fail(-2, "the cooperative step kernel does not fit an SM");
     }
@@ -727,7 +743,7 @@ int bio_groups_run(const bio_handle* handles, int32_t n_groups, const BioGroupBu
 int bio_set_grid(bio_handle hh, int32_t ctas) {
     ENTER(hh);
     ((HandleBase*)hh)->coop_grid = ctas > 0 ? ctas : 0;
-    return 0;
+    return DISPATCH(hh, pick_coop_shape<float>(H32(hh)), pick_coop_shape<double>(H64(hh)));
 }
 
 int bio_reset_host(bio_handle hh, const uint8_t* mask, void* obs) {
