@@ -525,19 +525,21 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        fp32_peak = None
-        try:
-            v = float(env.lib.bio_measure_fp32_peak(local_rank))   # FFMA chain, measured now, untimed
-            fp32_peak = v if v > 0 else None
+        is64 = env.dtype == torch.float64
+        fp_peak = None
+        try:                                       # FMA chain in the handle's scalar type, measured now, untimed
+            v = float((env.lib.bio_measure_fp64_peak if is64 else env.lib.bio_measure_fp32_peak)(local_rank))
+            fp_peak = v if v > 0 else None
         except Exception:
             pass
-        peak = fp32_peak or 148 * 128 * 2 * 1.965e9 / 1e12
+        peak = fp_peak or (148 * 128 * 2 * 1.965e9 / 1e12 / (64 if is64 else 1))
         if flops is not None:
             achieved = flops * N / (ms_launch * 1e-3) / 1e12
-            roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            roofline = {"bound": "fp64" if is64 else "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                         "frac": achieved / peak,
-                        "peak_source": "measured on this GPU by bio_measure_fp32_peak (FFMA chain, FMA = 2 flops)" if fp32_peak
-                        else "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (no measured FP32 peak yet)",
+                        "peak_source": ("measured on this GPU by bio_measure_%s_peak (%s chain, FMA = 2 flops)"
+                                        % (("fp64", "DFMA") if is64 else ("fp32", "FFMA"))) if fp_peak
+                        else "nominal (no measured peak)",
                         "flops_per_env_step": flops, "traffic": None}
             try:
                 roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))[

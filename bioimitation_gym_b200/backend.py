@@ -60,6 +60,7 @@ C_API = {
     "bio_obs_dim": (ctypes.c_int32, [ctypes.c_void_p]),
     "bio_n_act": (ctypes.c_int32, [ctypes.c_void_p]),
     "bio_measure_fp32_peak": (ctypes.c_double, [ctypes.c_int32]),
+    "bio_measure_fp64_peak": (ctypes.c_double, [ctypes.c_int32]),
 }
 
 

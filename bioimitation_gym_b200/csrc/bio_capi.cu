@@ -831,33 +831,34 @@ int32_t bio_n_act(bio_handle hh) { return hh ? ((HandleBase*)hh)->model.n_act : 
 // path (MEASURED_PEAKS.json only carries HBM and bf16 tensor peaks).
 // ---------------------------------------------------------------------------
 namespace {
-__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
-    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
-    float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+template <typename F>
+__global__ void __launch_bounds__(256) fma_peak_kernel(F* out, int iters, F a, F b) {
+    F x0 = threadIdx.x * F(1e-3), x1 = x0 + F(1), x2 = x0 + F(2), x3 = x0 + F(3);
+    F x4 = x0 + F(4), x5 = x0 + F(5), x6 = x0 + F(6), x7 = x0 + F(7);
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
-            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
         }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
-}  // namespace
 
-extern "C" double bio_measure_fp32_peak(int32_t device) {
+template <typename F>
+double measure_fma_peak(int32_t device, int iters) {
     if (cudaSetDevice(device) != cudaSuccess) return -1.0;
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const int blocks = sms * 8, threads = 256, iters = 4096;
-    float* out = nullptr;
-    if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return -1.0;
+    const int blocks = sms * 8, threads = 256;
+    F* out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(F)) != cudaSuccess) return -1.0;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     double best = 0.0;
     for (int rep = 0; rep < 5; rep++) {
         cudaEventRecord(e0);
-        fma_peak_kernel<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+        fma_peak_kernel<F><<<blocks, threads>>>(out, iters, F(0.999), F(0.001));
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0.f;
@@ -870,3 +871,8 @@ extern "C" double bio_measure_fp32_peak(int32_t device) {
     cudaFree(out);
     return cudaGetLastError() == cudaSuccess ? best : -1.0;
 }
+}  // namespace
+
+extern "C" double bio_measure_fp32_peak(int32_t device) { return measure_fma_peak<float>(device, 4096); }
+// the same chain in fp64 (DFMA), for the fp64 build's roofline
+extern "C" double bio_measure_fp64_peak(int32_t device) { return measure_fma_peak<double>(device, 256); }

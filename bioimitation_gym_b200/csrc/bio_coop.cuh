@@ -405,17 +405,20 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
                 }
             }
         }
-        const T fiso = m.mus_fiso[i], lopt = m.mus_lopt[i], h = m.mus_height[i], beta = m.mus_beta[i];
-        const T amin = m.mus_amin[i], lmin = m.mus_lm_min[i];
+        // per-muscle constants: three 16-byte reads (PlanarProg::mus_k), reciprocals from the host
+        T fiso, lopt, inv_lopt, h2, beta, amin, lmin, inv_lts, vmax_lopt, inv_tact, inv_tdeact, k11;
+        ld4(pr.mus_k[i], fiso, lopt, inv_lopt, h2);
+        ld4(pr.mus_k[i] + 4, beta, amin, lmin, inv_lts);
+        ld4(pr.mus_k[i] + 8, vmax_lopt, inv_tact, inv_tdeact, k11);
         const T lmi = E.lm[i];
         const T lmc = lmi < lmin ? lmin : lmi;
-        const T lat = Num<T>::sqrt_pos(lmc * lmc - h * h);
+        const T lat = Num<T>::sqrt_pos(lmc * lmc - h2);
         const T cosa = Num<T>::div(lat, lmc);
         T fal, fpe, ft, fv, dfv, dfal, dfpe, dft;
-        const T lnorm = Num<T>::div(lmc, lopt);
+        const T lnorm = lmc * inv_lopt;
         curve_eval(m, 0, lnorm, fal, dfal);
         curve_eval(m, 2, lnorm, fpe, dfpe);
-        curve_eval(m, 3, Num<T>::div(L - lat, m.mus_lts[i]), ft, dft);
+        curve_eval(m, 3, (L - lat) * inv_lts, ft, dft);
         const T ac = clampv(E.act[i], amin, T(1));
         const T afal = ac * fal;
         // Newton on the damped-equilibrium residual, warm-started from the root of the previous
@@ -445,12 +448,12 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         // substep evaluations (h_imp > 0); the full evaluation (h_imp = 0) reports the fibre velocity itself
         T gain = T(1);
         if (h_imp > T(0))
-            gain = fibre_gain(h_imp, m.mus_vmax[i] * lopt, derr, ac * dfal * fv + dfpe, Num<T>::rcp(lopt), cosa, fsum, lmc, lat,
-                              h * h, dft, Num<T>::rcp(m.mus_lts[i]));
-        E.lmdot[i] = vn * m.mus_vmax[i] * lopt * gain;
+            gain = fibre_gain(h_imp, vmax_lopt, derr, ac * dfal * fv + dfpe, inv_lopt, cosa, fsum, lmc, lat, h2, dft, inv_lts);
+        E.lmdot[i] = vn * vmax_lopt * gain;
+        // activation ODE: adot = (e - a) / tau, tau = tact (0.5 + 1.5 a) rising, tdeact / (0.5 + 1.5 a) falling
         const T ec = clampv(E.ctrl[i], amin, T(1));
-        const T tau = ec > ac ? m.mus_tact[i] * (T(0.5) + T(1.5) * ac) : Num<T>::div(m.mus_tdeact[i], T(0.5) + T(1.5) * ac);
-        E.adot[i] = Num<T>::div(ec - ac, tau);
+        const T wa = T(0.5) + T(1.5) * ac;
+        E.adot[i] = (ec - ac) * (ec > ac ? inv_tact * Num<T>::rcp(wa) : inv_tdeact * wa);
         const T tension = fiso * ft;
         if (full) {
             curve_eval(m, 1, vn, fv, dfv);
@@ -474,10 +477,14 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     // ---- phase D: lane = contact sphere | coordinate limit ----
     if (lane < m.n_spheres) {
         const int s = lane, b = m.sph_body[s];
+        // per-sphere constants: three 16-byte reads (PlanarProg::sph_k)
+        T loc[3], rad, kk, c15, ud, us2, uv, vt, inv_vt, k11;
+        ld4(m.prog.sph_k[s], loc[0], loc[1], loc[2], rad);
+        ld4(m.prog.sph_k[s] + 4, kk, c15, ud, us2);
+        ld4(m.prog.sph_k[s] + 8, uv, vt, inv_vt, k11);
         T xc[3];
-        matvec3(K.R[b], m.sph_loc[s], xc);
+        matvec3(K.R[b], loc, xc);
         for (int c = 0; c < 3; c++) xc[c] += K.r[b][c];
-        const T rad = m.sph_radius[s];
         const T depth = rad - (xc[1] + E.O[1]);
         T F[3] = {T(0), T(0), T(0)}, D0 = T(0), D1 = T(0);
         T p[3] = {xc[0], T(-0.5) * depth - E.O[1], xc[2]};
@@ -486,34 +493,36 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             cross3(K.V[b], p, v);
             for (int c = 0; c < 3; c++) v[c] += K.V[b][3 + c];
             const T vn = -v[1];
-            const T kk = m.sph_k[s];
             const T fH = T(4.0 / 3.0) * kk * depth * Num<T>::sqrt_pos(rad * kk * depth);
-            const T f = fH * (T(1) + T(1.5) * m.sph_c[s] * vn);
+            const T f = fH * (T(1) + c15 * vn);
             if (f > T(0)) {
                 F[1] = f;
                 const T vs = Num<T>::sqrt_fast(v[0] * v[0] + v[2] * v[2]);
-                const T vrel = Num<T>::div(vs, m.sph_vt[s]);
-                const T strib = m.sph_ud[s] + Num<T>::div(T(2) * (m.sph_us[s] - m.sph_ud[s]), T(1) + vrel * vrel);
+                const T vrel = vs * inv_vt;
+                const T strib = ud + Num<T>::div(us2, T(1) + vrel * vrel);
                 if (vs != T(0)) {
-                    const T ff = f * ((vrel < T(1) ? vrel : T(1)) * strib + m.sph_uv[s] * vs);
+                    const T ff = f * ((vrel < T(1) ? vrel : T(1)) * strib + uv * vs);
                     const T fs = -Num<T>::div(ff, vs);
                     F[0] = fs * v[0];
                     F[2] = fs * v[2];
                 }
-                D0 = f * (Num<T>::rcp(vrel < T(1) ? m.sph_vt[s] : vs) * strib + m.sph_uv[s]);
-                D1 = T(1.5) * m.sph_c[s] * fH;
+                D0 = f * ((vrel < T(1) ? inv_vt : Num<T>::rcp(vs)) * strib + uv);
+                D1 = c15 * fH;
             }
         }
         for (int c = 0; c < 3; c++) { E.sphx[s][c] = p[c]; E.sphF[s][c] = F[c]; }
         E.sphD[s][0] = D0; E.sphD[s][1] = D1;
     } else if (lane - m.n_spheres < m.n_limits) {
         const int l = lane - m.n_spheres, d = m.lim_dof[l];
-        const T w = m.lim_w[l], qq = E.q[d];
-        const T sup = step5(Num<T>::div(qq - m.lim_qup[l], w));
-        const T slo = T(1) - step5(Num<T>::div(qq - (m.lim_qlo[l] - w), w));
-        E.limf[l] = -m.lim_kup[l] * sup * (qq - m.lim_qup[l]) + m.lim_klo[l] * slo * (m.lim_qlo[l] - qq) -
-                    m.lim_damp[l] * (sup + slo) * E.u[d];
-        E.limD[l] = m.lim_damp[l] * (sup + slo);
+        // per-limit constants: two 16-byte reads (PlanarProg::lim_k)
+        T qup, qlo, kup, klo, damp, inv_w, w, k7;
+        ld4(m.prog.lim_k[l], qup, qlo, kup, klo);
+        ld4(m.prog.lim_k[l] + 4, damp, inv_w, w, k7);
+        const T qq = E.q[d];
+        const T sup = step5((qq - qup) * inv_w);
+        const T slo = T(1) - step5((qq - (qlo - w)) * inv_w);
+        E.limf[l] = -kup * sup * (qq - qup) + klo * slo * (qlo - qq) - damp * (sup + slo) * E.u[d];
+        E.limD[l] = damp * (sup + slo);
     }
     gsync<G>();
 

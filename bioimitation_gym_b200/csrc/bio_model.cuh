@@ -631,6 +631,26 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     memset(&pr, 0, sizeof(pr));
     for (int b = 0; b < s.n_bodies && b < BIO_MAX_BODIES; b++)       // contact spheres of every body (any model)
         for (int sp = 0; sp < s.n_spheres && sp < BIO_MAX_SPHERES; sp++) if (s.sph_body[sp] == b) pr.body_sph_mask[b] |= 1 << sp;
+    // per-muscle / per-sphere / per-limit constants packed for 16-byte reads, reciprocals from the host (any model:
+    // the planar program and the spatial evaluation both read them; a planar model's sphere carries the constant z
+    // of its body)
+    for (int i = 0; i < s.n_muscles && i < BIO_MAX_MUSCLES; i++) {
+        const double k12[12] = {s.mus_fiso[i], s.mus_lopt[i], 1.0 / s.mus_lopt[i], s.mus_height[i] * s.mus_height[i],
+                                s.mus_beta[i], s.mus_amin[i], s.mus_lm_min[i], 1.0 / s.mus_lts[i],
+                                s.mus_vmax[i] * s.mus_lopt[i], 1.0 / s.mus_tact[i], 1.0 / s.mus_tdeact[i], 0.0};
+        for (int c = 0; c < 12; c++) pr.mus_k[i][c] = (T)k12[c];
+    }
+    for (int sp = 0; sp < s.n_spheres && sp < BIO_MAX_SPHERES; sp++) {
+        const double zb = d.planar ? (double)d.body_z[s.sph_body[sp]] : 0.0;
+        const double k12[12] = {s.sph_loc[sp][0], s.sph_loc[sp][1], s.sph_loc[sp][2] + zb, s.sph_radius[sp],
+                                s.sph_k[sp], 1.5 * s.sph_c[sp], s.sph_ud[sp], 2.0 * (s.sph_us[sp] - s.sph_ud[sp]),
+                                s.sph_uv[sp], s.sph_vt[sp], 1.0 / s.sph_vt[sp], 0.0};
+        for (int c = 0; c < 12; c++) pr.sph_k[sp][c] = (T)k12[c];
+    }
+    for (int l = 0; l < s.n_limits && l < BIO_MAX_LIMITS; l++) {
+        const double k8[8] = {s.lim_qup[l], s.lim_qlo[l], s.lim_kup[l], s.lim_klo[l], s.lim_damp[l], 1.0 / s.lim_w[l], s.lim_w[l], 0.0};
+        for (int c = 0; c < 8; c++) pr.lim_k[l][c] = (T)k8[c];
+    }
     // ---- stage 1 (any model): root body 0 carrying <= P2_MAXBR unbranched chains; the walk root joint ->
     // leaf of every chain as a list of elementary-axis steps (used by the planar program and by the scan
     // form of the spatial kinematics) ----
@@ -891,22 +911,6 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     }
     for (int r = 0; r < 3; r++) pr.root_i4[r] = r < pr.root_ndof ? pr.root_dof[r] : -1;
     pr.root_i4[3] = pr.root_body;
-    for (int i = 0; i < s.n_muscles; i++) {
-        const double k12[12] = {s.mus_fiso[i], s.mus_lopt[i], 1.0 / s.mus_lopt[i], s.mus_height[i] * s.mus_height[i],
-                                s.mus_beta[i], s.mus_amin[i], s.mus_lm_min[i], 1.0 / s.mus_lts[i],
-                                s.mus_vmax[i] * s.mus_lopt[i], 1.0 / s.mus_tact[i], 1.0 / s.mus_tdeact[i], 0.0};
-        for (int c = 0; c < 12; c++) pr.mus_k[i][c] = (T)k12[c];
-    }
-    for (int sp = 0; sp < s.n_spheres; sp++) {
-        const double k12[12] = {s.sph_loc[sp][0], s.sph_loc[sp][1], s.sph_loc[sp][2] + (double)d.body_z[s.sph_body[sp]], s.sph_radius[sp],
-                                s.sph_k[sp], 1.5 * s.sph_c[sp], s.sph_ud[sp], 2.0 * (s.sph_us[sp] - s.sph_ud[sp]),
-                                s.sph_uv[sp], s.sph_vt[sp], 1.0 / s.sph_vt[sp], 0.0};
-        for (int c = 0; c < 12; c++) pr.sph_k[sp][c] = (T)k12[c];
-    }
-    for (int l = 0; l < s.n_limits; l++) {
-        const double k8[8] = {s.lim_qup[l], s.lim_qlo[l], s.lim_kup[l], s.lim_klo[l], s.lim_damp[l], 1.0 / s.lim_w[l], s.lim_w[l], 0.0};
-        for (int c = 0; c < 8; c++) pr.lim_k[l][c] = (T)k8[c];
-    }
     pr.sph_src0 = n_src;
     for (int sp = 0; sp < s.n_spheres; sp++) { if (n_src >= P2_MAXSRC) return; src_body[n_src++] = s.sph_body[sp]; }
     pr.n_src = n_src;

@@ -20,6 +20,8 @@ run MuscleWalkingImitation3D-v0 8192 100
 run MusclePalsyImitation3D-v0 131072 20
 run MuscleLockedKneeImitation3D-v0 131072 20
 run TorqueWalkingImitation3D-v0 16384 100
+# fp64 build of the default workload (roofline against the DFMA chain measured in the same run)
+python bench.py --no-cpu-baseline --dtype float64 --steps 50 --warmup 10 > gpurun_out/bench_fp64.json 2> gpurun_out/bench_fp64.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:bio_coop_step_kernel -s 10 -c 1 -f -o gpurun_out/prof \
