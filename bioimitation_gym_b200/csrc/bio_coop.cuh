@@ -87,8 +87,13 @@ static_assert(sizeof(WorkReadout<double, CoopCls<1>>) <= 128 * sizeof(double), "
 template <typename T>
 struct WorkSources { alignas(16) T w[P2_MAXSRC][4]; };                                                 // planar program
 #define COOP_MAXSRC6 48      // wrench sources of a 3D model (one per body a muscle touches; the reference's models: 46)
+// general evaluation: moment about O and the x force [a: n0 n1 n2 f0], y / z force [b: f1 f2] -- two arrays of
+// 16- and 8-byte records instead of one of 32 bytes: a quarter fewer shared-memory bytes per source on both sides
+// (the 3D kernels keep the shared-memory pipe 72 % busy), and the muscle lanes, which store records 2..3 sources
+// apart, spread over the banks (ncu: 44 wavefronts per evaluation for the six 16-byte stores of 22 lanes with the
+// 32-byte records, 18 would do)
 template <typename T>
-struct WorkSources6 { alignas(16) T w[COOP_MAXSRC6][8]; };   // general evaluation: moment about O [0..2], force [3..5]
+struct WorkSources6 { alignas(16) T a[COOP_MAXSRC6][4]; alignas(16) T b[COOP_MAXSRC6][2]; };
 
 // Size class 0 (half-warp per env) runs the planar program only, so its buffer holds no arrays of the
 // general evaluation; class 1 (warp per env) keeps both.
@@ -466,9 +471,8 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
 #pragma unroll
             for (int sl = 0; sl < P2_MAXSLOT; sl++) {
                 if (sl < ns) {
-                    T* w = E.x.src6.w[s0 + sl];
-                    st4(w, tension * Wv[sl][0], tension * Wv[sl][1], tension * Wv[sl][2], tension * Wv[sl][3]);
-                    st4(w + 4, tension * Wv[sl][4], tension * Wv[sl][5], T(0), T(0));
+                    st4(E.x.src6.a[s0 + sl], tension * Wv[sl][0], tension * Wv[sl][1], tension * Wv[sl][2], tension * Wv[sl][3]);
+                    st2(E.x.src6.b[s0 + sl], tension * Wv[sl][4], tension * Wv[sl][5]);
                 }
             }
             if (mov >= 0) K.mq[mov] = tension * mqu;
@@ -541,10 +545,10 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         const int gb = lane / PARTS, part = lane % PARTS;
         if (gb < EV_NB) {
             for (int k = m.prog.inc_begin[gb] + part; k < m.prog.inc_begin[gb + 1]; k += PARTS) {
-                T w0, w1, w2, w3, w4, w5, w6, w7;
-                const T* w = E.x.src6.w[m.prog.inc_src[k]];
-                ld4(w, w0, w1, w2, w3);
-                ld4(w + 4, w4, w5, w6, w7);
+                T w0, w1, w2, w3, w4, w5;
+                const int e = m.prog.inc_src[k];
+                ld4(E.x.src6.a[e], w0, w1, w2, w3);
+                ld2(E.x.src6.b[e], w4, w5);
                 Wn[0] += w0; Wn[1] += w1; Wn[2] += w2; Wf[0] += w3; Wf[1] += w4; Wf[2] += w5;
             }
         }

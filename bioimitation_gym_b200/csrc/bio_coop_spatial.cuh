@@ -247,10 +247,10 @@ __device__ __forceinline__ void p3_phase_e(const DevModel<T>& m, EnvWork<T, CLS>
     if (live) {
         if (ldv(m.n_muscles) > 0) {
             for (int k = pr.inc_begin[b] + part; k < pr.inc_begin[b + 1]; k += 4) {
-                T w0, w1, w2, w3, w4, w5, w6, w7;
-                const T* w = E.x.src6.w[pr.inc_src[k]];
-                ld4(w, w0, w1, w2, w3);
-                ld4(w + 4, w4, w5, w6, w7);
+                T w0, w1, w2, w3, w4, w5;
+                const int e = pr.inc_src[k];
+                ld4(E.x.src6.a[e], w0, w1, w2, w3);
+                ld2(E.x.src6.b[e], w4, w5);
                 Wn0 += w0; Wn1 += w1; Wn2 += w2; Wf0 += w3; Wf1 += w4; Wf2 += w5;
             }
         }
