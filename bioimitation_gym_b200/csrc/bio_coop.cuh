@@ -26,7 +26,11 @@ template <> struct CoopCls<1> { enum { G = 32, ND = 16, NM = 24, NP = 80, NAX = 
 // storage (a warp of the 3D kernels owns 6.1 KB, so that 28 warps fit one SM next to the model block).
 template <typename T, typename C>
 struct WorkGeneral {
-    T R[BIO_MAX_BODIES][9], r[BIO_MAX_BODIES][3], V[BIO_MAX_BODIES][6], A[BIO_MAX_BODIES][6];
+    // pose of every body: row i of the rotation with component i of the position about O in its fourth column
+    // (three 16-byte reads per use instead of twelve scalar ones: the lanes of a phase share a few bodies, so a
+    // 16-byte read of 22 lanes is one or two shared-memory wavefronts where the scalar reads were twelve)
+    alignas(16) T Rr[BIO_MAX_BODIES][12];
+    T V[BIO_MAX_BODIES][6], A[BIO_MAX_BODIES][6];
     alignas(16) T S[C::ND][8];                     // motion vector of every dof, [6..7] unused (16-byte reads)
     union {
         struct {
@@ -163,6 +167,22 @@ static_assert(sizeof(EnvWork<float, 0>) == EnvWorkSize<float, 0>::want && sizeof
 // VOTE/branch sequence in front of every shuffle group.  Shuffles stay inside the env through their width;
 // ballots are cut to the env's lanes by group_ballot.
 template <int G> __device__ __forceinline__ unsigned group_mask() { return 0xffffffffu; }
+
+// pose helpers (WorkGeneral::Rr)
+template <typename T> __device__ __forceinline__ void pose_load(const T* Rr, T* R, T* r) {
+    ld4(Rr, R[0], R[1], R[2], r[0]); ld4(Rr + 4, R[3], R[4], R[5], r[1]); ld4(Rr + 8, R[6], R[7], R[8], r[2]);
+}
+template <typename T> __device__ __forceinline__ void pose_store(T* Rr, const T* R, const T* r) {
+    st4(Rr, R[0], R[1], R[2], r[0]); st4(Rr + 4, R[3], R[4], R[5], r[1]); st4(Rr + 8, R[6], R[7], R[8], r[2]);
+}
+// R loc + r: a point of the body in ground axes about O
+template <typename T> __device__ __forceinline__ void pose_point(const T* Rr, const T* loc, T* x) {
+    T R[9], r[3];
+    pose_load(Rr, R, r);
+    x[0] = R[0] * loc[0] + R[1] * loc[1] + R[2] * loc[2] + r[0];
+    x[1] = R[3] * loc[0] + R[4] * loc[1] + R[5] * loc[2] + r[1];
+    x[2] = R[6] * loc[0] + R[7] * loc[1] + R[8] * loc[2] + r[2];
+}
 template <int G> __device__ __forceinline__ void gsync() { __syncwarp(); }
 template <int G> __device__ __forceinline__ unsigned group_ballot(bool pred) {
     const unsigned b = __ballot_sync(0xffffffffu, pred);
@@ -253,9 +273,10 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             const int b = m.level_body[lb], p = m.body_parent[b];
             T Rp[9], R[9], r[3], V[6], A[6];
             if (p >= 0) {
-                for (int c = 0; c < 9; c++) Rp[c] = K.R[p][c];
+                T rp[3];
+                pose_load(K.Rr[p], Rp, rp);
                 matvec3(Rp, m.body_joint_loc[b], r);
-                for (int c = 0; c < 3; c++) r[c] += K.r[p][c];
+                for (int c = 0; c < 3; c++) r[c] += rp[c];
                 for (int c = 0; c < 6; c++) { V[c] = K.V[p][c]; A[c] = K.A[p][c]; }
             } else {
                 Rp[0] = T(1); Rp[1] = T(0); Rp[2] = T(0); Rp[3] = T(0); Rp[4] = T(1); Rp[5] = T(0);
@@ -330,8 +351,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             }
             if (dprev >= 0) for (int c = 0; c < 6; c++) K.S[dprev][c] = Sd[c];
             if (root_open) { for (int c = 0; c < 3; c++) { E.O[c] = r[c]; r[c] = T(0); } }
-            for (int c = 0; c < 9; c++) K.R[b][c] = R[c];
-            for (int c = 0; c < 3; c++) K.r[b][c] = r[c];
+            pose_store(K.Rr[b], R, r);
             for (int c = 0; c < 6; c++) { K.V[b][c] = V[c]; K.A[b][c] = A[c]; }
         }
         gsync<G>();
@@ -377,19 +397,20 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
                 const int p = (seg >> (8 * e)) & 255u;
                 const int info = pr.pt_info[p];
                 const int b = info & 15;
-                T loc[3];
+                T loc[3], Rb[9], rb[3];
+                pose_load(K.Rr[b], Rb, rb);
                 mv2[e] = ((info >> 4) & 3) == BIO_PT_MOVING;
                 if (mv2[e]) {
                     mov = (info >> 13) & 7;
                     T dl[3];
                     for (int c = 0; c < 3; c++) { loc[c] = K.mv[mov][c]; dl[c] = K.mv[mov][3 + c]; }
-                    matvec3(K.R[b], dl, mdw);
+                    matvec3(Rb, dl, mdw);
                 } else {
                     T l3;
                     ld4(pr.pt_xyz[p], loc[0], loc[1], loc[2], l3);
                 }
-                matvec3(K.R[b], loc, xe[e]);
-                for (int c = 0; c < 3; c++) xe[e][c] += K.r[b][c];
+                matvec3(Rb, loc, xe[e]);
+                for (int c = 0; c < 3; c++) xe[e][c] += rb[c];
                 slot2[e] = (info >> 11) & 3;
             }
             const T dx = xe[1][0] - xe[0][0], dy = xe[1][1] - xe[0][1], dz = xe[1][2] - xe[0][2];
@@ -487,8 +508,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         ld4(m.prog.sph_k[s] + 4, kk, c15, ud, us2);
         ld4(m.prog.sph_k[s] + 8, uv, vt, inv_vt, k11);
         T xc[3];
-        matvec3(K.R[b], loc, xc);
-        for (int c = 0; c < 3; c++) xc[c] += K.r[b][c];
+        pose_point(K.Rr[b], loc, xc);
         const T depth = rad - (xc[1] + E.O[1]);
         T F[3] = {T(0), T(0), T(0)}, D0 = T(0), D1 = T(0);
         T p[3] = {xc[0], T(-0.5) * depth - E.O[1], xc[2]};
@@ -579,15 +599,14 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         if (ext_pt >= 0 && m.obs_body[ext_pt] == b) {
             T x[3], n[3];
             const T fx[3] = {EV_EXT_FX, T(0), T(0)};
-            matvec3(K.R[b], m.obs_loc[ext_pt], x);
-            for (int c = 0; c < 3; c++) x[c] += K.r[b][c];
+            pose_point(K.Rr[b], m.obs_loc[ext_pt], x);
             cross3(x, fx, n);
             for (int c = 0; c < 3; c++) { Wn[c] += n[c]; Wf[c] += fx[c]; }
         }
-        T cpos[3];
-        matvec3(K.R[b], m.body_com[b], cpos);
-        for (int c = 0; c < 3; c++) cpos[c] += K.r[b][c];
-        const T* R = K.R[b];
+        T cpos[3], R[9], rb[3];
+        pose_load(K.Rr[b], R, rb);
+        matvec3(R, m.body_com[b], cpos);
+        for (int c = 0; c < 3; c++) cpos[c] += rb[c];
         const T* i6 = m.body_inertia[b];
         T t[9];
         for (int r_ = 0; r_ < 3; r_++) {
@@ -655,15 +674,13 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         if (lane < nb) {
             const int b = lane;
             T cpos[3], vc[3];
-            matvec3(K.R[b], m.body_com[b], cpos);
-            for (int c = 0; c < 3; c++) cpos[c] += K.r[b][c];
+            pose_point(K.Rr[b], m.body_com[b], cpos);
             cross3(K.V[b], cpos, vc);
             for (int c = 0; c < 3; c++) { E.x.out.comp[b][c] = m.body_mass[b] * cpos[c]; E.x.out.comp[b][3 + c] = m.body_mass[b] * (vc[c] + K.V[b][3 + c]); }
         } else if (lane - nb < m.n_obspts) {
             const int p = lane - nb, b = m.obs_body[p];
             T x[3], v[3];
-            matvec3(K.R[b], m.obs_loc[p], x);
-            for (int c = 0; c < 3; c++) x[c] += K.r[b][c];
+            pose_point(K.Rr[b], m.obs_loc[p], x);
             cross3(K.V[b], x, v);
             for (int c = 0; c < 3; c++) { E.x.out.obs_pos[p][c] = x[c] + E.O[c]; E.x.out.obs_vel[p][c] = v[c] + K.V[b][3 + c]; }
         }

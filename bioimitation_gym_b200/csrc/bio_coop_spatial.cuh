@@ -163,12 +163,10 @@ __device__ __forceinline__ void p3_phase_b_scan(const DevModel<T>& m, EnvWork<T,
             const int b = (code >> 8) & 15;
             const T xx = qx * qx, yy = qy * qy, zz = qz * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz;
             const T wx = qw * qx, wy = qw * qy, wz = qw * qz;
-            T* R = K.R[b];
-            R[0] = T(1) - T(2) * (yy + zz); R[1] = T(2) * (xy - wz); R[2] = T(2) * (xz + wy);
-            R[3] = T(2) * (xy + wz); R[4] = T(1) - T(2) * (xx + zz); R[5] = T(2) * (yz - wx);
-            R[6] = T(2) * (xz - wy); R[7] = T(2) * (yz + wx); R[8] = T(1) - T(2) * (xx + yy);
-#pragma unroll
-            for (int c = 0; c < 3; c++) K.r[b][c] = r[c];
+            T* R = K.Rr[b];                        // rows of the rotation, position in the fourth column
+            st4(R, T(1) - T(2) * (yy + zz), T(2) * (xy - wz), T(2) * (xz + wy), r[0]);
+            st4(R + 4, T(2) * (xy + wz), T(1) - T(2) * (xx + zz), T(2) * (yz - wx), r[1]);
+            st4(R + 8, T(2) * (xz - wy), T(2) * (yz + wx), T(1) - T(2) * (xx + yy), r[2]);
 #pragma unroll
             for (int c = 0; c < 6; c++) { K.V[b][c] = V[c]; K.A[b][c] = A[c]; }
         }
@@ -265,8 +263,7 @@ __device__ __forceinline__ void p3_phase_e(const DevModel<T>& m, EnvWork<T, CLS>
         if (part == 3 && ext_pt >= 0 && m.obs_body[ext_pt] == b) {
             T x[3], n[3];
             const T fx[3] = {ldv(E.ev.fx), T(0), T(0)};
-            matvec3(K.R[b], m.obs_loc[ext_pt], x);
-            for (int c = 0; c < 3; c++) x[c] += K.r[b][c];
+            pose_point(K.Rr[b], m.obs_loc[ext_pt], x);
             cross3(x, fx, n);
             Wn0 += n[0]; Wn1 += n[1]; Wn2 += n[2]; Wf0 += fx[0];
         }
@@ -278,14 +275,14 @@ __device__ __forceinline__ void p3_phase_e(const DevModel<T>& m, EnvWork<T, CLS>
     {
         const int p = part < 3 ? part : 0;
         const T ux = p == 0 ? T(1) : T(0), uy = p == 1 ? T(1) : T(0), uz = p == 2 ? T(1) : T(0);
-        const T* R = K.R[b];
-        const T R0 = R[0], R1 = R[1], R2 = R[2], R3 = R[3], R4 = R[4], R5 = R[5], R6 = R[6], R7 = R[7], R8 = R[8];
-        const T r0 = R[3 * p], r1 = R[3 * p + 1], r2 = R[3 * p + 2];
+        T R0, R1, R2, R3, R4, R5, R6, R7, R8, q0, q1, q2, r0, r1, r2, qp;
+        ld4(K.Rr[b], R0, R1, R2, q0); ld4(K.Rr[b] + 4, R3, R4, R5, q1); ld4(K.Rr[b] + 8, R6, R7, R8, q2);
+        ld4(K.Rr[b] + 4 * p, r0, r1, r2, qp);        // row p of the pose
         const T cm0 = m.body_com[b][0], cm1 = m.body_com[b][1], cm2 = m.body_com[b][2];
-        const T cx = R0 * cm0 + R1 * cm1 + R2 * cm2 + K.r[b][0];
-        const T cy = R3 * cm0 + R4 * cm1 + R5 * cm2 + K.r[b][1];
-        const T cz = R6 * cm0 + R7 * cm1 + R8 * cm2 + K.r[b][2];
-        const T cp = r0 * cm0 + r1 * cm1 + r2 * cm2 + K.r[b][p];
+        const T cx = R0 * cm0 + R1 * cm1 + R2 * cm2 + q0;
+        const T cy = R3 * cm0 + R4 * cm1 + R5 * cm2 + q1;
+        const T cz = R6 * cm0 + R7 * cm1 + R8 * cm2 + q2;
+        const T cp = r0 * cm0 + r1 * cm1 + r2 * cm2 + qp;
         const T mb = m.body_mass[b], mcc = mb * (cx * cx + cy * cy + cz * cz), mcp = mb * cp;
         const T* i6 = m.body_inertia[b];
         const T i0 = i6[0], i1 = i6[1], i2 = i6[2], i3 = i6[3], i4 = i6[4], i5 = i6[5];
