@@ -30,7 +30,8 @@ struct WorkGeneral {
     // (three 16-byte reads per use instead of twelve scalar ones: the lanes of a phase share a few bodies, so a
     // 16-byte read of 22 lanes is one or two shared-memory wavefronts where the scalar reads were twelve)
     alignas(16) T Rr[BIO_MAX_BODIES][12];
-    T V[BIO_MAX_BODIES][6], A[BIO_MAX_BODIES][6];
+    // spatial velocity [0..5] and bias acceleration [6..11] of every body (about O, ground axes), 16-byte rows
+    alignas(16) T VA[BIO_MAX_BODIES][12];
     alignas(16) T S[C::ND][8];                     // motion vector of every dof, [6..7] unused (16-byte reads)
     union {
         struct {
@@ -277,7 +278,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
                 pose_load(K.Rr[p], Rp, rp);
                 matvec3(Rp, m.body_joint_loc[b], r);
                 for (int c = 0; c < 3; c++) r[c] += rp[c];
-                for (int c = 0; c < 6; c++) { V[c] = K.V[p][c]; A[c] = K.A[p][c]; }
+                for (int c = 0; c < 6; c++) { V[c] = K.VA[p][c]; A[c] = K.VA[p][6 + c]; }
             } else {
                 Rp[0] = T(1); Rp[1] = T(0); Rp[2] = T(0); Rp[3] = T(0); Rp[4] = T(1); Rp[5] = T(0);
                 Rp[6] = T(0); Rp[7] = T(0); Rp[8] = T(1);
@@ -352,7 +353,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             if (dprev >= 0) for (int c = 0; c < 6; c++) K.S[dprev][c] = Sd[c];
             if (root_open) { for (int c = 0; c < 3; c++) { E.O[c] = r[c]; r[c] = T(0); } }
             pose_store(K.Rr[b], R, r);
-            for (int c = 0; c < 6; c++) { K.V[b][c] = V[c]; K.A[b][c] = A[c]; }
+            for (int c = 0; c < 6; c++) { K.VA[b][c] = V[c]; K.VA[b][6 + c] = A[c]; }
         }
         gsync<G>();
     }
@@ -514,8 +515,10 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         T p[3] = {xc[0], T(-0.5) * depth - E.O[1], xc[2]};
         if (depth > T(0)) {
             T v[3];
-            cross3(K.V[b], p, v);
-            for (int c = 0; c < 3; c++) v[c] += K.V[b][3 + c];
+            T Vb[6];
+            ld4(K.VA[b], Vb[0], Vb[1], Vb[2], Vb[3]); ld2(K.VA[b] + 4, Vb[4], Vb[5]);
+            cross3(Vb, p, v);
+            for (int c = 0; c < 3; c++) v[c] += Vb[3 + c];
             const T vn = -v[1];
             const T fH = T(4.0 / 3.0) * kk * depth * Num<T>::sqrt_pos(rad * kk * depth);
             const T f = fH * (T(1) + c15 * vn);
@@ -624,7 +627,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
         I6[5] = t[3] * R[6] + t[4] * R[7] + t[5] * R[8] - mb * cpos[1] * cpos[2];
         const T hh[3] = {mb * cpos[0], mb * cpos[1], mb * cpos[2]};
         T V[6], A[6];
-        for (int c = 0; c < 6; c++) { V[c] = K.V[b][c]; A[c] = K.A[b][c]; }
+        for (int c = 0; c < 6; c++) { V[c] = K.VA[b][c]; A[c] = K.VA[b][6 + c]; }
         T IV[6], IA[6], t1[3], t2[3];
         IV[0] = I6[0] * V[0] + I6[3] * V[1] + I6[4] * V[2];
         IV[1] = I6[3] * V[0] + I6[1] * V[1] + I6[5] * V[2];
@@ -675,14 +678,14 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
             const int b = lane;
             T cpos[3], vc[3];
             pose_point(K.Rr[b], m.body_com[b], cpos);
-            cross3(K.V[b], cpos, vc);
-            for (int c = 0; c < 3; c++) { E.x.out.comp[b][c] = m.body_mass[b] * cpos[c]; E.x.out.comp[b][3 + c] = m.body_mass[b] * (vc[c] + K.V[b][3 + c]); }
+            cross3(K.VA[b], cpos, vc);
+            for (int c = 0; c < 3; c++) { E.x.out.comp[b][c] = m.body_mass[b] * cpos[c]; E.x.out.comp[b][3 + c] = m.body_mass[b] * (vc[c] + K.VA[b][3 + c]); }
         } else if (lane - nb < m.n_obspts) {
             const int p = lane - nb, b = m.obs_body[p];
             T x[3], v[3];
             pose_point(K.Rr[b], m.obs_loc[p], x);
-            cross3(K.V[b], x, v);
-            for (int c = 0; c < 3; c++) { E.x.out.obs_pos[p][c] = x[c] + E.O[c]; E.x.out.obs_vel[p][c] = v[c] + K.V[b][3 + c]; }
+            cross3(K.VA[b], x, v);
+            for (int c = 0; c < 3; c++) { E.x.out.obs_pos[p][c] = x[c] + E.O[c]; E.x.out.obs_vel[p][c] = v[c] + K.VA[b][3 + c]; }
         }
         gsync<G>();
         if (lane < 3) {

@@ -9,7 +9,7 @@
 //   velocity      sum of (motion vector * rate), spatial 6-vectors about O in ground axes
 //   bias accel.   sum of motion vector * d2s/dq2 q'^2 + (velocity before the step) x (motion vector) * rate
 // 4 shuffle rounds per prefix instead of a level-by-level walk with a barrier per tree level.  Results
-// go to the arrays of the general evaluation (K.R, K.r, K.V, K.A, K.S, E.O), so the other phases of
+// go to the arrays of the general evaluation (K.Rr, K.VA, K.S, E.O), so the other phases of
 // coop_eval are unchanged.  Used when the host found the root-plus-chains shape (PlanarProg::chain_ok).
 #pragma once
 
@@ -155,8 +155,7 @@ __device__ __forceinline__ void p3_phase_b_scan(const DevModel<T>& m, EnvWork<T,
     if (live) {
         if (code & P2_F_SPUB) {
             const int d = (code >> 12) & 31;
-#pragma unroll
-            for (int c = 0; c < 6; c++) K.S[d][c] = Sd[c];
+            st4(K.S[d], Sd[0], Sd[1], Sd[2], Sd[3]); st2(K.S[d] + 4, Sd[4], Sd[5]);
         }
         if (i == o_step) { E.O[0] = o[0]; E.O[1] = o[1]; E.O[2] = o[2]; }
         if (code & P2_F_LAST) {
@@ -167,8 +166,8 @@ __device__ __forceinline__ void p3_phase_b_scan(const DevModel<T>& m, EnvWork<T,
             st4(R, T(1) - T(2) * (yy + zz), T(2) * (xy - wz), T(2) * (xz + wy), r[0]);
             st4(R + 4, T(2) * (xy + wz), T(1) - T(2) * (xx + zz), T(2) * (yz - wx), r[1]);
             st4(R + 8, T(2) * (xz - wy), T(2) * (yz + wx), T(1) - T(2) * (xx + yy), r[2]);
-#pragma unroll
-            for (int c = 0; c < 6; c++) { K.V[b][c] = V[c]; K.A[b][c] = A[c]; }
+            st4(K.VA[b], V[0], V[1], V[2], V[3]); st4(K.VA[b] + 4, V[4], V[5], A[0], A[1]);
+            st4(K.VA[b] + 8, A[2], A[3], A[4], A[5]);
         }
     }
 }
@@ -293,8 +292,8 @@ __device__ __forceinline__ void p3_phase_e(const DevModel<T>& m, EnvWork<T, CLS>
         const T Ig2 = t0 * R6 + t1 * R7 + t2 * R8 - mcp * cz + uz * mcc;
         const T hx = mb * cx, hy = mb * cy, hz = mb * cz;
         const T g0 = uy * hz - uz * hy, g1 = uz * hx - ux * hz, g2 = ux * hy - uy * hx;      // e_p x h
-        const T V0 = K.V[b][0], V1 = K.V[b][1], V2 = K.V[b][2], V3 = K.V[b][3], V4 = K.V[b][4], V5 = K.V[b][5];
-        const T A0 = K.A[b][0], A1 = K.A[b][1], A2 = K.A[b][2], A3 = K.A[b][3], A4 = K.A[b][4], A5 = K.A[b][5];
+        T V0, V1, V2, V3, V4, V5, A0, A1, A2, A3, A4, A5;
+        ld4(K.VA[b], V0, V1, V2, V3); ld4(K.VA[b] + 4, V4, V5, A0, A1); ld4(K.VA[b] + 8, A2, A3, A4, A5);
         // component p of I V and I A: angular Ig . w + (h x v)_p, linear m v_p - (h x w)_p
         const T IVn = Ig0 * V0 + Ig1 * V1 + Ig2 * V2 + (g0 * V3 + g1 * V4 + g2 * V5);
         const T IVf = mb * (ux * V3 + uy * V4 + uz * V5) - (g0 * V0 + g1 * V1 + g2 * V2);
@@ -447,16 +446,15 @@ __device__ __forceinline__ void p3_aba(const DevModel<T>& m, EnvWork<T, CLS>& E,
         T* g = K.BIc[pr.root_body];
         st2(g + cc * 6, col[0], col[1]); st2(g + cc * 6 + 2, col[2], col[3]); st2(g + cc * 6 + 4, col[4], col[5]);
         __syncwarp();
+        // (16-byte reads of the 42 words; the root is body 0, its block starts on a 16-byte boundary; u_ = unused rows
+        // 3..5 of the first three columns, the transpose of B)
         T A00, A10, A20, A01, A11, A21, A02, A12, A22;              // A[i][j] = column j, row i
-        ld2(g, A00, A10); A20 = g[2];
-        ld2(g + 6, A01, A11); A21 = g[8];
-        ld2(g + 12, A02, A12); A22 = g[14];
         T B00, B10, B20, M00, M10, M20, B01, B11, B21, M01, M11, M21, B02, B12, B22, M02, M12, M22;
-        ld2(g + 18, B00, B10); ld2(g + 20, B20, M00); ld2(g + 22, M10, M20);      // column 3: B[:,0], M[:,0]
-        ld2(g + 24, B01, B11); ld2(g + 26, B21, M01); ld2(g + 28, M11, M21);      // column 4
-        ld2(g + 30, B02, B12); ld2(g + 32, B22, M02); ld2(g + 34, M12, M22);      // column 5
-        T n0, n1, n2, f0, f1, f2;
-        ld2(g + 36, n0, n1); ld2(g + 38, n2, f0); ld2(g + 40, f1, f2);
+        T n0, n1, n2, f0, f1, f2, u0_, u1_, u2_;
+        ld4(g, A00, A10, A20, u0_); ld4(g + 4, u1_, u2_, A01, A11); ld4(g + 8, A21, u0_, u1_, u2_);
+        ld4(g + 12, A02, A12, A22, u0_); ld4(g + 16, u1_, u2_, B00, B10); ld4(g + 20, B20, M00, M10, M20);
+        ld4(g + 24, B01, B11, B21, M01); ld4(g + 28, M11, M21, B02, B12); ld4(g + 32, B22, M02, M12, M22);
+        ld4(g + 36, n0, n1, n2, f0); ld2(g + 40, f1, f2);
         // Minv = M^-1 (symmetric, cofactors)
         T c00 = M11 * M22 - M12 * M12, c01 = M02 * M12 - M01 * M22, c02 = M01 * M12 - M02 * M11;
         T c11 = M00 * M22 - M02 * M02, c12 = M01 * M02 - M00 * M12, c22 = M00 * M11 - M01 * M01;
