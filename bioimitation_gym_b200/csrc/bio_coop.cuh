@@ -218,7 +218,7 @@ namespace bio {
 // controls in E.ctrl).  Results: E.udot, E.adot, E.lmdot and, when full, the
 // read-outs for obs / reward / done.  All G lanes of the env must call this.
 // ---------------------------------------------------------------------------
-template <typename T, int CLS>
+template <typename T, int CLS, bool FAST>
 __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
     typedef CoopCls<CLS> C;
     constexpr int G = C::G;
@@ -243,10 +243,15 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     // ---- phase A: joint functions of the coordinates, and the location functions of moving path
     // points (task n_axes + 3 k + c: component c of moving point k); the spline interval of the
     // previous evaluation is the search hint ----
+    // (FAST: the instantiation for models that take the packed phase A, the kinematics scan, the three-lane phase E
+    // and the articulated-body pass -- every shipped 3D model -- holds nothing else: the hot loop's text shrinks from
+    // ~100 KB with the other paths' code in between to what it executes; ncu had 16 % of the instruction-cache
+    // requests missing and 0.8 no-instruction stall cycles per issued instruction)
     bool a_done = false;
     if constexpr (G == 32) {
-        if (ldv(m.prog.atask_ok) != 0) { p3_phase_a<T, CLS>(m, E, lane); a_done = true; }
+        if (FAST || ldv(m.prog.atask_ok) != 0) { p3_phase_a<T, CLS>(m, E, lane); a_done = true; }
     }
+    if constexpr (!FAST)
     if (!a_done)
     for (int a = lane; a < m.n_axes + 3 * m.n_moving; a += G) {
         T s, ds, dds;
@@ -264,10 +269,11 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
 
     // ---- phase B: kinematics; root-plus-chains models on a full warp: prefix scans over the steps of
     // every chain (bio_coop_spatial.cuh), else one tree level at a time, lane = body of the level ----
-    if (G == 32 && m.prog.chain_ok) {
+    if (FAST || (G == 32 && m.prog.chain_ok)) {
         if constexpr (G == 32) p3_phase_b_scan<T, CLS>(m, E, lane);
         gsync<G>();
     } else
+    if constexpr (!FAST)
     for (int lev = 0; lev < m.n_levels; lev++) {
         const int lb = m.level_begin[lev] + lane;
         if (lb < m.level_begin[lev + 1]) {
@@ -557,8 +563,9 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
     // (p3_phase_e, bio_coop_spatial.cuh).  Else: lane = body (wrench gather, inertia, body force) | dof ----
     bool e_done = false;
     if constexpr (G == 32) {
-        if (EV_ABA) { p3_phase_e<T, CLS>(m, E, lane); e_done = true; }
+        if (FAST || EV_ABA) { p3_phase_e<T, CLS, FAST>(m, E, lane); e_done = true; }
     }
+    if constexpr (!FAST)
     if (!e_done) {
     // wrench of the path points on every body: on a full warp four lanes share the point list of a
     // body (the pelvis carries a third of all points), quad butterfly, then the body lane fetches the sum
@@ -714,8 +721,9 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
 
     // ---- root-plus-chains models on a full warp: articulated-body pass (bio_coop_spatial.cuh) ----
     if constexpr (G == 32) {
-        if (EV_ABA) { p3_aba<T, CLS>(m, E, lane, EV_H_IMP); return; }
+        if (FAST || EV_ABA) { p3_aba<T, CLS>(m, E, lane, EV_H_IMP); return; }
     }
+    if constexpr (!FAST) {
 
     // ---- phase F: composite inertias / subtree forces.  Root-plus-chains models on a full warp: lane =
     // (chain, value) runs the suffix sum down its chain, then 16 lanes add the chain heads to the root;
@@ -805,6 +813,7 @@ __device__ __noinline__ void coop_eval(const DevModel<T>& m, EnvWork<T, CLS>& E,
 
     // ---- phase H: sparse L^T D L along the tree + solve (bio_coop_planar.cuh) ----
     coop_solve<T, CLS>(m, E, lane);
+    }   // !FAST
 }
 #undef EV_NB
 #undef EV_ND
@@ -829,7 +838,8 @@ __device__ __forceinline__ void coop_eval_any(const DevModel<T>& m, EnvWork<T, C
         E.ev.fx = ext_fx; E.ev.himp = h_imp;
         E.ev.flags = (newton_iters & 255) | ((ext_pt + 1) << 8) | ((full ? 1 : 0) << 16) | (sub_next << 24);
         if (m.prog.ok) coop_eval_planar<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
-        else coop_eval<T, CLS>(m, E, lane);
+        else if ((ldv(m.prog.aba_ok) & 2) != 0) coop_eval<T, CLS, true>(m, E, lane);     // see coop_eval: FAST
+        else coop_eval<T, CLS, false>(m, E, lane);
     }
 }
 

@@ -233,7 +233,7 @@ __device__ __forceinline__ void p3_phase_a(const DevModel<T>& m, EnvWork<T, CLS>
 // generalized force and limit damping next to the motion vector.  (7 busy lanes -> 21; ncu: phase E was 11 % of the
 // instructions at 13 threads per instruction.)
 // ---------------------------------------------------------------------------
-template <typename T, int CLS>
+template <typename T, int CLS, bool FAST = false>
 __device__ __forceinline__ void p3_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
     const PlanarProg<T>& pr = m.prog;
     auto& K = E.k.g;
@@ -317,7 +317,7 @@ __device__ __forceinline__ void p3_phase_e(const DevModel<T>& m, EnvWork<T, CLS>
     if (lane < ldv(m.n_dof)) {
         const int d = lane;
         T qf = T(0), ld = T(0);
-        if (m.gdof_ok) {
+        if (FAST || m.gdof_ok) {
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 const int l = m.gdof_lim[d][j], pt = m.gdof_movpt[d][j];

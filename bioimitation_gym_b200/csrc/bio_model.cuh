@@ -795,6 +795,9 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
         { const char* z = getenv("BIO_NO_ABA"); if (z && z[0] == '1') ok = false; }   // tests: joint-space L^T D L instead
         pr.aba_nsteps = nmax; pr.aba_nroot = nroot > 8 ? 8 : nroot; pr.aba_ok = ok ? 1 : 0;
         pr.atask_ok = (build_atasks(false) && n_mov == d.n_moving) ? 1 : 0;   // packed phase-A tasks (p3_phase_a)
+        // bit 1 of aba_ok: the model takes the packed phase A, the scan, the three-lane phase E with the host's dof
+        // lists and the articulated-body pass -- coop_eval's FAST instantiation (BIO_NO_FAST3D=1: the general one)
+        if (pr.aba_ok && pr.atask_ok && pr.chain_ok && d.gdof_ok && !getenv("BIO_NO_FAST3D")) pr.aba_ok |= 2;
         {   // free root joint: translations along +x, +y, +z of the ground (unit rate) before three rotations (unit rate)
             bool fr = ok && s.body_axis_count[0] == 6 && nroot == 6 && d.gdof_ok;
             int dt[3] = {-1, -1, -1}, drot[3] = {-1, -1, -1};
