@@ -832,7 +832,8 @@ __device__ __forceinline__ void coop_eval_any(const DevModel<T>& m, EnvWork<T, C
                                               const int newton_iters, const T ext_fx, const int ext_pt, const T h_imp,
                                               const bool full, const int sub_next = 0) {
     if constexpr (CLS == 0) {
-        coop_eval_planar<T, CLS>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
+        if ((m.prog.coop_aba & 2) != 0) coop_eval_planar<T, CLS, true>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
+        else coop_eval_planar<T, CLS, false>(m, E, lane, newton_iters, ext_fx, ext_pt, h_imp, full);
     } else {
         // every lane stores the same words, so no barrier is needed before a lane reads them back
         E.ev.fx = ext_fx; E.ev.himp = h_imp;

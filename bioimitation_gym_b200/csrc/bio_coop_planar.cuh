@@ -289,7 +289,7 @@ __device__ __forceinline__ void p2_phase_b_scan(const DevModel<T>& m, EnvWork<T,
 }
 
 // ---- phase C: lane = muscle ----
-template <typename T, int CLS>
+template <typename T, int CLS, bool FAST = false>
 BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane, const int newton_iters,
                         const T h_imp, const bool full) {
     const PlanarProg<T>& pr = m.prog;
@@ -306,7 +306,7 @@ BIO_DEV void p2_phase_c(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     T mdx = T(0), mdy = T(0), mdz = T(0);        // moving point: d(location)/dq in ground axes
     T mqu = T(0);                                // and (e_out - e_in) . d(location)/dq
     int mov = -1;
-    if (pr.path_ok) {
+    if (FAST || pr.path_ok) {
         // compiled path: variant from the muscle's conditional points, constant length of the variant, then
         // its live segments (same count on every lane: no divergence between muscles)
         int var = 0;
@@ -545,7 +545,7 @@ BIO_DEV void p2_phase_d(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
 // inertia about O and force (inertial - applied); the contact damping of its active spheres,
 // h J^T D J with J = [[-py, 1, 0], [px, 0, 1]], is part of the inertia.
 // lane n_bodies + d: generalized force on dof d from limits, moving path points and actuators ----
-template <typename T, int CLS>
+template <typename T, int CLS, bool FAST = false>
 BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane, const T h_imp, const T ext_fx,
                         const int ext_pt) {
     const PlanarProg<T>& pr = m.prog;
@@ -553,7 +553,7 @@ BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
     if (lane < m.n_bodies) {
         const int b = lane;
         T Wn = T(0), Wx = T(0), Wy = T(0);
-        if (pr.inc8_ok) {
+        if (FAST || pr.inc8_ok) {
             // source indices of the body in 8 bytes: the (<= 8) loads below are issued together
             const uint32_t p0 = pr.inc_pk[b][0], p1 = pr.inc_pk[b][1];
 #pragma unroll
@@ -597,7 +597,7 @@ BIO_DEV void p2_phase_e(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
         const T ffx = IAx - w * py - Wx;
         const T ffy = IAy + w * px - Wy;
         if (h_imp > T(0)) {
-            if (pr.inc8_ok) {                    // spheres of the body in 4 bytes (zero terms for a sphere out of contact)
+            if (FAST || pr.inc8_ok) {            // spheres of the body in 4 bytes (zero terms for a sphere out of contact)
                 const uint32_t sp4 = pr.sph_pk[b];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -781,7 +781,7 @@ BIO_DEV void p2_phase_g(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane
 // column_c -= U (U_c - [c = 3] Q) / D  (I^a = I^A - U U^T / D,  p^a = p^A + U (Q - S . p^A) / D);  the coefficients
 // (U / D, -(Q - S . p^A) / D) stay in shared memory for the way back.  The two chains swap their heads by a shuffle,
 // every group adds the root body and eliminates the root's dofs, and every lane walks the accelerations back down. ----
-template <typename T, int CLS>
+template <typename T, int CLS, bool FAST = false>
 __device__ __forceinline__ void p2_aba_coop(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane) {
     constexpr int G = CoopCls<CLS>::G;
     const PlanarProg<T>& pr = m.prog;
@@ -827,7 +827,7 @@ __device__ __forceinline__ void p2_aba_coop(const DevModel<T>& m, EnvWork<T, CLS
     }
     // way back: qdd = u / D - (U / D) . a(parent), a(body) = a(parent) + S qdd
     T a0 = T(0), a1 = T(0), a2 = T(0);
-    if (pr.root_ident) {
+    if (FAST || pr.root_ident) {
         // Free planar root (translations along +x, +y of the ground, then a rotation about +z through O; no limit or
         // moving point on its dofs: PlanarProg::root_id4): its motion vectors are the unit vectors of (w, x, y), so the
         // root's acceleration solves  I^A a = Q - p^A  directly (one symmetric 3 x 3 inverse instead of three
@@ -857,7 +857,7 @@ __device__ __forceinline__ void p2_aba_coop(const DevModel<T>& m, EnvWork<T, CLS
         if (store) E.udot[d] = qdd;
         a0 += S0 * qdd; a1 += S1 * qdd; a2 += S2 * qdd;
     };
-    if (!pr.root_ident) {
+    if (!FAST && !pr.root_ident) {
 #pragma unroll
         for (int r = 0; r < 3; r++) if (rdof[r] >= 0) back(rdof[r], lane == 0);
     }
@@ -934,7 +934,10 @@ BIO_DEV void p2_readout_2(const DevModel<T>& m, EnvWork<T, CLS>& E, const int la
 #define P2_CLK(k) do { } while (0)
 #endif
 
-template <typename T, int CLS>
+// FAST: the instantiation for models that take the scan kinematics, the compiled muscle paths, the packed source
+// lists, the cooperative articulated-body pass and the direct root solve (every shipped 2D model on a half-warp);
+// it holds no other path's code, so the text of the hot loop is what the loop executes (instruction cache).
+template <typename T, int CLS, bool FAST = false>
 __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, CLS>& E, const int lane,
                                               const int newton_iters, const T ext_fx, const int ext_pt, const T h_imp,
                                               const bool full) {
@@ -948,25 +951,25 @@ __device__ __noinline__ void coop_eval_planar(const DevModel<T>& m, EnvWork<T, C
     p2_phase_a<T, CLS>(m, E, lane);
     gsync<G>();
     P2_CLK(0);
-    if (m.prog.scan_ok && G == 16) p2_phase_b_scan<T, CLS>(m, E, lane);
+    if (G == 16 && (FAST || m.prog.scan_ok)) p2_phase_b_scan<T, CLS>(m, E, lane);
     else p2_phase_b<T, CLS>(m, E, lane);
     gsync<G>();
     P2_CLK(1);
-    p2_phase_c<T, CLS>(m, E, lane, newton_iters, h_imp, full);
+    p2_phase_c<T, CLS, FAST>(m, E, lane, newton_iters, h_imp, full);
     P2_CLK(2);
     p2_phase_d<T, CLS>(m, E, lane, h_imp);
     gsync<G>();
     P2_CLK(3);
-    p2_phase_e<T, CLS>(m, E, lane, h_imp, ext_fx, ext_pt);
+    p2_phase_e<T, CLS, FAST>(m, E, lane, h_imp, ext_fx, ext_pt);
     gsync<G>();
     P2_CLK(4);
 #ifdef __CUDA_ARCH__
-    if (m.prog.coop_aba) {
-        p2_aba_coop<T, CLS>(m, E, lane);
+    if (FAST || m.prog.coop_aba) {
+        p2_aba_coop<T, CLS, FAST>(m, E, lane);
         P2_CLK(5);
     } else
 #endif
-    {
+    if constexpr (!FAST) {
         p2_phase_f<T, CLS>(m, E, lane);
         gsync<G>();
         P2_CLK(5);

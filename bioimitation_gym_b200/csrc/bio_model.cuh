@@ -991,6 +991,9 @@ void build_planar_prog(const BioModelTables& s, DevModel<T>& d) {
     pr.ok = 1;
     pr.coop_aba = 1;
     { const char* z = getenv("BIO_PLANAR_SERIAL_ABA"); if (z && z[0] == '1') pr.coop_aba = 0; }   // tests: one lane per chain
+    // bit 1 of coop_aba: coop_eval_planar's FAST instantiation (scan kinematics, compiled paths, packed source lists,
+    // cooperative pass with the direct root solve); BIO_NO_FAST2D=1: the general one
+    if (pr.coop_aba && pr.scan_ok && pr.path_ok && pr.inc8_ok && pr.root_ident && !getenv("BIO_NO_FAST2D")) pr.coop_aba |= 2;
 }
 
 // Observation layout as a descriptor per slot (same order as write_obs in
