@@ -194,6 +194,44 @@ def test_dof_by_dof_root_of_the_articulated_body_pass_fp64(env_id, monkeypatch):
     env.close()
 
 
+@pytest.mark.parametrize("env_id,var", [("MuscleWalkingImitation2D-v0", "BIO_NO_FAST2D"),
+                                        ("TorqueWalkingImitation2D-v0", "BIO_NO_FAST2D"),
+                                        ("MuscleWalkingImitation3D-v0", "BIO_NO_FAST3D"),
+                                        ("TorqueWalkingImitation3D-v0", "BIO_NO_FAST3D")])
+def test_general_instantiation_equals_the_fast_one_fp32(env_id, var, monkeypatch):
+    """coop_eval / coop_eval_planar exist twice: the FAST instantiation the shipped models take (only their own
+    path's code in the hot loop's text) and the general one (BIO_NO_FAST2D / BIO_NO_FAST3D at create time).  Same
+    arithmetic; the compiler is free to contract the two copies differently, so: one control step from identical
+    states (the general env takes the fast env's state before every step), 40 steps with auto-resets, post-step
+    states (q, u, activations, fibre lengths) and rewards within a few fp32 roundings of each other (measured: bit-identical), dones identical."""
+    import torch
+    n = 96
+    fast, _ = _mk(env_id, n, "float32")
+    monkeypatch.setenv(var, "1")
+    gen, _ = _mk(env_id, n, "float32")
+    monkeypatch.delenv(var)
+    rng = np.random.default_rng(23)
+    o0, o1 = fast.reset(), gen.reset()
+    assert torch.equal(o0, o1)
+    n_done, worst = 0, 0.0
+    for k in range(40):
+        gen.set_state(fast.get_state())
+        a = torch.as_tensor(_actions(fast, rng, n), dtype=fast.dtype, device=fast.device)
+        of, rf, df, _ = fast.step(a)
+        og, rg, dg, _ = gen.step(a)
+        assert torch.equal(df, dg), "step %d" % k
+        sf, sg = fast.get_state(), gen.get_state()
+        for key in ("q", "u", "act", "lm"):
+            if sf[key].numel():
+                worst = max(worst, float(np.max(_rel(_np(sf[key]), _np(sg[key]), 1.0))))
+        worst = max(worst, float((rf - rg).abs().max()))
+        n_done += int(df.sum())
+    print(env_id, var, "general vs FAST instantiation, fp32 per step: worst %.2e" % worst)
+    assert worst < 2e-5
+    fast.close()
+    gen.close()
+
+
 @pytest.mark.parametrize("env_id", ["MuscleWalkingImitation2D-v0", "TorqueLockedKneeImitation2D-v0"])
 def test_one_lane_per_chain_pass_of_the_planar_program_fp64(env_id, monkeypatch):
     """BIO_PLANAR_SERIAL_ABA=1: phases F and G of the planar program with one lane per chain (the form the host
