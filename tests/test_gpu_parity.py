@@ -785,6 +785,34 @@ def test_env_groups_send_recv_equal_the_single_batch():
     full.close()
 
 
+def test_set_grid_repicks_the_launch_shape():
+    """bio_set_grid: the launch shape follows the items per SM of the handle's own grid -- a quarter of a batch on a
+    quarter of the SMs is as dense as the whole batch on all of them (2048 3D envs on 148 SMs: 512 threads; on 37
+    SMs: 55 items per SM, the 896-thread shape) -- and stepping with either shape gives the same rows."""
+    import torch
+    from bioimitation_gym_b200 import backend
+    env_id, n = "MuscleWalkingImitation3D-v0", 2048
+    a_env = backend.VecEnv(env_id, dict(num_envs=n, seed=3))
+    b_env = backend.VecEnv(env_id, dict(num_envs=n, seed=3))
+    sms = torch.cuda.get_device_properties(a_env.device).multi_processor_count
+    assert a_env.coop_shape()[:2] == (1, 512)
+    b_env.set_grid(sms // 4)
+    assert b_env.coop_shape()[:2] == (1, 896)
+    b_env.set_grid(0)
+    assert b_env.coop_shape()[:2] == (1, 512)
+    b_env.set_grid(sms // 4)
+    a_env.reset()
+    b_env.reset()
+    g = torch.Generator(device=a_env.device).manual_seed(5)
+    for _ in range(3):
+        a = torch.rand((n, a_env.n_act), generator=g, device=a_env.device)
+        oa, ra, da, _ = a_env.step(a)
+        ob, rb, db, _ = b_env.step(a)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    a_env.close()
+    b_env.close()
+
+
 def test_native_group_loop_equals_the_single_batch():
     """EnvGroups.run (bio_groups_run, the native send / recv loop): 40 steps with a replayed action ring, then 40
     steps with a policy callback, give bit for bit the rows of one VecEnv of the same seeded batch."""
