@@ -17,6 +17,13 @@ host cores -- the benchmark build of the oracle (-O3 -march=native, FMA
 contraction, OpenMP over envs, compiled on the host that runs it), the SAME
 batch as the CUDA arm (4096 envs), INNER control steps per timed "step".
 
+`e2e`: every control step reads its actions from and writes its observation / reward / done / terms rows to
+page-locked HOST memory (the step kernel does both in place, over PCIe).  Two public calls are timed and the
+better one is `e2e.value` (`e2e.api` names it): the native env-group loop `bio_groups_run` (the batch as 4 groups
+on disjoint SMs, a group relaunched when its rows have landed, so one group's PCIe tail hides behind the others'
+substeps) and the synchronous whole-batch call `bio_step_host` (`e2e.synchronous`); `e2e.pipelined` is the same
+group pipeline driven by a Python send / recv loop.
+
 Before anything is timed the CUDA arm rolls the batch 150 control steps
 (untimed, independent of --warmup), so that the timed window holds the
 auto-resets of a steady-state rollout (`rollout.episodes` counts the episodes
