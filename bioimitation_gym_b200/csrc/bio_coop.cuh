@@ -1057,8 +1057,11 @@ __device__ __forceinline__ void coop_flush_obs(EnvWork<T, CLS>* works, T* __rest
 #ifndef BIO_COOP_HI3D
 #define BIO_COOP_HI3D 896
 #endif
+#ifndef BIO_COOP_HI2D
+#define BIO_COOP_HI2D 640
+#endif
 #define COOP_THREADS_LO(T) (sizeof(T) == 4 ? BIO_COOP_LO : 256)
-#define COOP_THREADS_HI(T, CLS) (sizeof(T) == 4 ? ((CLS) == 1 ? BIO_COOP_HI3D : 640) : 256)
+#define COOP_THREADS_HI(T, CLS) (sizeof(T) == 4 ? ((CLS) == 1 ? BIO_COOP_HI3D : BIO_COOP_HI2D) : 256)
 // time of one round of items with the HI shape relative to the LO shape
 #define COOP_SHAPE_COST(CLS) ((CLS) == 1 ? 1.45 : 1.12)
 
